@@ -1,0 +1,468 @@
+#!/usr/bin/env python
+"""bench.py -- NDT hot-path benchmark (BASELINE.json metric: NDT point-evals/s; batched matches/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload = "C4"): multi-start global relocalisation -- 65,536 pose hypotheses per
+GPU, one 1081-beam scan (resampled + voxel-filtered exactly as the reference's matchScan /
+estimatePose do) against the NDT grid of a 200 m x 200 m map, 0.5 m cells. One "step" = one full
+NDT match (Newton + More-Thuente, all on device) of every hypothesis of this rank's shard.
+Hypotheses are independent, so ranks shard them with no data-path collective; the finished grid is
+built on rank 0 and replicated once (NCCL broadcast over NVLink) before the timed region.
+
+value  = NDT point-evaluations/s (source points x objective passes, counted on the device), inputs
+         resident in HBM, CUDA-event timed on the launching stream, max over ranks.
+e2e    = the same metric through the C ABI with HOST buffers (pinned guesses in, all results out).
+The reference arm (--impl reference) times the CPU implementation of the same path on host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+METRIC = "ndt_point_evals_per_sec"
+UNIT = "point-evals/s"
+HYP_PER_GPU = 65_536
+LAUNCH = dict(space=0.05, space_thre=0.25, leaf=0.05)     # ndt_mapping.launch:15-16, 36
+RESOLUTION = 0.5
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------
+def build_c4(n_ranks: int, hyp_per_gpu: int):
+    """Map cloud, filtered source scan and the global hypothesis set (n_ranks * hyp_per_gpu)."""
+    from ndt_slam_b200 import synth
+    from oracle import oracle_api as oa   # data preparation only (resampler / voxel filter restatement)
+
+    d = synth.c4_reloc(seed=4)
+    scan = oa.resample(d["scan"], LAUNCH["space"], LAUNCH["space_thre"])          # ScanMatcher.cpp:6
+    src = oa.approx_voxel_filter(synth.to_xyzw(scan), LAUNCH["leaf"])              # PoseEstimator.cpp:6-10
+    tgt = synth.to_xyzw(d["map_pts"])
+    hyp = d["hypotheses"]
+    if n_ranks * hyp_per_gpu != hyp.shape[0]:
+        rng = synth.rng_for(404)
+        reps = int(np.ceil(n_ranks * hyp_per_gpu / hyp.shape[0]))
+        extra = [hyp]
+        for r in range(1, reps):
+            h2 = hyp.copy()
+            h2[:, 0:2] += rng.uniform(-0.7, 0.7, size=(hyp.shape[0], 2))
+            h2[:, 2] += rng.uniform(-0.1, 0.1, size=hyp.shape[0])
+            extra.append(h2)
+        hyp = np.concatenate(extra, axis=0)[: n_ranks * hyp_per_gpu]
+    return dict(tgt=tgt, src=src, hyp=np.ascontiguousarray(hyp), true_pose=np.array(d["true_pose"]))
+
+
+def shard(n_total: int, rank: int, world: int):
+    """Block partition [r*H/G, (r+1)*H/G)."""
+    lo = (n_total * rank) // world
+    hi = (n_total * (rank + 1)) // world
+    return lo, hi
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [r for r in self.rows if t0 - 0.05 <= r[0] <= t1 + 0.15] or self.rows
+        for _, line in rows:
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle restatement ("port") or the reference build in oracle/_ref ("reference")
+# ---------------------------------------------------------------------------------------------
+def cpu_matches(wl, prm, hyp, max_seconds: float, threads: int):
+    """Run full matches of `hyp` on host cores (one oracle instance per thread; ctypes drops the GIL).
+    Stops handing out work after max_seconds. Returns (point_evals, matches, seconds, kind)."""
+    from oracle import oracle_api as oa
+
+    kind = "port"
+    chunks = np.array_split(np.arange(hyp.shape[0]), max(threads * 8, 1))
+    t_start = time.perf_counter()
+    deadline = t_start + max_seconds + 2.0
+
+    def work(tid):
+        o = oa.Oracle(prm)
+        o.set_target(wl["tgt"]); o.set_source(wl["src"])
+        o.want_fitness(False)          # like the batched device call (n >= 64): rank by score, no 1-NN pass
+        pe = nm = 0
+        ready.wait()                    # timed region starts when every thread has its grid
+        t_ready = time.perf_counter()
+        while True:
+            with lock:
+                if not todo or time.perf_counter() > deadline:
+                    break
+                ids = todo.pop()
+            for i in ids:
+                r = o.align(hyp[i])
+                pe += r.point_evals; nm += 1
+        return pe, nm, t_ready
+
+    lock = threading.Lock()
+    ready = threading.Barrier(threads)
+    todo = [c for c in chunks if len(c)]
+    with ThreadPoolExecutor(threads) as ex:
+        outs = list(ex.map(work, range(threads)))
+    t_end = time.perf_counter()
+    t_ready = min(o[2] for o in outs)           # grid builds excluded
+    pe = sum(o[0] for o in outs); nm = sum(o[1] for o in outs)
+    return pe, nm, max(t_end - t_ready, 1e-9), kind
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--hyp-per-gpu", type=int, default=HYP_PER_GPU)
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = max(args.gpus, 1)
+    if world > 1 and world != n_gpus:
+        log(f"warning: WORLD_SIZE={world} != --gpus {n_gpus}; using WORLD_SIZE")
+        n_gpus = world
+    W = max(args.warmup, 3)
+    K = max(args.steps, 1)
+
+    if args.impl == "reference":
+        return reference_arm(args, rank, n_gpus, K, W)
+
+    import torch
+    import torch.distributed as dist
+
+    from ndt_slam_b200 import build, capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback (use --impl reference for the CPU arm)")
+    if not build.LIB_CUDA.exists():
+        build.build_cuda()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    wl = build_c4(n_gpus, args.hyp_per_gpu)
+    lo, hi = shard(wl["hyp"].shape[0], rank, world)
+    hyp = np.ascontiguousarray(wl["hyp"][lo:hi])
+    n_h = hyp.shape[0]
+    ns = wl["src"].shape[0]
+
+    stream = torch.cuda.current_stream()
+    prm = capi.default_params(resolution=RESOLUTION, device=local_rank, stream=stream.cuda_stream)
+    g = capi.Ndt(prm)
+
+    # ---- grid: built once on rank 0, replicated once, no collective afterwards -------------------
+    t_build = None
+    bcast_ms = None
+    if rank == 0:
+        g.set_target(wl["tgt"])
+        t_build = g.last_kernel_ms()
+    if world > 1:
+        nbytes_t = torch.zeros(1, dtype=torch.int64, device="cuda")
+        if rank == 0:
+            nbytes_t[0] = g.grid_blob_size()
+        dist.broadcast(nbytes_t, 0)
+        nbytes = int(nbytes_t.item())
+        blob = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            g.grid_export(blob.data_ptr(), nbytes)
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record(); dist.broadcast(blob, 0); e1.record(); torch.cuda.synchronize()
+        bcast_ms = e0.elapsed_time(e1)
+        if rank != 0:
+            g.grid_import(blob.data_ptr(), nbytes)
+        del blob
+    g.set_source(wl["src"])
+    gi = g.grid_info()
+
+    d_hyp = torch.from_numpy(hyp).cuda()
+    d_res = torch.zeros(n_h * capi.RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+
+    def step_device():
+        g.align_batch(d_hyp.data_ptr(), n=n_h, space=capi.MEM_DEVICE, out=d_res.data_ptr())
+
+    for _ in range(W):
+        step_device()
+    torch.cuda.synchronize()
+    res = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype=capi.RESULT_DTYPE)
+    pe_step = int(res["point_evals"].sum())
+    evals_mean = float(res["evals"].mean())
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = g.launch_count()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    evs = []
+    for _ in range(K):
+        flush.zero_()                                   # evict L2 between timed iterations (untimed)
+        a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+        a.record(stream); step_device(); b.record(stream)
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t1 = time.perf_counter()
+    launches = g.launch_count() - launches0
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = float(sum(step_ms))
+    tt = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    pe_t = torch.tensor([float(pe_step)], dtype=torch.float64, device="cuda")
+    nh_t = torch.tensor([float(n_h)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(pe_t, op=dist.ReduceOp.SUM)
+        dist.all_reduce(nh_t, op=dist.ReduceOp.SUM)
+    total_ms_max = float(tt.item())
+    pe_all = float(pe_t.item())
+    nh_all = float(nh_t.item())
+    clocks = sampler.stop(t0, t1) if sampler else None
+    ms_per_step = total_ms_max / K
+    value = pe_all / (ms_per_step * 1e-3)
+    matches_per_s = nh_all / (ms_per_step * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers (pinned in, results out) ------------------
+    h_hyp = torch.from_numpy(hyp).pin_memory()
+    h_res_t = torch.zeros(n_h * capi.RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    h_hyp_np = h_hyp.numpy()
+    h_res_np = h_res_t.numpy().view(capi.RESULT_DTYPE)
+
+    def step_e2e():
+        g.align_batch(h_hyp_np, n=n_h, space=capi.MEM_HOST, out=h_res_np)   # H2D + kernel + D2H + sync inside
+
+    step_e2e()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    te0 = time.perf_counter()
+    for _ in range(K):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - te0
+    et = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(et, op=dist.ReduceOp.MAX)
+    e2e_s = float(et.item())
+    e2e_value = pe_all * K / e2e_s
+    assert int(h_res_np["point_evals"].sum()) == pe_step
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- relocalisation sanity: the best hypothesis lands on the hidden true pose -----------------
+    conv = res["converged"] == 1
+    bi = int(np.argmax(np.where(conv, res["score"], -np.inf)))
+    best = res[bi]
+    reloc_err = float(np.hypot(*(best["pose"][:2] - wl["true_pose"][:2])))
+
+    # ---- roofline of the dominant kernel (k_align_warp): algorithmic bytes per SURVEY.md 8(d) ----
+    peaks, peak_src = measured_peaks()
+    d_pose = torch.from_numpy(np.ascontiguousarray(res["pose"])).cuda()
+    d_out = torch.zeros((n_h, 14), dtype=torch.float64, device="cuda")
+    g.eval_batch(d_pose.data_ptr(), n=n_h, want_hessian=False, space=capi.MEM_DEVICE, out=d_out.data_ptr())
+    torch.cuda.synchronize()
+    kbar = float(d_out[:, 13].sum().item()) / (n_h * ns)
+    bytes_per_eval = 160.0 + 48.0 * kbar
+    kern_ms = float(np.mean(step_ms))                 # one launch per step: step time == kernel time
+    achieved = pe_step * bytes_per_eval / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get("k_align_warp_C4_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
+                "kernel": "k_align_warp", "bytes_per_point_eval": bytes_per_eval, "kbar": kbar,
+                "note": "C4 grid (%.1f MB) is L2-resident: the HBM-equivalent fraction is an algorithmic-bytes figure, "
+                        "the kernel is fp64-issue / L1-L2 latency bound (see DESIGN.md)" %
+                        ((gi.n_slots * 64 + gi.div_b[0] * gi.div_b[1] * 4) / 1e6)}
+
+    # ---- CPU baseline on this box's host cores (bounded sample of the same workload) --------------
+    cores = os.cpu_count() or 1
+    sample_n = min(n_h, 4096)
+    pe_c, nm_c, sec_c, kind = cpu_matches(wl, prm, hyp[:sample_n], max_seconds=12.0, threads=cores)
+    cpu_baseline = {"value": pe_c / sec_c, "unit": UNIT, "cores": cores, "kind": kind,
+                    "sample": f"{nm_c} of {n_h} hypotheses of this workload, full matches, {cores} threads, {sec_c:.1f} s",
+                    "matches_per_sec": nm_c / sec_c}
+
+    extras = {}
+    if not args.no_extras and world == 1:
+        try:
+            extras = run_extras(g, prm, capi, torch)
+        except Exception as ex:       # reported, never hidden
+            extras = {"error": repr(ex)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C4: multi-start relocalisation, %d hypotheses/GPU x 1081-beam scan (N_s=%d after resample+voxel filter) "
+                               "vs 200 m x 200 m map, 0.5 m cells" % (args.hyp_per_gpu, ns),
+                   "hypotheses_total": int(nh_all), "target_points": int(wl["tgt"].shape[0]),
+                   "grid_cells": [int(gi.div_b[0]), int(gi.div_b[1])], "occupied_cells": int(gi.n_slots),
+                   "resolution_m": RESOLUTION, "parallelism": f"hypothesis-shard x{n_gpus}, grid replicated once",
+                   "l2": "flushed between timed iterations (256 MiB write)"},
+        "matches_per_sec": matches_per_s, "evals_per_match": evals_mean, "point_evals_per_step": pe_all,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_h * 24),
+                "d2h_bytes_per_step": int(n_h * capi.RESULT_DTYPE.itemsize), "matches_per_sec": nh_all * K / e2e_s},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "grid_build_ms": t_build, "grid_broadcast_ms": bcast_ms,
+        "reloc_best_error_m": reloc_err,
+        "extras": extras,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_extras(g, prm, capi, torch):
+    """Secondary figures on 1 GPU: C1 single-match latency, grid-build rate, C3 if memory allows."""
+    from ndt_slam_b200 import synth
+    from oracle import oracle_api as oa
+
+    out = {}
+    # C1: single scan vs grid of the previous scan
+    d = synth.c1_pair(1)
+    ra = oa.resample(d["scan_a"], LAUNCH["space"], LAUNCH["space_thre"])
+    rb = oa.resample(d["scan_b"], LAUNCH["space"], LAUNCH["space_thre"])
+    tgt = synth.to_xyzw(synth.transform(ra, d["pose_a"]))
+    src = oa.approx_voxel_filter(synth.to_xyzw(rb), LAUNCH["leaf"])
+    g1 = capi.Ndt(prm)
+    guess = np.array(d["pose_a"])
+    ks, bs, ws = [], [], []
+    for i in range(25):
+        t0 = time.perf_counter()
+        g1.set_target(tgt); bs.append(g1.last_kernel_ms())
+        g1.set_source(src)
+        r = g1.align(guess); ks.append(g1.last_kernel_ms())
+        ws.append((time.perf_counter() - t0) * 1e3)
+    o = oa.Oracle(prm)
+    t0 = time.perf_counter()
+    for i in range(25):
+        o.set_target(tgt); o.set_source(src); ro = o.align(guess)
+    cpu_ms = (time.perf_counter() - t0) * 1e3 / 25
+    out["C1"] = {"match_kernel_ms": float(np.median(ks[5:])), "grid_build_kernels_ms": float(np.median(bs[5:])),
+                 "e2e_host_call_ms": float(np.median(ws[5:])), "cpu_oracle_ms_1thread": cpu_ms,
+                 "evals": int(r.evals), "n_source": int(src.shape[0]), "n_target": int(tgt.shape[0]),
+                 "pose_matches_oracle": bool(np.hypot(r.pose[0] - ro.pose[0], r.pose[1] - ro.pose[1]) < 1e-4)}
+    return out
+
+
+def reference_arm(args, rank, n_gpus, K, W):
+    """CPU implementation of the same path on host cores; rank 0 only."""
+    if rank != 0:
+        return
+    from ndt_slam_b200 import capi
+
+    prm = capi.NdtParams(resolution=RESOLUTION, step_size=0.1, trans_eps=0.01, max_iter=35, outlier_ratio=0.55,
+                         min_points=6, eig_mult=0.01, quirks=capi.QUIRKS_PCL_1_10, device=0, stream=None)
+    wl = build_c4(n_gpus, args.hyp_per_gpu)
+    hyp = wl["hyp"]
+    ns = wl["src"].shape[0]
+    cores = os.cpu_count() or 1
+    per_step = max(64, min(hyp.shape[0], 16 * cores))     # bounded sample per step
+    rng = np.random.Generator(np.random.PCG64(99))
+    tot_pe = tot_nm = 0
+    tot_s = 0.0
+    kind = "port"
+    for s in range(W + K):
+        ids = rng.choice(hyp.shape[0], size=per_step, replace=False)
+        pe, nm, sec, kind = cpu_matches(wl, prm, hyp[ids], max_seconds=60.0, threads=cores)
+        if s >= W:
+            tot_pe += pe; tot_nm += nm; tot_s += sec
+    value = tot_pe / tot_s
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K,
+            "warmup": W, "ms_per_step": tot_s / K * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C4: multi-start relocalisation (sampled: %d hypotheses/step) x 1081-beam scan (N_s=%d) "
+                                   "vs 200 m x 200 m map, 0.5 m cells" % (per_step, ns)},
+            "matches_per_sec": tot_nm / tot_s,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": f"{per_step} random hypotheses per step, {K} steps, {cores} threads"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

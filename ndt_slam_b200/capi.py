@@ -1,0 +1,272 @@
+"""ctypes binding of the C ABI in include/ndt_b200.h (libndt_b200.so).
+
+This is plumbing for tests and bench.py: numpy host buffers or raw device pointers (torch tensors'
+data_ptr()) go straight to the C entry points. There is no fallback of any kind: if the CUDA
+library is missing, importing `load()` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+from . import build as _build
+
+MEM_HOST, MEM_DEVICE = 0, 1
+
+QUIRK_COV_INIT_IDENTITY = 1 << 0
+QUIRK_COV_SCALE_NM1_N = 1 << 1
+QUIRK_MT_INTERVAL_LT0 = 1 << 2
+QUIRK_ANGLE_SNAP = 1 << 3
+QUIRK_TRANSFORM_SSE_ORDER = 1 << 4
+QUIRKS_PCL_1_10 = QUIRK_COV_INIT_IDENTITY | QUIRK_COV_SCALE_NM1_N | QUIRK_MT_INTERVAL_LT0 | QUIRK_ANGLE_SNAP
+
+
+class NdtParams(C.Structure):
+    _fields_ = [("resolution", C.c_float), ("step_size", C.c_double), ("trans_eps", C.c_double),
+                ("max_iter", C.c_int32), ("outlier_ratio", C.c_double), ("min_points", C.c_int32),
+                ("eig_mult", C.c_double), ("quirks", C.c_int32), ("device", C.c_int32),
+                ("stream", C.c_void_p)]
+
+
+class NdtEvalOut(C.Structure):
+    _fields_ = [("score", C.c_double), ("grad", C.c_double * 3), ("hess", C.c_double * 9),
+                ("n_pairs", C.c_int64)]
+
+
+class NdtResult(C.Structure):
+    _fields_ = [("pose", C.c_double * 3), ("T", C.c_float * 16), ("score", C.c_double),
+                ("trans_prob", C.c_double), ("fitness", C.c_double), ("hess", C.c_double * 9),
+                ("converged", C.c_int32), ("iters", C.c_int32), ("evals", C.c_int32),
+                ("reserved", C.c_int32), ("point_evals", C.c_int64)]
+
+
+class NdtGridInfo(C.Structure):
+    _fields_ = [("min_b", C.c_int32 * 2), ("div_b", C.c_int32 * 2), ("n_points", C.c_int64),
+                ("n_leaves", C.c_int32), ("n_slots", C.c_int32), ("n_valid", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+# numpy view of ndt_result for batched calls (must match the C layout; checked in tests)
+RESULT_DTYPE = np.dtype([("pose", "<f8", 3), ("T", "<f4", 16), ("score", "<f8"), ("trans_prob", "<f8"),
+                         ("fitness", "<f8"), ("hess", "<f8", 9), ("converged", "<i4"), ("iters", "<i4"),
+                         ("evals", "<i4"), ("reserved", "<i4"), ("point_evals", "<i8")], align=True)
+
+EXPORTS = [
+    "ndt_params_default", "ndt_create", "ndt_destroy", "ndt_last_error", "ndt_version",
+    "ndt_set_target", "ndt_get_grid_info", "ndt_grid_readback", "ndt_cell_index",
+    "ndt_set_source", "ndt_approx_voxel_filter", "ndt_eval", "ndt_eval_batch",
+    "ndt_align", "ndt_align_batch", "ndt_best_of", "ndt_match_pairs",
+    "ndt_grid_blob_size", "ndt_grid_export", "ndt_grid_import",
+    "ndt_launch_count", "ndt_last_kernel_ms", "ndt_synchronize",
+]
+
+_lib = None
+
+
+def lib_path() -> Path:
+    return _build.LIB_CUDA
+
+
+def load() -> C.CDLL:
+    """dlopen libndt_b200.so (no compute call, works without a GPU). Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not p.exists():
+        raise RuntimeError(f"{p} is not built -- run `python -m ndt_slam_b200.build` (there is no CPU fallback)")
+    L = C.CDLL(str(p))
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
+    L.ndt_params_default.argtypes = [C.POINTER(NdtParams)]
+    L.ndt_create.argtypes = [C.POINTER(NdtParams), C.POINTER(vp)]
+    L.ndt_destroy.argtypes = [vp]
+    L.ndt_last_error.argtypes = [vp]
+    L.ndt_last_error.restype = C.c_char_p
+    L.ndt_version.restype = C.c_char_p
+    L.ndt_set_target.argtypes = [vp, vp, i64, i32]
+    L.ndt_get_grid_info.argtypes = [vp, C.POINTER(NdtGridInfo)]
+    L.ndt_grid_readback.argtypes = [vp, i64, vp, vp, vp, vp, vp, C.POINTER(i64)]
+    L.ndt_cell_index.argtypes = [vp, vp, i64, i32, vp]
+    L.ndt_set_source.argtypes = [vp, vp, i64, i32]
+    L.ndt_approx_voxel_filter.argtypes = [vp, vp, i64, C.c_float, i32, vp, C.POINTER(i64)]
+    L.ndt_eval.argtypes = [vp, C.POINTER(C.c_double), i32, C.POINTER(NdtEvalOut)]
+    L.ndt_eval_batch.argtypes = [vp, vp, i64, i32, i32, vp]
+    L.ndt_align.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(NdtResult)]
+    L.ndt_align_batch.argtypes = [vp, vp, i64, i32, vp]
+    L.ndt_best_of.argtypes = [vp, vp, i64, i32, C.POINTER(i64), C.POINTER(NdtResult)]
+    L.ndt_match_pairs.argtypes = [vp, vp, vp, vp, vp, vp, i64, C.c_float, i32, vp]
+    L.ndt_grid_blob_size.argtypes = [vp, C.POINTER(i64)]
+    L.ndt_grid_export.argtypes = [vp, vp, i64]
+    L.ndt_grid_import.argtypes = [vp, vp, i64]
+    L.ndt_launch_count.argtypes = [vp, C.POINTER(i64)]
+    L.ndt_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.ndt_synchronize.argtypes = [vp]
+    for name in EXPORTS:
+        if name not in ("ndt_last_error", "ndt_version"):
+            getattr(L, name).restype = C.c_int
+    _lib = L
+    return L
+
+
+class NdtError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    """numpy array -> void*, int -> device pointer passthrough."""
+    if a is None:
+        return None
+    if isinstance(a, (int,)):
+        return C.c_void_p(a)
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def default_params(**kw) -> NdtParams:
+    p = NdtParams()
+    load().ndt_params_default(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+class Ndt:
+    """Thin object wrapper over one ndt_handle."""
+
+    def __init__(self, params: NdtParams | None = None, **kw):
+        self.L = load()
+        self.params = params if params is not None else default_params(**kw)
+        self.h = C.c_void_p()
+        rc = self.L.ndt_create(C.byref(self.params), C.byref(self.h))
+        if rc != 0:
+            msg = self.L.ndt_last_error(None)
+            raise NdtError(f"ndt_create failed ({rc}): {msg.decode() if msg else ''}")
+
+    def close(self):
+        if self.h:
+            self.L.ndt_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self.L.ndt_last_error(self.h)
+            raise NdtError(f"ndt call failed ({rc}): {msg.decode() if msg else ''}")
+
+    # -- grid --
+    def set_target(self, xyzw, n=None, space=MEM_HOST):
+        if n is None:
+            n = xyzw.shape[0]
+        self._ck(self.L.ndt_set_target(self.h, _ptr(xyzw), n, space))
+
+    def grid_info(self) -> NdtGridInfo:
+        gi = NdtGridInfo()
+        self._ck(self.L.ndt_get_grid_info(self.h, C.byref(gi)))
+        return gi
+
+    def grid_readback(self):
+        gi = self.grid_info()
+        n = gi.n_leaves
+        idx = np.zeros(n, np.int32); cnt = np.zeros(n, np.int32)
+        mean = np.zeros((n, 2)); icov = np.zeros((n, 4)); cen = np.zeros((n, 2), np.float32)
+        nout = C.c_int64()
+        self._ck(self.L.ndt_grid_readback(self.h, n, _ptr(idx), _ptr(cnt), _ptr(mean), _ptr(icov), _ptr(cen), C.byref(nout)))
+        assert nout.value == n
+        return dict(cell_idx=idx, nr_points=cnt, mean=mean, icov=icov, centroid=cen)
+
+    def cell_index(self, xyzw, n=None, space=MEM_HOST):
+        if n is None:
+            n = xyzw.shape[0]
+        out = np.zeros(n, np.int32)
+        self._ck(self.L.ndt_cell_index(self.h, _ptr(xyzw), n, space, _ptr(out)))
+        return out
+
+    # -- source --
+    def set_source(self, xyzw, n=None, space=MEM_HOST):
+        if n is None:
+            n = xyzw.shape[0]
+        self._ck(self.L.ndt_set_source(self.h, _ptr(xyzw), n, space))
+
+    def approx_voxel_filter(self, xyzw, leaf: float):
+        n = xyzw.shape[0]
+        out = np.zeros((n, 4), np.float32)
+        nout = C.c_int64()
+        self._ck(self.L.ndt_approx_voxel_filter(self.h, _ptr(xyzw), n, leaf, MEM_HOST, _ptr(out), C.byref(nout)))
+        return np.ascontiguousarray(out[: nout.value])
+
+    # -- objective --
+    def eval(self, pose, want_hessian=True) -> NdtEvalOut:
+        p = (C.c_double * 3)(*pose)
+        out = NdtEvalOut()
+        self._ck(self.L.ndt_eval(self.h, p, int(want_hessian), C.byref(out)))
+        return out
+
+    def eval_batch(self, poses, n=None, want_hessian=True, space=MEM_HOST, out=None):
+        if n is None:
+            n = poses.shape[0]
+        if out is None:
+            out = np.zeros((n, 14))
+        self._ck(self.L.ndt_eval_batch(self.h, _ptr(poses), n, int(want_hessian), space, _ptr(out)))
+        return out
+
+    # -- matching --
+    def align(self, guess) -> NdtResult:
+        g = (C.c_double * 3)(*guess)
+        r = NdtResult()
+        self._ck(self.L.ndt_align(self.h, g, C.byref(r)))
+        return r
+
+    def align_batch(self, guesses, n=None, space=MEM_HOST, out=None):
+        if n is None:
+            n = guesses.shape[0]
+        if out is None:
+            out = np.zeros(n, RESULT_DTYPE)
+        self._ck(self.L.ndt_align_batch(self.h, _ptr(guesses), n, space, _ptr(out)))
+        return out
+
+    def best_of(self, results, n=None, space=MEM_HOST):
+        if n is None:
+            n = results.shape[0]
+        bi = C.c_int64(); best = NdtResult()
+        self._ck(self.L.ndt_best_of(self.h, _ptr(results), n, space, C.byref(bi), C.byref(best)))
+        return bi.value, best
+
+    def match_pairs(self, src, src_off, tgt, tgt_off, guesses, n_pairs, source_leaf=0.0, space=MEM_HOST, out=None):
+        if out is None:
+            out = np.zeros(n_pairs, RESULT_DTYPE)
+        self._ck(self.L.ndt_match_pairs(self.h, _ptr(src), _ptr(src_off), _ptr(tgt), _ptr(tgt_off), _ptr(guesses),
+                                        n_pairs, source_leaf, space, _ptr(out)))
+        return out
+
+    # -- replication --
+    def grid_blob_size(self) -> int:
+        b = C.c_int64()
+        self._ck(self.L.ndt_grid_blob_size(self.h, C.byref(b)))
+        return b.value
+
+    def grid_export(self, dev_ptr: int, nbytes: int):
+        self._ck(self.L.ndt_grid_export(self.h, C.c_void_p(dev_ptr), nbytes))
+
+    def grid_import(self, dev_ptr: int, nbytes: int):
+        self._ck(self.L.ndt_grid_import(self.h, C.c_void_p(dev_ptr), nbytes))
+
+    # -- instrumentation --
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        self._ck(self.L.ndt_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float()
+        self._ck(self.L.ndt_last_kernel_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def synchronize(self):
+        self._ck(self.L.ndt_synchronize(self.h))

@@ -1,0 +1,514 @@
+// capi.cu -- the extern "C" boundary declared in include/ndt_b200.h.
+// Each entry point names the reference call it replaces (see the header). No torch types, no
+// exceptions, no CPU fallback: without a CUDA device ndt_create fails with NDT_ERR_NO_DEVICE.
+#include "ndt_host.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+namespace ndt {
+
+static thread_local std::string g_create_err;
+
+int set_err(Handle *h, int code, const char *what, cudaError_t e) {
+  std::string m = what ? what : "";
+  if (e != cudaSuccess) { m += ": "; m += cudaGetErrorString(e); (void)cudaGetLastError(); }
+  if (h) h->err = m; else g_create_err = m;
+  return code;
+}
+
+int ensure_pinned(Handle *h, size_t bytes) {
+  if (bytes <= h->pinned_cap) return 0;
+  if (h->pinned) cudaFreeHost(h->pinned);
+  h->pinned = nullptr; h->pinned_cap = 0;
+  size_t want = bytes + bytes / 4 + 4096;
+  cudaError_t e = cudaMallocHost(&h->pinned, want);
+  if (e != cudaSuccess) { set_err(h, NDT_ERR_CUDA, "cudaMallocHost", e); return 1; }
+  h->pinned_cap = want;
+  return 0;
+}
+
+// header of the flat grid blob used for replication
+struct BlobHeader {
+  uint64_t magic;
+  GridDims gd;
+  int32_t counters[CTR_COUNT];
+  int64_t off_slot, off_recs, off_leaf_id, off_leaf_start, off_leaf_n, off_sorted, off_tgt, total;
+};
+static constexpr uint64_t kBlobMagic = 0x4e44544232303042ull;  // "NDTB200B"
+
+static inline int64_t align256(int64_t v) { return (v + 255) & ~int64_t(255); }
+
+static BlobHeader blob_layout(const Handle *h) {
+  BlobHeader b{};
+  b.magic = kBlobMagic;
+  b.gd = h->gd;
+  std::memcpy(b.counters, h->h_counters, sizeof(b.counters));
+  const int64_t nc = h->gd.n_cells, nl = h->h_counters[CTR_LEAVES], nsl = h->h_counters[CTR_SLOTS], nt = h->gd.n_tgt;
+  int64_t o = align256(sizeof(BlobHeader));
+  b.off_slot = o; o = align256(o + nc * 4);
+  b.off_recs = o; o = align256(o + nsl * (int64_t)sizeof(CellRec));
+  b.off_leaf_id = o; o = align256(o + nc * 4);
+  b.off_leaf_start = o; o = align256(o + nl * 4);
+  b.off_leaf_n = o; o = align256(o + nl * 4);
+  b.off_sorted = o; o = align256(o + nt * 4);
+  b.off_tgt = o; o = align256(o + nt * (int64_t)sizeof(float4));
+  b.total = o;
+  return b;
+}
+
+}  // namespace ndt
+
+using namespace ndt;
+
+#define H_OR_FAIL(hh)                                     \
+  Handle *h = reinterpret_cast<Handle *>(hh);             \
+  if (!h) return NDT_ERR_ARG;                             \
+  if (cudaSetDevice(h->device) != cudaSuccess) return set_err(h, NDT_ERR_CUDA, "cudaSetDevice")
+
+extern "C" {
+
+const char *ndt_version(void) { return "ndt_b200 0.1.0 (sm_100a)"; }
+
+int ndt_params_default(ndt_params *p) {
+  if (!p) return NDT_ERR_ARG;
+  // C++ defaults of PoseEstimator (include/ndt_slam/PoseEstimator.h:63-64) + PCL's internal constants
+  p->resolution = 1.0f;
+  p->step_size = 0.1;
+  p->trans_eps = 0.01;
+  p->max_iter = 35;
+  p->outlier_ratio = 0.55;
+  p->min_points = 6;
+  p->eig_mult = 0.01;
+  p->quirks = NDT_QUIRKS_PCL_1_10;
+  p->device = 0;
+  p->stream = nullptr;
+  return NDT_OK;
+}
+
+int ndt_create(const ndt_params *p, ndt_handle *out) {
+  if (!p || !out) return NDT_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    set_err(nullptr, NDT_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)", e);
+    return NDT_ERR_NO_DEVICE;
+  }
+  if (p->device < 0 || p->device >= ndev) { set_err(nullptr, NDT_ERR_ARG, "bad device ordinal"); return NDT_ERR_ARG; }
+  if (!(p->resolution > 0.f)) { set_err(nullptr, NDT_ERR_ARG, "resolution must be > 0"); return NDT_ERR_ARG; }
+  if (cudaSetDevice(p->device) != cudaSuccess) { set_err(nullptr, NDT_ERR_CUDA, "cudaSetDevice"); return NDT_ERR_CUDA; }
+  Handle *h = new Handle();
+  h->prm = *p;
+  h->device = p->device;
+  if (p->stream) { h->stream = (cudaStream_t)p->stream; h->own_stream = false; }
+  else {
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+      set_err(nullptr, NDT_ERR_CUDA, "cudaStreamCreate", e); delete h; return NDT_ERR_CUDA;
+    }
+    h->own_stream = true;
+  }
+  cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
+  cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
+  cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+  if ((e = h->gb.counters.reserve((CTR_COUNT + 4) * sizeof(int32_t))) != cudaSuccess ||
+      (e = h->stage.reserve(4096)) != cudaSuccess) {
+    set_err(nullptr, NDT_ERR_CUDA, "cudaMalloc", e); delete h; return NDT_ERR_CUDA;
+  }
+  *out = reinterpret_cast<ndt_handle>(h);
+  return NDT_OK;
+}
+
+int ndt_destroy(ndt_handle hh) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return NDT_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  GridBuffers &g = h->gb;
+  DevBuf *all[] = {&g.tgt, &g.cell_of, &g.rank_of, &g.list, &g.sorted_idx, &g.slot, &g.leaf_id, &g.leaf_cell,
+                   &g.leaf_n, &g.leaf_start, &g.leaf_nr, &g.leaf_mean, &g.leaf_icov, &g.leaf_cen, &g.recs,
+                   &g.counters, &h->src, &h->scratch, &h->scratch2, &h->stage, &h->io};
+  for (DevBuf *b : all) b->release();
+  if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return NDT_OK;
+}
+
+const char *ndt_last_error(ndt_handle hh) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  return h ? h->err.c_str() : g_create_err.c_str();
+}
+
+int ndt_set_target(ndt_handle hh, const float *xyzw, int64_t n, int memspace) {
+  H_OR_FAIL(hh);
+  return grid_build(h, xyzw, n, memspace);
+}
+
+int ndt_get_grid_info(ndt_handle hh, ndt_grid_info *info) {
+  H_OR_FAIL(hh);
+  if (!info) return NDT_ERR_ARG;
+  if (!h->have_grid) return set_err(h, NDT_ERR_STATE, "ndt_get_grid_info: no target set");
+  std::memset(info, 0, sizeof(*info));
+  info->min_b[0] = h->gd.min_bx; info->min_b[1] = h->gd.min_by;
+  info->div_b[0] = h->gd.div_x; info->div_b[1] = h->gd.div_y;
+  info->n_points = h->h_counters[CTR_PTS];
+  info->n_leaves = h->h_counters[CTR_LEAVES];
+  info->n_slots = h->h_counters[CTR_SLOTS];
+  info->n_valid = h->h_counters[CTR_VALID];
+  return NDT_OK;
+}
+
+int ndt_grid_readback(ndt_handle hh, int64_t cap, int32_t *cell_idx, int32_t *nr_points, double *mean2,
+                      double *icov4, float *centroid2, int64_t *n_out) {
+  H_OR_FAIL(hh);
+  if (!h->have_grid) return set_err(h, NDT_ERR_STATE, "ndt_grid_readback: no target set");
+  const int64_t nl = h->h_counters[CTR_LEAVES];
+  if (n_out) *n_out = nl;
+  if (nl == 0 || cap <= 0) return NDT_OK;
+  std::vector<int32_t> cell(nl), nr(nl);
+  std::vector<double> mean(2 * nl), icov(4 * nl);
+  std::vector<float> cen(2 * nl);
+  cudaStream_t st = h->stream;
+  NDT_CUDA(h, cudaMemcpyAsync(cell.data(), h->gb.leaf_cell.p, nl * 4, cudaMemcpyDeviceToHost, st));
+  NDT_CUDA(h, cudaMemcpyAsync(nr.data(), h->gb.leaf_nr.p, nl * 4, cudaMemcpyDeviceToHost, st));
+  NDT_CUDA(h, cudaMemcpyAsync(mean.data(), h->gb.leaf_mean.p, nl * 16, cudaMemcpyDeviceToHost, st));
+  NDT_CUDA(h, cudaMemcpyAsync(icov.data(), h->gb.leaf_icov.p, nl * 32, cudaMemcpyDeviceToHost, st));
+  NDT_CUDA(h, cudaMemcpyAsync(cen.data(), h->gb.leaf_cen.p, nl * 8, cudaMemcpyDeviceToHost, st));
+  NDT_CUDA(h, cudaStreamSynchronize(st));
+  // PCL keeps leaves in a std::map keyed by cell index: report in that order
+  std::vector<int64_t> order(nl);
+  std::iota(order.begin(), order.end(), 0);
+  std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return cell[a] < cell[b]; });
+  const int64_t m = std::min(cap, nl);
+  for (int64_t k = 0; k < m; ++k) {
+    const int64_t s = order[k];
+    if (cell_idx) cell_idx[k] = cell[s];
+    if (nr_points) nr_points[k] = nr[s];
+    if (mean2) { mean2[2 * k] = mean[2 * s]; mean2[2 * k + 1] = mean[2 * s + 1]; }
+    if (icov4) for (int a = 0; a < 4; ++a) icov4[4 * k + a] = icov[4 * s + a];
+    if (centroid2) { centroid2[2 * k] = cen[2 * s]; centroid2[2 * k + 1] = cen[2 * s + 1]; }
+  }
+  return NDT_OK;
+}
+
+int ndt_cell_index(ndt_handle hh, const float *xyzw, int64_t n, int memspace, int32_t *idx_out) {
+  H_OR_FAIL(hh);
+  if (n > 0 && (!xyzw || !idx_out)) return set_err(h, NDT_ERR_ARG, "ndt_cell_index: null buffer");
+  return grid_cell_index(h, xyzw, n, memspace, idx_out);
+}
+
+int ndt_set_source(ndt_handle hh, const float *xyzw, int64_t n, int memspace) {
+  H_OR_FAIL(hh);
+  if (n < 0 || (n > 0 && !xyzw)) return set_err(h, NDT_ERR_ARG, "ndt_set_source: bad points");
+  if (n > 0x7fffffffLL) return set_err(h, NDT_ERR_CAPACITY, "ndt_set_source: too many points");
+  h->have_src = false;
+  NDT_CUDA(h, h->src.reserve((size_t)std::max<int64_t>(n, 1) * sizeof(float4)));
+  if (n > 0) {
+    if (memspace == NDT_MEM_HOST) {
+      if (ensure_pinned(h, (size_t)n * sizeof(float4))) return NDT_ERR_CUDA;
+      std::memcpy(h->pinned, xyzw, (size_t)n * sizeof(float4));
+      NDT_CUDA(h, cudaMemcpyAsync(h->src.p, h->pinned, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+      NDT_CUDA(h, cudaStreamSynchronize(h->stream));   // the pinned stage is reused by later calls
+    } else {
+      NDT_CUDA(h, cudaMemcpyAsync(h->src.p, xyzw, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
+    }
+  }
+  h->ns = n;
+  h->have_src = true;
+  return NDT_OK;
+}
+
+int ndt_approx_voxel_filter(ndt_handle hh, const float *xyzw, int64_t n, float leaf, int memspace,
+                            float *out_xyzw, int64_t *n_out) {
+  H_OR_FAIL(hh);
+  if (n < 0 || !n_out || (n > 0 && (!xyzw || !out_xyzw)) || !(leaf > 0.f))
+    return set_err(h, NDT_ERR_ARG, "ndt_approx_voxel_filter: bad argument");
+  *n_out = 0;
+  if (n == 0) return NDT_OK;
+  cudaStream_t st = h->stream;
+  const size_t bytes = (size_t)n * sizeof(float4);
+  NDT_CUDA(h, h->scratch.reserve(2 * bytes + 256));
+  float4 *d_in = h->scratch.as<float4>();
+  float4 *d_out = d_in + n;
+  int32_t *d_n = h->gb.counters.as<int32_t>() + CTR_JOB;
+  const float4 *in = reinterpret_cast<const float4 *>(xyzw);
+  if (memspace == NDT_MEM_HOST) {
+    NDT_CUDA(h, cudaMemcpyAsync(d_in, xyzw, bytes, cudaMemcpyHostToDevice, st));
+    in = d_in;
+  }
+  float4 *outp = (memspace == NDT_MEM_HOST) ? d_out : reinterpret_cast<float4 *>(out_xyzw);
+  int rc = launch_voxel_filter(h, in, n, leaf, outp, d_n);
+  if (rc) return rc;
+  int32_t m = 0;
+  NDT_CUDA(h, cudaMemcpyAsync(&m, d_n, 4, cudaMemcpyDeviceToHost, st));
+  NDT_CUDA(h, cudaStreamSynchronize(st));
+  if (memspace == NDT_MEM_HOST && m > 0) {
+    NDT_CUDA(h, cudaMemcpyAsync(out_xyzw, d_out, (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost, st));
+    NDT_CUDA(h, cudaStreamSynchronize(st));
+  }
+  *n_out = m;
+  return NDT_OK;
+}
+
+static int need_ready(Handle *h, const char *who) {
+  if (!h->have_grid) return set_err(h, NDT_ERR_STATE, (std::string(who) + ": no target set").c_str());
+  if (!h->have_src) return set_err(h, NDT_ERR_STATE, (std::string(who) + ": no source set").c_str());
+  return NDT_OK;
+}
+
+int ndt_eval(ndt_handle hh, const double pose[3], int want_hessian, ndt_eval_out *out) {
+  H_OR_FAIL(hh);
+  if (!pose || !out) return set_err(h, NDT_ERR_ARG, "ndt_eval: null argument");
+  if (int rc = need_ready(h, "ndt_eval")) return rc;
+  cudaStream_t st = h->stream;
+  if (ensure_pinned(h, 256)) return NDT_ERR_CUDA;
+  static_assert(sizeof(double) * (3 + NACC + 1) + sizeof(int64_t) <= 256, "stage");
+  double *hp = (double *)h->pinned;
+  hp[0] = pose[0]; hp[1] = pose[1]; hp[2] = pose[2];
+  double *d_pose = h->stage.as<double>(), *d_out = d_pose + 3;
+  int64_t *d_pairs = (int64_t *)(d_out + NACC + 1);
+  NDT_CUDA(h, cudaMemcpyAsync(d_pose, hp, 24, cudaMemcpyHostToDevice, st));
+  int rc = launch_eval(h, d_pose, 1, want_hessian, d_out, d_pairs);
+  if (rc) return rc;
+  NDT_CUDA(h, cudaMemcpyAsync(hp + 3, d_out, sizeof(double) * (NACC + 1) + 8, cudaMemcpyDeviceToHost, st));
+  NDT_CUDA(h, cudaStreamSynchronize(st));
+  if (h->timing) cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
+  h->ms_pending = false;
+  out->score = hp[3];
+  for (int k = 0; k < 3; ++k) out->grad[k] = hp[4 + k];
+  for (int k = 0; k < 9; ++k) out->hess[k] = hp[7 + k];
+  std::memcpy(&out->n_pairs, hp + 3 + NACC + 1, 8);
+  return NDT_OK;
+}
+
+int ndt_eval_batch(ndt_handle hh, const double *poses, int64_t n, int want_hessian, int memspace, double *out14) {
+  H_OR_FAIL(hh);
+  if (n < 0 || (n > 0 && (!poses || !out14))) return set_err(h, NDT_ERR_ARG, "ndt_eval_batch: bad argument");
+  if (int rc = need_ready(h, "ndt_eval_batch")) return rc;
+  if (n == 0) return NDT_OK;
+  cudaStream_t st = h->stream;
+  if (memspace == NDT_MEM_DEVICE) {
+    h->ms_pending = true;
+    return launch_eval(h, poses, n, want_hessian, out14, nullptr);
+  }
+  const size_t pb = (size_t)n * 3 * sizeof(double), ob = (size_t)n * (NACC + 1) * sizeof(double);
+  NDT_CUDA(h, h->io.reserve(pb + ob));
+  double *d_poses = h->io.as<double>(), *d_out = d_poses + 3 * n;
+  NDT_CUDA(h, cudaMemcpyAsync(d_poses, poses, pb, cudaMemcpyHostToDevice, st));
+  int rc = launch_eval(h, d_poses, n, want_hessian, d_out, nullptr);
+  if (rc) return rc;
+  NDT_CUDA(h, cudaMemcpyAsync(out14, d_out, ob, cudaMemcpyDeviceToHost, st));
+  NDT_CUDA(h, cudaStreamSynchronize(st));
+  if (h->timing) cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
+  h->ms_pending = false;
+  return NDT_OK;
+}
+
+int ndt_align(ndt_handle hh, const double guess[3], ndt_result *out) {
+  H_OR_FAIL(hh);
+  if (!guess || !out) return set_err(h, NDT_ERR_ARG, "ndt_align: null argument");
+  if (int rc = need_ready(h, "ndt_align")) return rc;
+  cudaStream_t st = h->stream;
+  if (ensure_pinned(h, 1024)) return NDT_ERR_CUDA;
+  double *hp = (double *)h->pinned;
+  hp[0] = guess[0]; hp[1] = guess[1]; hp[2] = guess[2];
+  ndt_result *hres = (ndt_result *)(hp + 4);
+  double *d_guess = h->stage.as<double>();
+  ndt_result *d_res = (ndt_result *)(d_guess + 4);
+  NDT_CUDA(h, cudaMemcpyAsync(d_guess, hp, 24, cudaMemcpyHostToDevice, st));
+  int rc = launch_align(h, d_guess, 1, d_res, true);
+  if (rc) return rc;
+  NDT_CUDA(h, cudaMemcpyAsync(hres, d_res, sizeof(ndt_result), cudaMemcpyDeviceToHost, st));
+  NDT_CUDA(h, cudaStreamSynchronize(st));
+  if (h->timing) cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
+  h->ms_pending = false;
+  *out = *hres;
+  return NDT_OK;
+}
+
+int ndt_align_batch(ndt_handle hh, const double *guesses, int64_t n, int memspace, ndt_result *results) {
+  H_OR_FAIL(hh);
+  if (n < 0 || (n > 0 && (!guesses || !results))) return set_err(h, NDT_ERR_ARG, "ndt_align_batch: bad argument");
+  if (int rc = need_ready(h, "ndt_align_batch")) return rc;
+  if (n == 0) return NDT_OK;
+  cudaStream_t st = h->stream;
+  // batched results carry fitness only for small batches: an exact 1-NN for tens of thousands of
+  // far-off hypotheses is not part of ranking them (rank by score, then ndt_align the winner)
+  const bool want_fitness = n < 64;
+  if (memspace == NDT_MEM_DEVICE) { h->ms_pending = true; return launch_align(h, guesses, n, results, want_fitness); }
+  const size_t gbytes = (size_t)n * 3 * sizeof(double), rbytes = (size_t)n * sizeof(ndt_result);
+  NDT_CUDA(h, h->io.reserve(gbytes + rbytes + 256));
+  double *d_g = h->io.as<double>();
+  ndt_result *d_r = (ndt_result *)((char *)h->io.p + ((gbytes + 255) & ~size_t(255)));
+  NDT_CUDA(h, cudaMemcpyAsync(d_g, guesses, gbytes, cudaMemcpyHostToDevice, st));
+  int rc = launch_align(h, d_g, n, d_r, want_fitness);
+  if (rc) return rc;
+  NDT_CUDA(h, cudaMemcpyAsync(results, d_r, rbytes, cudaMemcpyDeviceToHost, st));
+  NDT_CUDA(h, cudaStreamSynchronize(st));
+  if (h->timing) cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
+  h->ms_pending = false;
+  return NDT_OK;
+}
+
+int ndt_best_of(ndt_handle hh, const ndt_result *results, int64_t n, int memspace, int64_t *best_index,
+                ndt_result *best) {
+  H_OR_FAIL(hh);
+  if (n <= 0 || !results || !best_index || !best) return set_err(h, NDT_ERR_ARG, "ndt_best_of: bad argument");
+  cudaStream_t st = h->stream;
+  if (ensure_pinned(h, 1024)) return NDT_ERR_CUDA;
+  const size_t rbytes = (size_t)n * sizeof(ndt_result);
+  if (memspace == NDT_MEM_HOST) NDT_CUDA(h, h->io.reserve(rbytes));
+  int64_t *d_bi = h->stage.as<int64_t>();
+  ndt_result *d_best = (ndt_result *)(d_bi + 2);
+  const ndt_result *d_res = results;
+  if (memspace == NDT_MEM_HOST) {
+    ndt_result *tmp = h->io.as<ndt_result>();
+    NDT_CUDA(h, cudaMemcpyAsync(tmp, results, rbytes, cudaMemcpyHostToDevice, st));
+    d_res = tmp;
+  }
+  int rc = launch_best_of(h, d_res, n, d_bi, d_best);
+  if (rc) return rc;
+  char *hp = (char *)h->pinned;
+  NDT_CUDA(h, cudaMemcpyAsync(hp, d_bi, 8, cudaMemcpyDeviceToHost, st));
+  NDT_CUDA(h, cudaMemcpyAsync(hp + 16, d_best, sizeof(ndt_result), cudaMemcpyDeviceToHost, st));
+  NDT_CUDA(h, cudaStreamSynchronize(st));
+  std::memcpy(best_index, hp, 8);
+  std::memcpy(best, hp + 16, sizeof(ndt_result));
+  return NDT_OK;
+}
+
+int ndt_match_pairs(ndt_handle hh, const float *src_xyzw, const int64_t *src_off, const float *tgt_xyzw,
+                    const int64_t *tgt_off, const double *guesses, int64_t n_pairs, float source_leaf,
+                    int memspace, ndt_result *results) {
+  H_OR_FAIL(hh);
+  if (n_pairs < 0 || (n_pairs > 0 && (!src_xyzw || !src_off || !tgt_xyzw || !tgt_off || !guesses || !results)))
+    return set_err(h, NDT_ERR_ARG, "ndt_match_pairs: bad argument");
+  if (memspace != NDT_MEM_HOST) return set_err(h, NDT_ERR_ARG, "ndt_match_pairs: device buffers not supported yet");
+  // Round-1 formulation: every pair runs the full device path (grid build kernels + persistent
+  // matcher) back to back on this handle's stream. A fused one-CTA-per-pair kernel is the next step.
+  cudaStream_t st = h->stream;
+  float total_ms = 0.f;
+  std::vector<float> filtered;
+  for (int64_t i = 0; i < n_pairs; ++i) {
+    const int64_t ns = src_off[i + 1] - src_off[i], nt = tgt_off[i + 1] - tgt_off[i];
+    int rc = grid_build(h, tgt_xyzw + 4 * tgt_off[i], nt, NDT_MEM_HOST);
+    if (rc) return rc;
+    total_ms += h->last_ms;
+    const float *sp = src_xyzw + 4 * src_off[i];
+    int64_t m = ns;
+    if (source_leaf > 0.f && ns > 0) {
+      filtered.resize((size_t)ns * 4);
+      rc = ndt_approx_voxel_filter(hh, sp, ns, source_leaf, NDT_MEM_HOST, filtered.data(), &m);
+      if (rc) return rc;
+      sp = filtered.data();
+    }
+    rc = ndt_set_source(hh, sp, m, NDT_MEM_HOST);
+    if (rc) return rc;
+    rc = ndt_align(hh, guesses + 3 * i, results + i);
+    if (rc) return rc;
+    total_ms += h->last_ms;
+  }
+  (void)st;
+  h->last_ms = total_ms;
+  h->ms_pending = false;
+  return NDT_OK;
+}
+
+int ndt_grid_blob_size(ndt_handle hh, int64_t *bytes) {
+  H_OR_FAIL(hh);
+  if (!bytes) return NDT_ERR_ARG;
+  if (!h->have_grid) return set_err(h, NDT_ERR_STATE, "ndt_grid_blob_size: no target set");
+  *bytes = blob_layout(h).total;
+  return NDT_OK;
+}
+
+int ndt_grid_export(ndt_handle hh, void *device_blob, int64_t bytes) {
+  H_OR_FAIL(hh);
+  if (!h->have_grid) return set_err(h, NDT_ERR_STATE, "ndt_grid_export: no target set");
+  const BlobHeader b = blob_layout(h);
+  if (!device_blob || bytes < b.total) return set_err(h, NDT_ERR_ARG, "ndt_grid_export: blob too small");
+  cudaStream_t st = h->stream;
+  char *d = (char *)device_blob;
+  const int64_t nc = h->gd.n_cells, nl = h->h_counters[CTR_LEAVES], nsl = h->h_counters[CTR_SLOTS], nt = h->gd.n_tgt;
+  if (ensure_pinned(h, sizeof(BlobHeader))) return NDT_ERR_CUDA;
+  std::memcpy(h->pinned, &b, sizeof(b));
+  NDT_CUDA(h, cudaMemcpyAsync(d, h->pinned, sizeof(b), cudaMemcpyHostToDevice, st));
+  auto cp = [&](int64_t off, const DevBuf &src, int64_t nbytes) -> cudaError_t {
+    if (nbytes <= 0) return cudaSuccess;
+    return cudaMemcpyAsync(d + off, src.p, (size_t)nbytes, cudaMemcpyDeviceToDevice, st);
+  };
+  NDT_CUDA(h, cp(b.off_slot, h->gb.slot, nc * 4));
+  NDT_CUDA(h, cp(b.off_recs, h->gb.recs, nsl * (int64_t)sizeof(CellRec)));
+  NDT_CUDA(h, cp(b.off_leaf_id, h->gb.leaf_id, nc * 4));
+  NDT_CUDA(h, cp(b.off_leaf_start, h->gb.leaf_start, nl * 4));
+  NDT_CUDA(h, cp(b.off_leaf_n, h->gb.leaf_n, nl * 4));
+  NDT_CUDA(h, cp(b.off_sorted, h->gb.sorted_idx, nt * 4));
+  NDT_CUDA(h, cp(b.off_tgt, h->gb.tgt, nt * (int64_t)sizeof(float4)));
+  NDT_CUDA(h, cudaStreamSynchronize(st));
+  return NDT_OK;
+}
+
+int ndt_grid_import(ndt_handle hh, const void *device_blob, int64_t bytes) {
+  H_OR_FAIL(hh);
+  if (!device_blob || bytes < (int64_t)sizeof(BlobHeader)) return set_err(h, NDT_ERR_ARG, "ndt_grid_import: bad blob");
+  cudaStream_t st = h->stream;
+  BlobHeader b{};
+  NDT_CUDA(h, cudaMemcpyAsync(&b, device_blob, sizeof(b), cudaMemcpyDeviceToHost, st));
+  NDT_CUDA(h, cudaStreamSynchronize(st));
+  if (b.magic != kBlobMagic || b.total > bytes) return set_err(h, NDT_ERR_ARG, "ndt_grid_import: not a grid blob");
+  h->have_grid = false;
+  h->gd = b.gd;
+  std::memcpy(h->h_counters, b.counters, sizeof(b.counters));
+  const int64_t nc = h->gd.n_cells, nl = h->h_counters[CTR_LEAVES], nsl = h->h_counters[CTR_SLOTS], nt = h->gd.n_tgt;
+  const char *d = (const char *)device_blob;
+  auto take = [&](DevBuf &dst, int64_t off, int64_t nbytes) -> cudaError_t {
+    cudaError_t e = dst.reserve((size_t)std::max<int64_t>(nbytes, 16));
+    if (e != cudaSuccess || nbytes <= 0) return e;
+    return cudaMemcpyAsync(dst.p, d + off, (size_t)nbytes, cudaMemcpyDeviceToDevice, st);
+  };
+  NDT_CUDA(h, take(h->gb.slot, b.off_slot, nc * 4));
+  NDT_CUDA(h, take(h->gb.recs, b.off_recs, nsl * (int64_t)sizeof(CellRec)));
+  NDT_CUDA(h, take(h->gb.leaf_id, b.off_leaf_id, nc * 4));
+  NDT_CUDA(h, take(h->gb.leaf_start, b.off_leaf_start, nl * 4));
+  NDT_CUDA(h, take(h->gb.leaf_n, b.off_leaf_n, nl * 4));
+  NDT_CUDA(h, take(h->gb.sorted_idx, b.off_sorted, nt * 4));
+  NDT_CUDA(h, take(h->gb.tgt, b.off_tgt, nt * (int64_t)sizeof(float4)));
+  NDT_CUDA(h, cudaStreamSynchronize(st));
+  h->have_grid = true;
+  return NDT_OK;
+}
+
+int ndt_launch_count(ndt_handle hh, int64_t *n) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h || !n) return NDT_ERR_ARG;
+  *n = h->launches;
+  return NDT_OK;
+}
+
+int ndt_last_kernel_ms(ndt_handle hh, float *ms) {
+  H_OR_FAIL(hh);
+  if (!ms) return NDT_ERR_ARG;
+  if (h->ms_pending) {   // device-space batch calls return before completion: resolve the event pair now
+    NDT_CUDA(h, cudaEventSynchronize(h->ev1));
+    NDT_CUDA(h, cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    h->ms_pending = false;
+  }
+  *ms = h->last_ms;
+  return NDT_OK;
+}
+
+int ndt_synchronize(ndt_handle hh) {
+  H_OR_FAIL(hh);
+  NDT_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NDT_OK;
+}
+
+}  // extern "C"

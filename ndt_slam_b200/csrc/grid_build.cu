@@ -1,0 +1,503 @@
+// grid_build.cu -- 2-D NDT grid construction on sm_100a: a scatter (count + bucket) followed by an
+// in-input-order per-cell reduction and the regularised inverse covariance.
+//
+// Replaces pcl::VoxelGridCovariance::applyFilter as run by ndt.setInputTarget(target_cloud)
+// [REF src/PoseEstimator.cpp:19; resolution set at include/ndt_slam/PoseEstimator.h:81].
+// Specification: SURVEY.md App. A.2.
+//
+// This translation unit is compiled with --fmad=false: every fp64 expression below is evaluated
+// as separate IEEE multiply / add / divide / sqrt, in the same order as the generic x86-64 code path
+// of the reference stack (and as the CPU oracle used by the tests), so counts, means, centroids and inverse
+// covariances come out bit-identical rather than merely within tolerance.
+//
+// Pipeline (all on the handle's stream; the only host round trip is the 6-int bounds read-back when
+// the points are already device-resident -- host inputs get their bounds during staging):
+//   k_bounds    float min/max + finite count                      (device inputs only)
+//   k_count     cell id per point (float32, bit-exact), warp-aggregated int atomics -> count + rank
+//   k_alloc     per dense cell: leaf ids and contiguous bucket ranges (warp-aggregated allocation)
+//   k_fill      scatter point indices into their leaf bucket
+//   k_finalize  one warp per leaf: order the bucket by point index, accumulate in input order
+//               (fp32 centroid, fp64 sums), mean, single-pass covariance, 2x2 eigen clamp, inverse,
+//               64-byte record + cell->slot table
+#include "ndt_host.h"
+
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+namespace ndt {
+
+namespace {
+
+__device__ __forceinline__ int float_ord(float f) {
+  const int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+inline float ord_float(int o) {
+  int i = o >= 0 ? o : o ^ 0x7fffffff;
+  float f;
+  std::memcpy(&f, &i, 4);
+  return f;
+}
+
+__global__ void k_init_counters(int32_t *ctr, int32_t *bounds) {
+  const int t = threadIdx.x;
+  if (t < CTR_COUNT) ctr[t] = 0;
+  if (t == 0) { bounds[0] = INT_MAX; bounds[1] = INT_MAX; bounds[2] = INT_MIN; bounds[3] = INT_MIN; }
+}
+
+// getMinMax3D over finite points
+__global__ void __launch_bounds__(256) k_bounds(const float4 *__restrict__ pts, int64_t n, int32_t *bounds,
+                                               int32_t *ctr) {
+  int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN, nf = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 p = __ldg(pts + i);
+    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+      const int ox = float_ord(p.x), oy = float_ord(p.y);
+      mnx = min(mnx, ox); mny = min(mny, oy); mxx = max(mxx, ox); mxy = max(mxy, oy);
+      ++nf;
+    }
+  }
+  mnx = __reduce_min_sync(0xffffffffu, mnx); mny = __reduce_min_sync(0xffffffffu, mny);
+  mxx = __reduce_max_sync(0xffffffffu, mxx); mxy = __reduce_max_sync(0xffffffffu, mxy);
+  nf = __reduce_add_sync(0xffffffffu, nf);
+  if ((threadIdx.x & 31) == 0 && nf > 0) {
+    atomicMin(bounds + 0, mnx); atomicMin(bounds + 1, mny);
+    atomicMax(bounds + 2, mxx); atomicMax(bounds + 3, mxy);
+    atomicAdd(ctr + CTR_NFIN, nf);
+  }
+}
+
+struct Dims { int32_t min_bx, min_by, div_x, div_y; float inv_leaf; };
+
+// pass 1a: cell of each point + a unique rank inside the cell (warp-aggregated int atomics)
+__global__ void __launch_bounds__(256) k_count(const float4 *__restrict__ pts, int64_t n, Dims d,
+                                              int32_t *__restrict__ count, int32_t *__restrict__ cell_of,
+                                              int32_t *__restrict__ rank_of) {
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n_round = ((n + 31) / 32) * 32;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+    int cell = -1;
+    if (i < n) {
+      const float4 p = __ldg(pts + i);
+      if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+        const int i0 = cell_coord(p.x, d.inv_leaf, d.min_bx);
+        const int i1 = cell_coord(p.y, d.inv_leaf, d.min_by);
+        cell = i0 + i1 * d.div_x;
+      }
+    }
+    // lanes of this warp that hit the same cell share one atomic
+    const unsigned grp = __match_any_sync(0xffffffffu, cell);
+    const int leader = __ffs(grp) - 1;
+    int base = 0;
+    if (cell >= 0 && lane == leader) base = atomicAdd(count + cell, __popc(grp));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (i < n) {
+      cell_of[i] = cell;
+      rank_of[i] = base + __popc(grp & ((1u << lane) - 1u));
+    }
+  }
+}
+
+// pass 1b: per dense cell, allocate a leaf id and a bucket range; the count table becomes the slot table
+__global__ void __launch_bounds__(256) k_alloc(int32_t *__restrict__ count_slot, int64_t n_cells,
+                                              int32_t *__restrict__ leaf_id, int32_t *__restrict__ leaf_cell,
+                                              int32_t *__restrict__ leaf_n, int32_t *__restrict__ leaf_start,
+                                              int32_t *__restrict__ ctr) {
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n_round = ((n_cells + 31) / 32) * 32;
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_round; c += stride) {
+    const int n = (c < n_cells) ? count_slot[c] : 0;
+    const bool has = n > 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, has);
+    if (bal == 0u) {
+      if (c < n_cells) { leaf_id[c] = -1; count_slot[c] = -1; }
+      continue;
+    }
+    int incl = n;
+#pragma unroll
+    for (int dlt = 1; dlt < 32; dlt <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, dlt);
+      if (lane >= dlt) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int base_leaf = 0, base_pts = 0;
+    if (lane == 0) {
+      base_leaf = atomicAdd(ctr + CTR_LEAVES, __popc(bal));
+      base_pts = atomicAdd(ctr + CTR_PTS, total);
+    }
+    base_leaf = __shfl_sync(0xffffffffu, base_leaf, 0);
+    base_pts = __shfl_sync(0xffffffffu, base_pts, 0);
+    if (c < n_cells) {
+      if (has) {
+        const int leaf = base_leaf + __popc(bal & ((1u << lane) - 1u));
+        leaf_id[c] = leaf;
+        leaf_cell[leaf] = (int32_t)c;
+        leaf_n[leaf] = n;
+        leaf_start[leaf] = base_pts + incl - n;
+      } else {
+        leaf_id[c] = -1;
+      }
+      count_slot[c] = -1;
+    }
+  }
+}
+
+// pass 1c: point index -> its leaf bucket
+__global__ void __launch_bounds__(256) k_fill(int64_t n, const int32_t *__restrict__ cell_of,
+                                             const int32_t *__restrict__ rank_of,
+                                             const int32_t *__restrict__ leaf_id,
+                                             const int32_t *__restrict__ leaf_start, int32_t *__restrict__ list) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cell = cell_of[i];
+    if (cell < 0) continue;
+    const int leaf = __ldg(leaf_id + cell);
+    list[__ldg(leaf_start + leaf) + rank_of[i]] = (int32_t)i;
+  }
+}
+
+// symmetric 2x2 eigen-decomposition (a b; b d): ascending eigenvalues, orthonormal columns.
+// Expression order is fixed (IEEE ops only) so results are reproducible bit for bit.
+__device__ inline void eig2(double a, double b, double d, double *lam, double *v0, double *v1) {
+  const double tr = a + d, df = a - d;
+  const double rt = sqrt(df * df + 4.0 * b * b);
+  double l1, l0;
+  if (tr >= 0) { l1 = 0.5 * (tr + rt); l0 = (l1 != 0.0) ? (a * d - b * b) / l1 : 0.5 * (tr - rt); }
+  else { l0 = 0.5 * (tr - rt); l1 = (l0 != 0.0) ? (a * d - b * b) / l0 : 0.5 * (tr + rt); }
+  if (l0 > l1) { const double t = l0; l0 = l1; l1 = t; }
+  lam[0] = l0; lam[1] = l1;
+  double ex, ey;
+  if (fabs(b) > 0) {
+    if (fabs(l1 - a) > fabs(l1 - d)) { ex = b; ey = l1 - a; }
+    else { ex = l1 - d; ey = b; }
+    double nn = sqrt(ex * ex + ey * ey);
+    if (nn == 0) { ex = 1; ey = 0; nn = 1; }
+    ex /= nn; ey /= nn;
+  } else {
+    if (a >= d) { ex = 1; ey = 0; } else { ex = 0; ey = 1; }
+  }
+  v1[0] = ex; v1[1] = ey;
+  v0[0] = -ey; v0[1] = ex;
+}
+
+struct FinalizeParams { int32_t min_points; double eig_mult; int32_t quirks; };
+
+// pass 2: one warp per leaf
+__global__ void __launch_bounds__(256) k_finalize(const float4 *__restrict__ pts, const int32_t *__restrict__ list,
+                                                 int32_t *__restrict__ sorted_idx,
+                                                 const int32_t *__restrict__ leaf_cell,
+                                                 const int32_t *__restrict__ leaf_n,
+                                                 const int32_t *__restrict__ leaf_start,
+                                                 int32_t *__restrict__ leaf_nr, double2 *__restrict__ leaf_mean,
+                                                 double *__restrict__ leaf_icov, float2 *__restrict__ leaf_cen,
+                                                 int32_t *__restrict__ slot, CellRec *__restrict__ recs,
+                                                 int32_t *__restrict__ ctr, FinalizeParams fp) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  const int n_leaves = ctr[CTR_LEAVES];
+  for (int leaf = warp; leaf < n_leaves; leaf += n_warps) {
+    const int n = leaf_n[leaf], st = leaf_start[leaf];
+    // order the bucket by point index: rank by counting (buckets are short; O(n^2 / 32) per warp)
+    for (int i = lane; i < n; i += 32) {
+      const int v = list[st + i];
+      int r = 0;
+      for (int j = 0; j < n; ++j) r += (list[st + j] < v) ? 1 : 0;
+      sorted_idx[st + r] = v;
+    }
+    __syncwarp();
+    // accumulate in input order; every lane keeps the same running sums
+    double sx = 0, sy = 0, sxx = 0, syx = 0, syy = 0;
+    float cx = 0.f, cy = 0.f;
+    for (int base = 0; base < n; base += 32) {
+      float px = 0.f, py = 0.f;
+      if (base + lane < n) {
+        const float4 p = __ldg(pts + sorted_idx[st + base + lane]);
+        px = p.x; py = p.y;
+      }
+      const int m = min(32, n - base);
+      for (int k = 0; k < m; ++k) {
+        const float x = __shfl_sync(0xffffffffu, px, k), y = __shfl_sync(0xffffffffu, py, k);
+        const double xd = (double)x, yd = (double)y;
+        sx += xd; sy += yd;
+        sxx += xd * xd; syx += yd * xd; syy += yd * yd;
+        cx = __fadd_rn(cx, x); cy = __fadd_rn(cy, y);
+      }
+    }
+    if (lane != 0) continue;
+    const double nn = (double)n;
+    cx = cx / (float)n; cy = cy / (float)n;
+    const double psx = sx, psy = sy;
+    const double m0 = sx / nn, m1 = sy / nn;
+    int nr = n;
+    double ic0 = 0, ic1 = 0, ic2 = 0, ic3 = 0;
+    const bool in_tree = n >= fp.min_points;
+    if (in_tree) {
+      const double id = (fp.quirks & NDT_QUIRK_COV_INIT_IDENTITY) ? 1.0 : 0.0;
+      const double Cxx = id + sxx, Cyy = id + syy, Cyx = syx, Cxy = syx, Czz = id;
+      double cxx, cxy, cyx, cyy, czz;
+      if (fp.quirks & NDT_QUIRK_COV_SCALE_NM1_N) {
+        cxx = (Cxx - 2.0 * (psx * m0)) / nn + m0 * m0;
+        cxy = (Cxy - 2.0 * (psx * m1)) / nn + m0 * m1;
+        cyx = (Cyx - 2.0 * (psy * m0)) / nn + m1 * m0;
+        cyy = (Cyy - 2.0 * (psy * m1)) / nn + m1 * m1;
+        czz = Czz / nn;
+        const double sc = (nn - 1.0) / nn;
+        cxx *= sc; cxy *= sc; cyx *= sc; cyy *= sc; czz *= sc;
+      } else {
+        const double dn = nn - 1.0;
+        cxx = (Cxx - psx * m0) / dn; cxy = (Cxy - psx * m1) / dn;
+        cyx = (Cyx - psy * m0) / dn; cyy = (Cyy - psy * m1) / dn;
+        czz = Czz / dn;
+      }
+      double lam2[2], v0[2], v1[2];
+      eig2(cxx, cyx, cyy, lam2, v0, v1);
+      double ev[3] = {czz, lam2[0], lam2[1]};
+      int which[3] = {2, 0, 1};
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = a + 1; b < 3; ++b)
+          if (ev[b] < ev[a]) { double t = ev[a]; ev[a] = ev[b]; ev[b] = t; int w = which[a]; which[a] = which[b]; which[b] = w; }
+      if (ev[0] < 0 || ev[1] < 0 || ev[2] <= 0) {
+        nr = -1;
+      } else {
+        const double mcv = fp.eig_mult * ev[2];
+        if (ev[0] < mcv) {
+          ev[0] = mcv;
+          if (ev[1] < mcv) ev[1] = mcv;
+          double l0 = lam2[0], l1 = lam2[1];
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            if (which[a] == 0) l0 = ev[a];
+            else if (which[a] == 1) l1 = ev[a];
+            else czz = ev[a];
+          }
+          const double det = v0[0] * v1[1] - v1[0] * v0[1];
+          const double i00 = v1[1] / det, i01 = -v1[0] / det, i10 = -v0[1] / det, i11 = v0[0] / det;
+          const double a00 = v0[0] * l0, a01 = v1[0] * l1, a10 = v0[1] * l0, a11 = v1[1] * l1;
+          cxx = a00 * i00 + a01 * i10; cxy = a00 * i01 + a01 * i11;
+          cyx = a10 * i00 + a11 * i10; cyy = a10 * i01 + a11 * i11;
+        }
+        const double det = cxx * cyy - cxy * cyx;
+        ic0 = cyy / det; ic1 = -cxy / det; ic2 = -cyx / det; ic3 = cxx / det;
+        const double izz = 1.0 / czz;
+        const double mxc = fmax(fmax(fmax(ic0, ic1), fmax(ic2, ic3)), fmax(izz, 0.0));
+        const double mnc = fmin(fmin(fmin(ic0, ic1), fmin(ic2, ic3)), fmin(izz, 0.0));
+        if (mxc == (double)INFINITY || mnc == -(double)INFINITY) nr = -1;
+      }
+    }
+    leaf_nr[leaf] = nr;
+    leaf_mean[leaf] = make_double2(m0, m1);
+    leaf_icov[4 * (size_t)leaf + 0] = ic0; leaf_icov[4 * (size_t)leaf + 1] = ic1;
+    leaf_icov[4 * (size_t)leaf + 2] = ic2; leaf_icov[4 * (size_t)leaf + 3] = ic3;
+    leaf_cen[leaf] = make_float2(cx, cy);
+    if (in_tree) {
+      const int s = atomicAdd(ctr + CTR_SLOTS, 1);
+      if (nr > 0) atomicAdd(ctr + CTR_VALID, 1);
+      CellRec r;
+      r.cx = cx; r.cy = cy; r.nr_points = nr; r.cell = leaf_cell[leaf];
+      r.mx = m0; r.my = m1; r.c00 = ic0; r.c01 = ic1; r.c10 = ic2; r.c11 = ic3;
+      recs[s] = r;
+      slot[leaf_cell[leaf]] = s;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_cell_index(const float4 *__restrict__ pts, int64_t n, Dims d,
+                                                   int32_t *__restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 p = __ldg(pts + i);
+    out[i] = cell_coord(p.x, d.inv_leaf, d.min_bx) + cell_coord(p.y, d.inv_leaf, d.min_by) * d.div_x;
+  }
+}
+
+inline int grid_for(int64_t work, int threads, int sm_count, int per_sm = 8) {
+  int64_t b = (work + threads - 1) / threads;
+  const int64_t cap = (int64_t)sm_count * per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace
+
+int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace) {
+  GridBuffers &gb = h->gb;
+  GridDims &gd = h->gd;
+  cudaStream_t st = h->stream;
+  h->have_grid = false;
+  if (n < 0 || (n > 0 && !xyzw)) return set_err(h, NDT_ERR_ARG, "ndt_set_target: bad points");
+  if (n > (int64_t)INT_MAX) return set_err(h, NDT_ERR_CAPACITY, "ndt_set_target: more than 2^31-1 points");
+  const size_t npad = (size_t)(n > 0 ? n : 1);
+  NDT_CUDA(h, gb.tgt.reserve(npad * sizeof(float4)));
+  NDT_CUDA(h, gb.counters.reserve((CTR_COUNT + 4) * sizeof(int32_t)));
+  int32_t *ctr = gb.counters.as<int32_t>();
+  int32_t *bounds = ctr + CTR_COUNT;
+  gd = GridDims();
+  gd.leaf = h->prm.resolution;
+  gd.inv_leaf = 1.0f / gd.leaf;
+  gd.r2 = (float)((double)gd.leaf * (double)gd.leaf);
+  gd.n_tgt = n;
+  std::memset(h->h_counters, 0, sizeof(h->h_counters));
+
+  float mn[2] = {std::numeric_limits<float>::max(), std::numeric_limits<float>::max()};
+  float mx[2] = {-std::numeric_limits<float>::max(), -std::numeric_limits<float>::max()};
+  int64_t nfin = 0;
+  if (h->timing) cudaEventRecord(h->ev0, st);
+  k_init_counters<<<1, 32, 0, st>>>(ctr, bounds);
+  ++h->launches;
+  if (memspace == NDT_MEM_HOST) {
+    // stage through pinned memory; bounds come for free while the points pass through the host cache
+    if (ensure_pinned(h, npad * sizeof(float4))) return NDT_ERR_CUDA;
+    float *stage = (float *)h->pinned;
+    for (int64_t i = 0; i < n; ++i) {
+      const float x = xyzw[4 * i], y = xyzw[4 * i + 1], z = xyzw[4 * i + 2];
+      stage[4 * i] = x; stage[4 * i + 1] = y; stage[4 * i + 2] = z; stage[4 * i + 3] = xyzw[4 * i + 3];
+      if (std::isfinite(x) && std::isfinite(y) && std::isfinite(z)) {
+        mn[0] = std::min(mn[0], x); mn[1] = std::min(mn[1], y);
+        mx[0] = std::max(mx[0], x); mx[1] = std::max(mx[1], y);
+        ++nfin;
+      }
+    }
+    if (n > 0) NDT_CUDA(h, cudaMemcpyAsync(gb.tgt.p, stage, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, st));
+  } else {
+    if (n > 0) {
+      NDT_CUDA(h, cudaMemcpyAsync(gb.tgt.p, xyzw, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+      k_bounds<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(gb.tgt.as<float4>(), n, bounds, ctr);
+      ++h->launches;
+      int32_t hb[CTR_COUNT + 4];
+      NDT_CUDA(h, cudaMemcpyAsync(hb, ctr, sizeof(hb), cudaMemcpyDeviceToHost, st));
+      NDT_CUDA(h, cudaStreamSynchronize(st));
+      nfin = hb[CTR_NFIN];
+      if (nfin > 0) {
+        mn[0] = ord_float(hb[CTR_COUNT + 0]); mn[1] = ord_float(hb[CTR_COUNT + 1]);
+        mx[0] = ord_float(hb[CTR_COUNT + 2]); mx[1] = ord_float(hb[CTR_COUNT + 3]);
+      }
+    }
+  }
+  bool empty = (nfin == 0);
+  if (!empty) {
+    const int64_t dx = (int64_t)((mx[0] - mn[0]) * gd.inv_leaf) + 1;
+    const int64_t dy = (int64_t)((mx[1] - mn[1]) * gd.inv_leaf) + 1;
+    if (dx * dy > (int64_t)std::numeric_limits<int32_t>::max()) empty = true;  // PCL: "leaf size too small", empty grid
+  }
+  if (!empty) {
+    const int min_bx = (int)std::floor(mn[0] * gd.inv_leaf), min_by = (int)std::floor(mn[1] * gd.inv_leaf);
+    const int max_bx = (int)std::floor(mx[0] * gd.inv_leaf), max_by = (int)std::floor(mx[1] * gd.inv_leaf);
+    gd.min_bx = min_bx; gd.min_by = min_by;
+    gd.div_x = max_bx - min_bx + 1; gd.div_y = max_by - min_by + 1;
+    gd.n_cells = (int64_t)gd.div_x * gd.div_y;
+    if (gd.n_cells > (int64_t)INT_MAX) return set_err(h, NDT_ERR_CAPACITY, "ndt_set_target: grid exceeds 2^31-1 cells");
+  }
+  if (empty) {
+    gd.div_x = gd.div_y = 0; gd.n_cells = 0;
+    h->have_grid = true;
+    if (h->timing) { cudaEventRecord(h->ev1, st); }
+    NDT_CUDA(h, cudaStreamSynchronize(st));
+    if (h->timing) cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
+    return NDT_OK;
+  }
+  const size_t nc = (size_t)gd.n_cells;
+  NDT_CUDA(h, gb.cell_of.reserve(npad * 4));
+  NDT_CUDA(h, gb.rank_of.reserve(npad * 4));
+  NDT_CUDA(h, gb.list.reserve(npad * 4));
+  NDT_CUDA(h, gb.sorted_idx.reserve(npad * 4));
+  NDT_CUDA(h, gb.slot.reserve(nc * 4));
+  NDT_CUDA(h, gb.leaf_id.reserve(nc * 4));
+  const size_t max_leaves = std::min(npad, nc);
+  NDT_CUDA(h, gb.leaf_cell.reserve(max_leaves * 4));
+  NDT_CUDA(h, gb.leaf_n.reserve(max_leaves * 4));
+  NDT_CUDA(h, gb.leaf_start.reserve(max_leaves * 4));
+  NDT_CUDA(h, gb.leaf_nr.reserve(max_leaves * 4));
+  NDT_CUDA(h, gb.leaf_mean.reserve(max_leaves * sizeof(double2)));
+  NDT_CUDA(h, gb.leaf_icov.reserve(max_leaves * 4 * sizeof(double)));
+  NDT_CUDA(h, gb.leaf_cen.reserve(max_leaves * sizeof(float2)));
+  NDT_CUDA(h, gb.recs.reserve(max_leaves * sizeof(CellRec)));
+
+  Dims d{gd.min_bx, gd.min_by, gd.div_x, gd.div_y, gd.inv_leaf};
+  NDT_CUDA(h, cudaMemsetAsync(gb.slot.p, 0, nc * 4, st));
+  k_count<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(gb.tgt.as<float4>(), n, d, gb.slot.as<int32_t>(),
+                                                        gb.cell_of.as<int32_t>(), gb.rank_of.as<int32_t>());
+  k_alloc<<<grid_for(gd.n_cells, 256, h->sm_count), 256, 0, st>>>(gb.slot.as<int32_t>(), gd.n_cells,
+                                                                 gb.leaf_id.as<int32_t>(), gb.leaf_cell.as<int32_t>(),
+                                                                 gb.leaf_n.as<int32_t>(), gb.leaf_start.as<int32_t>(), ctr);
+  k_fill<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(n, gb.cell_of.as<int32_t>(), gb.rank_of.as<int32_t>(),
+                                                       gb.leaf_id.as<int32_t>(), gb.leaf_start.as<int32_t>(),
+                                                       gb.list.as<int32_t>());
+  FinalizeParams fp{h->prm.min_points, h->prm.eig_mult, h->prm.quirks};
+  const int64_t warps_needed = (int64_t)max_leaves;
+  k_finalize<<<grid_for(warps_needed * 32, 256, h->sm_count), 256, 0, st>>>(
+      gb.tgt.as<float4>(), gb.list.as<int32_t>(), gb.sorted_idx.as<int32_t>(), gb.leaf_cell.as<int32_t>(),
+      gb.leaf_n.as<int32_t>(), gb.leaf_start.as<int32_t>(), gb.leaf_nr.as<int32_t>(), gb.leaf_mean.as<double2>(),
+      gb.leaf_icov.as<double>(), gb.leaf_cen.as<float2>(), gb.slot.as<int32_t>(), gb.recs.as<CellRec>(), ctr, fp);
+  h->launches += 4;
+  if (h->timing) cudaEventRecord(h->ev1, st);
+  NDT_CUDA(h, cudaMemcpyAsync(h->h_counters, ctr, sizeof(h->h_counters), cudaMemcpyDeviceToHost, st));
+  NDT_CUDA(h, cudaStreamSynchronize(st));
+  NDT_CUDA(h, cudaGetLastError());
+  if (h->timing) cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
+  h->h_counters[CTR_NFIN] = (int32_t)nfin;
+  h->have_grid = true;
+  return NDT_OK;
+}
+
+int grid_cell_index(Handle *h, const float *xyzw, int64_t n, int memspace, int32_t *idx_out) {
+  if (!h->have_grid) return set_err(h, NDT_ERR_STATE, "ndt_cell_index: no target set");
+  if (n <= 0) return NDT_OK;
+  cudaStream_t st = h->stream;
+  NDT_CUDA(h, h->scratch.reserve((size_t)n * sizeof(float4)));
+  NDT_CUDA(h, h->scratch2.reserve((size_t)n * 4));
+  const float4 *d_in = reinterpret_cast<const float4 *>(xyzw);
+  if (memspace == NDT_MEM_HOST) {
+    NDT_CUDA(h, cudaMemcpyAsync(h->scratch.p, xyzw, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, st));
+    d_in = h->scratch.as<float4>();
+  }
+  Dims d{h->gd.min_bx, h->gd.min_by, h->gd.div_x, h->gd.div_y, h->gd.inv_leaf};
+  k_cell_index<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(d_in, n, d, h->scratch2.as<int32_t>());
+  ++h->launches;
+  // idx_out is always a host buffer (parity hook)
+  NDT_CUDA(h, cudaMemcpyAsync(idx_out, h->scratch2.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  NDT_CUDA(h, cudaStreamSynchronize(st));
+  return NDT_OK;
+}
+
+GridView grid_view(const Handle *h) {
+  GridView G{};
+  const GridBuffers &gb = h->gb;
+  G.slot = gb.slot.as<int32_t>();
+  G.recs = gb.recs.as<CellRec>();
+  G.min_bx = h->gd.min_bx; G.min_by = h->gd.min_by; G.div_x = h->gd.div_x; G.div_y = h->gd.div_y;
+  G.inv_leaf = h->gd.inv_leaf; G.r2 = h->gd.r2; G.leaf = h->gd.leaf;
+  G.leaf_id = gb.leaf_id.as<int32_t>();
+  G.leaf_start = gb.leaf_start.as<int32_t>();
+  G.leaf_n = gb.leaf_n.as<int32_t>();
+  G.sorted_idx = gb.sorted_idx.as<int32_t>();
+  G.tgt = gb.tgt.as<float4>();
+  G.n_tgt = h->gd.n_tgt;
+  return G;
+}
+
+MatchParams match_params(const Handle *h, bool want_fitness) {
+  MatchParams mp{};
+  // PCL computeTransformation; resolution_ is a float member
+  const double r = (double)h->prm.resolution;
+  const double c1 = 10.0 * (1.0 - h->prm.outlier_ratio);
+  const double c2 = h->prm.outlier_ratio / std::pow(r, 3);
+  const double d3 = -std::log(c2);
+  mp.d1 = -std::log(c1 + c2) - d3;
+  mp.d2 = -2.0 * std::log((-std::log(c1 * std::exp(-0.5) + c2) - d3) / mp.d1);
+  mp.step_size = h->prm.step_size;
+  mp.step_min = h->prm.trans_eps / 2;
+  mp.trans_eps = h->prm.trans_eps;
+  mp.max_iter = h->prm.max_iter;
+  mp.quirks = h->prm.quirks;
+  mp.want_fitness = want_fitness ? 1 : 0;
+  return mp;
+}
+
+}  // namespace ndt

@@ -1,0 +1,464 @@
+// match_kernels.cu -- NDT objective evaluation and the persistent Newton / More-Thuente matcher (sm_100a).
+//
+// Replaces, for z = 0 data, pcl::NormalDistributionsTransform::{computeDerivatives, computeHessian,
+// computeTransformation, computeStepLengthMT} and Registration::getFitnessScore as called by
+// PoseEstimator::estimatePose [REF src/PoseEstimator.cpp:28, 43, 56]. The whole optimisation runs
+// inside one kernel launch: no host round trip per iteration.
+//
+// Kernels
+//   k_eval_partial / k_eval_final  one objective pass for n poses (parity hook, relocalisation sweep)
+//   k_align_block   one CTA per match, optional shared-memory tile of the whole grid (single scans)
+//   k_align_cluster one thread-block cluster per match, DSMEM reduction (large source clouds)
+//   k_align_warp    persistent CTAs, one warp per match pulled from an atomic work counter (batches)
+//   k_best_of       arg-max of the batch results
+//   k_voxel_filter  ApproximateVoxelGrid, one thread per cloud (sequential hash history)
+#include "ndt_host.h"
+
+#include <cooperative_groups.h>
+#include <algorithm>
+#include <cstring>
+
+namespace cg = cooperative_groups;
+
+namespace ndt {
+
+namespace {
+
+struct GlobalSrc {
+  const float4 *__restrict__ p;
+  __device__ __forceinline__ float2 operator()(int i) const {
+    const float4 v = __ldg(p + i);   // coalesced 16-byte loads
+    return make_float2(v.x, v.y);
+  }
+};
+struct SmemSrc {
+  const float2 *p;
+  __device__ __forceinline__ float2 operator()(int i) const { return p[i]; }
+};
+
+// One cooperative objective pass. All threads of the group call pass<MODE>() with identical
+// arguments and leave with identical totals.
+template <class Coop, class SlotL, class RecL, class SrcL>
+struct Objective {
+  const GridView &G;
+  SlotL slot;
+  RecL rec;
+  SrcL src;
+  int ns;
+  const MatchParams &mp;
+  const Coop &coop;
+
+  template <int MODE>
+  __device__ __noinline__ void pass(const double *p, const AngleCache &ac, double *acc) {
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+    const PoseF pf = pose_to_float(p);
+    const bool sse = (mp.quirks & NDT_QUIRK_TRANSFORM_SSE_ORDER) != 0;
+    int pairs = 0;
+    const int r = coop.rank(), sz = coop.size();
+    for (int i = r; i < ns; i += sz) {
+      const float2 xy = src(i);
+      eval_point<MODE>(G, slot, rec, xy.x, xy.y, pf, sse, ac.cs, ac.sn, mp.d1, mp.d2, acc, pairs);
+    }
+    if (MODE == 0) coop.template allreduce<13>(acc);
+    else if (MODE == 1) coop.template allreduce<4>(acc);
+    else coop.template allreduce<9>(acc + 4);
+  }
+};
+
+template <class Coop, class SrcL>
+__device__ inline double fitness_pass(const GridView &G, const SrcL &src, int ns, const MatchParams &mp,
+                                      const double *p, const Coop &coop) {
+  const PoseF pf = pose_to_float(p);
+  const bool sse = (mp.quirks & NDT_QUIRK_TRANSFORM_SSE_ORDER) != 0;
+  double sum[1] = {0.0};
+  for (int i = coop.rank(); i < ns; i += coop.size()) {
+    const float2 xy = src(i);
+    float xt, yt;
+    xform(pf, sse, xy.x, xy.y, xt, yt);
+    sum[0] += (double)nn_dist2(G, xt, yt, 48);
+  }
+  coop.template allreduce<1>(sum);
+  return sum[0];
+}
+
+__device__ inline void write_result(ndt_result *out, const MatchOut &mo, int ns, double fitness_sum,
+                                    bool have_fitness, int64_t n_tgt) {
+  ndt_result r;
+  r.pose[0] = mo.p[0]; r.pose[1] = mo.p[1]; r.pose[2] = mo.p[2];
+  const PoseF pf = pose_to_float(mo.p);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) r.T[k] = 0.f;
+  r.T[0] = pf.c; r.T[1] = pf.s; r.T[4] = -pf.s; r.T[5] = pf.c; r.T[10] = 1.f; r.T[15] = 1.f;
+  r.T[12] = pf.tx; r.T[13] = pf.ty;
+  r.score = mo.score;
+  r.trans_prob = ns ? mo.score / (double)ns : 0.0;
+  if (have_fitness) r.fitness = (ns > 0 && n_tgt > 0) ? fitness_sum / (double)ns : DBL_MAX;
+  else r.fitness = nan("");
+#pragma unroll
+  for (int k = 0; k < 9; ++k) r.hess[k] = mo.H[k];
+  r.converged = mo.converged; r.iters = mo.iters; r.evals = mo.evals; r.reserved = 0;
+  r.point_evals = (int64_t)mo.evals * (int64_t)ns;
+  *out = r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// objective only
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) k_eval_partial(GridView G, MatchParams mp, const float4 *__restrict__ src,
+                                                     int ns, const double *__restrict__ poses, int slices,
+                                                     double *__restrict__ partial, int *__restrict__ pairs_out) {
+  __shared__ double scratch[8 * NACC];
+  __shared__ int s_pairs[8];
+  const int pose_i = blockIdx.x / slices, slice = blockIdx.x % slices;
+  const double p[3] = {poses[3 * pose_i], poses[3 * pose_i + 1], poses[3 * pose_i + 2]};
+  AngleCache ac;
+  angle_terms(mp, p[2], ac);
+  const PoseF pf = pose_to_float(p);
+  const bool sse = (mp.quirks & NDT_QUIRK_TRANSFORM_SSE_ORDER) != 0;
+  double acc[NACC];
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+  int pairs = 0;
+  const GlobalSlot slot{G.slot};
+  const GlobalRec rec{G.recs};
+  // slice s owns points [s * chunk, (s + 1) * chunk)
+  const int chunk = (ns + slices - 1) / slices;
+  const int lo = slice * chunk, hi = min(ns, lo + chunk);
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const float4 v = __ldg(src + i);
+    eval_point<MODE>(G, slot, rec, v.x, v.y, pf, sse, ac.cs, ac.sn, mp.d1, mp.d2, acc, pairs);
+  }
+  BlockCoop coop{scratch};
+  coop.allreduce<NACC>(acc);
+  pairs = __reduce_add_sync(0xffffffffu, pairs);
+  if ((threadIdx.x & 31) == 0) s_pairs[threadIdx.x >> 5] = pairs;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tp = 0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) tp += s_pairs[w];
+    double *o = partial + (size_t)blockIdx.x * NACC;
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) o[k] = acc[k];
+    pairs_out[blockIdx.x] = tp;
+  }
+}
+
+__global__ void k_eval_final(const double *__restrict__ partial, const int *__restrict__ pairs_in, int slices,
+                             int64_t n_poses, double *__restrict__ out14, int64_t *__restrict__ pairs_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_poses) return;
+  double acc[NACC];
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+  int64_t tp = 0;
+  for (int s = 0; s < slices; ++s) {
+    const double *q = partial + ((size_t)i * slices + s) * NACC;
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] += q[k];
+    tp += pairs_in[(size_t)i * slices + s];
+  }
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) out14[(size_t)i * (NACC + 1) + k] = acc[k];
+  out14[(size_t)i * (NACC + 1) + NACC] = (double)tp;
+  if (pairs_out) pairs_out[i] = tp;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one CTA per match
+// ---------------------------------------------------------------------------------------------
+template <bool TILE>
+__global__ void __launch_bounds__(256) k_align_block(GridView G, MatchParams mp, const float4 *__restrict__ src,
+                                                    int ns, const double *__restrict__ guesses,
+                                                    ndt_result *__restrict__ out, int n_slots, int n_cells) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double scratch[8 * NACC];
+  BlockCoop coop{scratch};
+  const int job = blockIdx.x;
+  const double guess[3] = {guesses[3 * job], guesses[3 * job + 1], guesses[3 * job + 2]};
+  const GlobalSrc gsrc{src};
+  MatchOut mo;
+  if (TILE) {
+    // stage the local map tile (here: the whole grid) in shared memory: records first (64-B aligned), then slots
+    CellRec *s_recs = reinterpret_cast<CellRec *>(smem_raw);
+    int32_t *s_slot = reinterpret_cast<int32_t *>(smem_raw + (size_t)n_slots * sizeof(CellRec));
+    const int4 *gr = reinterpret_cast<const int4 *>(G.recs);
+    int4 *sr = reinterpret_cast<int4 *>(s_recs);
+    for (int i = threadIdx.x; i < n_slots * 4; i += blockDim.x) sr[i] = __ldg(gr + i);
+    for (int i = threadIdx.x; i < n_cells; i += blockDim.x) s_slot[i] = __ldg(G.slot + i);
+    __syncthreads();
+    Objective<BlockCoop, SmemSlot, SmemRec, GlobalSrc> obj{G, SmemSlot{s_slot}, SmemRec{s_recs}, gsrc, ns, mp, coop};
+    match_device(obj, mp, guess, mo);
+  } else {
+    Objective<BlockCoop, GlobalSlot, GlobalRec, GlobalSrc> obj{G, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, mp, coop};
+    match_device(obj, mp, guess, mo);
+  }
+  double fsum = 0.0;
+  if (mp.want_fitness) fsum = fitness_pass(G, gsrc, ns, mp, mo.p, coop);
+  if (threadIdx.x == 0) write_result(out + job, mo, ns, fsum, mp.want_fitness != 0, G.n_tgt);
+}
+
+// ---------------------------------------------------------------------------------------------
+// one thread-block cluster per match: block reduction, then a DSMEM exchange of the 13 partials
+// ---------------------------------------------------------------------------------------------
+struct ClusterCoop {
+  double *scratch;       // [8 * NACC] block scratch
+  double *xchg;          // [NACC] this CTA's partial, read by every CTA of the cluster through DSMEM
+  int crank, csize;
+  __device__ __forceinline__ int rank() const { return crank * blockDim.x + threadIdx.x; }
+  __device__ __forceinline__ int size() const { return csize * blockDim.x; }
+  template <int N> __device__ __forceinline__ void allreduce(double *v) const {
+    cg::cluster_group cluster = cg::this_cluster();
+    BlockCoop b{scratch};
+    b.allreduce<N>(v);
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      if (threadIdx.x == k) xchg[k] = v[k];
+    cluster.sync();
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = 0.0;
+    for (int r = 0; r < csize; ++r) {
+      const double *remote = cluster.map_shared_rank(xchg, r);
+#pragma unroll
+      for (int k = 0; k < N; ++k) v[k] += remote[k];
+    }
+    cluster.sync();
+  }
+};
+
+__global__ void __launch_bounds__(256) k_align_cluster(GridView G, MatchParams mp, const float4 *__restrict__ src,
+                                                      int ns, const double *__restrict__ guesses,
+                                                      ndt_result *__restrict__ out) {
+  __shared__ double scratch[8 * NACC];
+  __shared__ double xchg[NACC];
+  cg::cluster_group cluster = cg::this_cluster();
+  ClusterCoop coop{scratch, xchg, (int)cluster.block_rank(), (int)cluster.num_blocks()};
+  const int job = blockIdx.x / coop.csize;
+  const double guess[3] = {guesses[3 * job], guesses[3 * job + 1], guesses[3 * job + 2]};
+  const GlobalSrc gsrc{src};
+  MatchOut mo;
+  Objective<ClusterCoop, GlobalSlot, GlobalRec, GlobalSrc> obj{G, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, mp, coop};
+  match_device(obj, mp, guess, mo);
+  double fsum = 0.0;
+  if (mp.want_fitness) fsum = fitness_pass(G, gsrc, ns, mp, mo.p, coop);
+  if (coop.crank == 0 && threadIdx.x == 0) write_result(out + job, mo, ns, fsum, mp.want_fitness != 0, G.n_tgt);
+}
+
+// ---------------------------------------------------------------------------------------------
+// persistent batch matcher: one warp per match, work pulled from an atomic counter
+// ---------------------------------------------------------------------------------------------
+template <bool SRC_SMEM>
+__global__ void __launch_bounds__(256) k_align_warp(GridView G, MatchParams mp, const float4 *__restrict__ src,
+                                                   int ns, const double *__restrict__ guesses,
+                                                   ndt_result *__restrict__ out, int64_t n_jobs,
+                                                   int32_t *__restrict__ job_counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *s_src = reinterpret_cast<float2 *>(smem_raw);
+  if (SRC_SMEM) {
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+      const float4 v = __ldg(src + i);
+      s_src[i] = make_float2(v.x, v.y);
+    }
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  WarpCoop coop{lane};
+  const GlobalSrc gsrc{src};
+  const SmemSrc ssrc{s_src};
+  for (;;) {
+    int job = 0;
+    if (lane == 0) job = atomicAdd(job_counter, 1);
+    job = __shfl_sync(0xffffffffu, job, 0);
+    if (job >= n_jobs) break;
+    const double guess[3] = {guesses[3 * (size_t)job], guesses[3 * (size_t)job + 1], guesses[3 * (size_t)job + 2]};
+    MatchOut mo;
+    double fsum = 0.0;
+    if (SRC_SMEM) {
+      Objective<WarpCoop, GlobalSlot, GlobalRec, SmemSrc> obj{G, GlobalSlot{G.slot}, GlobalRec{G.recs}, ssrc, ns, mp, coop};
+      match_device(obj, mp, guess, mo);
+      if (mp.want_fitness) fsum = fitness_pass(G, ssrc, ns, mp, mo.p, coop);
+    } else {
+      Objective<WarpCoop, GlobalSlot, GlobalRec, GlobalSrc> obj{G, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, mp, coop};
+      match_device(obj, mp, guess, mo);
+      if (mp.want_fitness) fsum = fitness_pass(G, gsrc, ns, mp, mo.p, coop);
+    }
+    if (lane == 0) write_result(out + job, mo, ns, fsum, mp.want_fitness != 0, G.n_tgt);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// arg-max over batch results: highest score among converged matches, lowest index on ties
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_best_of(const ndt_result *__restrict__ res, int64_t n,
+                                                 int64_t *__restrict__ best_index, ndt_result *__restrict__ best) {
+  __shared__ double s_score[32];
+  __shared__ long long s_idx[32];
+  double bs = -DBL_MAX;
+  long long bi = -1;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double s = res[i].score;
+    if (res[i].converged && (s > bs)) { bs = s; bi = i; }
+  }
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    const double os = __shfl_xor_sync(0xffffffffu, bs, m);
+    const long long oi = __shfl_xor_sync(0xffffffffu, bi, m);
+    if (oi >= 0 && (bi < 0 || os > bs || (os == bs && oi < bi))) { bs = os; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { s_score[threadIdx.x >> 5] = bs; s_idx[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    bs = -DBL_MAX; bi = -1;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      const double os = s_score[w]; const long long oi = s_idx[w];
+      if (oi >= 0 && (bi < 0 || os > bs || (os == bs && oi < bi))) { bs = os; bi = oi; }
+    }
+    *best_index = bi;
+    if (bi >= 0) *best = res[bi];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pcl::ApproximateVoxelGrid<PointXYZ>::applyFilter: inherently sequential
+// (order-dependent 512-entry hash history), so one thread walks one cloud.
+// ---------------------------------------------------------------------------------------------
+struct HistEntry { int ix, iy, iz, count; float cx, cy, cz; };
+
+__global__ void k_voxel_filter(const float4 *__restrict__ in, int64_t n, float leaf, float4 *__restrict__ out,
+                               int32_t *__restrict__ n_out) {
+  __shared__ HistEntry he[512];
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) { he[i].count = 0; he[i].cx = he[i].cy = he[i].cz = 0.f; he[i].ix = he[i].iy = he[i].iz = 0; }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const float inv = __fdiv_rn(1.0f, leaf);
+  int op = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const float4 p = __ldg(in + i);
+    const int ix = (int)floorf(__fmul_rn(p.x, inv)), iy = (int)floorf(__fmul_rn(p.y, inv)), iz = (int)floorf(__fmul_rn(p.z, inv));
+    const unsigned hash = ((unsigned)ix * 7171u + (unsigned)iy * 3079u + (unsigned)iz * 4231u) & 511u;
+    HistEntry &e = he[hash];
+    if (e.count && (ix != e.ix || iy != e.iy || iz != e.iz)) {
+      const float c = (float)e.count;
+      out[op++] = make_float4(__fdiv_rn(e.cx, c), __fdiv_rn(e.cy, c), __fdiv_rn(e.cz, c), 0.f);
+      e.count = 0; e.cx = e.cy = e.cz = 0.f;
+    }
+    e.ix = ix; e.iy = iy; e.iz = iz; e.count++;
+    e.cx = __fadd_rn(e.cx, p.x); e.cy = __fadd_rn(e.cy, p.y); e.cz = __fadd_rn(e.cz, p.z);
+  }
+  for (int k = 0; k < 512; ++k) {
+    HistEntry &e = he[k];
+    if (e.count) {
+      const float c = (float)e.count;
+      out[op++] = make_float4(__fdiv_rn(e.cx, c), __fdiv_rn(e.cy, c), __fdiv_rn(e.cz, c), 0.f);
+    }
+  }
+  *n_out = op;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+int launch_eval(Handle *h, const double *d_poses, int64_t n, int want_hessian, double *d_out14, int64_t *d_pairs) {
+  if (n <= 0) return NDT_OK;
+  const int ns = (int)h->ns;
+  cudaStream_t st = h->stream;
+  int slices = 1;
+  if (n < 4 * h->sm_count) {
+    slices = (int)std::min<int64_t>((ns + 1023) / 1024, std::max<int64_t>(1, (4 * h->sm_count) / n));
+    if (slices < 1) slices = 1;
+  }
+  const int64_t blocks = n * slices;
+  if (blocks > 0x7fffffffLL) return set_err(h, NDT_ERR_CAPACITY, "ndt_eval_batch: too many poses");
+  NDT_CUDA(h, h->scratch.reserve((size_t)blocks * NACC * sizeof(double)));
+  NDT_CUDA(h, h->scratch2.reserve((size_t)blocks * sizeof(int)));
+  const GridView G = grid_view(h);
+  const MatchParams mp = match_params(h, false);
+  const float4 *src = h->src.as<float4>();
+  if (h->timing) cudaEventRecord(h->ev0, st);
+  if (want_hessian)
+    k_eval_partial<0><<<(unsigned)blocks, 256, 0, st>>>(G, mp, src, ns, d_poses, slices, h->scratch.as<double>(), h->scratch2.as<int>());
+  else
+    k_eval_partial<1><<<(unsigned)blocks, 256, 0, st>>>(G, mp, src, ns, d_poses, slices, h->scratch.as<double>(), h->scratch2.as<int>());
+  k_eval_final<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(h->scratch.as<double>(), h->scratch2.as<int>(), slices, n, d_out14, d_pairs);
+  h->launches += 2;
+  if (h->timing) cudaEventRecord(h->ev1, st);
+  NDT_CUDA(h, cudaGetLastError());
+  return NDT_OK;
+}
+
+int launch_align(Handle *h, const double *d_guesses, int64_t n, ndt_result *d_results, bool want_fitness) {
+  if (n <= 0) return NDT_OK;
+  const int ns = (int)h->ns;
+  cudaStream_t st = h->stream;
+  const GridView G = grid_view(h);
+  const MatchParams mp = match_params(h, want_fitness);
+  const float4 *src = h->src.as<float4>();
+  int32_t *ctr = h->gb.counters.as<int32_t>();
+  if (h->timing) cudaEventRecord(h->ev0, st);
+  if (n >= 64) {
+    // batch: persistent CTAs, one warp per match
+    NDT_CUDA(h, cudaMemsetAsync(ctr + CTR_JOB, 0, sizeof(int32_t), st));
+    const bool src_smem = (size_t)ns * sizeof(float2) <= 64 * 1024;
+    const size_t smem = src_smem ? (size_t)ns * sizeof(float2) : 0;
+    const int ctas_per_sm = 4;
+    int64_t grid = (int64_t)h->sm_count * ctas_per_sm;
+    grid = std::min<int64_t>(grid, (n + 7) / 8);
+    if (src_smem) {
+      NDT_CUDA(h, cudaFuncSetAttribute(k_align_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_align_warp<true><<<(unsigned)grid, 256, smem, st>>>(G, mp, src, ns, d_guesses, d_results, n, ctr + CTR_JOB);
+    } else {
+      k_align_warp<false><<<(unsigned)grid, 256, 0, st>>>(G, mp, src, ns, d_guesses, d_results, n, ctr + CTR_JOB);
+    }
+  } else if (ns > 4096) {
+    // large source cloud: spread one match over a thread-block cluster (DSMEM reduction)
+    int csize = 8;
+    if (ns > 16384) {
+      cudaError_t e = cudaFuncSetAttribute(k_align_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      if (e == cudaSuccess) csize = 16; else (void)cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(n * csize));
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    NDT_CUDA(h, cudaLaunchKernelEx(&cfg, k_align_cluster, G, mp, src, ns, d_guesses, d_results));
+  } else {
+    const int n_slots = h->h_counters[CTR_SLOTS];
+    const int n_cells = (int)h->gd.n_cells;
+    const size_t tile = (size_t)n_slots * sizeof(CellRec) + (size_t)n_cells * sizeof(int32_t);
+    const size_t budget = (size_t)h->max_smem_optin > 4096 ? (size_t)h->max_smem_optin - 4096 : 0;
+    if (tile > 0 && tile <= budget) {
+      NDT_CUDA(h, cudaFuncSetAttribute(k_align_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile));
+      k_align_block<true><<<(unsigned)n, 256, tile, st>>>(G, mp, src, ns, d_guesses, d_results, n_slots, n_cells);
+    } else {
+      k_align_block<false><<<(unsigned)n, 256, 0, st>>>(G, mp, src, ns, d_guesses, d_results, n_slots, n_cells);
+    }
+  }
+  ++h->launches;
+  if (h->timing) cudaEventRecord(h->ev1, st);
+  NDT_CUDA(h, cudaGetLastError());
+  return NDT_OK;
+}
+
+int launch_best_of(Handle *h, const ndt_result *d_results, int64_t n, int64_t *d_best_index, ndt_result *d_best) {
+  k_best_of<<<1, 1024, 0, h->stream>>>(d_results, n, d_best_index, d_best);
+  ++h->launches;
+  NDT_CUDA(h, cudaGetLastError());
+  return NDT_OK;
+}
+
+int launch_voxel_filter(Handle *h, const float4 *d_in, int64_t n, float leaf, float4 *d_out, int32_t *d_nout) {
+  k_voxel_filter<<<1, 128, 0, h->stream>>>(d_in, n, leaf, d_out, d_nout);
+  ++h->launches;
+  NDT_CUDA(h, cudaGetLastError());
+  return NDT_OK;
+}
+
+}  // namespace ndt

@@ -1,0 +1,112 @@
+// ndt_host.h -- host-side state of one ndt_handle and the launcher entry points shared between the
+// translation units (grid_build.cu is compiled with --fmad=false, match_kernels.cu with FMA on).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "ndt_b200.h"
+#include "ndt_device.cuh"
+
+namespace ndt {
+
+// growable device buffer (capacity only ever grows; no cudaMalloc on the steady-state path)
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// device-side counters written by the build kernels
+enum { CTR_LEAVES = 0, CTR_PTS = 1, CTR_SLOTS = 2, CTR_VALID = 3, CTR_NFIN = 4, CTR_JOB = 5, CTR_COUNT = 8 };
+
+struct GridBuffers {
+  DevBuf tgt;          // float4[n]       target points (device copy or alias source)
+  DevBuf cell_of;      // int32[n]        cell of each point (-1 = non-finite)
+  DevBuf rank_of;      // int32[n]        arbitrary unique rank of the point inside its cell
+  DevBuf list;         // int32[n]        per-leaf point indices, arbitrary order
+  DevBuf sorted_idx;   // int32[n]        per-leaf point indices, ascending (input order)
+  DevBuf slot;         // int32[n_cells]  count during the build, then cell -> record slot
+  DevBuf leaf_id;      // int32[n_cells]  cell -> leaf or -1
+  DevBuf leaf_cell;    // int32[n]        per leaf: cell index
+  DevBuf leaf_n;       // int32[n]
+  DevBuf leaf_start;   // int32[n]
+  DevBuf leaf_nr;      // int32[n]        PCL nr_points after pass 2 (n or -1)
+  DevBuf leaf_mean;    // double2[n]
+  DevBuf leaf_icov;    // double4[n] as 4 doubles
+  DevBuf leaf_cen;     // float2[n]
+  DevBuf recs;         // CellRec[n]      compact records (n >= min_points)
+  DevBuf counters;     // int32[CTR_COUNT] + bounds int32[4]
+};
+
+struct GridDims {
+  int32_t min_bx = 0, min_by = 0, div_x = 0, div_y = 0;
+  float leaf = 1.f, inv_leaf = 1.f, r2 = 1.f;
+  int64_t n_cells = 0;
+  int64_t n_tgt = 0;       // points handed to set_target
+};
+
+struct Handle {
+  ndt_params prm{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  float last_ms = 0.f;
+  int sm_count = 148;
+  int max_smem_optin = 0;
+
+  GridBuffers gb;
+  GridDims gd;
+  bool have_grid = false;
+  int32_t h_counters[CTR_COUNT] = {0};   // host copy after the last build
+
+  DevBuf src;          // float4[ns]
+  int64_t ns = 0;
+  bool have_src = false;
+
+  DevBuf scratch;      // misc device scratch (eval partials, guesses, results staging)
+  DevBuf scratch2;
+  DevBuf stage;        // 4 KB persistent staging (single pose / single result)
+  DevBuf io;           // host<->device staging of batched poses / results
+  bool ms_pending = false;  // last_ms not yet resolved (async device-space call)
+  void *pinned = nullptr;       // pinned host staging
+  size_t pinned_cap = 0;
+  bool timing = true;           // record ev0/ev1 around kernels
+};
+
+// grid_build.cu
+int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace);
+int grid_cell_index(Handle *h, const float *xyzw, int64_t n, int memspace, int32_t *idx_out);
+GridView grid_view(const Handle *h);
+MatchParams match_params(const Handle *h, bool want_fitness);
+
+// match_kernels.cu
+int launch_eval(Handle *h, const double *d_poses, int64_t n, int want_hessian, double *d_out14, int64_t *d_pairs);
+int launch_align(Handle *h, const double *d_guesses, int64_t n, ndt_result *d_results, bool want_fitness);
+int launch_best_of(Handle *h, const ndt_result *d_results, int64_t n, int64_t *d_best_index, ndt_result *d_best);
+int launch_voxel_filter(Handle *h, const float4 *d_in, int64_t n, float leaf, float4 *d_out, int32_t *d_nout);
+
+// helpers (capi.cu)
+int set_err(Handle *h, int code, const char *what, cudaError_t e = cudaSuccess);
+int ensure_pinned(Handle *h, size_t bytes);
+
+#define NDT_CUDA(h, call)                                                   \
+  do {                                                                      \
+    cudaError_t _e = (call);                                                \
+    if (_e != cudaSuccess) return ::ndt::set_err((h), NDT_ERR_CUDA, #call, _e); \
+  } while (0)
+
+}  // namespace ndt

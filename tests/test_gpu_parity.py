@@ -1,0 +1,244 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs.
+
+Bars (BASELINE.json north_star): integer cell indexing and counts bit-exact; per-evaluation
+score / gradient / Hessian within 1e-6 relative; final pose within 1e-4 m and 1e-5 rad."""
+import numpy as np
+import pytest
+import torch
+
+import ndt_common as common
+from ndt_slam_b200 import capi, synth
+from oracle import oracle_api as oa
+
+pytestmark = pytest.mark.gpu
+
+REL_EVAL = 1e-6
+POSE_M, POSE_RAD = 1e-4, 1e-5
+
+
+@pytest.fixture(scope="module")
+def c1():
+    pb = common.c1_problem()
+    prm = common.params(resolution=0.5)
+    g = capi.Ndt(prm)
+    o = oa.Oracle(prm)
+    g.set_target(pb["tgt"]); g.set_source(pb["src"])
+    o.set_target(pb["tgt"]); o.set_source(pb["src"])
+    return pb, g, o
+
+
+def _assert_grid_equal(g, o, exact_float=True):
+    gi_g, gi_o = g.grid_info(), o.grid_info()
+    for f in ("n_points", "n_leaves", "n_slots", "n_valid"):
+        assert getattr(gi_g, f) == getattr(gi_o, f), f
+    assert list(gi_g.min_b) == list(gi_o.min_b) and list(gi_g.div_b) == list(gi_o.div_b)
+    a, b = g.grid_readback(), o.grid_readback()
+    assert np.array_equal(a["cell_idx"], b["cell_idx"])          # bit-exact indexing
+    assert np.array_equal(a["nr_points"], b["nr_points"])        # bit-exact counts (incl. -1 flags)
+    assert np.array_equal(a["centroid"], b["centroid"])          # float32 centroid, input-order sum
+    if exact_float:
+        assert np.array_equal(a["mean"], b["mean"])
+        assert np.array_equal(a["icov"], b["icov"])
+    else:
+        assert common.rel_err(a["mean"], b["mean"]) < 1e-9
+        assert common.rel_err(a["icov"], b["icov"]) < 1e-6
+
+
+def test_c1_grid_bit_exact(c1):
+    pb, g, o = c1
+    _assert_grid_equal(g, o)
+    assert np.array_equal(g.cell_index(pb["tgt"]), o.cell_index(pb["tgt"]))
+
+
+@pytest.mark.parametrize("res,n,extent,seed", [(0.5, 20_000, 60.0, 3), (0.1, 200_000, 150.0, 4), (1.0, 3_000, 30.0, 5)])
+def test_grid_bit_exact_random_walls(res, n, extent, seed):
+    tgt = common.random_cloud(seed, n, extent)
+    prm = common.params(resolution=res)
+    g, o = capi.Ndt(prm), oa.Oracle(prm)
+    g.set_target(tgt); o.set_target(tgt)
+    _assert_grid_equal(g, o)
+    assert np.array_equal(g.cell_index(tgt), o.cell_index(tgt))
+
+
+def test_grid_scattered_points_and_quirk_variants():
+    """Uniform scatter (many n < 6 leaves, degenerate cells) and the non-default covariance switches."""
+    tgt = common.random_cloud(9, 50_000, 20.0, walls=False)
+    for quirks in (capi.QUIRKS_PCL_1_10, capi.QUIRK_MT_INTERVAL_LT0 | capi.QUIRK_ANGLE_SNAP,
+                   capi.QUIRKS_PCL_1_10 & ~capi.QUIRK_COV_INIT_IDENTITY):
+        prm = common.params(resolution=0.5, quirks=quirks)
+        g, o = capi.Ndt(prm), oa.Oracle(prm)
+        g.set_target(tgt); o.set_target(tgt)
+        _assert_grid_equal(g, o)
+
+
+def test_grid_device_resident_input_and_nonfinite_points():
+    tgt = common.random_cloud(6, 10_000, 40.0).copy()
+    tgt[17, 0] = np.nan; tgt[4000, 1] = np.inf
+    prm = common.params(resolution=0.5)
+    g, o = capi.Ndt(prm), oa.Oracle(prm)
+    o.set_target(tgt)
+    d = torch.from_numpy(tgt).cuda()
+    g.set_target(d.data_ptr(), n=tgt.shape[0], space=capi.MEM_DEVICE)
+    _assert_grid_equal(g, o)
+    assert g.grid_info().n_points == tgt.shape[0] - 2
+
+
+def test_grid_edge_cases():
+    prm = common.params(resolution=0.5)
+    g, o = capi.Ndt(prm), oa.Oracle(prm)
+    empty = np.zeros((0, 4), np.float32)
+    g.set_target(empty); o.set_target(empty)
+    assert g.grid_info().n_leaves == 0 == o.grid_info().n_leaves
+    one = np.array([[1.0, 2.0, 0, 0]], np.float32)
+    g.set_target(one); o.set_target(one)
+    _assert_grid_equal(g, o)
+    # many identical points in one cell (long bucket)
+    same = np.tile(np.array([[3.3, -4.4, 0, 0]], np.float32), (5000, 1))
+    same[:, 0] += np.linspace(0, 0.05, 5000, dtype=np.float32)
+    g.set_target(same); o.set_target(same)
+    _assert_grid_equal(g, o)
+
+
+def test_c1_eval_parity(c1):
+    pb, g, o = c1
+    rng = synth.rng_for(21)
+    worst = 0.0
+    for k in range(24):
+        pose = pb["guess"] + rng.normal(0, [0.05, 0.05, 0.01])
+        for want_h in (True, False):
+            a, b = g.eval(pose, want_h), o.eval(pose, want_h)
+            assert a.n_pairs == b.n_pairs            # identical neighbour sets (float32 radius test)
+            assert a.score == pytest.approx(b.score, rel=REL_EVAL)
+            worst = max(worst, common.rel_err(a.grad, b.grad))
+            if want_h:
+                worst = max(worst, common.rel_err(a.hess, b.hess))
+            else:
+                assert not np.any(np.array(a.hess))
+    assert worst < REL_EVAL, worst
+
+
+def test_eval_batch_matches_single(c1):
+    pb, g, o = c1
+    rng = synth.rng_for(22)
+    poses = pb["guess"] + rng.normal(0, [0.2, 0.2, 0.05], size=(300, 3))
+    out = g.eval_batch(poses)
+    for k in (0, 17, 299):
+        b = o.eval(poses[k])
+        assert out[k, 0] == pytest.approx(b.score, rel=REL_EVAL)
+        assert common.rel_err(out[k, 1:4], b.grad) < REL_EVAL
+        assert common.rel_err(out[k, 4:13], b.hess) < REL_EVAL
+        assert out[k, 13] == b.n_pairs
+    d_p = torch.from_numpy(poses).cuda(); d_o = torch.zeros((300, 14), dtype=torch.float64, device="cuda")
+    g.eval_batch(d_p.data_ptr(), n=300, space=capi.MEM_DEVICE, out=d_o.data_ptr())
+    g.synchronize()
+    assert np.array_equal(d_o.cpu().numpy(), out)      # deterministic, same kernel either way
+
+
+def _assert_result_close(a, b):
+    assert a.converged == b.converged and a.iters == b.iters and a.evals == b.evals
+    assert a.point_evals == b.point_evals
+    pa, pb_ = np.array(a.pose), np.array(b.pose)
+    assert np.hypot(pa[0] - pb_[0], pa[1] - pb_[1]) < POSE_M
+    assert abs(pa[2] - pb_[2]) < POSE_RAD
+    assert a.score == pytest.approx(b.score, rel=REL_EVAL)
+    assert a.trans_prob == pytest.approx(b.trans_prob, rel=REL_EVAL)
+    assert common.rel_err(a.hess, b.hess) < REL_EVAL
+    assert np.allclose(np.array(a.T), np.array(b.T), rtol=0, atol=2e-7)
+    assert a.fitness == pytest.approx(b.fitness, rel=1e-9)
+
+
+def test_c1_align_parity(c1):
+    pb, g, o = c1
+    a, b = g.align(pb["guess"]), o.align(pb["guess"])
+    _assert_result_close(a, b)
+    err = np.array(a.pose) - pb["truth"]
+    assert np.hypot(err[0], err[1]) < 0.03
+
+
+def test_align_parity_many_guesses_block_and_warp_kernels(c1):
+    """The one-CTA-per-match kernel (n < 64) and the persistent warp-per-match kernel (n >= 64)."""
+    pb, g, o = c1
+    rng = synth.rng_for(23)
+    guesses = pb["guess"] + rng.normal(0, [0.15, 0.15, 0.03], size=(96, 3))
+    few = g.align_batch(guesses[:8])
+    many = g.align_batch(guesses)
+    trial_evals = 0
+    for k in range(96):
+        b = o.align(guesses[k])
+        r = many[k]
+        assert r["converged"] == b.converged and r["iters"] == b.iters and r["evals"] == b.evals, k
+        assert np.hypot(r["pose"][0] - b.pose[0], r["pose"][1] - b.pose[1]) < POSE_M
+        assert abs(r["pose"][2] - b.pose[2]) < POSE_RAD
+        assert r["score"] == pytest.approx(b.score, rel=REL_EVAL)
+        assert common.rel_err(r["hess"], b.hess) < REL_EVAL
+        trial_evals += b.evals - b.iters - 1
+        if k < 8:
+            f = few[k]
+            assert f["iters"] == b.iters and f["evals"] == b.evals
+            assert np.allclose(f["pose"], r["pose"], rtol=0, atol=1e-9)
+            assert f["fitness"] == pytest.approx(b.fitness, rel=1e-9)
+    assert trial_evals > 0      # the More-Thuente inner loop was exercised
+    bi, best = g.best_of(many)
+    conv = many["converged"] == 1
+    assert bi == int(np.argmax(np.where(conv, many["score"], -np.inf)))
+    assert best.score == many["score"][bi]
+
+
+def test_align_empty_overlap(c1):
+    pb, g, o = c1
+    far = pb["src"].copy(); far[:, 0] += 500.0
+    g.set_source(far); o.set_source(far)
+    a, b = g.align([0.0, 0.0, 0.0]), o.align([0.0, 0.0, 0.0])
+    assert a.converged == 1 == b.converged and a.iters == 0 and a.evals == 1
+    assert list(a.pose) == [0.0, 0.0, 0.0] and a.trans_prob == 0.0
+    assert a.fitness == pytest.approx(b.fitness, rel=1e-9)   # exhaustive 1-NN fallback
+    g.set_source(pb["src"]); o.set_source(pb["src"])
+
+
+def test_voxel_filter_device_matches_oracle():
+    for seed in (1, 2, 3):
+        d = synth.c1_pair(seed)
+        xyzw = synth.to_xyzw(common.prep_scan(d["scan_b"]))
+        g = capi.Ndt(common.params())
+        for leaf in (0.05, 0.1, 0.2):
+            assert np.array_equal(g.approx_voxel_filter(xyzw, leaf), oa.approx_voxel_filter(xyzw, leaf))
+
+
+def test_large_source_cluster_kernel():
+    """> 4096 source points: the thread-block-cluster matcher (DSMEM reduction)."""
+    rng = synth.rng_for(31)
+    segs = synth.office(31, 60.0, 40.0, 20)
+    tgt_xy = synth.sample_walls(segs, 0.02, 0.01, rng)
+    pick = np.sort(rng.choice(tgt_xy.shape[0], 20_000, replace=False))
+    true = (0.06, -0.04, np.deg2rad(0.4))
+    c, s = np.cos(true[2]), np.sin(true[2])
+    dd = tgt_xy[pick] + rng.normal(0, 0.005, (20_000, 2)) - np.array(true[:2])
+    src = synth.to_xyzw(np.stack([c * dd[:, 0] + s * dd[:, 1], -s * dd[:, 0] + c * dd[:, 1]], axis=1))
+    tgt = synth.to_xyzw(tgt_xy)
+    prm = common.params(resolution=0.5)
+    g, o = capi.Ndt(prm), oa.Oracle(prm)
+    g.set_target(tgt); g.set_source(src); o.set_target(tgt); o.set_source(src)
+    _assert_grid_equal(g, o)
+    a, b = g.align([0.0, 0.0, 0.0]), o.align([0.0, 0.0, 0.0])
+    _assert_result_close(a, b)
+    assert np.hypot(a.pose[0] - true[0], a.pose[1] - true[1]) < 0.02
+
+
+def test_grid_export_import_roundtrip(c1):
+    pb, g, o = c1
+    nbytes = g.grid_blob_size()
+    blob = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    g.grid_export(blob.data_ptr(), nbytes)
+    g2 = capi.Ndt(common.params(resolution=0.5))
+    g2.grid_import(blob.data_ptr(), nbytes)
+    g2.set_source(pb["src"])
+    a, b = g2.align(pb["guess"]), g.align(pb["guess"])
+    assert bytes(a) == bytes(b)        # bit-identical result from the replicated grid
+
+
+def test_run_to_run_determinism(c1):
+    pb, g, o = c1
+    r1, r2 = g.align(pb["guess"]), g.align(pb["guess"])
+    assert bytes(r1) == bytes(r2)
+    e1, e2 = g.eval(pb["guess"]), g.eval(pb["guess"])
+    assert bytes(e1) == bytes(e2)
