@@ -47,23 +47,31 @@ struct Objective {
   int ns;
   const MatchParams &mp;
   const Coop &coop;
+  HitQueue Q;          // this warp's hit queue (shared memory)
 
   template <int MODE>
-  __device__ __noinline__ void pass(const double *p, const AngleCache &ac, double *acc) {
+  __device__ __noinline__ void pass(const double *p, const AngleCache &ac, double *out) {
+    double acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
     const PoseF pf = pose_to_float(p);
     const bool sse = (mp.quirks & NDT_QUIRK_TRANSFORM_SSE_ORDER) != 0;
     int pairs = 0;
-    const int r = coop.rank(), sz = coop.size();
-    for (int i = r; i < ns; i += sz) {
-      const float2 xy = src(i);
-      eval_point<MODE>(G, slot, rec, xy.x, xy.y, pf, sse, ac.cs, ac.sn, mp.d1, mp.d2, acc, pairs);
-    }
+    accumulate_points<MODE>(G, slot, rec, src, coop.rank(), coop.size(), ns, pf, sse, ac.cs, ac.sn, mp.d1, mp.d2,
+                            Q, acc, pairs);
     if (MODE == 0) coop.template allreduce<13>(acc);
     else if (MODE == 1) coop.template allreduce<4>(acc);
     else coop.template allreduce<9>(acc + 4);
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) out[k] = acc[k];
   }
+};
+
+// per-warp queue storage carved from static shared memory of the CTA (8 warps)
+struct QueueStore {
+  float4 xy[8][QCAP];
+  int slot[8][QCAP];
+  __device__ __forceinline__ HitQueue mine() { const int w = threadIdx.x >> 5; return HitQueue{xy[w], slot[w]}; }
 };
 
 template <class Coop, class SrcL>
@@ -111,6 +119,7 @@ __global__ void __launch_bounds__(256) k_eval_partial(GridView G, MatchParams mp
                                                      double *__restrict__ partial, int *__restrict__ pairs_out) {
   __shared__ double scratch[8 * NACC];
   __shared__ int s_pairs[8];
+  __shared__ QueueStore qs;
   const int pose_i = blockIdx.x / slices, slice = blockIdx.x % slices;
   const double p[3] = {poses[3 * pose_i], poses[3 * pose_i + 1], poses[3 * pose_i + 2]};
   AngleCache ac;
@@ -121,19 +130,14 @@ __global__ void __launch_bounds__(256) k_eval_partial(GridView G, MatchParams mp
 #pragma unroll
   for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
   int pairs = 0;
-  const GlobalSlot slot{G.slot};
-  const GlobalRec rec{G.recs};
   // slice s owns points [s * chunk, (s + 1) * chunk)
   const int chunk = (ns + slices - 1) / slices;
   const int lo = slice * chunk, hi = min(ns, lo + chunk);
-  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    const float4 v = __ldg(src + i);
-    eval_point<MODE>(G, slot, rec, v.x, v.y, pf, sse, ac.cs, ac.sn, mp.d1, mp.d2, acc, pairs);
-  }
+  accumulate_points<MODE>(G, GlobalSlot{G.slot}, GlobalRec{G.recs}, GlobalSrc{src}, lo + (int)threadIdx.x,
+                          (int)blockDim.x, hi, pf, sse, ac.cs, ac.sn, mp.d1, mp.d2, qs.mine(), acc, pairs);
   BlockCoop coop{scratch};
   coop.allreduce<NACC>(acc);
-  pairs = __reduce_add_sync(0xffffffffu, pairs);
-  if ((threadIdx.x & 31) == 0) s_pairs[threadIdx.x >> 5] = pairs;
+  if ((threadIdx.x & 31) == 0) s_pairs[threadIdx.x >> 5] = pairs;   // warp-uniform count
   __syncthreads();
   if (threadIdx.x == 0) {
     int tp = 0;
@@ -174,6 +178,7 @@ __global__ void __launch_bounds__(256) k_align_block(GridView G, MatchParams mp,
                                                     ndt_result *__restrict__ out, int n_slots, int n_cells) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double scratch[8 * NACC];
+  __shared__ QueueStore qs;
   BlockCoop coop{scratch};
   const int job = blockIdx.x;
   const double guess[3] = {guesses[3 * job], guesses[3 * job + 1], guesses[3 * job + 2]};
@@ -188,10 +193,10 @@ __global__ void __launch_bounds__(256) k_align_block(GridView G, MatchParams mp,
     for (int i = threadIdx.x; i < n_slots * 4; i += blockDim.x) sr[i] = __ldg(gr + i);
     for (int i = threadIdx.x; i < n_cells; i += blockDim.x) s_slot[i] = __ldg(G.slot + i);
     __syncthreads();
-    Objective<BlockCoop, SmemSlot, SmemRec, GlobalSrc> obj{G, SmemSlot{s_slot}, SmemRec{s_recs}, gsrc, ns, mp, coop};
+    Objective<BlockCoop, SmemSlot, SmemRec, GlobalSrc> obj{G, SmemSlot{s_slot}, SmemRec{s_recs}, gsrc, ns, mp, coop, qs.mine()};
     match_device(obj, mp, guess, mo);
   } else {
-    Objective<BlockCoop, GlobalSlot, GlobalRec, GlobalSrc> obj{G, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, mp, coop};
+    Objective<BlockCoop, GlobalSlot, GlobalRec, GlobalSrc> obj{G, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, mp, coop, qs.mine()};
     match_device(obj, mp, guess, mo);
   }
   double fsum = 0.0;
@@ -232,13 +237,14 @@ __global__ void __launch_bounds__(256) k_align_cluster(GridView G, MatchParams m
                                                       ndt_result *__restrict__ out) {
   __shared__ double scratch[8 * NACC];
   __shared__ double xchg[NACC];
+  __shared__ QueueStore qs;
   cg::cluster_group cluster = cg::this_cluster();
   ClusterCoop coop{scratch, xchg, (int)cluster.block_rank(), (int)cluster.num_blocks()};
   const int job = blockIdx.x / coop.csize;
   const double guess[3] = {guesses[3 * job], guesses[3 * job + 1], guesses[3 * job + 2]};
   const GlobalSrc gsrc{src};
   MatchOut mo;
-  Objective<ClusterCoop, GlobalSlot, GlobalRec, GlobalSrc> obj{G, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, mp, coop};
+  Objective<ClusterCoop, GlobalSlot, GlobalRec, GlobalSrc> obj{G, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, mp, coop, qs.mine()};
   match_device(obj, mp, guess, mo);
   double fsum = 0.0;
   if (mp.want_fitness) fsum = fitness_pass(G, gsrc, ns, mp, mo.p, coop);
@@ -254,6 +260,7 @@ __global__ void __launch_bounds__(256) k_align_warp(GridView G, MatchParams mp, 
                                                    ndt_result *__restrict__ out, int64_t n_jobs,
                                                    int32_t *__restrict__ job_counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ QueueStore qs;
   float2 *s_src = reinterpret_cast<float2 *>(smem_raw);
   if (SRC_SMEM) {
     for (int i = threadIdx.x; i < ns; i += blockDim.x) {
@@ -275,11 +282,11 @@ __global__ void __launch_bounds__(256) k_align_warp(GridView G, MatchParams mp, 
     MatchOut mo;
     double fsum = 0.0;
     if (SRC_SMEM) {
-      Objective<WarpCoop, GlobalSlot, GlobalRec, SmemSrc> obj{G, GlobalSlot{G.slot}, GlobalRec{G.recs}, ssrc, ns, mp, coop};
+      Objective<WarpCoop, GlobalSlot, GlobalRec, SmemSrc> obj{G, GlobalSlot{G.slot}, GlobalRec{G.recs}, ssrc, ns, mp, coop, qs.mine()};
       match_device(obj, mp, guess, mo);
       if (mp.want_fitness) fsum = fitness_pass(G, ssrc, ns, mp, mo.p, coop);
     } else {
-      Objective<WarpCoop, GlobalSlot, GlobalRec, GlobalSrc> obj{G, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, mp, coop};
+      Objective<WarpCoop, GlobalSlot, GlobalRec, GlobalSrc> obj{G, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, mp, coop, qs.mine()};
       match_device(obj, mp, guess, mo);
       if (mp.want_fitness) fsum = fitness_pass(G, gsrc, ns, mp, mo.p, coop);
     }

@@ -97,74 +97,135 @@ __device__ __forceinline__ float dist2f(float ax, float ay, float bx, float by) 
 }
 
 // ------------------------------------------------------------------------------------------------
-// objective: one source point against its 3x3 neighbourhood
+// objective
 // MODE 0: score + gradient + Hessian; 1: score + gradient; 2: Hessian only (computeHessian)
 // acc layout: [0] score, [1..3] gradient, [4..12] Hessian row-major
+//
+// Two phases per warp step (32 source points):
+//   probe  each lane transforms its point (float32, bit-exact), reads the 3x3 block of the
+//          cell->slot table and runs the float32 centroid radius test; every (point, cell) hit is
+//          pushed into a per-warp ring queue in shared memory (ballot + popc offsets);
+//   drain  whenever 32 hits are queued, all 32 lanes pop one hit each and run the fp64 hit path
+//          fully converged. Without the queue the hit path would run once per neighbour position
+//          with a handful of active lanes (k = 0.3 .. 2 hits per point spread over 9 positions).
 // ------------------------------------------------------------------------------------------------
 constexpr int NACC = 13;
+constexpr int QCAP = 64;            // per-warp queue capacity (push happens with < 32 queued, adds <= 32)
 
-template <int MODE, class SlotLoad, class RecLoad>
-__device__ __forceinline__ void eval_point(const GridView &G, const SlotLoad &slot_at, const RecLoad &rec_at,
-                                           float xf, float yf, const PoseF &pf, bool sse_order, double cs,
-                                           double sn, double d1, double d2, double *acc, int &pairs) {
-  float xt, yt;
-  xform(pf, sse_order, xf, yf, xt, yt);
-  const int ci = cell_coord(xt, G.inv_leaf, G.min_bx);
-  const int cj = cell_coord(yt, G.inv_leaf, G.min_by);
-  if (ci < -1 || cj < -1 || ci > G.div_x || cj > G.div_y) return;
-  const double x = (double)xf, y = (double)yf;
+struct HitQueue {
+  float4 *xy;     // [QCAP] xt, yt (transformed, float32), xf, yf (original)
+  int *slot;      // [QCAP]
+};
+
+template <int MODE, class RecL>
+__device__ __forceinline__ void hit_path(const RecL &rec_at, const float4 e, const int s, const double cs,
+                                         const double sn, const double d1, const double d2, double *acc) {
+  double2 m, r0, r1;
+  rec_at.body(s, m, r0, r1);
+  const double x = (double)e.z, y = (double)e.w;
+  const double dx = (double)e.x - m.x, dy = (double)e.y - m.y;
+  const double c00 = r0.x, c01 = r0.y, c10 = r1.x, c11 = r1.y;
+  const double Cdx = c00 * dx + c01 * dy, Cdy = c10 * dx + c11 * dy;
+  const double q = dx * Cdx + dy * Cdy;
+  double ex = exp(-d2 * q / 2.0);
+  const double score_inc = -d1 * ex;
+  ex = d2 * ex;
+  if (ex > 1.0 || ex < 0.0 || ex != ex) return;
+  ex *= d1;
   const double Jx = -sn * x - cs * y, Jy = cs * x - sn * y;
-  const double Hx = -cs * x + sn * y, Hy = -sn * x - cs * y;
-  const double xtd = (double)xt, ytd = (double)yt;
+  // cov_dxd_pi = C * J_i for i = x, y, yaw ; a_i = d . (C J_i)
+  const double CJ2x = c00 * Jx + c01 * Jy, CJ2y = c10 * Jx + c11 * Jy;
+  const double a0 = dx * c00 + dy * c10;
+  const double a1 = dx * c01 + dy * c11;
+  const double a2 = dx * CJ2x + dy * CJ2y;
+  if (MODE != 2) {
+    acc[0] += score_inc;
+    acc[1] += a0 * ex; acc[2] += a1 * ex; acc[3] += a2 * ex;
+  }
+  if (MODE != 1) {
+    const double Hx = -cs * x + sn * y, Hy = -sn * x - cs * y;
+    const double dCH = dx * (c00 * Hx + c01 * Hy) + dy * (c10 * Hx + c11 * Hy);
+    const double k0 = -d2 * a0, k1 = -d2 * a1, k2 = -d2 * a2;
+    // H(i,j) += e * (-d2 a_i a_j + J_j . (C J_i) [+ d.(C H_yawyaw) for i = j = yaw])
+    acc[4]  += ex * (k0 * a0 + c00);
+    acc[5]  += ex * (k0 * a1 + c10);
+    acc[6]  += ex * (k0 * a2 + (Jx * c00 + Jy * c10));
+    acc[7]  += ex * (k1 * a0 + c01);
+    acc[8]  += ex * (k1 * a1 + c11);
+    acc[9]  += ex * (k1 * a2 + (Jx * c01 + Jy * c11));
+    acc[10] += ex * (k2 * a0 + CJ2x);
+    acc[11] += ex * (k2 * a1 + CJ2y);
+    acc[12] += ex * (k2 * a2 + (Jx * CJ2x + Jy * CJ2y) + dCH);
+  }
+}
+
+// Accumulate the objective over points i = first + k * stride (k = 0, 1, ...), i < hi, where `first`
+// is lane-contiguous inside a warp (first = warp_first + lane): every lane of a warp iterates the same
+// number of times. acc must be a register array of the caller. pairs: warp-uniform hit count.
+template <int MODE, class SlotL, class RecL, class SrcL>
+__device__ __forceinline__ void accumulate_points(const GridView &G, const SlotL &slot_at, const RecL &rec_at,
+                                                  const SrcL &src, const int first, const int stride, const int hi,
+                                                  const PoseF &pf, const bool sse_order, const double cs,
+                                                  const double sn, const double d1, const double d2,
+                                                  const HitQueue &Q, double *acc, int &pairs) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  int qhead = 0, qn = 0;
+  for (int i0 = first - lane; i0 < hi; i0 += stride) {
+    const int i = i0 + lane;
+    float xt = 0.f, yt = 0.f, xf = 0.f, yf = 0.f;
+    int sl[9];
 #pragma unroll
-  for (int dj = -1; dj <= 1; ++dj) {
-    const int b = cj + dj;
-    if (b < 0 || b >= G.div_y) continue;
+    for (int k = 0; k < 9; ++k) sl[k] = -1;
+    if (i < hi) {
+      const float2 xy = src(i);
+      xf = xy.x; yf = xy.y;
+      xform(pf, sse_order, xf, yf, xt, yt);
+      const int ci = cell_coord(xt, G.inv_leaf, G.min_bx);
+      const int cj = cell_coord(yt, G.inv_leaf, G.min_by);
+      if (ci >= -1 && cj >= -1 && ci <= G.div_x && cj <= G.div_y) {
+        // all nine table reads are issued before any is consumed
 #pragma unroll
-    for (int di = -1; di <= 1; ++di) {
-      const int a = ci + di;
-      if (a < 0 || a >= G.div_x) continue;
-      const int s = slot_at(b * G.div_x + a);
-      if (s < 0) continue;
-      const float4 head = rec_at.head(s);     // cx, cy, nr_points, cell
-      if (!(dist2f(xt, yt, head.x, head.y) < G.r2)) continue;
-      ++pairs;
-      double2 m, r0, r1;
-      rec_at.body(s, m, r0, r1);
-      const double dx = xtd - m.x, dy = ytd - m.y;
-      const double c00 = r0.x, c01 = r0.y, c10 = r1.x, c11 = r1.y;
-      const double Cdx = c00 * dx + c01 * dy, Cdy = c10 * dx + c11 * dy;
-      const double q = dx * Cdx + dy * Cdy;
-      double e = exp(-d2 * q / 2.0);
-      const double score_inc = -d1 * e;
-      e = d2 * e;
-      if (e > 1.0 || e < 0.0 || e != e) continue;
-      e *= d1;
-      // cov_dxd_pi = C * J_i for i = x, y, yaw
-      const double CJ2x = c00 * Jx + c01 * Jy, CJ2y = c10 * Jx + c11 * Jy;
-      const double a0 = dx * c00 + dy * c10;
-      const double a1 = dx * c01 + dy * c11;
-      const double a2 = dx * CJ2x + dy * CJ2y;
-      if (MODE != 2) {
-        acc[0] += score_inc;
-        acc[1] += a0 * e; acc[2] += a1 * e; acc[3] += a2 * e;
+        for (int k = 0; k < 9; ++k) {
+          const int a = ci + (k % 3) - 1, b = cj + (k / 3) - 1;
+          if (a >= 0 && a < G.div_x && b >= 0 && b < G.div_y) sl[k] = slot_at(b * G.div_x + a);
+        }
       }
-      if (MODE != 1) {
-        const double CHx = c00 * Hx + c01 * Hy, CHy = c10 * Hx + c11 * Hy;
-        const double dCH = dx * CHx + dy * CHy;
-        // H(i,j) += e * (-d2 a_i a_j + J_j . (C J_i) [+ d.(C H_yawyaw) for i=j=yaw])
-        acc[4]  += e * (-d2 * a0 * a0 + c00);
-        acc[5]  += e * (-d2 * a0 * a1 + c10);
-        acc[6]  += e * (-d2 * a0 * a2 + (Jx * c00 + Jy * c10));
-        acc[7]  += e * (-d2 * a1 * a0 + c01);
-        acc[8]  += e * (-d2 * a1 * a1 + c11);
-        acc[9]  += e * (-d2 * a1 * a2 + (Jx * c01 + Jy * c11));
-        acc[10] += e * (-d2 * a2 * a0 + CJ2x);
-        acc[11] += e * (-d2 * a2 * a1 + CJ2y);
-        acc[12] += e * (-d2 * a2 * a2 + (Jx * CJ2x + Jy * CJ2y) + dCH);
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      bool hit = false;
+      if (sl[k] >= 0) {
+        const float4 head = rec_at.head(sl[k]);     // cx, cy, nr_points, cell
+        hit = dist2f(xt, yt, head.x, head.y) < G.r2;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (m) {
+        if (hit) {
+          const int pos = (qhead + qn + __popc(m & lt)) & (QCAP - 1);
+          Q.xy[pos] = make_float4(xt, yt, xf, yf);
+          Q.slot[pos] = sl[k];
+        }
+        qn += __popc(m);
+        if (qn >= 32) {
+          __syncwarp();
+          const int pos = (qhead + lane) & (QCAP - 1);
+          hit_path<MODE>(rec_at, Q.xy[pos], Q.slot[pos], cs, sn, d1, d2, acc);
+          __syncwarp();
+          qhead = (qhead + 32) & (QCAP - 1);
+          qn -= 32;
+          pairs += 32;
+        }
       }
     }
   }
+  __syncwarp();
+  if (lane < qn) {
+    const int pos = (qhead + lane) & (QCAP - 1);
+    hit_path<MODE>(rec_at, Q.xy[pos], Q.slot[pos], cs, sn, d1, d2, acc);
+  }
+  pairs += qn;
+  __syncwarp();
 }
 
 // global-memory accessors (read-only path, L1/L2 cached)
@@ -246,12 +307,34 @@ struct BlockCoop {            // one CTA per match; scratch = [nwarps][NACC] dou
 // default rank threshold (diagSize * epsilon * sigma_max, diagSize = 6 in PCL's 6x6 solve)
 // ------------------------------------------------------------------------------------------------
 __device__ inline void svd_solve3(const double *Hin, const double *b, double *x) {
+  {
+    // Fast path: a well-conditioned H has full rank under Eigen's threshold, and the pseudo-inverse
+    // solution is H^-1 b. Adjugate solve (one division); the condition estimate
+    // ||H||_F ||adj H||_F / |det| decides whether the Jacobi SVD below is needed at all.
+    const double h00 = Hin[0], h01 = Hin[1], h02 = Hin[2], h10 = Hin[3], h11 = Hin[4], h12 = Hin[5],
+                 h20 = Hin[6], h21 = Hin[7], h22 = Hin[8];
+    const double c00 = h11 * h22 - h12 * h21, c01 = h12 * h20 - h10 * h22, c02 = h10 * h21 - h11 * h20;
+    const double c10 = h02 * h21 - h01 * h22, c11 = h00 * h22 - h02 * h20, c12 = h01 * h20 - h00 * h21;
+    const double c20 = h01 * h12 - h02 * h11, c21 = h02 * h10 - h00 * h12, c22 = h00 * h11 - h01 * h10;
+    const double det = h00 * c00 + h01 * c01 + h02 * c02;
+    const double nh = h00 * h00 + h01 * h01 + h02 * h02 + h10 * h10 + h11 * h11 + h12 * h12 + h20 * h20 + h21 * h21 + h22 * h22;
+    const double na = c00 * c00 + c01 * c01 + c02 * c02 + c10 * c10 + c11 * c11 + c12 * c12 + c20 * c20 + c21 * c21 + c22 * c22;
+    // cond^2 ~ nh * na / det^2 ; accept cond < 1e7 (1e14 squared). NaN / inf / zero fall through.
+    if (nh * na < 1e14 * det * det) {
+      const double id = 1.0 / det;
+      // inverse = adj / det, adj = cofactor^T
+      x[0] = (c00 * b[0] + c10 * b[1] + c20 * b[2]) * id;
+      x[1] = (c01 * b[0] + c11 * b[1] + c21 * b[2]) * id;
+      x[2] = (c02 * b[0] + c12 * b[1] + c22 * b[2]) * id;
+      return;
+    }
+  }
   double A[3][3], V[3][3];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int j = 0; j < 3; ++j) { A[i][j] = Hin[i * 3 + j]; V[i][j] = (i == j) ? 1.0 : 0.0; }
-  for (int sweep = 0; sweep < 60; ++sweep) {
+  for (int sweep = 0; sweep < 30; ++sweep) {
     double off = 0.0;
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
@@ -275,7 +358,7 @@ __device__ inline void svd_solve3(const double *Hin, const double *b, double *x)
         }
       }
     }
-    if (off < 1e-17) break;
+    if (off < 1e-15) break;   // columns orthogonal to working precision (quadratic convergence: ~4-6 sweeps)
   }
   double sig[3];
 #pragma unroll

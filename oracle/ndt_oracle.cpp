@@ -357,7 +357,7 @@ void objective(Oracle &o, const double p[3], int mode, double &score, double g[3
 void svd_solve3(const double Hin[9], const double b[3], double x[3]) {
   double A[3][3], V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
   for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) A[i][j] = Hin[i * 3 + j];
-  for (int sweep = 0; sweep < 60; ++sweep) {
+  for (int sweep = 0; sweep < 30; ++sweep) {
     double off = 0;
     for (int p = 0; p < 2; ++p)
       for (int q = p + 1; q < 3; ++q) {
@@ -375,7 +375,7 @@ void svd_solve3(const double Hin[9], const double b[3], double x[3]) {
           V[k][p] = c * vp - s * vq; V[k][q] = s * vp + c * vq;
         }
       }
-    if (off < 1e-300 || off < 1e-17) break;
+    if (off < 1e-15) break;
   }
   double sig[3];
   for (int j = 0; j < 3; ++j) sig[j] = std::sqrt(A[0][j] * A[0][j] + A[1][j] * A[1][j] + A[2][j] * A[2][j]);

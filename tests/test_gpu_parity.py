@@ -208,7 +208,7 @@ def test_large_source_cluster_kernel():
     """> 4096 source points: the thread-block-cluster matcher (DSMEM reduction)."""
     rng = synth.rng_for(31)
     segs = synth.office(31, 60.0, 40.0, 20)
-    tgt_xy = synth.sample_walls(segs, 0.02, 0.01, rng)
+    tgt_xy = synth.sample_walls(segs, 0.005, 0.01, rng)
     pick = np.sort(rng.choice(tgt_xy.shape[0], 20_000, replace=False))
     true = (0.06, -0.04, np.deg2rad(0.4))
     c, s = np.cos(true[2]), np.sin(true[2])
