@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -38,7 +39,7 @@ struct BlobHeader {
   uint64_t magic;
   GridDims gd;
   int32_t counters[CTR_COUNT];
-  int64_t off_slot, off_recs, off_leaf_id, off_leaf_start, off_leaf_n, off_sorted, off_tgt, total;
+  int64_t off_slot, off_recs, off_leaf_id, off_leaf_range, off_sorted, off_tgt, total;
 };
 static constexpr uint64_t kBlobMagic = 0x4e44544232303042ull;  // "NDTB200B"
 
@@ -51,12 +52,12 @@ static BlobHeader blob_layout(const Handle *h) {
   std::memcpy(b.counters, h->h_counters, sizeof(b.counters));
   const int64_t nc = h->gd.n_cells, nl = h->h_counters[CTR_LEAVES], nsl = h->h_counters[CTR_SLOTS], nt = h->gd.n_tgt;
   int64_t o = align256(sizeof(BlobHeader));
-  b.off_slot = o; o = align256(o + nc * 4);
+  const int64_t npad = nc > 0 ? (int64_t)(h->gd.div_x + 4) * (h->gd.div_y + 4) : 0;
+  b.off_slot = o; o = align256(o + npad * 4);
   b.off_recs = o; o = align256(o + nsl * (int64_t)sizeof(CellRec));
   b.off_leaf_id = o; o = align256(o + nc * 4);
-  b.off_leaf_start = o; o = align256(o + nl * 4);
-  b.off_leaf_n = o; o = align256(o + nl * 4);
-  b.off_sorted = o; o = align256(o + nt * 4);
+  b.off_leaf_range = o; o = align256(o + nl * 8);
+  b.off_sorted = o; o = align256(o + nt * 8);
   b.off_tgt = o; o = align256(o + nt * (int64_t)sizeof(float4));
   b.total = o;
   return b;
@@ -132,7 +133,7 @@ int ndt_destroy(ndt_handle hh) {
   GridBuffers &g = h->gb;
   DevBuf *all[] = {&g.tgt, &g.cell_of, &g.rank_of, &g.list, &g.sorted_idx, &g.slot, &g.leaf_id, &g.leaf_cell,
                    &g.leaf_n, &g.leaf_start, &g.leaf_nr, &g.leaf_mean, &g.leaf_icov, &g.leaf_cen, &g.recs,
-                   &g.counters, &h->src, &h->scratch, &h->scratch2, &h->stage, &h->io};
+                   &g.counters, &g.tgt_sorted, &g.leaf_range, &h->src, &h->scratch, &h->scratch2, &h->stage, &h->io};
   for (DevBuf *b : all) b->release();
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -324,7 +325,8 @@ int ndt_align(ndt_handle hh, const double guess[3], ndt_result *out) {
   double *d_guess = h->stage.as<double>();
   ndt_result *d_res = (ndt_result *)(d_guess + 4);
   NDT_CUDA(h, cudaMemcpyAsync(d_guess, hp, 24, cudaMemcpyHostToDevice, st));
-  int rc = launch_align(h, d_guess, 1, d_res, true);
+  static const bool dbg_nofit = getenv("NDT_B200_DEBUG_NO_FITNESS") != nullptr;   // timing breakdowns only
+  int rc = launch_align(h, d_guess, 1, d_res, !dbg_nofit);
   if (rc) return rc;
   NDT_CUDA(h, cudaMemcpyAsync(hres, d_res, sizeof(ndt_result), cudaMemcpyDeviceToHost, st));
   NDT_CUDA(h, cudaStreamSynchronize(st));
@@ -445,12 +447,12 @@ int ndt_grid_export(ndt_handle hh, void *device_blob, int64_t bytes) {
     if (nbytes <= 0) return cudaSuccess;
     return cudaMemcpyAsync(d + off, src.p, (size_t)nbytes, cudaMemcpyDeviceToDevice, st);
   };
-  NDT_CUDA(h, cp(b.off_slot, h->gb.slot, nc * 4));
+  const int64_t npad = nc > 0 ? (int64_t)(h->gd.div_x + 4) * (h->gd.div_y + 4) : 0;
+  NDT_CUDA(h, cp(b.off_slot, h->gb.slot, npad * 4));
   NDT_CUDA(h, cp(b.off_recs, h->gb.recs, nsl * (int64_t)sizeof(CellRec)));
   NDT_CUDA(h, cp(b.off_leaf_id, h->gb.leaf_id, nc * 4));
-  NDT_CUDA(h, cp(b.off_leaf_start, h->gb.leaf_start, nl * 4));
-  NDT_CUDA(h, cp(b.off_leaf_n, h->gb.leaf_n, nl * 4));
-  NDT_CUDA(h, cp(b.off_sorted, h->gb.sorted_idx, nt * 4));
+  NDT_CUDA(h, cp(b.off_leaf_range, h->gb.leaf_range, nl * 8));
+  NDT_CUDA(h, cp(b.off_sorted, h->gb.tgt_sorted, nt * 8));
   NDT_CUDA(h, cp(b.off_tgt, h->gb.tgt, nt * (int64_t)sizeof(float4)));
   NDT_CUDA(h, cudaStreamSynchronize(st));
   return NDT_OK;
@@ -474,12 +476,12 @@ int ndt_grid_import(ndt_handle hh, const void *device_blob, int64_t bytes) {
     if (e != cudaSuccess || nbytes <= 0) return e;
     return cudaMemcpyAsync(dst.p, d + off, (size_t)nbytes, cudaMemcpyDeviceToDevice, st);
   };
-  NDT_CUDA(h, take(h->gb.slot, b.off_slot, nc * 4));
+  const int64_t npad = nc > 0 ? (int64_t)(h->gd.div_x + 4) * (h->gd.div_y + 4) : 0;
+  NDT_CUDA(h, take(h->gb.slot, b.off_slot, npad * 4));
   NDT_CUDA(h, take(h->gb.recs, b.off_recs, nsl * (int64_t)sizeof(CellRec)));
   NDT_CUDA(h, take(h->gb.leaf_id, b.off_leaf_id, nc * 4));
-  NDT_CUDA(h, take(h->gb.leaf_start, b.off_leaf_start, nl * 4));
-  NDT_CUDA(h, take(h->gb.leaf_n, b.off_leaf_n, nl * 4));
-  NDT_CUDA(h, take(h->gb.sorted_idx, b.off_sorted, nt * 4));
+  NDT_CUDA(h, take(h->gb.leaf_range, b.off_leaf_range, nl * 8));
+  NDT_CUDA(h, take(h->gb.tgt_sorted, b.off_sorted, nt * 8));
   NDT_CUDA(h, take(h->gb.tgt, b.off_tgt, nt * (int64_t)sizeof(float4)));
   NDT_CUDA(h, cudaStreamSynchronize(st));
   h->have_grid = true;

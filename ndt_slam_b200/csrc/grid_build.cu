@@ -80,20 +80,21 @@ __global__ void __launch_bounds__(256) k_count(const float4 *__restrict__ pts, i
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t n_round = ((n + 31) / 32) * 32;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-    int cell = -1;
+    int cell = -1, pcell = -1;
     if (i < n) {
       const float4 p = __ldg(pts + i);
       if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
         const int i0 = cell_coord(p.x, d.inv_leaf, d.min_bx);
         const int i1 = cell_coord(p.y, d.inv_leaf, d.min_by);
         cell = i0 + i1 * d.div_x;
+        pcell = (i1 + 2) * (d.div_x + 4) + i0 + 2;     // position in the padded count / slot table
       }
     }
     // lanes of this warp that hit the same cell share one atomic
     const unsigned grp = __match_any_sync(0xffffffffu, cell);
     const int leader = __ffs(grp) - 1;
     int base = 0;
-    if (cell >= 0 && lane == leader) base = atomicAdd(count + cell, __popc(grp));
+    if (cell >= 0 && lane == leader) base = atomicAdd(count + pcell, __popc(grp));
     base = __shfl_sync(0xffffffffu, base, leader);
     if (i < n) {
       cell_of[i] = cell;
@@ -102,48 +103,53 @@ __global__ void __launch_bounds__(256) k_count(const float4 *__restrict__ pts, i
   }
 }
 
-// pass 1b: per dense cell, allocate a leaf id and a bucket range; the count table becomes the slot table
-__global__ void __launch_bounds__(256) k_alloc(int32_t *__restrict__ count_slot, int64_t n_cells,
+// pass 1b: walk the padded count table; every occupied cell gets a leaf id and a bucket range, and the
+// count table turns into the slot table (-1 everywhere until k_finalize fills in the tree members)
+__global__ void __launch_bounds__(256) k_alloc(int32_t *__restrict__ count_slot, int div_x, int div_y,
                                               int32_t *__restrict__ leaf_id, int32_t *__restrict__ leaf_cell,
                                               int32_t *__restrict__ leaf_n, int32_t *__restrict__ leaf_start,
                                               int32_t *__restrict__ ctr) {
   const int lane = threadIdx.x & 31;
+  const int W = div_x + 4;
+  const int64_t n_pad = (int64_t)W * (div_y + 4);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t n_round = ((n_cells + 31) / 32) * 32;
-  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_round; c += stride) {
-    const int n = (c < n_cells) ? count_slot[c] : 0;
+  const int64_t n_round = ((n_pad + 31) / 32) * 32;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_round; q += stride) {
+    int n = 0, cell = -1;
+    if (q < n_pad) {
+      const int r = (int)(q / W), c = (int)(q - (int64_t)r * W);
+      if (r >= 2 && r < div_y + 2 && c >= 2 && c < div_x + 2) {
+        cell = (r - 2) * div_x + (c - 2);
+        n = count_slot[q];
+      }
+    }
     const bool has = n > 0;
     const unsigned bal = __ballot_sync(0xffffffffu, has);
-    if (bal == 0u) {
-      if (c < n_cells) { leaf_id[c] = -1; count_slot[c] = -1; }
-      continue;
-    }
-    int incl = n;
+    if (bal != 0u) {
+      int incl = n;
 #pragma unroll
-    for (int dlt = 1; dlt < 32; dlt <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, dlt);
-      if (lane >= dlt) incl += t;
-    }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    int base_leaf = 0, base_pts = 0;
-    if (lane == 0) {
-      base_leaf = atomicAdd(ctr + CTR_LEAVES, __popc(bal));
-      base_pts = atomicAdd(ctr + CTR_PTS, total);
-    }
-    base_leaf = __shfl_sync(0xffffffffu, base_leaf, 0);
-    base_pts = __shfl_sync(0xffffffffu, base_pts, 0);
-    if (c < n_cells) {
+      for (int dlt = 1; dlt < 32; dlt <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, dlt);
+        if (lane >= dlt) incl += t;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      int base_leaf = 0, base_pts = 0;
+      if (lane == 0) {
+        base_leaf = atomicAdd(ctr + CTR_LEAVES, __popc(bal));
+        base_pts = atomicAdd(ctr + CTR_PTS, total);
+      }
+      base_leaf = __shfl_sync(0xffffffffu, base_leaf, 0);
+      base_pts = __shfl_sync(0xffffffffu, base_pts, 0);
       if (has) {
         const int leaf = base_leaf + __popc(bal & ((1u << lane) - 1u));
-        leaf_id[c] = leaf;
-        leaf_cell[leaf] = (int32_t)c;
+        leaf_id[cell] = leaf;
+        leaf_cell[leaf] = cell;
         leaf_n[leaf] = n;
         leaf_start[leaf] = base_pts + incl - n;
-      } else {
-        leaf_id[c] = -1;
       }
-      count_slot[c] = -1;
     }
+    if (cell >= 0 && !has) leaf_id[cell] = -1;
+    if (q < n_pad) count_slot[q] = -1;
   }
 }
 
@@ -188,14 +194,15 @@ struct FinalizeParams { int32_t min_points; double eig_mult; int32_t quirks; };
 
 // pass 2: one warp per leaf
 __global__ void __launch_bounds__(256) k_finalize(const float4 *__restrict__ pts, const int32_t *__restrict__ list,
-                                                 int32_t *__restrict__ sorted_idx,
+                                                 int32_t *__restrict__ sorted_idx, float2 *__restrict__ tgt_sorted,
+                                                 int2 *__restrict__ leaf_range,
                                                  const int32_t *__restrict__ leaf_cell,
                                                  const int32_t *__restrict__ leaf_n,
                                                  const int32_t *__restrict__ leaf_start,
                                                  int32_t *__restrict__ leaf_nr, double2 *__restrict__ leaf_mean,
                                                  double *__restrict__ leaf_icov, float2 *__restrict__ leaf_cen,
                                                  int32_t *__restrict__ slot, CellRec *__restrict__ recs,
-                                                 int32_t *__restrict__ ctr, FinalizeParams fp) {
+                                                 int32_t *__restrict__ ctr, FinalizeParams fp, int div_x) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -218,6 +225,7 @@ __global__ void __launch_bounds__(256) k_finalize(const float4 *__restrict__ pts
       if (base + lane < n) {
         const float4 p = __ldg(pts + sorted_idx[st + base + lane]);
         px = p.x; py = p.y;
+        tgt_sorted[st + base + lane] = make_float2(px, py);
       }
       const int m = min(32, n - base);
       for (int k = 0; k < m; ++k) {
@@ -229,6 +237,7 @@ __global__ void __launch_bounds__(256) k_finalize(const float4 *__restrict__ pts
       }
     }
     if (lane != 0) continue;
+    leaf_range[leaf] = make_int2(st, n);
     const double nn = (double)n;
     cx = cx / (float)n; cy = cy / (float)n;
     const double psx = sx, psy = sy;
@@ -303,7 +312,9 @@ __global__ void __launch_bounds__(256) k_finalize(const float4 *__restrict__ pts
       r.cx = cx; r.cy = cy; r.nr_points = nr; r.cell = leaf_cell[leaf];
       r.mx = m0; r.my = m1; r.c00 = ic0; r.c01 = ic1; r.c10 = ic2; r.c11 = ic3;
       recs[s] = r;
-      slot[leaf_cell[leaf]] = s;
+      const int cell = leaf_cell[leaf];
+      const int j = cell / div_x, i = cell - j * div_x;
+      slot[(j + 2) * (div_x + 4) + i + 2] = s;
     }
   }
 }
@@ -333,8 +344,8 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace) {
   h->have_grid = false;
   if (n < 0 || (n > 0 && !xyzw)) return set_err(h, NDT_ERR_ARG, "ndt_set_target: bad points");
   if (n > (int64_t)INT_MAX) return set_err(h, NDT_ERR_CAPACITY, "ndt_set_target: more than 2^31-1 points");
-  const size_t npad = (size_t)(n > 0 ? n : 1);
-  NDT_CUDA(h, gb.tgt.reserve(npad * sizeof(float4)));
+  const size_t npts = (size_t)(n > 0 ? n : 1);
+  NDT_CUDA(h, gb.tgt.reserve(npts * sizeof(float4)));
   NDT_CUDA(h, gb.counters.reserve((CTR_COUNT + 4) * sizeof(int32_t)));
   int32_t *ctr = gb.counters.as<int32_t>();
   int32_t *bounds = ctr + CTR_COUNT;
@@ -353,7 +364,7 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace) {
   ++h->launches;
   if (memspace == NDT_MEM_HOST) {
     // stage through pinned memory; bounds come for free while the points pass through the host cache
-    if (ensure_pinned(h, npad * sizeof(float4))) return NDT_ERR_CUDA;
+    if (ensure_pinned(h, npts * sizeof(float4))) return NDT_ERR_CUDA;
     float *stage = (float *)h->pinned;
     for (int64_t i = 0; i < n; ++i) {
       const float x = xyzw[4 * i], y = xyzw[4 * i + 1], z = xyzw[4 * i + 2];
@@ -403,16 +414,19 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace) {
     return NDT_OK;
   }
   const size_t nc = (size_t)gd.n_cells;
-  NDT_CUDA(h, gb.cell_of.reserve(npad * 4));
-  NDT_CUDA(h, gb.rank_of.reserve(npad * 4));
-  NDT_CUDA(h, gb.list.reserve(npad * 4));
-  NDT_CUDA(h, gb.sorted_idx.reserve(npad * 4));
-  NDT_CUDA(h, gb.slot.reserve(nc * 4));
+  NDT_CUDA(h, gb.cell_of.reserve(npts * 4));
+  NDT_CUDA(h, gb.rank_of.reserve(npts * 4));
+  NDT_CUDA(h, gb.list.reserve(npts * 4));
+  NDT_CUDA(h, gb.sorted_idx.reserve(npts * 4));
+  NDT_CUDA(h, gb.tgt_sorted.reserve(npts * sizeof(float2)));
+  const size_t npad = (size_t)(gd.div_x + 4) * (size_t)(gd.div_y + 4);
+  NDT_CUDA(h, gb.slot.reserve(npad * 4));
   NDT_CUDA(h, gb.leaf_id.reserve(nc * 4));
-  const size_t max_leaves = std::min(npad, nc);
+  const size_t max_leaves = std::min(npts, nc);
   NDT_CUDA(h, gb.leaf_cell.reserve(max_leaves * 4));
   NDT_CUDA(h, gb.leaf_n.reserve(max_leaves * 4));
   NDT_CUDA(h, gb.leaf_start.reserve(max_leaves * 4));
+  NDT_CUDA(h, gb.leaf_range.reserve(max_leaves * sizeof(int2)));
   NDT_CUDA(h, gb.leaf_nr.reserve(max_leaves * 4));
   NDT_CUDA(h, gb.leaf_mean.reserve(max_leaves * sizeof(double2)));
   NDT_CUDA(h, gb.leaf_icov.reserve(max_leaves * 4 * sizeof(double)));
@@ -420,10 +434,10 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace) {
   NDT_CUDA(h, gb.recs.reserve(max_leaves * sizeof(CellRec)));
 
   Dims d{gd.min_bx, gd.min_by, gd.div_x, gd.div_y, gd.inv_leaf};
-  NDT_CUDA(h, cudaMemsetAsync(gb.slot.p, 0, nc * 4, st));
+  NDT_CUDA(h, cudaMemsetAsync(gb.slot.p, 0, npad * 4, st));
   k_count<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(gb.tgt.as<float4>(), n, d, gb.slot.as<int32_t>(),
                                                         gb.cell_of.as<int32_t>(), gb.rank_of.as<int32_t>());
-  k_alloc<<<grid_for(gd.n_cells, 256, h->sm_count), 256, 0, st>>>(gb.slot.as<int32_t>(), gd.n_cells,
+  k_alloc<<<grid_for((int64_t)npad, 256, h->sm_count), 256, 0, st>>>(gb.slot.as<int32_t>(), gd.div_x, gd.div_y,
                                                                  gb.leaf_id.as<int32_t>(), gb.leaf_cell.as<int32_t>(),
                                                                  gb.leaf_n.as<int32_t>(), gb.leaf_start.as<int32_t>(), ctr);
   k_fill<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(n, gb.cell_of.as<int32_t>(), gb.rank_of.as<int32_t>(),
@@ -432,9 +446,10 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace) {
   FinalizeParams fp{h->prm.min_points, h->prm.eig_mult, h->prm.quirks};
   const int64_t warps_needed = (int64_t)max_leaves;
   k_finalize<<<grid_for(warps_needed * 32, 256, h->sm_count), 256, 0, st>>>(
-      gb.tgt.as<float4>(), gb.list.as<int32_t>(), gb.sorted_idx.as<int32_t>(), gb.leaf_cell.as<int32_t>(),
+      gb.tgt.as<float4>(), gb.list.as<int32_t>(), gb.sorted_idx.as<int32_t>(), gb.tgt_sorted.as<float2>(),
+      gb.leaf_range.as<int2>(), gb.leaf_cell.as<int32_t>(),
       gb.leaf_n.as<int32_t>(), gb.leaf_start.as<int32_t>(), gb.leaf_nr.as<int32_t>(), gb.leaf_mean.as<double2>(),
-      gb.leaf_icov.as<double>(), gb.leaf_cen.as<float2>(), gb.slot.as<int32_t>(), gb.recs.as<CellRec>(), ctr, fp);
+      gb.leaf_icov.as<double>(), gb.leaf_cen.as<float2>(), gb.slot.as<int32_t>(), gb.recs.as<CellRec>(), ctr, fp, gd.div_x);
   h->launches += 4;
   if (h->timing) cudaEventRecord(h->ev1, st);
   NDT_CUDA(h, cudaMemcpyAsync(h->h_counters, ctr, sizeof(h->h_counters), cudaMemcpyDeviceToHost, st));
@@ -470,13 +485,13 @@ GridView grid_view(const Handle *h) {
   GridView G{};
   const GridBuffers &gb = h->gb;
   G.slot = gb.slot.as<int32_t>();
+  G.slot_w = h->gd.div_x + 4;
   G.recs = gb.recs.as<CellRec>();
   G.min_bx = h->gd.min_bx; G.min_by = h->gd.min_by; G.div_x = h->gd.div_x; G.div_y = h->gd.div_y;
   G.inv_leaf = h->gd.inv_leaf; G.r2 = h->gd.r2; G.leaf = h->gd.leaf;
   G.leaf_id = gb.leaf_id.as<int32_t>();
-  G.leaf_start = gb.leaf_start.as<int32_t>();
-  G.leaf_n = gb.leaf_n.as<int32_t>();
-  G.sorted_idx = gb.sorted_idx.as<int32_t>();
+  G.leaf_range = gb.leaf_range.as<int2>();
+  G.tgt_sorted = gb.tgt_sorted.as<float2>();
   G.tgt = gb.tgt.as<float4>();
   G.n_tgt = h->gd.n_tgt;
   return G;

@@ -438,7 +438,7 @@ int launch_align(Handle *h, const double *d_guesses, int64_t n, ndt_result *d_re
     NDT_CUDA(h, cudaLaunchKernelEx(&cfg, k_align_cluster, G, mp, src, ns, d_guesses, d_results));
   } else {
     const int n_slots = h->h_counters[CTR_SLOTS];
-    const int n_cells = (int)h->gd.n_cells;
+    const int n_cells = h->gd.n_cells > 0 ? (h->gd.div_x + 4) * (h->gd.div_y + 4) : 0;   // padded table
     const size_t tile = (size_t)n_slots * sizeof(CellRec) + (size_t)n_cells * sizeof(int32_t);
     const size_t budget = (size_t)h->max_smem_optin > 4096 ? (size_t)h->max_smem_optin - 4096 : 0;
     if (tile > 0 && tile <= budget) {

@@ -34,7 +34,9 @@ struct __align__(16) CellRec {   // 64 bytes
 static_assert(sizeof(CellRec) == 64, "CellRec must be 64 bytes");
 
 struct GridView {
-  const int32_t *__restrict__ slot;     // [div_x * div_y] -> record index, -1 = not in the centroid tree
+  const int32_t *__restrict__ slot;     // [(div_x + 4) * (div_y + 4)] padded by 2 cells of -1 on every side:
+                                        // cell (i, j) lives at (j + 2) * slot_w + i + 2; value = record index or -1
+  int32_t slot_w;                       // div_x + 4
   const CellRec *__restrict__ recs;     // compact records of cells with n >= min_points
   int32_t min_bx, min_by, div_x, div_y;
   float inv_leaf;                       // 1.0f / leaf
@@ -42,10 +44,9 @@ struct GridView {
   float leaf;
   // 1-NN buckets (fitness): every occupied cell
   const int32_t *__restrict__ leaf_id;  // [div_x * div_y] -> leaf index or -1
-  const int32_t *__restrict__ leaf_start;
-  const int32_t *__restrict__ leaf_n;
-  const int32_t *__restrict__ sorted_idx;
-  const float4 *__restrict__ tgt;       // target points
+  const int2 *__restrict__ leaf_range;  // per leaf: (start, n) into tgt_sorted
+  const float2 *__restrict__ tgt_sorted;// target (x, y) in bucket order (cell by cell, input order inside a cell)
+  const float4 *__restrict__ tgt;       // target points, input order
   int64_t n_tgt;
 };
 
@@ -110,7 +111,7 @@ __device__ __forceinline__ float dist2f(float ax, float ay, float bx, float by) 
 //          with a handful of active lanes (k = 0.3 .. 2 hits per point spread over 9 positions).
 // ------------------------------------------------------------------------------------------------
 constexpr int NACC = 13;
-constexpr int QCAP = 64;            // per-warp queue capacity (push happens with < 32 queued, adds <= 32)
+constexpr int QCAP = 128;           // per-warp queue capacity: < 32 queued before a row is probed, a row adds <= 96
 
 struct HitQueue {
   float4 *xy;     // [QCAP] xt, yt (transformed, float32), xf, yf (original)
@@ -162,6 +163,9 @@ __device__ __forceinline__ void hit_path(const RecL &rec_at, const float4 e, con
 // Accumulate the objective over points i = first + k * stride (k = 0, 1, ...), i < hi, where `first`
 // is lane-contiguous inside a warp (first = warp_first + lane): every lane of a warp iterates the same
 // number of times. acc must be a register array of the caller. pairs: warp-uniform hit count.
+//
+// Written as a small warp-uniform state machine so that the probe code and the fp64 hit path each
+// exist exactly once in the instruction stream (the matcher is instruction-cache sensitive).
 template <int MODE, class SlotL, class RecL, class SrcL>
 __device__ __forceinline__ void accumulate_points(const GridView &G, const SlotL &slot_at, const RecL &rec_at,
                                                   const SrcL &src, const int first, const int stride, const int hi,
@@ -170,61 +174,67 @@ __device__ __forceinline__ void accumulate_points(const GridView &G, const SlotL
                                                   const HitQueue &Q, double *acc, int &pairs) {
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
+  const int W = G.slot_w;
   int qhead = 0, qn = 0;
-  for (int i0 = first - lane; i0 < hi; i0 += stride) {
-    const int i = i0 + lane;
-    float xt = 0.f, yt = 0.f, xf = 0.f, yf = 0.f;
-    int sl[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) sl[k] = -1;
-    if (i < hi) {
-      const float2 xy = src(i);
-      xf = xy.x; yf = xy.y;
-      xform(pf, sse_order, xf, yf, xt, yt);
-      const int ci = cell_coord(xt, G.inv_leaf, G.min_bx);
-      const int cj = cell_coord(yt, G.inv_leaf, G.min_by);
-      if (ci >= -1 && cj >= -1 && ci <= G.div_x && cj <= G.div_y) {
-        // all nine table reads are issued before any is consumed
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          const int a = ci + (k % 3) - 1, b = cj + (k / 3) - 1;
-          if (a >= 0 && a < G.div_x && b >= 0 && b < G.div_y) sl[k] = slot_at(b * G.div_x + a);
-        }
+  int i0 = first - lane;
+  int row = 3;                       // 3: fetch the next point; 0..2: probe that row of the 3x3 block
+  int base = -1;                     // padded-table index of the point's own cell, -1 = nothing to probe
+  float xt = 0.f, yt = 0.f, xf = 0.f, yf = 0.f;
+  for (;;) {
+    const bool done = (row == 3) && (i0 >= hi);
+    if (qn >= 32 || (done && qn > 0)) {
+      // drain: every lane pops one queued (point, cell) hit and runs the fp64 hit path converged
+      const int n = min(qn, 32);
+      __syncwarp();
+      if (lane < n) {
+        const int pos = (qhead + lane) & (QCAP - 1);
+        hit_path<MODE>(rec_at, Q.xy[pos], Q.slot[pos], cs, sn, d1, d2, acc);
+      }
+      __syncwarp();
+      qhead = (qhead + n) & (QCAP - 1);
+      qn -= n;
+      pairs += n;
+      continue;
+    }
+    if (done) break;
+    if (row == 3) {
+      const int i = i0 + lane;
+      i0 += stride;
+      row = 0;
+      base = -1;
+      if (i < hi) {
+        const float2 xy = src(i);
+        xf = xy.x; yf = xy.y;
+        xform(pf, sse_order, xf, yf, xt, yt);
+        const int ci = cell_coord(xt, G.inv_leaf, G.min_bx);
+        const int cj = cell_coord(yt, G.inv_leaf, G.min_by);
+        if (ci >= -1 && cj >= -1 && ci <= G.div_x && cj <= G.div_y) base = (cj + 2) * W + ci + 2;
       }
     }
+    // probe one row of the 3x3 block: three adjacent table entries, no bounds checks (padded table)
+    int s0 = -1, s1 = -1, s2 = -1;
+    if (base >= 0) {
+      const int r = base + (row - 1) * W;
+      s0 = slot_at(r - 1); s1 = slot_at(r); s2 = slot_at(r + 1);
+    }
+    ++row;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
+    for (int k = 0; k < 3; ++k) {
+      const int sk = (k == 0) ? s0 : (k == 1 ? s1 : s2);
       bool hit = false;
-      if (sl[k] >= 0) {
-        const float4 head = rec_at.head(sl[k]);     // cx, cy, nr_points, cell
+      if (sk >= 0) {
+        const float4 head = rec_at.head(sk);       // cx, cy, nr_points, cell
         hit = dist2f(xt, yt, head.x, head.y) < G.r2;
       }
       const unsigned m = __ballot_sync(0xffffffffu, hit);
-      if (m) {
-        if (hit) {
-          const int pos = (qhead + qn + __popc(m & lt)) & (QCAP - 1);
-          Q.xy[pos] = make_float4(xt, yt, xf, yf);
-          Q.slot[pos] = sl[k];
-        }
-        qn += __popc(m);
-        if (qn >= 32) {
-          __syncwarp();
-          const int pos = (qhead + lane) & (QCAP - 1);
-          hit_path<MODE>(rec_at, Q.xy[pos], Q.slot[pos], cs, sn, d1, d2, acc);
-          __syncwarp();
-          qhead = (qhead + 32) & (QCAP - 1);
-          qn -= 32;
-          pairs += 32;
-        }
+      if (hit) {
+        const int pos = (qhead + qn + __popc(m & lt)) & (QCAP - 1);
+        Q.xy[pos] = make_float4(xt, yt, xf, yf);
+        Q.slot[pos] = sk;
       }
+      qn += __popc(m);
     }
   }
-  __syncwarp();
-  if (lane < qn) {
-    const int pos = (qhead + lane) & (QCAP - 1);
-    hit_path<MODE>(rec_at, Q.xy[pos], Q.slot[pos], cs, sn, d1, d2, acc);
-  }
-  pairs += qn;
   __syncwarp();
 }
 
@@ -551,16 +561,22 @@ __device__ inline void match_device(Obj &obj, const MatchParams &mp, const doubl
 // Registration::getFitnessScore: exact float 1-NN squared distance via ring search over the cell
 // buckets built with the grid; exhaustive scan if nothing is found within `max_rings`.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void nn_visit(const GridView &G, int a, int b, float xt, float yt, float &best) {
-  if (a < 0 || a >= G.div_x || b < 0 || b >= G.div_y) return;
-  const int lf = __ldg(G.leaf_id + (size_t)b * G.div_x + a);
+__device__ __forceinline__ void nn_scan(const GridView &G, int lf, float xt, float yt, float &best) {
   if (lf < 0) return;
-  const int st = __ldg(G.leaf_start + lf), n = __ldg(G.leaf_n + lf);
-  for (int k = 0; k < n; ++k) {
-    const float4 t = __ldg(G.tgt + __ldg(G.sorted_idx + st + k));
+  const int2 rg = __ldg(G.leaf_range + lf);
+  const float2 *__restrict__ p = G.tgt_sorted + rg.x;
+  for (int k = 0; k < rg.y; ++k) {
+    const float2 t = __ldg(p + k);
     const float dd = dist2f(xt, yt, t.x, t.y);
     if (dd < best) best = dd;
   }
+}
+__device__ __forceinline__ int nn_leaf(const GridView &G, int a, int b) {
+  if (a < 0 || a >= G.div_x || b < 0 || b >= G.div_y) return -1;
+  return __ldg(G.leaf_id + (size_t)b * G.div_x + a);
+}
+__device__ __forceinline__ void nn_visit(const GridView &G, int a, int b, float xt, float yt, float &best) {
+  nn_scan(G, nn_leaf(G, a, b), xt, yt, best);
 }
 
 __device__ inline float nn_dist2(const GridView &G, float xt, float yt, int max_rings) {
@@ -573,7 +589,17 @@ __device__ inline float nn_dist2(const GridView &G, float xt, float yt, int max_
     if (ci < 0) ox = -ci; else if (ci >= G.div_x) ox = ci - (G.div_x - 1);
     if (cj < 0) oy = -cj; else if (cj >= G.div_y) oy = cj - (G.div_y - 1);
     const int r_start = max(ox, oy);
-    for (int ring = r_start; ring <= r_start + max_rings; ++ring) {
+    if (r_start == 0) {
+      // rings 0 and 1 together (the common case: the neighbour is next door); lookups issued up front
+      int lf[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) lf[k] = nn_leaf(G, ci + (k % 3) - 1, cj + (k / 3) - 1);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) nn_scan(G, lf[k], xt, yt, best);
+      const double lim1 = 0.99 * (double)G.leaf;
+      if ((double)best < lim1 * lim1) return best;
+    }
+    for (int ring = (r_start == 0 ? 2 : r_start); ring <= r_start + max_rings; ++ring) {
       if (ring == 0) {
         nn_visit(G, ci, cj, xt, yt, best);
       } else {

@@ -36,6 +36,8 @@ struct GridBuffers {
   DevBuf rank_of;      // int32[n]        arbitrary unique rank of the point inside its cell
   DevBuf list;         // int32[n]        per-leaf point indices, arbitrary order
   DevBuf sorted_idx;   // int32[n]        per-leaf point indices, ascending (input order)
+  DevBuf tgt_sorted;   // float2[n]       target (x, y) in bucket order (1-NN scans read this contiguously)
+  DevBuf leaf_range;   // int2[n]         per leaf (start, n)
   DevBuf slot;         // int32[n_cells]  count during the build, then cell -> record slot
   DevBuf leaf_id;      // int32[n_cells]  cell -> leaf or -1
   DevBuf leaf_cell;    // int32[n]        per leaf: cell index

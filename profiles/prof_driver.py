@@ -31,4 +31,6 @@ for _ in range(3):
     g1.set_target(tgt); g1.set_source(src)
     r = g1.align(np.array(d["pose_a"]))
 print("C1 align kernel_ms", g1.last_kernel_ms(), "evals", r.evals)
+e = g1.eval(np.array(d["pose_a"])); e = g1.eval(np.array(d["pose_a"]))
+print("C1 single eval (2 kernels) ms", g1.last_kernel_ms())
 torch.cuda.synchronize()
