@@ -69,6 +69,23 @@ def _run(cmd, log: Path | None = None) -> str:
     return p.stdout
 
 
+def build_variant(tag: str, defines: list[str]) -> Path:
+    """Experimental build with extra -D flags into ndt_slam_b200/build/libndt_b200_<tag>.so (A/B tuning)."""
+    objdir = PKG / "build" / tag
+    objdir.mkdir(parents=True, exist_ok=True)
+    out = PKG / "build" / f"libndt_b200_{tag}.so"
+    objs = []
+    for s in sorted(CSRC.glob("*.cu")):
+        o = objdir / (s.stem + ".o")
+        flags = list(NVCC_FLAGS)
+        if s.name in NO_FMAD:
+            flags[flags.index("--fmad=true")] = "--fmad=false"
+        _run([_nvcc(), *flags, *[f"-D{d}" for d in defines], "-c", "-I", str(ROOT / "include"), "-I", str(CSRC), "-o", str(o), str(s)])
+        objs.append(o)
+    _run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(out), *map(str, objs), "-lcudart"])
+    return out
+
+
 def build_cuda(force: bool = False) -> Path:
     """libndt_b200.so: the hand-written sm_100a kernels + the C ABI (include/ndt_b200.h)."""
     srcs = sorted(CSRC.glob("*.cu"))

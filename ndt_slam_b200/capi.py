@@ -66,7 +66,9 @@ _lib = None
 
 
 def lib_path() -> Path:
-    return _build.LIB_CUDA
+    """In-tree library; NDT_B200_LIB overrides it for A/B experiments with differently tuned builds."""
+    import os
+    return Path(os.environ["NDT_B200_LIB"]) if os.environ.get("NDT_B200_LIB") else _build.LIB_CUDA
 
 
 def load() -> C.CDLL:

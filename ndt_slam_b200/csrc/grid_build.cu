@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) k_count(const float4 *__restrict__ pts, i
 
 // pass 1b: walk the padded count table; every occupied cell gets a leaf id and a bucket range, and the
 // count table turns into the slot table (-1 everywhere until k_finalize fills in the tree members)
-__global__ void __launch_bounds__(256) k_alloc(int32_t *__restrict__ count_slot, int div_x, int div_y,
+__global__ void __launch_bounds__(256) k_alloc(int32_t *__restrict__ count_slot, float2 *__restrict__ cen, int div_x, int div_y,
                                               int32_t *__restrict__ leaf_id, int32_t *__restrict__ leaf_cell,
                                               int32_t *__restrict__ leaf_n, int32_t *__restrict__ leaf_start,
                                               int32_t *__restrict__ ctr) {
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256) k_alloc(int32_t *__restrict__ count_slot,
       }
     }
     if (cell >= 0 && !has) leaf_id[cell] = -1;
-    if (q < n_pad) count_slot[q] = -1;
+    if (q < n_pad) { count_slot[q] = -1; cen[q] = make_float2(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000)); }
   }
 }
 
@@ -201,7 +201,8 @@ __global__ void __launch_bounds__(256) k_finalize(const float4 *__restrict__ pts
                                                  const int32_t *__restrict__ leaf_start,
                                                  int32_t *__restrict__ leaf_nr, double2 *__restrict__ leaf_mean,
                                                  double *__restrict__ leaf_icov, float2 *__restrict__ leaf_cen,
-                                                 int32_t *__restrict__ slot, CellRec *__restrict__ recs,
+                                                 int32_t *__restrict__ slot, float2 *__restrict__ cen_tab,
+                                                 CellRec *__restrict__ recs,
                                                  int32_t *__restrict__ ctr, FinalizeParams fp, int div_x) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -315,6 +316,7 @@ __global__ void __launch_bounds__(256) k_finalize(const float4 *__restrict__ pts
       const int cell = leaf_cell[leaf];
       const int j = cell / div_x, i = cell - j * div_x;
       slot[(j + 2) * (div_x + 4) + i + 2] = s;
+      cen_tab[(j + 2) * (div_x + 4) + i + 2] = make_float2(cx, cy);
     }
   }
 }
@@ -421,6 +423,7 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace) {
   NDT_CUDA(h, gb.tgt_sorted.reserve(npts * sizeof(float2)));
   const size_t npad = (size_t)(gd.div_x + 4) * (size_t)(gd.div_y + 4);
   NDT_CUDA(h, gb.slot.reserve(npad * 4));
+  NDT_CUDA(h, gb.cen.reserve(npad * sizeof(float2)));
   NDT_CUDA(h, gb.leaf_id.reserve(nc * 4));
   const size_t max_leaves = std::min(npts, nc);
   NDT_CUDA(h, gb.leaf_cell.reserve(max_leaves * 4));
@@ -437,7 +440,7 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace) {
   NDT_CUDA(h, cudaMemsetAsync(gb.slot.p, 0, npad * 4, st));
   k_count<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(gb.tgt.as<float4>(), n, d, gb.slot.as<int32_t>(),
                                                         gb.cell_of.as<int32_t>(), gb.rank_of.as<int32_t>());
-  k_alloc<<<grid_for((int64_t)npad, 256, h->sm_count), 256, 0, st>>>(gb.slot.as<int32_t>(), gd.div_x, gd.div_y,
+  k_alloc<<<grid_for((int64_t)npad, 256, h->sm_count), 256, 0, st>>>(gb.slot.as<int32_t>(), gb.cen.as<float2>(), gd.div_x, gd.div_y,
                                                                  gb.leaf_id.as<int32_t>(), gb.leaf_cell.as<int32_t>(),
                                                                  gb.leaf_n.as<int32_t>(), gb.leaf_start.as<int32_t>(), ctr);
   k_fill<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(n, gb.cell_of.as<int32_t>(), gb.rank_of.as<int32_t>(),
@@ -449,7 +452,7 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace) {
       gb.tgt.as<float4>(), gb.list.as<int32_t>(), gb.sorted_idx.as<int32_t>(), gb.tgt_sorted.as<float2>(),
       gb.leaf_range.as<int2>(), gb.leaf_cell.as<int32_t>(),
       gb.leaf_n.as<int32_t>(), gb.leaf_start.as<int32_t>(), gb.leaf_nr.as<int32_t>(), gb.leaf_mean.as<double2>(),
-      gb.leaf_icov.as<double>(), gb.leaf_cen.as<float2>(), gb.slot.as<int32_t>(), gb.recs.as<CellRec>(), ctr, fp, gd.div_x);
+      gb.leaf_icov.as<double>(), gb.leaf_cen.as<float2>(), gb.slot.as<int32_t>(), gb.cen.as<float2>(), gb.recs.as<CellRec>(), ctr, fp, gd.div_x);
   h->launches += 4;
   if (h->timing) cudaEventRecord(h->ev1, st);
   NDT_CUDA(h, cudaMemcpyAsync(h->h_counters, ctr, sizeof(h->h_counters), cudaMemcpyDeviceToHost, st));
@@ -486,6 +489,7 @@ GridView grid_view(const Handle *h) {
   const GridBuffers &gb = h->gb;
   G.slot = gb.slot.as<int32_t>();
   G.slot_w = h->gd.div_x + 4;
+  G.cen = gb.cen.as<float2>();
   G.recs = gb.recs.as<CellRec>();
   G.min_bx = h->gd.min_bx; G.min_by = h->gd.min_by; G.div_x = h->gd.div_x; G.div_y = h->gd.div_y;
   G.inv_leaf = h->gd.inv_leaf; G.r2 = h->gd.r2; G.leaf = h->gd.leaf;

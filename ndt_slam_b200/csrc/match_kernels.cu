@@ -37,16 +37,19 @@ struct SmemSrc {
 };
 
 // One cooperative objective pass. All threads of the group call pass<MODE>() with identical
-// arguments and leave with identical totals.
-template <class Coop, class SlotL, class RecL, class SrcL>
+// arguments and leave with identical totals. Everything the hot loop touches is copied into
+// locals first (the object itself lives in local memory behind `this`).
+template <class Coop, class CenL, class SlotL, class RecL, class SrcL>
 struct Objective {
-  const GridView &G;
+  ProbeGeom geom;
+  CenL cen;
   SlotL slot;
   RecL rec;
   SrcL src;
   int ns;
-  const MatchParams &mp;
-  const Coop &coop;
+  double d1, d2;
+  int sse;
+  Coop coop;
   HitQueue Q;          // this warp's hit queue (shared memory)
 
   template <int MODE>
@@ -55,23 +58,31 @@ struct Objective {
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
     const PoseF pf = pose_to_float(p);
-    const bool sse = (mp.quirks & NDT_QUIRK_TRANSFORM_SSE_ORDER) != 0;
+    const Coop co = coop;
     int pairs = 0;
-    accumulate_points<MODE>(G, slot, rec, src, coop.rank(), coop.size(), ns, pf, sse, ac.cs, ac.sn, mp.d1, mp.d2,
+    accumulate_points<MODE>(geom, cen, slot, rec, src, co.rank(), co.size(), ns, pf, sse != 0, ac.cs, ac.sn, d1, d2,
                             Q, acc, pairs);
-    if (MODE == 0) coop.template allreduce<13>(acc);
-    else if (MODE == 1) coop.template allreduce<4>(acc);
-    else coop.template allreduce<9>(acc + 4);
+    if (MODE == 0) co.template allreduce<13>(acc);
+    else if (MODE == 1) co.template allreduce<4>(acc);
+    else co.template allreduce<9>(acc + 4);
 #pragma unroll
     for (int k = 0; k < NACC; ++k) out[k] = acc[k];
   }
 };
 
+template <class Coop, class CenL, class SlotL, class RecL, class SrcL>
+__device__ __forceinline__ Objective<Coop, CenL, SlotL, RecL, SrcL> make_objective(
+    const GridView &G, const MatchParams &mp, const Coop &coop, CenL cen, SlotL slot, RecL rec, SrcL src, int ns,
+    HitQueue Q) {
+  return Objective<Coop, CenL, SlotL, RecL, SrcL>{probe_geom(G), cen, slot, rec, src, ns, mp.d1, mp.d2,
+                                                  (mp.quirks & NDT_QUIRK_TRANSFORM_SSE_ORDER) ? 1 : 0, coop, Q};
+}
+
 // per-warp queue storage carved from static shared memory of the CTA (8 warps)
 struct QueueStore {
   float4 xy[8][QCAP];
-  int slot[8][QCAP];
-  __device__ __forceinline__ HitQueue mine() { const int w = threadIdx.x >> 5; return HitQueue{xy[w], slot[w]}; }
+  int cell[8][QCAP];
+  __device__ __forceinline__ HitQueue mine() { const int w = threadIdx.x >> 5; return HitQueue{xy[w], cell[w]}; }
 };
 
 template <class Coop, class SrcL>
@@ -133,8 +144,9 @@ __global__ void __launch_bounds__(256) k_eval_partial(GridView G, MatchParams mp
   // slice s owns points [s * chunk, (s + 1) * chunk)
   const int chunk = (ns + slices - 1) / slices;
   const int lo = slice * chunk, hi = min(ns, lo + chunk);
-  accumulate_points<MODE>(G, GlobalSlot{G.slot}, GlobalRec{G.recs}, GlobalSrc{src}, lo + (int)threadIdx.x,
-                          (int)blockDim.x, hi, pf, sse, ac.cs, ac.sn, mp.d1, mp.d2, qs.mine(), acc, pairs);
+  accumulate_points<MODE>(probe_geom(G), GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, GlobalSrc{src},
+                          lo + (int)threadIdx.x, (int)blockDim.x, hi, pf, sse, ac.cs, ac.sn, mp.d1, mp.d2, qs.mine(),
+                          acc, pairs);
   BlockCoop coop{scratch};
   coop.allreduce<NACC>(acc);
   if ((threadIdx.x & 31) == 0) s_pairs[threadIdx.x >> 5] = pairs;   // warp-uniform count
@@ -187,16 +199,17 @@ __global__ void __launch_bounds__(256) k_align_block(GridView G, MatchParams mp,
   if (TILE) {
     // stage the local map tile (here: the whole grid) in shared memory: records first (64-B aligned), then slots
     CellRec *s_recs = reinterpret_cast<CellRec *>(smem_raw);
-    int32_t *s_slot = reinterpret_cast<int32_t *>(smem_raw + (size_t)n_slots * sizeof(CellRec));
+    float2 *s_cen = reinterpret_cast<float2 *>(smem_raw + (size_t)n_slots * sizeof(CellRec));
+    int32_t *s_slot = reinterpret_cast<int32_t *>(s_cen + n_cells);
     const int4 *gr = reinterpret_cast<const int4 *>(G.recs);
     int4 *sr = reinterpret_cast<int4 *>(s_recs);
     for (int i = threadIdx.x; i < n_slots * 4; i += blockDim.x) sr[i] = __ldg(gr + i);
-    for (int i = threadIdx.x; i < n_cells; i += blockDim.x) s_slot[i] = __ldg(G.slot + i);
+    for (int i = threadIdx.x; i < n_cells; i += blockDim.x) { s_cen[i] = __ldg(G.cen + i); s_slot[i] = __ldg(G.slot + i); }
     __syncthreads();
-    Objective<BlockCoop, SmemSlot, SmemRec, GlobalSrc> obj{G, SmemSlot{s_slot}, SmemRec{s_recs}, gsrc, ns, mp, coop, qs.mine()};
+    auto obj = make_objective(G, mp, coop, SmemCen{s_cen}, SmemSlot{s_slot}, SmemRec{s_recs}, gsrc, ns, qs.mine());
     match_device(obj, mp, guess, mo);
   } else {
-    Objective<BlockCoop, GlobalSlot, GlobalRec, GlobalSrc> obj{G, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, mp, coop, qs.mine()};
+    auto obj = make_objective(G, mp, coop, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, qs.mine());
     match_device(obj, mp, guess, mo);
   }
   double fsum = 0.0;
@@ -244,7 +257,7 @@ __global__ void __launch_bounds__(256) k_align_cluster(GridView G, MatchParams m
   const double guess[3] = {guesses[3 * job], guesses[3 * job + 1], guesses[3 * job + 2]};
   const GlobalSrc gsrc{src};
   MatchOut mo;
-  Objective<ClusterCoop, GlobalSlot, GlobalRec, GlobalSrc> obj{G, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, mp, coop, qs.mine()};
+  auto obj = make_objective(G, mp, coop, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, qs.mine());
   match_device(obj, mp, guess, mo);
   double fsum = 0.0;
   if (mp.want_fitness) fsum = fitness_pass(G, gsrc, ns, mp, mo.p, coop);
@@ -254,8 +267,11 @@ __global__ void __launch_bounds__(256) k_align_cluster(GridView G, MatchParams m
 // ---------------------------------------------------------------------------------------------
 // persistent batch matcher: one warp per match, work pulled from an atomic counter
 // ---------------------------------------------------------------------------------------------
+#ifndef NDT_WARP_KERNEL_MIN_CTAS
+#define NDT_WARP_KERNEL_MIN_CTAS 2
+#endif
 template <bool SRC_SMEM>
-__global__ void __launch_bounds__(256) k_align_warp(GridView G, MatchParams mp, const float4 *__restrict__ src,
+__global__ void __launch_bounds__(256, NDT_WARP_KERNEL_MIN_CTAS) k_align_warp(GridView G, MatchParams mp, const float4 *__restrict__ src,
                                                    int ns, const double *__restrict__ guesses,
                                                    ndt_result *__restrict__ out, int64_t n_jobs,
                                                    int32_t *__restrict__ job_counter) {
@@ -282,11 +298,11 @@ __global__ void __launch_bounds__(256) k_align_warp(GridView G, MatchParams mp, 
     MatchOut mo;
     double fsum = 0.0;
     if (SRC_SMEM) {
-      Objective<WarpCoop, GlobalSlot, GlobalRec, SmemSrc> obj{G, GlobalSlot{G.slot}, GlobalRec{G.recs}, ssrc, ns, mp, coop, qs.mine()};
+      auto obj = make_objective(G, mp, coop, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, ssrc, ns, qs.mine());
       match_device(obj, mp, guess, mo);
       if (mp.want_fitness) fsum = fitness_pass(G, ssrc, ns, mp, mo.p, coop);
     } else {
-      Objective<WarpCoop, GlobalSlot, GlobalRec, GlobalSrc> obj{G, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, mp, coop, qs.mine()};
+      auto obj = make_objective(G, mp, coop, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, qs.mine());
       match_device(obj, mp, guess, mo);
       if (mp.want_fitness) fsum = fitness_pass(G, gsrc, ns, mp, mo.p, coop);
     }
@@ -410,7 +426,7 @@ int launch_align(Handle *h, const double *d_guesses, int64_t n, ndt_result *d_re
     NDT_CUDA(h, cudaMemsetAsync(ctr + CTR_JOB, 0, sizeof(int32_t), st));
     const bool src_smem = (size_t)ns * sizeof(float2) <= 64 * 1024;
     const size_t smem = src_smem ? (size_t)ns * sizeof(float2) : 0;
-    const int ctas_per_sm = 4;
+    const int ctas_per_sm = NDT_WARP_KERNEL_MIN_CTAS;
     int64_t grid = (int64_t)h->sm_count * ctas_per_sm;
     grid = std::min<int64_t>(grid, (n + 7) / 8);
     if (src_smem) {
@@ -439,7 +455,7 @@ int launch_align(Handle *h, const double *d_guesses, int64_t n, ndt_result *d_re
   } else {
     const int n_slots = h->h_counters[CTR_SLOTS];
     const int n_cells = h->gd.n_cells > 0 ? (h->gd.div_x + 4) * (h->gd.div_y + 4) : 0;   // padded table
-    const size_t tile = (size_t)n_slots * sizeof(CellRec) + (size_t)n_cells * sizeof(int32_t);
+    const size_t tile = (size_t)n_slots * sizeof(CellRec) + (size_t)n_cells * (sizeof(float2) + sizeof(int32_t));
     const size_t budget = (size_t)h->max_smem_optin > 4096 ? (size_t)h->max_smem_optin - 4096 : 0;
     if (tile > 0 && tile <= budget) {
       NDT_CUDA(h, cudaFuncSetAttribute(k_align_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile));

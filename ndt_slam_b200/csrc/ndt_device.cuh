@@ -37,6 +37,8 @@ struct GridView {
   const int32_t *__restrict__ slot;     // [(div_x + 4) * (div_y + 4)] padded by 2 cells of -1 on every side:
                                         // cell (i, j) lives at (j + 2) * slot_w + i + 2; value = record index or -1
   int32_t slot_w;                       // div_x + 4
+  const float2 *__restrict__ cen;       // same padded indexing: float32 centroid of tree cells, NaN elsewhere
+                                        // (the probe is one load + a float compare: NaN < r2 is false)
   const CellRec *__restrict__ recs;     // compact records of cells with n >= min_points
   int32_t min_bx, min_by, div_x, div_y;
   float inv_leaf;                       // 1.0f / leaf
@@ -115,7 +117,7 @@ constexpr int QCAP = 128;           // per-warp queue capacity: < 32 queued befo
 
 struct HitQueue {
   float4 *xy;     // [QCAP] xt, yt (transformed, float32), xf, yf (original)
-  int *slot;      // [QCAP]
+  int *cell;      // [QCAP] padded-table index of the hit cell
 };
 
 template <int MODE, class RecL>
@@ -160,25 +162,34 @@ __device__ __forceinline__ void hit_path(const RecL &rec_at, const float4 e, con
   }
 }
 
+// the scalars of the grid the probe loop needs, held in registers (not re-read through a struct pointer)
+struct ProbeGeom {
+  int W, div_x, div_y, min_bx, min_by;
+  float inv_leaf, r2;
+};
+__device__ __forceinline__ ProbeGeom probe_geom(const GridView &G) {
+  return ProbeGeom{G.slot_w, G.div_x, G.div_y, G.min_bx, G.min_by, G.inv_leaf, G.r2};
+}
+
 // Accumulate the objective over points i = first + k * stride (k = 0, 1, ...), i < hi, where `first`
 // is lane-contiguous inside a warp (first = warp_first + lane): every lane of a warp iterates the same
 // number of times. acc must be a register array of the caller. pairs: warp-uniform hit count.
 //
 // Written as a small warp-uniform state machine so that the probe code and the fp64 hit path each
 // exist exactly once in the instruction stream (the matcher is instruction-cache sensitive).
-template <int MODE, class SlotL, class RecL, class SrcL>
-__device__ __forceinline__ void accumulate_points(const GridView &G, const SlotL &slot_at, const RecL &rec_at,
-                                                  const SrcL &src, const int first, const int stride, const int hi,
-                                                  const PoseF &pf, const bool sse_order, const double cs,
-                                                  const double sn, const double d1, const double d2,
-                                                  const HitQueue &Q, double *acc, int &pairs) {
+template <int MODE, class CenL, class SlotL, class RecL, class SrcL>
+__device__ __forceinline__ void accumulate_points(const ProbeGeom g, const CenL cen_at, const SlotL slot_at,
+                                                  const RecL rec_at, const SrcL src, const int first,
+                                                  const int stride, const int hi, const PoseF pf,
+                                                  const bool sse_order, const double cs, const double sn,
+                                                  const double d1, const double d2, const HitQueue Q, double *acc,
+                                                  int &pairs) {
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
-  const int W = G.slot_w;
   int qhead = 0, qn = 0;
   int i0 = first - lane;
   int row = 3;                       // 3: fetch the next point; 0..2: probe that row of the 3x3 block
-  int base = -1;                     // padded-table index of the point's own cell, -1 = nothing to probe
+  int base = 0;                      // padded-table index of the point's own cell (0 = a border cell: all NaN)
   float xt = 0.f, yt = 0.f, xf = 0.f, yf = 0.f;
   for (;;) {
     const bool done = (row == 3) && (i0 >= hi);
@@ -188,7 +199,7 @@ __device__ __forceinline__ void accumulate_points(const GridView &G, const SlotL
       __syncwarp();
       if (lane < n) {
         const int pos = (qhead + lane) & (QCAP - 1);
-        hit_path<MODE>(rec_at, Q.xy[pos], Q.slot[pos], cs, sn, d1, d2, acc);
+        hit_path<MODE>(rec_at, Q.xy[pos], slot_at(Q.cell[pos]), cs, sn, d1, d2, acc);
       }
       __syncwarp();
       qhead = (qhead + n) & (QCAP - 1);
@@ -201,44 +212,47 @@ __device__ __forceinline__ void accumulate_points(const GridView &G, const SlotL
       const int i = i0 + lane;
       i0 += stride;
       row = 0;
-      base = -1;
+      base = g.W + 1;                // (1, 1) of the padded table: its 3x3 block is all border (NaN)
       if (i < hi) {
         const float2 xy = src(i);
         xf = xy.x; yf = xy.y;
         xform(pf, sse_order, xf, yf, xt, yt);
-        const int ci = cell_coord(xt, G.inv_leaf, G.min_bx);
-        const int cj = cell_coord(yt, G.inv_leaf, G.min_by);
-        if (ci >= -1 && cj >= -1 && ci <= G.div_x && cj <= G.div_y) base = (cj + 2) * W + ci + 2;
+        const int ci = cell_coord(xt, g.inv_leaf, g.min_bx);
+        const int cj = cell_coord(yt, g.inv_leaf, g.min_by);
+        if (ci >= -1 && cj >= -1 && ci <= g.div_x && cj <= g.div_y) base = (cj + 2) * g.W + ci + 2;
       }
     }
-    // probe one row of the 3x3 block: three adjacent table entries, no bounds checks (padded table)
-    int s0 = -1, s1 = -1, s2 = -1;
-    if (base >= 0) {
-      const int r = base + (row - 1) * W;
-      s0 = slot_at(r - 1); s1 = slot_at(r); s2 = slot_at(r + 1);
-    }
+    // probe one row of the 3x3 block: three adjacent centroids, branch-free (NaN = not a tree cell)
+    const int r = base + (row - 1) * g.W;
+    const float2 c0 = cen_at(r - 1), c1 = cen_at(r), c2 = cen_at(r + 1);
     ++row;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const int sk = (k == 0) ? s0 : (k == 1 ? s1 : s2);
-      bool hit = false;
-      if (sk >= 0) {
-        const float4 head = rec_at.head(sk);       // cx, cy, nr_points, cell
-        hit = dist2f(xt, yt, head.x, head.y) < G.r2;
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, hit);
-      if (hit) {
-        const int pos = (qhead + qn + __popc(m & lt)) & (QCAP - 1);
-        Q.xy[pos] = make_float4(xt, yt, xf, yf);
-        Q.slot[pos] = sk;
-      }
-      qn += __popc(m);
+    const bool h0 = dist2f(xt, yt, c0.x, c0.y) < g.r2;
+    const bool h1 = dist2f(xt, yt, c1.x, c1.y) < g.r2;
+    const bool h2 = dist2f(xt, yt, c2.x, c2.y) < g.r2;
+    const unsigned m0 = __ballot_sync(0xffffffffu, h0);
+    const unsigned m1 = __ballot_sync(0xffffffffu, h1);
+    const unsigned m2 = __ballot_sync(0xffffffffu, h2);
+    if ((m0 | m1 | m2) != 0u) {
+      const int n0 = __popc(m0), n1 = __popc(m1);
+      const int b0 = qhead + qn;
+      if (h0) { const int pos = (b0 + __popc(m0 & lt)) & (QCAP - 1); Q.xy[pos] = make_float4(xt, yt, xf, yf); Q.cell[pos] = r - 1; }
+      if (h1) { const int pos = (b0 + n0 + __popc(m1 & lt)) & (QCAP - 1); Q.xy[pos] = make_float4(xt, yt, xf, yf); Q.cell[pos] = r; }
+      if (h2) { const int pos = (b0 + n0 + n1 + __popc(m2 & lt)) & (QCAP - 1); Q.xy[pos] = make_float4(xt, yt, xf, yf); Q.cell[pos] = r + 1; }
+      qn += n0 + n1 + __popc(m2);
     }
   }
   __syncwarp();
 }
 
 // global-memory accessors (read-only path, L1/L2 cached)
+struct GlobalCen {
+  const float2 *__restrict__ p;
+  __device__ __forceinline__ float2 operator()(int i) const { return __ldg(p + i); }
+};
+struct SmemCen {
+  const float2 *p;
+  __device__ __forceinline__ float2 operator()(int i) const { return p[i]; }
+};
 struct GlobalSlot {
   const int32_t *__restrict__ p;
   __device__ __forceinline__ int operator()(int i) const { return __ldg(p + i); }

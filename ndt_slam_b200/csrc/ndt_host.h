@@ -38,7 +38,8 @@ struct GridBuffers {
   DevBuf sorted_idx;   // int32[n]        per-leaf point indices, ascending (input order)
   DevBuf tgt_sorted;   // float2[n]       target (x, y) in bucket order (1-NN scans read this contiguously)
   DevBuf leaf_range;   // int2[n]         per leaf (start, n)
-  DevBuf slot;         // int32[n_cells]  count during the build, then cell -> record slot
+  DevBuf slot;         // int32[padded]   count during the build, then cell -> record slot
+  DevBuf cen;          // float2[padded]  probe table: float32 centroid of tree cells, NaN elsewhere
   DevBuf leaf_id;      // int32[n_cells]  cell -> leaf or -1
   DevBuf leaf_cell;    // int32[n]        per leaf: cell index
   DevBuf leaf_n;       // int32[n]
