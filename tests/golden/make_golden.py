@@ -1,0 +1,96 @@
+"""Generates tests/golden/*.npz from oracle/_ref (the reference's own sources + the restated 6-DoF
+mini-PCL). Run in the container that has /root/reference:  python tests/golden/make_golden.py
+The vectors pin the hot path independently of the plain oracle and travel with the repo (the GPU box
+has no /root/reference)."""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+import ndt_common as common  # noqa: E402
+from ndt_slam_b200 import synth  # noqa: E402
+from oracle import ref_api as ra  # noqa: E402
+
+OUT = Path(__file__).resolve().parent
+
+
+def c1_vectors(seed, resolution):
+    ra.set_params(Resolution=resolution)
+    d = synth.c1_pair(seed)
+    rsa, rsb = ra.resample(d["scan_a"]), ra.resample(d["scan_b"])           # ScanPointResampler (reference code)
+    tgt = synth.to_xyzw(synth.transform(rsa, d["pose_a"]))
+    src = ra.voxel_filter(synth.to_xyzw(rsb), 0.05)                           # ApproximateVoxelGrid (restated)
+    n = ra.RefNdt(resolution)
+    n.set_target(tgt); n.set_source(src)
+    g = n.grid()
+    rng = synth.rng_for(900 + seed)
+    guess = np.array(d["pose_a"])
+    poses = guess + rng.normal(0, [0.05, 0.05, 0.01], size=(12, 3))
+    ev = np.array([np.concatenate([[e["score"]], e["grad"], e["hess"]]) for e in (n.eval(p) for p in poses)])
+    guesses = guess + rng.normal(0, [0.12, 0.12, 0.025], size=(10, 3))
+    guesses[0] = guess
+    al = [n.align(q) for q in guesses]
+    init_deg = [guess[0], guess[1], np.rad2deg(guess[2])]
+    cost, est, cov = ra.estimate_pose(rsb, tgt, init_deg)                     # PoseEstimator::estimatePose (reference code)
+    np.savez_compressed(
+        OUT / f"c1_seed{seed}_res{resolution}.npz",
+        scan_a=d["scan_a"], scan_b=d["scan_b"], pose_a=np.array(d["pose_a"]), pose_b=np.array(d["pose_b"]),
+        resampled_a=rsa, resampled_b=rsb, tgt=tgt, src=src,
+        grid_cell=g["cell_idx"], grid_nr=g["nr_points"], grid_mean=g["mean"], grid_icov=g["icov"], grid_centroid=g["centroid"],
+        grid_min_b=g["min_b"], grid_div_b=g["div_b"],
+        eval_poses=poses, eval_out=ev,
+        align_guesses=guesses, align_pose=np.array([a["pose"] for a in al]), align_score=np.array([a["score"] for a in al]),
+        align_iters=np.array([a["iters"] for a in al]), align_evals=np.array([a["evals"] for a in al]),
+        align_fitness=np.array([a["fitness"] for a in al]), align_hess=np.array([a["hess"] for a in al]),
+        est_init_deg=np.array(init_deg), est_cost=cost, est_pose_deg=est, est_cov=cov, resolution=resolution)
+
+
+def host_vectors():
+    """Pose algebra + EKF fusion from the reference's Pose2D.cpp / MyUtil.cpp / PoseFuser.cpp."""
+    ra.set_params()
+    rng = synth.rng_for(77)
+    rows = []
+    for _ in range(40):
+        last = np.array([rng.uniform(-20, 20), rng.uniform(-20, 20), rng.uniform(-180, 180)])
+        motion = np.array([rng.uniform(0, 0.3), rng.uniform(-0.05, 0.05), rng.uniform(-5, 5)])
+        pred = ra.cal_pred_pose(motion, last)
+        est = pred + np.array([rng.normal(0, 0.02), rng.normal(0, 0.02), rng.normal(0, 0.3)])
+        A = rng.normal(size=(3, 3)) * 0.01
+        last_cov = A @ A.T + np.diag([1e-4, 1e-4, 1e-5])
+        B = rng.normal(size=(3, 3)) * 0.01
+        Q = B @ B.T + np.diag([2e-4, 2e-4, 5e-6])
+        fused, cov = ra.fuse_pose(pred, est, motion, last, last_cov, Q)
+        ocov = ra.odometry_cov(motion, last, last_cov)
+        cur = np.array([last[0] + rng.uniform(-1, 1), last[1] + rng.uniform(-1, 1), rng.uniform(-180, 180)])
+        rows.append(np.concatenate([last, motion, pred, est, last_cov.ravel(), Q.ravel(), fused, cov.ravel(), ocov.ravel(),
+                                    cur, ra.cal_motion(cur, last)]))
+    np.savez_compressed(OUT / "host_math.npz", rows=np.array(rows),
+                        layout="last3 motion3 pred3 est3 lastCov9 Q9 fused3 cov9 odoCov9 cur3 calMotion3 (delTime 0.5, coeVel 0.1, coeOmega 0.5)")
+
+
+def sequence_vectors(n_scans=60):
+    """Short C2-style run through the reference FrontEnd (FrontEnd.cpp / ScanMatcher.cpp / PointCloudMap.cpp)."""
+    ra.set_params(Resolution=0.5)
+    seq = synth.c2_sequence(seed=2, n_scans=2000)
+    slam = ra.RefSlam()
+    odo_deg = np.column_stack([seq["odo"][:, 0], seq["odo"][:, 1], np.rad2deg(seq["odo"][:, 2])])
+    odo_deg[:, 2] = (odo_deg[:, 2] + 180.0) % 360.0 - 180.0
+    for i in range(n_scans):
+        slam.process(i, odo_deg[i], seq["scans"][i])
+    np.savez_compressed(OUT / "c2_first60.npz", poses=slam.poses(), odo_deg=odo_deg[:n_scans],
+                        local_map=slam.local_map(),
+                        n_submaps=slam.submaps(), truth=seq["traj"][:n_scans])
+
+
+if __name__ == "__main__":
+    if not ra.available():
+        raise SystemExit("oracle/_ref is not built (needs /root/reference): run `make -C oracle`")
+    c1_vectors(1, 0.5)
+    c1_vectors(2, 0.5)
+    c1_vectors(3, 1.0)
+    host_vectors()
+    sequence_vectors()
+    for p in sorted(OUT.glob("*.npz")):
+        print(p.name, p.stat().st_size)

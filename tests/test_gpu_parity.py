@@ -242,3 +242,35 @@ def test_run_to_run_determinism(c1):
     assert bytes(r1) == bytes(r2)
     e1, e2 = g.eval(pb["guess"]), g.eval(pb["guess"])
     assert bytes(e1) == bytes(e2)
+
+
+# ---- golden vectors generated by oracle/_ref (reference sources + 6-DoF mini-PCL) -------------------
+from pathlib import Path  # noqa: E402
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+@pytest.mark.parametrize("path", sorted(GOLD.glob("c1_seed*.npz")), ids=lambda p: p.stem)
+def test_cuda_path_matches_golden_vectors(path):
+    z = np.load(path)
+    prm = common.params(resolution=float(z["resolution"]))
+    g = capi.Ndt(prm)
+    assert np.array_equal(g.approx_voxel_filter(synth.to_xyzw(z["resampled_b"]), 0.05), z["src"])
+    g.set_target(z["tgt"]); g.set_source(z["src"])
+    a = g.grid_readback(); gi = g.grid_info()
+    assert list(gi.min_b) == list(z["grid_min_b"]) and list(gi.div_b) == list(z["grid_div_b"])
+    assert np.array_equal(a["cell_idx"], z["grid_cell"]) and np.array_equal(a["nr_points"], z["grid_nr"])
+    assert np.array_equal(a["centroid"], z["grid_centroid"]) and np.array_equal(a["mean"], z["grid_mean"])
+    m = z["grid_nr"] >= 6
+    assert common.rel_err(a["icov"][m], z["grid_icov"][m]) < 1e-9
+    out = g.eval_batch(np.ascontiguousarray(z["eval_poses"]))
+    for k in range(out.shape[0]):
+        assert out[k, 0] == pytest.approx(z["eval_out"][k, 0], rel=REL_EVAL)
+        assert common.rel_err(out[k, 1:4], z["eval_out"][k, 1:4]) < REL_EVAL
+        assert common.rel_err(out[k, 4:13], z["eval_out"][k, 4:13]) < REL_EVAL
+    res = g.align_batch(np.ascontiguousarray(z["align_guesses"]))
+    for k in range(res.shape[0]):
+        assert res[k]["iters"] == z["align_iters"][k] and res[k]["evals"] == z["align_evals"][k]
+        assert np.hypot(*(res[k]["pose"][:2] - z["align_pose"][k][:2])) < POSE_M
+        assert abs(res[k]["pose"][2] - z["align_pose"][k][2]) < POSE_RAD
+        assert res[k]["fitness"] == pytest.approx(z["align_fitness"][k], rel=1e-4)

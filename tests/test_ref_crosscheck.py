@@ -1,0 +1,54 @@
+"""Live cross-checks against oracle/_ref (reference sources + restated mini-PCL). They need the built
+library, which exists wherever /root/reference was available at build time; otherwise they skip and the
+committed golden vectors (test_golden.py) carry the same comparisons."""
+import numpy as np
+import pytest
+
+import ndt_common as common
+from ndt_slam_b200 import synth
+from oracle import oracle_api as oa, ref_api as ra
+
+pytestmark = pytest.mark.skipif(not ra.available(), reason="oracle/_ref not built (needs /root/reference)")
+
+
+def test_two_restatements_agree_on_random_walls():
+    ra.set_params()
+    for seed, res in ((41, 0.5), (42, 0.3), (43, 1.0)):
+        tgt = common.random_cloud(seed, 6000, 40.0)
+        rng = synth.rng_for(seed)
+        src = tgt[np.sort(rng.choice(tgt.shape[0], 700, replace=False))].copy()
+        src[:, :2] += rng.normal(0, 0.01, (700, 2)).astype(np.float32)
+        o = oa.Oracle(common.params(resolution=res)); o.set_target(tgt); o.set_source(src)
+        r = ra.RefNdt(res); r.set_target(tgt); r.set_source(src)
+        g1, g2 = r.grid(), o.grid_readback()
+        assert np.array_equal(g1["cell_idx"], g2["cell_idx"]) and np.array_equal(g1["nr_points"], g2["nr_points"])
+        assert np.array_equal(g1["centroid"], g2["centroid"]) and np.array_equal(g1["mean"], g2["mean"])
+        m = g2["nr_points"] >= 6
+        assert common.rel_err(g1["icov"][m], g2["icov"][m]) < 1e-9
+        for _ in range(5):
+            pose = rng.normal(0, [0.05, 0.05, 0.01])
+            e1, e2 = r.eval(pose), o.eval(pose)
+            assert e1["off_block"] == 0.0          # z = 0: the 6-DoF problem decouples exactly
+            assert e1["score"] == pytest.approx(e2.score, rel=1e-12)
+            assert common.rel_err(e1["grad"], e2.grad) < 1e-9 and common.rel_err(e1["hess"], e2.hess) < 1e-9
+        a1, a2 = r.align([0.03, -0.02, 0.004]), o.align([0.03, -0.02, 0.004])
+        assert a1["iters"] == a2.iters and a1["evals"] == a2.evals
+        assert np.hypot(a1["pose"][0] - a2.pose[0], a1["pose"][1] - a2.pose[1]) < 1e-5
+
+
+def test_reference_frontend_runs_and_tracks_truth():
+    """FrontEnd::process over a short synthetic sequence, reference code end to end."""
+    z = np.load(common.GOLD / "c2_first60.npz") if hasattr(common, "GOLD") else None
+    ra.set_params(Resolution=0.5)
+    seq = synth.c2_sequence(seed=2, n_scans=2000)
+    slam = ra.RefSlam()
+    odo_deg = np.column_stack([seq["odo"][:, 0], seq["odo"][:, 1], np.rad2deg(seq["odo"][:, 2])])
+    for i in range(25):
+        slam.process(i, odo_deg[i], seq["scans"][i])
+    poses = slam.poses()
+    assert poses.shape == (25, 3)
+    # map frame = odometry frame of the first scan: compare relative motion with ground truth
+    t = seq["traj"][:25]
+    d_true = np.hypot(*(t[-1, :2] - t[0, :2]))
+    d_est = np.hypot(*(poses[-1, :2] - poses[0, :2]))
+    assert abs(d_true - d_est) < 0.05
