@@ -115,13 +115,13 @@ def build_host(force: bool = False) -> Path:
     srcs = sorted((HOST / "src").glob("*.cpp"))
     if not srcs:
         raise RuntimeError("no host sources")
-    deps = srcs + sorted((HOST / "include").rglob("*.h")) + [ROOT / "include" / "ndt_b200.h"]
-    flags = ["-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-variable"]
+    deps = srcs + sorted(p for p in (HOST / "include").rglob("*") if p.is_file()) + [ROOT / "include" / "ndt_b200.h"]
+    flags = ["-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-Wno-unused-variable"]
     stamp = _stamp(deps, " ".join(flags))
     if not force and _up_to_date(LIB_HOST, stamp):
         return LIB_HOST
     build_cuda()
-    cmd = ["g++", *flags, "-I", str(ROOT / "include"), "-I", str(HOST / "include"),
+    cmd = ["g++", *flags, "-I", str(ROOT / "include"), "-I", str(HOST / "include"), "-I", str(HOST / "include" / "compat"),
            "-o", str(LIB_HOST), *map(str, srcs),
            "-L", str(PKG), "-lndt_b200", "-Wl,-rpath,$ORIGIN"]
     _run(cmd, log=PKG / "build_host.log")

@@ -1,0 +1,96 @@
+// PointCloudMap.h -- trajectory, sub-maps and the local / global map clouds.
+// Same public data and methods as the reference [REF include/ndt_slam/PointCloudMap.h:22-145,
+// src/PointCloudMap.cpp:4-134]. localMap_cloud is the only coupling into the matcher
+// (ScanMatcher.cpp:40): it becomes the NDT target, i.e. the input of the device grid build.
+#ifndef NDT_SLAM_B200_POINTCLOUDMAP_H_
+#define NDT_SLAM_B200_POINTCLOUDMAP_H_
+
+#include <string>
+#include <vector>
+#include <pcl/point_cloud.h>
+#include <ros/ros.h>
+
+#include "LPoint2D.h"
+#include "PCFilter.h"
+#include "Pose2D.h"
+#include "Scan2D.h"
+#include "Timer.h"
+
+class Submap {
+ public:
+  PCFilter pcf;
+
+  double atdS;        // accumulated travel distance where this sub-map starts
+  size_t cntS;        // first scan number
+  size_t cntE;        // last scan number
+  bool newest;
+
+  bool removeMoving;
+
+  pcl::PointCloud<pcl::PointXYZ>::Ptr p_cloud;
+  std::vector<pcl::PointCloud<pcl::PointXYZ>::Ptr> scans;
+
+  double LeafSize;
+  Timer timer;
+
+  Submap() : atdS(0), cntS(0), cntE(static_cast<size_t>(-1)), newest(true), removeMoving(false), LeafSize(0.2) { readParams(); }
+  Submap(double a, size_t s) : atdS(a), cntS(s), cntE(static_cast<size_t>(-1)), newest(true), removeMoving(false), LeafSize(0.2) { readParams(); }
+
+  void addPoints(pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_ptr) { scans.emplace_back(cloud_ptr); }
+  pcl::PointCloud<pcl::PointXYZ>::Ptr filterPoints();
+  void makeMap();
+
+ private:
+  void readParams() {
+    ros::param::get("removeMoving", removeMoving);
+    ros::param::get("LeafSize", LeafSize);
+    p_cloud = std::make_shared<pcl::PointCloud<pcl::PointXYZ>>();
+  }
+};
+
+class PointCloudMap {
+ public:
+  std::vector<Pose2D> poses;
+  Pose2D lastPose;
+  Scan2D lastScan;
+  int startFrame;
+
+  pcl::PointCloud<pcl::PointXYZ>::Ptr globalMap_cloud;
+  pcl::PointCloud<pcl::PointXYZ>::Ptr localMap_cloud;
+
+  double sepThre;     // travel distance after which a new sub-map is started [m]
+  double atd;         // accumulated travel distance
+  std::vector<Submap> submaps;
+
+  Timer timer;
+
+  std::vector<pcl::PointCloud<pcl::PointXYZ>::Ptr> maps;
+  std::string map_name, separated_map_name;
+
+  PointCloudMap() : startFrame(0), sepThre(30), atd(0) {
+    ros::param::get("start_frame", startFrame);
+    ros::param::get("sepThre", sepThre);
+    ros::param::get("map_name", map_name);
+    ros::param::get("separated_map_name", separated_map_name);
+    globalMap_cloud = std::make_shared<pcl::PointCloud<pcl::PointXYZ>>();
+    localMap_cloud = std::make_shared<pcl::PointCloud<pcl::PointXYZ>>();
+    submaps.emplace_back(Submap());
+  }
+
+  void setLastPose(const Pose2D &p) { lastPose = p; }
+  Pose2D getLastPose() const { return lastPose; }
+  void setLastScan(const Scan2D &s) { lastScan = s; }
+  std::vector<Submap> &getSubmaps() { return submaps; }
+
+  void saveGlobalMap();     // PCD ASCII: the global map and one file per sub-map
+
+  void addPose(const Pose2D &p);
+  void addPoints(const std::vector<LPoint2D> &lps);
+  void makeGlobalMap();
+  void makeLocalMap();
+};
+
+// PCD v0.7 ASCII writer for x y z float clouds (what pcl::io::savePCDFileASCII emits)
+int savePCDFileASCII(const std::string &path, const pcl::PointCloud<pcl::PointXYZ> &cloud);
+
+#endif

@@ -1,0 +1,64 @@
+// PoseEstimator.h -- NDT pose estimation behind the reference's class interface
+// [REF include/ndt_slam/PoseEstimator.h:36-133, src/PoseEstimator.cpp:4-69].
+//
+// Where the reference owns a pcl::NDT object and calls ApproximateVoxelGrid / setInputSource /
+// setInputTarget / align / getFitnessScore / getHessian on it, this class owns one ndt_handle of the
+// C ABI (include/ndt_b200.h): the grid build and the whole Newton / More-Thuente match run as CUDA
+// kernels on the B200. Constructor parameters, setScanPair overloads, estimatePose signature, the
+// theta extraction, the cost sentinel and the covariance post-processing are the reference's.
+// There is no CPU fallback: estimatePose throws std::runtime_error if the device path is unavailable.
+#ifndef NDT_SLAM_B200_POSEESTIMATOR_H_
+#define NDT_SLAM_B200_POSEESTIMATOR_H_
+
+#include <Eigen/Core>
+#include <pcl/point_cloud.h>
+#include <ros/ros.h>
+
+#include "MyUtil.h"
+#include "Pose2D.h"
+#include "Scan2D.h"
+#include "Timer.h"
+#include "ndt_b200.h"
+
+class PoseEstimator {
+ private:
+  pcl::PointCloud<pcl::PointXYZ>::Ptr source_cloud;   // current scan, float32 (z = 0)
+  pcl::PointCloud<pcl::PointXYZ>::Ptr target_cloud;   // reference map (aliased, not copied)
+
+  const Scan2D *curScan;
+  const Scan2D *refScan;
+  double coeNDTCov;
+
+  double TransformationEpsilon;
+  double StepSize;
+  double Resolution;
+  int MaximumIterations;
+
+  double LeafSize;
+
+  ndt_handle ndt;       // stands where the reference has  pcl::NDT<pcl::PointXYZ, pcl::PointXYZ> ndt;
+  Timer timer;
+
+  void ensureHandle();
+  static void fillFromScan(const Scan2D *scan, pcl::PointCloud<pcl::PointXYZ> &cloud);
+
+ public:
+  double totalError;
+
+  // what the last estimatePose did (instrumentation; not in the reference)
+  ndt_result lastResult;
+  double lastGridMs, lastMatchMs, lastFilterMs;
+  int lastSourcePoints, lastTargetPoints;
+
+  PoseEstimator();
+  ~PoseEstimator();
+  PoseEstimator(const PoseEstimator &) = delete;
+  PoseEstimator &operator=(const PoseEstimator &) = delete;
+
+  void setScanPair(const Scan2D *curScan, pcl::PointCloud<pcl::PointXYZ>::Ptr refScan);
+  void setScanPair(const Scan2D *curScan, const Scan2D *refScan);
+
+  double estimatePose(Pose2D &initPose, Pose2D &estPose, Eigen::Matrix3d &cov);
+};
+
+#endif

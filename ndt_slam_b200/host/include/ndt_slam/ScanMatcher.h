@@ -1,0 +1,67 @@
+// ScanMatcher.h -- per-scan pipeline: resample, predict from odometry, NDT estimate, gate, fuse, grow map.
+// Same members and methods as the reference [REF include/ndt_slam/ScanMatcher.h:23-112,
+// src/ScanMatcher.cpp:4-117]. Differences: ROS PoseArray bookkeeping is reduced to a plain struct, and
+// lastCov starts at zero (the reference reads it uninitialised on the first fused scan).
+#ifndef NDT_SLAM_B200_SCANMATCHER_H_
+#define NDT_SLAM_B200_SCANMATCHER_H_
+
+#include <vector>
+#include <Eigen/Core>
+#include <ros/ros.h>
+
+#include "PointCloudMap.h"
+#include "PoseEstimator.h"
+#include "PoseFuser.h"
+#include "ScanPointResampler.h"
+#include "TFBroadcaster.h"
+#include "Timer.h"
+
+namespace geometry_msgs {
+struct Point { double x = 0, y = 0, z = 0; };
+struct Quaternion { double x = 0, y = 0, z = 0, w = 1; };
+struct Pose { Point position; Quaternion orientation; };
+struct PoseArray { std_msgs::Header header; std::vector<Pose> poses; };
+}  // namespace geometry_msgs
+
+class ScanMatcher {
+ private:
+  int cnt;               // logical time = number of scans processed
+  Scan2D prevScan;
+  Pose2D initPose;
+  double scthre;         // accept the NDT pose when cost <= scthre
+
+  static geometry_msgs::Pose toMsg(const Pose2D &pose);
+
+ public:
+  PoseEstimator *estim;
+  PointCloudMap *pcmap;
+  ScanPointResampler spres;
+  TFBroadcaster tfb;
+
+  PoseFuser pfu;
+  std::vector<Pose2D> poses;
+  std::vector<Eigen::Matrix3d> Covs;
+  Eigen::Matrix3d lastCov;
+
+  geometry_msgs::PoseArray poseArray;
+  Timer timer;
+
+  // per-stage wall time of the last matchScan [ms] (instrumentation; not in the reference)
+  double msResample, msEstimate, msFuse, msGrowMap;
+
+  ScanMatcher() : cnt(0), scthre(0.0), estim(nullptr), pcmap(nullptr), msResample(0), msEstimate(0), msFuse(0), msGrowMap(0) {
+    ros::param::get("score_thre", scthre);
+  }
+
+  void setPoseEstimator(PoseEstimator *estim_) { estim = estim_; }
+  void setPointCloudMap(PointCloudMap *pcmap_) { pcmap = pcmap_; }
+
+  void savePose(const std_msgs::Header &header, const Pose2D &pose, const Eigen::Matrix3d &cov);
+  void remakePoseArray(std::vector<Pose2D> &poses_);
+  geometry_msgs::PoseArray get_poseArray() { return poseArray; }
+
+  bool matchScan(Scan2D &scan);
+  void growMap(const Scan2D &scan, const Pose2D &pose);
+};
+
+#endif

@@ -1,0 +1,126 @@
+// PointCloudMap.cpp -- sub-map bookkeeping [REF src/PointCloudMap.cpp:4-134; PointCloudMap.h:124-136].
+#include "ndt_slam/PointCloudMap.h"
+
+#include <cmath>
+#include <fstream>
+#include <iomanip>
+#include <sstream>
+
+#include "ndt_slam/VoxelFilter.h"
+
+typedef pcl::PointCloud<pcl::PointXYZ> Cloud;
+
+Cloud::Ptr Submap::filterPoints() {
+  Cloud::Ptr thinned = std::make_shared<Cloud>();
+  ndt_host::approximate_voxel_grid(*p_cloud, static_cast<float>(LeafSize), *thinned);
+  return thinned;
+}
+
+// Rebuild p_cloud from the stored scans.
+//  removeMoving: for every consecutive triple (i, i+1, i+2) keep scan i+1 minus the points that lie near
+//                voxels seen only by i+1 and not by {i, i+2}; the first sub-map also keeps its first scan
+//                and the newest sub-map its latest scan unfiltered.
+//  otherwise:    plain concatenation; sub-maps after the first skip the two scans carried over from their
+//                predecessor.
+void Submap::makeMap() {
+  p_cloud->clear();
+  const int n = static_cast<int>(scans.size());
+  if (removeMoving) {
+    if (cntS == 0) *p_cloud += *scans[0];
+    for (int i = 0; i + 2 < n; ++i) {
+      Cloud::Ptr outer = std::make_shared<Cloud>();
+      *outer += *scans[i];
+      *outer += *scans[i + 2];
+      Cloud::Ptr transient = pcf.difference_extraction(outer, scans[i + 1]);
+      *p_cloud += *pcf.remove_neighborPoint(scans[i + 1], transient);
+    }
+    if (newest) *p_cloud += *scans[n - 1];
+    return;
+  }
+  for (int i = (cntS == 0 ? 0 : 2); i < n; ++i) *p_cloud += *scans[i];
+}
+
+void PointCloudMap::addPose(const Pose2D &p) {
+  if (poses.empty()) {
+    atd = 0.0;
+  } else {
+    const Pose2D &before = poses.back();
+    const double dx = p.tx - before.tx, dy = p.ty - before.ty;
+    atd += std::sqrt(dx * dx + dy * dy);
+  }
+  poses.emplace_back(p);
+}
+
+void PointCloudMap::addPoints(const std::vector<LPoint2D> &lps) {
+  Cloud::Ptr scan_cloud = std::make_shared<Cloud>();
+  scan_cloud->points.resize(lps.size());
+  for (size_t i = 0; i < lps.size(); ++i) {
+    scan_cloud->points[i].x = static_cast<float>(lps[i].x);   // map frame, double -> float32
+    scan_cloud->points[i].y = static_cast<float>(lps[i].y);
+    scan_cloud->points[i].z = 0.f;
+  }
+  scan_cloud->width = static_cast<uint32_t>(lps.size());
+  scan_cloud->height = 1;
+  scan_cloud->is_dense = false;
+
+  Submap &cur = submaps.back();
+  if (atd - cur.atdS < sepThre) {
+    cur.addPoints(scan_cloud);
+    cur.makeMap();
+    return;
+  }
+  // travelled far enough: freeze the current sub-map (thinned) and open the next one, seeded with the
+  // two most recent scans so the moving-object filter has its triples
+  const size_t n_poses = poses.size();             // the newest pose is already in
+  cur.cntE = n_poses - 2;
+  cur.p_cloud = cur.filterPoints();
+  cur.newest = false;
+
+  Submap next(atd, n_poses - 1);
+  const size_t have = cur.scans.size();
+  if (have >= 2) {
+    next.addPoints(cur.scans[have - 2]);
+    next.addPoints(cur.scans[have - 1]);
+  }
+  next.addPoints(scan_cloud);
+  next.makeMap();
+  submaps.emplace_back(next);
+}
+
+void PointCloudMap::makeGlobalMap() {
+  globalMap_cloud->clear();
+  maps.clear();
+  for (size_t i = 0; i + 1 < submaps.size(); ++i) {            // frozen sub-maps are already thinned
+    *globalMap_cloud += *submaps[i].p_cloud;
+    maps.emplace_back(submaps[i].p_cloud);
+  }
+  Cloud::Ptr current = submaps.back().filterPoints();
+  *globalMap_cloud += *current;
+  maps.emplace_back(current);
+}
+
+void PointCloudMap::makeLocalMap() {
+  localMap_cloud->clear();
+  if (submaps.size() >= 2) *localMap_cloud += *submaps[submaps.size() - 2].p_cloud;   // previous sub-map only
+  *localMap_cloud += *submaps.back().filterPoints();
+}
+
+int savePCDFileASCII(const std::string &path, const Cloud &cloud) {
+  std::ofstream out(path.c_str());
+  if (!out.is_open()) return -1;
+  const size_t n = cloud.points.size();
+  out << "# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\n"
+      << "WIDTH " << n << "\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS " << n << "\nDATA ascii\n";
+  out << std::setprecision(8);
+  for (const auto &p : cloud.points) out << p.x << " " << p.y << " " << p.z << "\n";
+  return 0;
+}
+
+void PointCloudMap::saveGlobalMap() {
+  savePCDFileASCII(map_name, *globalMap_cloud);
+  for (size_t i = 0; i < maps.size(); ++i) {
+    std::ostringstream name;
+    name << separated_map_name << i << ".pcd";
+    savePCDFileASCII(name.str(), *maps[i]);
+  }
+}

@@ -1,0 +1,162 @@
+// harness.cpp -- extern "C" test / bench entry points over the host classes (libndt_slam_host.so).
+// Mirrors oracle/ref_shim.cpp function for function so the same Python driver can run the reference
+// build and this build side by side.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "ndt_slam/FrontEnd.h"
+#include "ndt_slam/PointCloudMap.h"
+#include "ndt_slam/PoseEstimator.h"
+#include "ndt_slam/PoseFuser.h"
+#include "ndt_slam/ScanMatcher.h"
+#include "ndt_slam/ScanPointResampler.h"
+#include "ndt_slam/SlamLauncher.h"
+#include "ndt_slam/VoxelFilter.h"
+
+namespace {
+Scan2D make_scan(int sid, const double pose[3], const double *xy, int64_t n) {
+  Scan2D s;
+  s.sid = sid;
+  s.pose.setPose(pose[0], pose[1], pose[2]);
+  s.lps.resize(n);
+  for (int64_t i = 0; i < n; ++i) s.lps[i].setData(sid, xy[2 * i], xy[2 * i + 1]);
+  return s;
+}
+Eigen::Matrix3d m3(const double *a) { Eigen::Matrix3d m; for (int i = 0; i < 9; ++i) m(i / 3, i % 3) = a[i]; return m; }
+void m3out(const Eigen::Matrix3d &m, double *a) { for (int i = 0; i < 9; ++i) a[i] = m(i / 3, i % 3); }
+pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_of(const float *xyzw, int64_t n) {
+  auto c = std::make_shared<pcl::PointCloud<pcl::PointXYZ>>();
+  c->points.resize(n);
+  if (n) std::memcpy(c->points.data(), xyzw, sizeof(float) * 4 * n);
+  c->width = (uint32_t)n; c->height = 1; c->is_dense = false;
+  return c;
+}
+int64_t cloud_out(const pcl::PointCloud<pcl::PointXYZ> &c, float *xyzw, int64_t cap) {
+  const int64_t m = std::min<int64_t>(cap, (int64_t)c.points.size());
+  for (int64_t i = 0; i < m; ++i) { xyzw[4 * i] = c.points[i].x; xyzw[4 * i + 1] = c.points[i].y; xyzw[4 * i + 2] = c.points[i].z; xyzw[4 * i + 3] = 0.f; }
+  return (int64_t)c.points.size();
+}
+struct Slam {
+  PointCloudMap pcmap; FrontEnd fe; PoseEstimator estim;
+  double ms[6] = {0, 0, 0, 0, 0, 0};    // resample, estimate, fuse, growMap, device grid kernels, device match kernel
+  int64_t evals = 0, point_evals = 0, matches = 0;
+  Slam() { fe.setPoseEstimator(&estim); fe.setPointCloudMap(&pcmap); }
+};
+char g_err[512] = "";
+}  // namespace
+
+extern "C" {
+
+const char *host_last_error() { return g_err; }
+void host_param_set(const char *k, const char *v) { ros::param::set(k, v); }
+void host_param_clear() { ros::param::clear(); }
+
+int64_t host_resample(const double *xy, int64_t n, double *out, int64_t cap) {
+  const double zero[3] = {0, 0, 0};
+  Scan2D s = make_scan(0, zero, xy, n);
+  ScanPointResampler r;
+  r.resamplePoints(&s);
+  const int64_t m = (int64_t)s.lps.size();
+  if (m > cap) return -m;
+  for (int64_t i = 0; i < m; ++i) { out[2 * i] = s.lps[i].x; out[2 * i + 1] = s.lps[i].y; }
+  return m;
+}
+int64_t host_voxel_filter(const float *xyzw, int64_t n, float leaf, float *out) {
+  pcl::PointCloud<pcl::PointXYZ> f;
+  ndt_host::approximate_voxel_grid(*cloud_of(xyzw, n), leaf, f);
+  return cloud_out(f, out, n);
+}
+double host_add_angle(double a, double b) { return MyUtil::add_angle(a, b); }
+double host_sub_angle(double a, double b) { return MyUtil::sub_angle(a, b); }
+void host_cal_motion(const double cur[3], const double prev[3], double m[3]) {
+  Pose2D o; Pose2D::calMotion(Pose2D(cur[0], cur[1], cur[2]), Pose2D(prev[0], prev[1], prev[2]), o);
+  m[0] = o.tx; m[1] = o.ty; m[2] = o.th;
+}
+void host_cal_pred_pose(const double motion[3], const double last[3], double pred[3]) {
+  Pose2D o; Pose2D::calPredPose(Pose2D(motion[0], motion[1], motion[2]), Pose2D(last[0], last[1], last[2]), o);
+  pred[0] = o.tx; pred[1] = o.ty; pred[2] = o.th;
+}
+void host_odometry_cov(const double motion[3], const double last[3], const double lastCov[9], double cov[9]) {
+  PoseFuser f; Eigen::Matrix3d c;
+  f.calOdometryCovariance(Pose2D(motion[0], motion[1], motion[2]), Pose2D(last[0], last[1], last[2]), m3(lastCov), c);
+  m3out(c, cov);
+}
+void host_fuse_pose(const double pred[3], const double est[3], const double motion[3], const double last[3],
+                    const double lastCov[9], const double Q[9], double fused[3], double cov[9]) {
+  PoseFuser f; Eigen::Matrix3d c; Pose2D out;
+  f.fusePose(Pose2D(pred[0], pred[1], pred[2]), Pose2D(est[0], est[1], est[2]), Pose2D(motion[0], motion[1], motion[2]),
+             Pose2D(last[0], last[1], last[2]), m3(lastCov), m3(Q), out, c);
+  fused[0] = out.tx; fused[1] = out.ty; fused[2] = out.th; m3out(c, cov);
+}
+
+// PoseEstimator::setScanPair + estimatePose on the GPU. Returns the cost; -1e300 on failure (see host_last_error).
+double host_estimate_pose(const double *scan_xy, int64_t n, const float *tgt_xyzw, int64_t m, const double init[3],
+                          double est[3], double cov[9], ndt_result *res_out) {
+  try {
+    Scan2D s = make_scan(0, init, scan_xy, n);
+    PoseEstimator pe;
+    pe.setScanPair(&s, cloud_of(tgt_xyzw, m));
+    Pose2D ip(init[0], init[1], init[2]), ep; Eigen::Matrix3d c;
+    const double cost = pe.estimatePose(ip, ep, c);
+    est[0] = ep.tx; est[1] = ep.ty; est[2] = ep.th; m3out(c, cov);
+    if (res_out) *res_out = pe.lastResult;
+    return cost;
+  } catch (const std::exception &e) {
+    std::strncpy(g_err, e.what(), sizeof(g_err) - 1);
+    return -1e300;
+  }
+}
+
+void *host_slam_create() { return new Slam(); }
+void host_slam_destroy(void *h) { delete (Slam *)h; }
+int host_slam_process(void *h, int sid, const double odo[3], const double *xy, int64_t n) {
+  Slam *s = (Slam *)h;
+  try {
+    Scan2D scan = make_scan(sid, odo, xy, n);
+    s->fe.process(scan);
+    const ScanMatcher &sm = s->fe.matcher();
+    s->ms[0] += sm.msResample; s->ms[1] += sm.msEstimate; s->ms[2] += sm.msFuse; s->ms[3] += sm.msGrowMap;
+    if (sm.msEstimate > 0) {
+      s->ms[4] += s->estim.lastGridMs; s->ms[5] += s->estim.lastMatchMs;
+      s->evals += s->estim.lastResult.evals; s->point_evals += s->estim.lastResult.point_evals; s->matches += 1;
+    }
+    return 0;
+  } catch (const std::exception &e) {
+    std::strncpy(g_err, e.what(), sizeof(g_err) - 1);
+    return -1;
+  }
+}
+int64_t host_slam_poses(void *h, double *out3, int64_t cap) {
+  Slam *s = (Slam *)h;
+  std::vector<Pose2D> p = s->fe.get_poses();
+  const int64_t m = std::min<int64_t>(cap, (int64_t)p.size());
+  for (int64_t i = 0; i < m; ++i) { out3[3 * i] = p[i].tx; out3[3 * i + 1] = p[i].ty; out3[3 * i + 2] = p[i].th; }
+  return (int64_t)p.size();
+}
+int64_t host_slam_local_map(void *h, float *xyzw, int64_t cap) { return cloud_out(*((Slam *)h)->pcmap.localMap_cloud, xyzw, cap); }
+int64_t host_slam_global_map(void *h, float *xyzw, int64_t cap) { return cloud_out(*((Slam *)h)->pcmap.globalMap_cloud, xyzw, cap); }
+int host_slam_submaps(void *h) { return (int)((Slam *)h)->pcmap.submaps.size(); }
+// ms: resample, estimate, fuse, growMap, device grid kernels, device match kernel ; counts: matches, evals, point_evals
+void host_slam_stats(void *h, double ms6[6], int64_t counts3[3]) {
+  Slam *s = (Slam *)h;
+  for (int i = 0; i < 6; ++i) ms6[i] = s->ms[i];
+  counts3[0] = s->matches; counts3[1] = s->evals; counts3[2] = s->point_evals;
+}
+
+// SlamLauncher: run a text scan log end to end (parameters filename_in / poses_name / map_name ... must be set)
+int host_launcher_run() {
+  try {
+    SlamLauncher sl;
+    if (!sl.ok) { std::strncpy(g_err, "cannot open input / output file", sizeof(g_err) - 1); return -1; }
+    sl.init();
+    sl.loop_wait();
+    return sl.scansProcessed;
+  } catch (const std::exception &e) {
+    std::strncpy(g_err, e.what(), sizeof(g_err) - 1);
+    return -1;
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,181 @@
+"""ctypes binding of libndt_slam_host.so: the C++ mirror of the reference's classes (PoseEstimator,
+ScanMatcher, PointCloudMap, ScanPointResampler, PoseFuser, FrontEnd, SlamLauncher) running on top of
+the CUDA C ABI. Test / bench plumbing only."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import build as _build
+from .capi import NdtResult
+
+# ndt_mapping.launch values (reference config), Resolution per BASELINE configs; removeMoving off for the headline run
+LAUNCH_PARAMS = {
+    "space": "0.05", "space_thre": "0.25", "LeafSize": "0.05", "TransformationEpsilon": "0.01", "StepSize": "0.1",
+    "Resolution": "0.5", "MaximumIterations": "35", "coeNDTCov": "1.0", "score_thre": "0.5", "sepThre": "10.0",
+    "removeMoving": "false", "resol": "0.05", "thre_neighbor": "0.2", "delTime": "0.5", "coeVel": "0.1",
+    "coeOmega": "0.5", "keyframe_skip": "5", "start_frame": "0",
+}
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _build.LIB_HOST.exists():
+        raise RuntimeError(f"{_build.LIB_HOST} is not built -- run `python -m ndt_slam_b200.build`")
+    C.CDLL(str(_build.LIB_CUDA), mode=C.RTLD_GLOBAL)
+    L = C.CDLL(str(_build.LIB_HOST))
+    vp, i64, dp, d = C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.c_double
+    L.host_last_error.restype = C.c_char_p
+    L.host_param_set.argtypes = [C.c_char_p, C.c_char_p]
+    L.host_resample.argtypes = [vp, i64, vp, i64]; L.host_resample.restype = i64
+    L.host_voxel_filter.argtypes = [vp, i64, C.c_float, vp]; L.host_voxel_filter.restype = i64
+    L.host_add_angle.argtypes = [d, d]; L.host_add_angle.restype = d
+    L.host_sub_angle.argtypes = [d, d]; L.host_sub_angle.restype = d
+    L.host_cal_motion.argtypes = [dp, dp, dp]
+    L.host_cal_pred_pose.argtypes = [dp, dp, dp]
+    L.host_odometry_cov.argtypes = [dp, dp, dp, dp]
+    L.host_fuse_pose.argtypes = [dp] * 8
+    L.host_estimate_pose.argtypes = [vp, i64, vp, i64, dp, dp, dp, C.POINTER(NdtResult)]; L.host_estimate_pose.restype = d
+    L.host_slam_create.restype = vp
+    L.host_slam_destroy.argtypes = [vp]
+    L.host_slam_process.argtypes = [vp, C.c_int, dp, vp, i64]; L.host_slam_process.restype = C.c_int
+    L.host_slam_poses.argtypes = [vp, vp, i64]; L.host_slam_poses.restype = i64
+    L.host_slam_local_map.argtypes = [vp, vp, i64]; L.host_slam_local_map.restype = i64
+    L.host_slam_global_map.argtypes = [vp, vp, i64]; L.host_slam_global_map.restype = i64
+    L.host_slam_submaps.argtypes = [vp]; L.host_slam_submaps.restype = C.c_int
+    L.host_slam_stats.argtypes = [vp, dp, C.POINTER(C.c_int64)]
+    L.host_launcher_run.restype = C.c_int
+    _lib = L
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _d(v):
+    return (C.c_double * len(v))(*v)
+
+
+def set_params(**kw):
+    L = load()
+    L.host_param_clear()
+    p = dict(LAUNCH_PARAMS)
+    p.update({k: str(v) for k, v in kw.items()})
+    for k, v in p.items():
+        L.host_param_set(k.encode(), v.encode())
+
+
+def resample(xy):
+    L = load()
+    xy = np.ascontiguousarray(xy, np.float64)
+    out = np.zeros((4 * xy.shape[0] + 16, 2))
+    m = L.host_resample(_p(xy), xy.shape[0], _p(out), out.shape[0])
+    assert m >= 0
+    return np.ascontiguousarray(out[:m])
+
+
+def voxel_filter(xyzw, leaf):
+    L = load()
+    xyzw = np.ascontiguousarray(xyzw, np.float32)
+    out = np.zeros_like(xyzw)
+    m = L.host_voxel_filter(_p(xyzw), xyzw.shape[0], leaf, _p(out))
+    return np.ascontiguousarray(out[:m])
+
+
+def cal_motion(cur, prev):
+    L = load(); o = (C.c_double * 3)(); L.host_cal_motion(_d(cur), _d(prev), o); return np.array(o)
+
+
+def cal_pred_pose(motion, last):
+    L = load(); o = (C.c_double * 3)(); L.host_cal_pred_pose(_d(motion), _d(last), o); return np.array(o)
+
+
+def odometry_cov(motion, last, last_cov):
+    L = load(); c = (C.c_double * 9)()
+    L.host_odometry_cov(_d(motion), _d(last), _d(list(np.ravel(last_cov))), c)
+    return np.array(c).reshape(3, 3)
+
+
+def fuse_pose(pred, est, motion, last, last_cov, Q):
+    L = load(); f = (C.c_double * 3)(); c = (C.c_double * 9)()
+    L.host_fuse_pose(_d(pred), _d(est), _d(motion), _d(last), _d(list(np.ravel(last_cov))), _d(list(np.ravel(Q))), f, c)
+    return np.array(f), np.array(c).reshape(3, 3)
+
+
+def estimate_pose(scan_xy, tgt_xyzw, init_deg):
+    """PoseEstimator::setScanPair + estimatePose on the GPU. Returns (cost, est (x, y, th_deg), cov, ndt_result)."""
+    L = load()
+    scan_xy = np.ascontiguousarray(scan_xy, np.float64); tgt_xyzw = np.ascontiguousarray(tgt_xyzw, np.float32)
+    est = (C.c_double * 3)(); cov = (C.c_double * 9)(); res = NdtResult()
+    cost = L.host_estimate_pose(_p(scan_xy), scan_xy.shape[0], _p(tgt_xyzw), tgt_xyzw.shape[0], _d(init_deg), est, cov, C.byref(res))
+    if cost == -1e300:
+        raise RuntimeError(L.host_last_error().decode())
+    return cost, np.array(est), np.array(cov).reshape(3, 3), res
+
+
+class Slam:
+    """PointCloudMap + FrontEnd + PoseEstimator wired like SlamLauncher::init."""
+
+    def __init__(self):
+        self.L = load()
+        self.h = C.c_void_p(self.L.host_slam_create())
+
+    def __del__(self):
+        try:
+            self.L.host_slam_destroy(self.h)
+        except Exception:
+            pass
+
+    def process(self, sid, odo_deg, xy):
+        xy = np.ascontiguousarray(xy, np.float64)
+        if self.L.host_slam_process(self.h, sid, _d(list(odo_deg)), _p(xy), xy.shape[0]) != 0:
+            raise RuntimeError(self.L.host_last_error().decode())
+
+    def poses(self):
+        n = self.L.host_slam_poses(self.h, None, 0)
+        out = np.zeros((n, 3)); self.L.host_slam_poses(self.h, _p(out), n)
+        return out
+
+    def local_map(self):
+        n = self.L.host_slam_local_map(self.h, None, 0)
+        out = np.zeros((n, 4), np.float32); self.L.host_slam_local_map(self.h, _p(out), n)
+        return out
+
+    def global_map(self):
+        n = self.L.host_slam_global_map(self.h, None, 0)
+        out = np.zeros((n, 4), np.float32); self.L.host_slam_global_map(self.h, _p(out), n)
+        return out
+
+    def submaps(self):
+        return self.L.host_slam_submaps(self.h)
+
+    def stats(self):
+        ms = (C.c_double * 6)(); cnt = (C.c_int64 * 3)()
+        self.L.host_slam_stats(self.h, ms, cnt)
+        return dict(resample_ms=ms[0], estimate_ms=ms[1], fuse_ms=ms[2], growmap_ms=ms[3], device_grid_ms=ms[4],
+                    device_match_ms=ms[5], matches=cnt[0], evals=cnt[1], point_evals=cnt[2])
+
+
+def launcher_run() -> int:
+    L = load()
+    n = L.host_launcher_run()
+    if n < 0:
+        raise RuntimeError(L.host_last_error().decode())
+    return n
+
+
+def write_scan_log(path, odo_deg, scans, header_lines=("# synthetic", "# ndt_slam text log", "#", "#")):
+    """The reference's text scan log (SlamLauncher.cpp:37-105): 4 header lines, then per
+    scan 'stamp x y theta_deg image' and three point groups 'count x y x y ...' (front, left, right)."""
+    with open(path, "w") as f:
+        for h in header_lines:
+            f.write(h + "\n")
+        for i, (o, xy) in enumerate(zip(odo_deg, scans)):
+            f.write(f"{i} {float(o[0])!r} {float(o[1])!r} {float(o[2])!r} img{i}.png\n")
+            f.write(f"{xy.shape[0]} " + " ".join(f"{float(x)!r} {float(y)!r}" for x, y in xy) + " \n")
+            f.write("0 \n0 \n")
