@@ -186,6 +186,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--hyp-per-gpu", type=int, default=HYP_PER_GPU)
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--c2-scans", type=int, default=300)
     ap.add_argument("--no-cpu-baseline", action="store_true", help="profiling runs only")
     args = ap.parse_args()
 
@@ -375,7 +376,7 @@ def main():
     extras = {}
     if not args.no_extras and world == 1:
         try:
-            extras = run_extras(g, prm, capi, torch)
+            extras = run_extras(g, prm, capi, torch, c2_scans=args.c2_scans)
         except Exception as ex:       # reported, never hidden
             extras = {"error": repr(ex)}
 
@@ -405,17 +406,17 @@ def main():
         dist.destroy_process_group()
 
 
-def run_extras(g, prm, capi, torch):
-    """Secondary figures on 1 GPU: C1 single-match latency, grid-build rate, C3 if memory allows."""
+def run_extras(g, prm, capi, torch, c2_scans=300, c3=True):
+    """Secondary figures on 1 GPU: C1 single-match latency, C2 FrontEnd sequence, C3 dense single match."""
     from ndt_slam_b200 import synth
     from oracle import oracle_api as oa
 
     out = {}
-    # C1: single scan vs grid of the previous scan
+    # ---- C1: single scan vs grid of the previous scan -------------------------------------------------
     d = synth.c1_pair(1)
-    ra = oa.resample(d["scan_a"], LAUNCH["space"], LAUNCH["space_thre"])
+    ra_ = oa.resample(d["scan_a"], LAUNCH["space"], LAUNCH["space_thre"])
     rb = oa.resample(d["scan_b"], LAUNCH["space"], LAUNCH["space_thre"])
-    tgt = synth.to_xyzw(synth.transform(ra, d["pose_a"]))
+    tgt = synth.to_xyzw(synth.transform(ra_, d["pose_a"]))
     src = oa.approx_voxel_filter(synth.to_xyzw(rb), LAUNCH["leaf"])
     g1 = capi.Ndt(prm)
     guess = np.array(d["pose_a"])
@@ -435,6 +436,100 @@ def run_extras(g, prm, capi, torch):
                  "e2e_host_call_ms": float(np.median(ws[5:])), "cpu_oracle_ms_1thread": cpu_ms,
                  "evals": int(r.evals), "n_source": int(src.shape[0]), "n_target": int(tgt.shape[0]),
                  "pose_matches_oracle": bool(np.hypot(r.pose[0] - ro.pose[0], r.pose[1] - ro.pose[1]) < 1e-4)}
+
+    # ---- C2: synthetic office sequence through the full FrontEnd (host classes on the CUDA path) ------
+    try:
+        from ndt_slam_b200 import build, host_api as ha
+        from oracle import ref_api as rf
+        build.build_host()
+        seq = synth.c2_sequence(seed=2, n_scans=2000)
+        odo = np.column_stack([seq["odo"][:, 0], seq["odo"][:, 1], np.rad2deg(seq["odo"][:, 2])])
+        odo[:, 2] = (odo[:, 2] + 180.0) % 360.0 - 180.0
+        n = min(c2_scans, 2000)
+        ha.set_params(Resolution=RESOLUTION)
+        warm = ha.Slam()                                  # one-time costs (module load, allocator) stay out of the timing
+        for i in range(5):
+            warm.process(i, odo[i], seq["scans"][i])
+        del warm
+        slam = ha.Slam()
+        t0 = time.perf_counter()
+        for i in range(n):
+            slam.process(i, odo[i], seq["scans"][i])
+        gpu_s = time.perf_counter() - t0
+        st = slam.stats()
+        poses = slam.poses()
+        # trajectory error vs ground truth (map frame = first odometry pose = (0,0,0); truth is in world frame)
+        t = seq["traj"][:n]
+        c0, s0 = np.cos(t[0, 2]), np.sin(t[0, 2])
+        rel = np.stack([c0 * (t[:, 0] - t[0, 0]) + s0 * (t[:, 1] - t[0, 1]), -s0 * (t[:, 0] - t[0, 0]) + c0 * (t[:, 1] - t[0, 1])], axis=1)
+        err = float(np.max(np.hypot(poses[:, 0] - rel[:, 0], poses[:, 1] - rel[:, 1])))
+        c2 = {"scans": n, "scans_per_sec": n / gpu_s, "ms_per_scan": gpu_s / n * 1e3, "stage_ms_per_scan": {
+            "resample": st["resample_ms"] / n, "estimate_total": st["estimate_ms"] / n, "fuse": st["fuse_ms"] / n,
+            "grow_map_host": st["growmap_ms"] / n, "device_grid_kernels": st["device_grid_ms"] / max(st["matches"], 1),
+            "device_match_kernel": st["device_match_ms"] / max(st["matches"], 1),
+            "host_voxel_filter": st["host_filter_ms"] / max(st["matches"], 1),
+            "set_source_call": st["set_source_wall_ms"] / max(st["matches"], 1),
+            "set_target_call": st["set_target_wall_ms"] / max(st["matches"], 1),
+            "align_call": st["align_wall_ms"] / max(st["matches"], 1)},
+            "evals_per_match": st["evals"] / max(st["matches"], 1), "max_position_error_vs_truth_m": err,
+            "local_map_points_at_end": int(slam.local_map().shape[0]), "submaps": slam.submaps()}
+        if rf.available():
+            m = min(n, 60)
+            rf.set_params(Resolution=RESOLUTION)
+            rs = rf.RefSlam()
+            t0 = time.perf_counter()
+            for i in range(m):
+                rs.process(i, odo[i], seq["scans"][i])
+            ref_s = time.perf_counter() - t0
+            pr = rs.poses()
+            c2["cpu_reference"] = {"kind": "reference", "cores": 1, "scans": m, "scans_per_sec": m / ref_s,
+                                   "ms_per_scan": ref_s / m * 1e3,
+                                   "max_pose_diff_vs_gpu_m": float(np.max(np.hypot(pr[:, 0] - poses[:m, 0], pr[:, 1] - poses[:m, 1])))}
+        out["C2"] = c2
+    except Exception as ex:
+        out["C2"] = {"error": repr(ex)}
+
+    # ---- C3: 65,536 points vs a 4096 x 4096 grid at 0.1 m cells, single-match latency ---------------------
+    if c3:
+        try:
+            d3 = synth.c3_dense(seed=3)
+            tgt3, src3 = synth.to_xyzw(d3["target"]), synth.to_xyzw(d3["source"])
+            prm3 = capi.default_params(resolution=0.1, device=prm.device, stream=prm.stream)
+            g3 = capi.Ndt(prm3)
+            d_t = torch.from_numpy(tgt3).cuda()
+            bms = []
+            for _ in range(4):
+                g3.set_target(d_t.data_ptr(), n=tgt3.shape[0], space=capi.MEM_DEVICE); bms.append(g3.last_kernel_ms())
+            gi3 = g3.grid_info()
+            g3.set_source(src3)
+            kms = []
+            for _ in range(4):
+                r3 = g3.align(list(d3["guess"])); kms.append(g3.last_kernel_ms())
+            e3 = g3.eval(list(r3.pose))
+            kbar3 = e3.n_pairs / src3.shape[0]
+            peaks, _ = measured_peaks()
+            grid_bytes = 16.0 * tgt3.shape[0] + 64.0 * gi3.n_leaves
+            match_bytes = r3.point_evals * (160.0 + 48.0 * kbar3)
+            tp = d3["true_pose"]
+            out["C3"] = {"target_points": int(tgt3.shape[0]), "source_points": int(src3.shape[0]),
+                         "grid_cells": [int(gi3.div_b[0]), int(gi3.div_b[1])], "occupied_cells": int(gi3.n_leaves),
+                         "tree_cells": int(gi3.n_slots), "grid_build_ms": float(np.median(bms[1:])),
+                         "grid_build_points_per_sec": tgt3.shape[0] / (np.median(bms[1:]) * 1e-3),
+                         "grid_build_hbm_frac": grid_bytes / (np.median(bms[1:]) * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                         "match_latency_ms": float(np.median(kms[1:])), "evals": int(r3.evals), "iters": int(r3.iters),
+                         "kbar": kbar3, "point_evals_per_sec": r3.point_evals / (np.median(kms[1:]) * 1e-3),
+                         "match_hbm_equiv_frac": match_bytes / (np.median(kms[1:]) * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                         "pose_error_m": float(np.hypot(r3.pose[0] - tp[0], r3.pose[1] - tp[1])),
+                         "yaw_error_rad": float(abs(r3.pose[2] - tp[2]))}
+            o3 = oa.Oracle(prm3)
+            t0 = time.perf_counter(); o3.set_target(tgt3); tb = time.perf_counter() - t0
+            o3.set_source(src3); o3.want_fitness(False)
+            t0 = time.perf_counter(); ro3 = o3.align(list(d3["guess"])); tm = time.perf_counter() - t0
+            out["C3"]["cpu_oracle_1thread"] = {"grid_build_ms": tb * 1e3, "match_ms_no_fitness": tm * 1e3,
+                                               "pose_diff_vs_gpu_m": float(np.hypot(ro3.pose[0] - r3.pose[0], ro3.pose[1] - r3.pose[1])),
+                                               "same_iters_evals": bool(ro3.iters == r3.iters and ro3.evals == r3.evals)}
+        except Exception as ex:
+            out["C3"] = {"error": repr(ex)}
     return out
 
 

@@ -39,7 +39,7 @@ struct BlobHeader {
   uint64_t magic;
   GridDims gd;
   int32_t counters[CTR_COUNT];
-  int64_t off_slot, off_cen, off_recs, off_leaf_id, off_leaf_range, off_sorted, off_tgt, total;
+  int64_t off_slot, off_cen, off_recs, off_leaf_id, off_leaf_range, off_sorted, off_tgt, off_nn_range, off_nn_pts, total;
 };
 static constexpr uint64_t kBlobMagic = 0x4e44544232303042ull;  // "NDTB200B"
 
@@ -60,6 +60,9 @@ static BlobHeader blob_layout(const Handle *h) {
   b.off_leaf_range = o; o = align256(o + nl * 8);
   b.off_sorted = o; o = align256(o + nt * 8);
   b.off_tgt = o; o = align256(o + nt * (int64_t)sizeof(float4));
+  const int64_t ncf = h->gd.nn_f > 0 ? (int64_t)h->gd.nn_div_x * h->gd.nn_div_y : 0;
+  b.off_nn_range = o; o = align256(o + ncf * 8);
+  b.off_nn_pts = o; o = align256(o + (ncf > 0 ? nt * 8 : 0));
   b.total = o;
   return b;
 }
@@ -134,7 +137,7 @@ int ndt_destroy(ndt_handle hh) {
   GridBuffers &g = h->gb;
   DevBuf *all[] = {&g.tgt, &g.cell_of, &g.rank_of, &g.list, &g.sorted_idx, &g.slot, &g.leaf_id, &g.leaf_cell,
                    &g.leaf_n, &g.leaf_start, &g.leaf_nr, &g.leaf_mean, &g.leaf_icov, &g.leaf_cen, &g.recs,
-                   &g.counters, &g.cen, &g.tgt_sorted, &g.leaf_range, &h->src, &h->scratch, &h->scratch2, &h->stage, &h->io};
+                   &g.counters, &g.cen, &g.nn_cnt, &g.nn_range, &g.nn_pts, &g.tgt_sorted, &g.leaf_range, &h->src, &h->scratch, &h->scratch2, &h->stage, &h->io};
   for (DevBuf *b : all) b->release();
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -456,6 +459,9 @@ int ndt_grid_export(ndt_handle hh, void *device_blob, int64_t bytes) {
   NDT_CUDA(h, cp(b.off_leaf_range, h->gb.leaf_range, nl * 8));
   NDT_CUDA(h, cp(b.off_sorted, h->gb.tgt_sorted, nt * 8));
   NDT_CUDA(h, cp(b.off_tgt, h->gb.tgt, nt * (int64_t)sizeof(float4)));
+  const int64_t ncf = h->gd.nn_f > 0 ? (int64_t)h->gd.nn_div_x * h->gd.nn_div_y : 0;
+  NDT_CUDA(h, cp(b.off_nn_range, h->gb.nn_range, ncf * 8));
+  NDT_CUDA(h, cp(b.off_nn_pts, h->gb.nn_pts, ncf > 0 ? nt * 8 : 0));
   NDT_CUDA(h, cudaStreamSynchronize(st));
   return NDT_OK;
 }
@@ -486,6 +492,9 @@ int ndt_grid_import(ndt_handle hh, const void *device_blob, int64_t bytes) {
   NDT_CUDA(h, take(h->gb.leaf_range, b.off_leaf_range, nl * 8));
   NDT_CUDA(h, take(h->gb.tgt_sorted, b.off_sorted, nt * 8));
   NDT_CUDA(h, take(h->gb.tgt, b.off_tgt, nt * (int64_t)sizeof(float4)));
+  const int64_t ncf = h->gd.nn_f > 0 ? (int64_t)h->gd.nn_div_x * h->gd.nn_div_y : 0;
+  NDT_CUDA(h, take(h->gb.nn_range, b.off_nn_range, ncf * 8));
+  NDT_CUDA(h, take(h->gb.nn_pts, b.off_nn_pts, ncf > 0 ? nt * 8 : 0));
   NDT_CUDA(h, cudaStreamSynchronize(st));
   h->have_grid = true;
   return NDT_OK;

@@ -16,7 +16,8 @@
 //   k_count     cell id per point (float32, bit-exact), warp-aggregated int atomics -> count + rank
 //   k_alloc     per dense cell: leaf ids and contiguous bucket ranges (warp-aggregated allocation)
 //   k_fill      scatter point indices into their leaf bucket
-//   k_finalize  one warp per leaf: order the bucket by point index, accumulate in input order
+//   k_rank      one thread per bucket entry: order every bucket by point index (rank by counting)
+//   k_finalize  one warp per leaf: accumulate in input order
 //               (fp32 centroid, fp64 sums), mean, single-pass covariance, 2x2 eigen clamp, inverse,
 //               64-byte record + cell->slot table
 #include "ndt_host.h"
@@ -166,6 +167,26 @@ __global__ void __launch_bounds__(256) k_fill(int64_t n, const int32_t *__restri
   }
 }
 
+// pass 1d: order every bucket by point index. One thread per bucket entry: its rank is the number of
+// smaller indices in the same bucket (a thread does O(n) work for a bucket of n; the work of a dense
+// cell is spread over all of its points instead of one warp). Threads of a warp mostly share a bucket,
+// so the inner loads are broadcasts.
+__global__ void __launch_bounds__(256) k_rank(int64_t n, const int32_t *__restrict__ cell_of,
+                                             const int32_t *__restrict__ leaf_id,
+                                             const int32_t *__restrict__ leaf_start,
+                                             const int32_t *__restrict__ leaf_n, const int32_t *__restrict__ list,
+                                             int32_t *__restrict__ sorted_idx, int32_t *__restrict__ ctr) {
+  const int64_t n_bucketed = ctr[CTR_PTS];
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_bucketed; p += (int64_t)gridDim.x * blockDim.x) {
+    const int v = list[p];
+    const int leaf = __ldg(leaf_id + cell_of[v]);
+    const int st = __ldg(leaf_start + leaf), m = __ldg(leaf_n + leaf);
+    int r = 0;
+    for (int j = 0; j < m; ++j) r += (__ldg(list + st + j) < v) ? 1 : 0;
+    sorted_idx[st + r] = v;
+  }
+}
+
 // symmetric 2x2 eigen-decomposition (a b; b d): ascending eigenvalues, orthonormal columns.
 // Expression order is fixed (IEEE ops only) so results are reproducible bit for bit.
 __device__ inline void eig2(double a, double b, double d, double *lam, double *v0, double *v1) {
@@ -193,8 +214,8 @@ __device__ inline void eig2(double a, double b, double d, double *lam, double *v
 struct FinalizeParams { int32_t min_points; double eig_mult; int32_t quirks; };
 
 // pass 2: one warp per leaf
-__global__ void __launch_bounds__(256) k_finalize(const float4 *__restrict__ pts, const int32_t *__restrict__ list,
-                                                 int32_t *__restrict__ sorted_idx, float2 *__restrict__ tgt_sorted,
+__global__ void __launch_bounds__(256) k_finalize(const float4 *__restrict__ pts,
+                                                 const int32_t *__restrict__ sorted_idx, float2 *__restrict__ tgt_sorted,
                                                  int2 *__restrict__ leaf_range,
                                                  const int32_t *__restrict__ leaf_cell,
                                                  const int32_t *__restrict__ leaf_n,
@@ -210,15 +231,7 @@ __global__ void __launch_bounds__(256) k_finalize(const float4 *__restrict__ pts
   const int n_leaves = ctr[CTR_LEAVES];
   for (int leaf = warp; leaf < n_leaves; leaf += n_warps) {
     const int n = leaf_n[leaf], st = leaf_start[leaf];
-    // order the bucket by point index: rank by counting (buckets are short; O(n^2 / 32) per warp)
-    for (int i = lane; i < n; i += 32) {
-      const int v = list[st + i];
-      int r = 0;
-      for (int j = 0; j < n; ++j) r += (list[st + j] < v) ? 1 : 0;
-      sorted_idx[st + r] = v;
-    }
-    __syncwarp();
-    // accumulate in input order; every lane keeps the same running sums
+    // the bucket is already in input order (k_rank): accumulate sequentially; every lane keeps the same sums
     double sx = 0, sy = 0, sxx = 0, syx = 0, syy = 0;
     float cx = 0.f, cy = 0.f;
     for (int base = 0; base < n; base += 32) {
@@ -321,6 +334,65 @@ __global__ void __launch_bounds__(256) k_finalize(const float4 *__restrict__ pts
   }
 }
 
+// ---- fine nearest-neighbour lattice (unordered buckets: an exact minimum does not care about order) ----
+__global__ void __launch_bounds__(256) k_nn_count(const float4 *__restrict__ pts, int64_t n, Dims d,
+                                                 int32_t *__restrict__ cnt, int32_t *__restrict__ cell_of,
+                                                 int32_t *__restrict__ rank_of) {
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n_round = ((n + 31) / 32) * 32;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+    int cell = -1;
+    if (i < n) {
+      const float4 p = __ldg(pts + i);
+      if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+        int i0 = cell_coord(p.x, d.inv_leaf, d.min_bx), i1 = cell_coord(p.y, d.inv_leaf, d.min_by);
+        i0 = min(max(i0, 0), d.div_x - 1); i1 = min(max(i1, 0), d.div_y - 1);
+        cell = i0 + i1 * d.div_x;
+      }
+    }
+    const unsigned grp = __match_any_sync(0xffffffffu, cell);
+    const int leader = __ffs(grp) - 1;
+    int base = 0;
+    if (cell >= 0 && lane == leader) base = atomicAdd(cnt + cell, __popc(grp));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (i < n) { cell_of[i] = cell; rank_of[i] = base + __popc(grp & ((1u << lane) - 1u)); }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_nn_alloc(const int32_t *__restrict__ cnt, int64_t n_cells,
+                                                 int2 *__restrict__ range, int32_t *__restrict__ ctr) {
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n_round = ((n_cells + 31) / 32) * 32;
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_round; c += stride) {
+    const int n = (c < n_cells) ? cnt[c] : 0;
+    int incl = n;
+#pragma unroll
+    for (int dlt = 1; dlt < 32; dlt <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, dlt);
+      if (lane >= dlt) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int base = 0;
+    if (lane == 0 && total > 0) base = atomicAdd(ctr + CTR_JOB, total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (c < n_cells) range[c] = make_int2(base + incl - n, n);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_nn_fill(const float4 *__restrict__ pts, int64_t n,
+                                                const int32_t *__restrict__ cell_of,
+                                                const int32_t *__restrict__ rank_of, const int2 *__restrict__ range,
+                                                float2 *__restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cell = cell_of[i];
+    if (cell < 0) continue;
+    const float4 p = __ldg(pts + i);
+    out[__ldg(range + cell).x + rank_of[i]] = make_float2(p.x, p.y);
+  }
+}
+
 __global__ void __launch_bounds__(256) k_cell_index(const float4 *__restrict__ pts, int64_t n, Dims d,
                                                    int32_t *__restrict__ out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -361,9 +433,7 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace) {
   float mn[2] = {std::numeric_limits<float>::max(), std::numeric_limits<float>::max()};
   float mx[2] = {-std::numeric_limits<float>::max(), -std::numeric_limits<float>::max()};
   int64_t nfin = 0;
-  if (h->timing) cudaEventRecord(h->ev0, st);
-  k_init_counters<<<1, 32, 0, st>>>(ctr, bounds);
-  ++h->launches;
+  if (memspace != NDT_MEM_HOST && h->timing) cudaEventRecord(h->ev0, st);
   if (memspace == NDT_MEM_HOST) {
     // stage through pinned memory; bounds come for free while the points pass through the host cache
     if (ensure_pinned(h, npts * sizeof(float4))) return NDT_ERR_CUDA;
@@ -377,8 +447,13 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace) {
         ++nfin;
       }
     }
+    if (h->timing) cudaEventRecord(h->ev0, st);     // device time only: the host staging loop is not in it
+    k_init_counters<<<1, 32, 0, st>>>(ctr, bounds);
+    ++h->launches;
     if (n > 0) NDT_CUDA(h, cudaMemcpyAsync(gb.tgt.p, stage, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, st));
   } else {
+    k_init_counters<<<1, 32, 0, st>>>(ctr, bounds);
+    ++h->launches;
     if (n > 0) {
       NDT_CUDA(h, cudaMemcpyAsync(gb.tgt.p, xyzw, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, st));
       k_bounds<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(gb.tgt.as<float4>(), n, bounds, ctr);
@@ -448,18 +523,56 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace) {
                                                        gb.list.as<int32_t>());
   FinalizeParams fp{h->prm.min_points, h->prm.eig_mult, h->prm.quirks};
   const int64_t warps_needed = (int64_t)max_leaves;
+  k_rank<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(n, gb.cell_of.as<int32_t>(), gb.leaf_id.as<int32_t>(),
+                                                       gb.leaf_start.as<int32_t>(), gb.leaf_n.as<int32_t>(),
+                                                       gb.list.as<int32_t>(), gb.sorted_idx.as<int32_t>(), ctr);
   k_finalize<<<grid_for(warps_needed * 32, 256, h->sm_count), 256, 0, st>>>(
-      gb.tgt.as<float4>(), gb.list.as<int32_t>(), gb.sorted_idx.as<int32_t>(), gb.tgt_sorted.as<float2>(),
+      gb.tgt.as<float4>(), gb.sorted_idx.as<int32_t>(), gb.tgt_sorted.as<float2>(),
       gb.leaf_range.as<int2>(), gb.leaf_cell.as<int32_t>(),
       gb.leaf_n.as<int32_t>(), gb.leaf_start.as<int32_t>(), gb.leaf_nr.as<int32_t>(), gb.leaf_mean.as<double2>(),
       gb.leaf_icov.as<double>(), gb.leaf_cen.as<float2>(), gb.slot.as<int32_t>(), gb.cen.as<float2>(), gb.recs.as<CellRec>(), ctr, fp, gd.div_x);
-  h->launches += 4;
-  if (h->timing) cudaEventRecord(h->ev1, st);
+  h->launches += 5;
   NDT_CUDA(h, cudaMemcpyAsync(h->h_counters, ctr, sizeof(h->h_counters), cudaMemcpyDeviceToHost, st));
   NDT_CUDA(h, cudaStreamSynchronize(st));
   NDT_CUDA(h, cudaGetLastError());
-  if (h->timing) cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
   h->h_counters[CTR_NFIN] = (int32_t)nfin;
+
+  // Dense NDT buckets make the exact 1-NN of the fitness score expensive: add a finer lattice for it.
+  gd.nn_f = 0;
+  const int64_t n_leaves = h->h_counters[CTR_LEAVES];
+  if (n_leaves > 0 && nfin / n_leaves > 24) {
+    int f = 2;
+    while (f < 16 && nfin / (n_leaves * f) > 12) f *= 2;
+    while (f > 1 && (int64_t)gd.div_x * f * ((int64_t)gd.div_y * f) > (int64_t)64 * 1024 * 1024) f /= 2;
+    if (f > 1) {
+      gd.nn_f = f;
+      gd.nn_leaf = gd.leaf / (float)f;
+      gd.nn_inv_leaf = 1.0f / gd.nn_leaf;
+      gd.nn_min_bx = (int)std::floor(mn[0] * gd.nn_inv_leaf); gd.nn_min_by = (int)std::floor(mn[1] * gd.nn_inv_leaf);
+      gd.nn_div_x = (int)std::floor(mx[0] * gd.nn_inv_leaf) - gd.nn_min_bx + 1;
+      gd.nn_div_y = (int)std::floor(mx[1] * gd.nn_inv_leaf) - gd.nn_min_by + 1;
+      const int64_t ncf = (int64_t)gd.nn_div_x * gd.nn_div_y;
+      NDT_CUDA(h, gb.nn_cnt.reserve((size_t)ncf * 4));
+      NDT_CUDA(h, gb.nn_range.reserve((size_t)ncf * sizeof(int2)));
+      NDT_CUDA(h, gb.nn_pts.reserve(npts * sizeof(float2)));
+      NDT_CUDA(h, cudaMemsetAsync(gb.nn_cnt.p, 0, (size_t)ncf * 4, st));
+      NDT_CUDA(h, cudaMemsetAsync(ctr + CTR_JOB, 0, 4, st));
+      Dims df{gd.nn_min_bx, gd.nn_min_by, gd.nn_div_x, gd.nn_div_y, gd.nn_inv_leaf};
+      k_nn_count<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(gb.tgt.as<float4>(), n, df, gb.nn_cnt.as<int32_t>(),
+                                                               gb.cell_of.as<int32_t>(), gb.rank_of.as<int32_t>());
+      k_nn_alloc<<<grid_for(ncf, 256, h->sm_count), 256, 0, st>>>(gb.nn_cnt.as<int32_t>(), ncf, gb.nn_range.as<int2>(), ctr);
+      k_nn_fill<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(gb.tgt.as<float4>(), n, gb.cell_of.as<int32_t>(),
+                                                              gb.rank_of.as<int32_t>(), gb.nn_range.as<int2>(),
+                                                              gb.nn_pts.as<float2>());
+      h->launches += 3;
+    }
+  }
+  if (h->timing) {
+    cudaEventRecord(h->ev1, st);
+    NDT_CUDA(h, cudaEventSynchronize(h->ev1));
+    cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
+  }
+  NDT_CUDA(h, cudaGetLastError());
   h->have_grid = true;
   return NDT_OK;
 }
@@ -498,6 +611,11 @@ GridView grid_view(const Handle *h) {
   G.tgt_sorted = gb.tgt_sorted.as<float2>();
   G.tgt = gb.tgt.as<float4>();
   G.n_tgt = h->gd.n_tgt;
+  G.nn_f = h->gd.nn_f;
+  G.nn_min_bx = h->gd.nn_min_bx; G.nn_min_by = h->gd.nn_min_by; G.nn_div_x = h->gd.nn_div_x; G.nn_div_y = h->gd.nn_div_y;
+  G.nn_inv_leaf = h->gd.nn_inv_leaf; G.nn_leaf = h->gd.nn_leaf;
+  G.nn_range = gb.nn_range.as<int2>();
+  G.nn_pts = gb.nn_pts.as<float2>();
   return G;
 }
 

@@ -50,6 +50,13 @@ struct GridView {
   const float2 *__restrict__ tgt_sorted;// target (x, y) in bucket order (cell by cell, input order inside a cell)
   const float4 *__restrict__ tgt;       // target points, input order
   int64_t n_tgt;
+  // optional finer lattice used only for nearest-neighbour queries when the NDT buckets are dense
+  // (nn_f = 0: search the NDT buckets above; otherwise cells of leaf / nn_f with a dense (start, n) table)
+  int32_t nn_f;
+  int32_t nn_min_bx, nn_min_by, nn_div_x, nn_div_y;
+  float nn_inv_leaf, nn_leaf;
+  const int2 *__restrict__ nn_range;    // [nn_div_x * nn_div_y]
+  const float2 *__restrict__ nn_pts;    // target (x, y) in fine-bucket order
 };
 
 struct MatchParams {
@@ -593,40 +600,47 @@ __device__ __forceinline__ void nn_visit(const GridView &G, int a, int b, float 
   nn_scan(G, nn_leaf(G, a, b), xt, yt, best);
 }
 
+// fine-lattice variant: same ring search, direct (start, n) table
+__device__ __forceinline__ void nn_scan_fine(const GridView &G, int a, int b, float xt, float yt, float &best) {
+  if (a < 0 || a >= G.nn_div_x || b < 0 || b >= G.nn_div_y) return;
+  const int2 rg = __ldg(G.nn_range + (size_t)b * G.nn_div_x + a);
+  const float2 *__restrict__ p = G.nn_pts + rg.x;
+  for (int k = 0; k < rg.y; ++k) {
+    const float2 t = __ldg(p + k);
+    const float dd = dist2f(xt, yt, t.x, t.y);
+    if (dd < best) best = dd;
+  }
+}
+
 __device__ inline float nn_dist2(const GridView &G, float xt, float yt, int max_rings) {
   float best = FLT_MAX;
-  if (G.div_x > 0) {
-    const int ci = cell_coord(xt, G.inv_leaf, G.min_bx);
-    const int cj = cell_coord(yt, G.inv_leaf, G.min_by);
-    // rings that lie entirely outside the grid hold nothing: start at the first ring that touches it
+  const bool fine = G.nn_f > 0;
+  const int dvx = fine ? G.nn_div_x : G.div_x, dvy = fine ? G.nn_div_y : G.div_y;
+  const float inv = fine ? G.nn_inv_leaf : G.inv_leaf;
+  const double leaf = fine ? (double)G.nn_leaf : (double)G.leaf;
+  if (dvx > 0) {
+    const int ci = cell_coord(xt, inv, fine ? G.nn_min_bx : G.min_bx);
+    const int cj = cell_coord(yt, inv, fine ? G.nn_min_by : G.min_by);
+    // rings that lie entirely outside the lattice hold nothing: start at the first ring that touches it
     int ox = 0, oy = 0;
-    if (ci < 0) ox = -ci; else if (ci >= G.div_x) ox = ci - (G.div_x - 1);
-    if (cj < 0) oy = -cj; else if (cj >= G.div_y) oy = cj - (G.div_y - 1);
+    if (ci < 0) ox = -ci; else if (ci >= dvx) ox = ci - (dvx - 1);
+    if (cj < 0) oy = -cj; else if (cj >= dvy) oy = cj - (dvy - 1);
     const int r_start = max(ox, oy);
-    if (r_start == 0) {
-      // rings 0 and 1 together (the common case: the neighbour is next door); lookups issued up front
-      int lf[9];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) lf[k] = nn_leaf(G, ci + (k % 3) - 1, cj + (k / 3) - 1);
-#pragma unroll
-      for (int k = 0; k < 9; ++k) nn_scan(G, lf[k], xt, yt, best);
-      const double lim1 = 0.99 * (double)G.leaf;
-      if ((double)best < lim1 * lim1) return best;
-    }
-    for (int ring = (r_start == 0 ? 2 : r_start); ring <= r_start + max_rings; ++ring) {
+    if (fine) max_rings *= G.nn_f;
+    for (int ring = r_start; ring <= r_start + max_rings; ++ring) {
       if (ring == 0) {
-        nn_visit(G, ci, cj, xt, yt, best);
+        if (fine) nn_scan_fine(G, ci, cj, xt, yt, best); else nn_visit(G, ci, cj, xt, yt, best);
       } else {
         for (int di = -ring; di <= ring; ++di) {
-          nn_visit(G, ci + di, cj - ring, xt, yt, best);
-          nn_visit(G, ci + di, cj + ring, xt, yt, best);
+          if (fine) { nn_scan_fine(G, ci + di, cj - ring, xt, yt, best); nn_scan_fine(G, ci + di, cj + ring, xt, yt, best); }
+          else { nn_visit(G, ci + di, cj - ring, xt, yt, best); nn_visit(G, ci + di, cj + ring, xt, yt, best); }
         }
         for (int dj = -ring + 1; dj <= ring - 1; ++dj) {
-          nn_visit(G, ci - ring, cj + dj, xt, yt, best);
-          nn_visit(G, ci + ring, cj + dj, xt, yt, best);
+          if (fine) { nn_scan_fine(G, ci - ring, cj + dj, xt, yt, best); nn_scan_fine(G, ci + ring, cj + dj, xt, yt, best); }
+          else { nn_visit(G, ci - ring, cj + dj, xt, yt, best); nn_visit(G, ci + ring, cj + dj, xt, yt, best); }
         }
         // every point outside rings 0..ring is at least (ring - 0.01) cells away
-        const double lim = ((double)ring - 0.01) * (double)G.leaf;
+        const double lim = ((double)ring - 0.01) * leaf;
         if ((double)best < lim * lim) return best;
       }
     }

@@ -38,6 +38,9 @@ struct GridBuffers {
   DevBuf sorted_idx;   // int32[n]        per-leaf point indices, ascending (input order)
   DevBuf tgt_sorted;   // float2[n]       target (x, y) in bucket order (1-NN scans read this contiguously)
   DevBuf leaf_range;   // int2[n]         per leaf (start, n)
+  DevBuf nn_cnt;       // int32[nn cells] fine nearest-neighbour lattice: counts (build only)
+  DevBuf nn_range;     // int2[nn cells]  (start, n)
+  DevBuf nn_pts;       // float2[n]       target (x, y) in fine-bucket order
   DevBuf slot;         // int32[padded]   count during the build, then cell -> record slot
   DevBuf cen;          // float2[padded]  probe table: float32 centroid of tree cells, NaN elsewhere
   DevBuf leaf_id;      // int32[n_cells]  cell -> leaf or -1
@@ -57,6 +60,8 @@ struct GridDims {
   float leaf = 1.f, inv_leaf = 1.f, r2 = 1.f;
   int64_t n_cells = 0;
   int64_t n_tgt = 0;       // points handed to set_target
+  int32_t nn_f = 0, nn_min_bx = 0, nn_min_by = 0, nn_div_x = 0, nn_div_y = 0;   // fine 1-NN lattice (nn_f = 0: none)
+  float nn_leaf = 1.f, nn_inv_leaf = 1.f;
 };
 
 struct Handle {

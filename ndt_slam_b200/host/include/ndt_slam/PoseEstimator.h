@@ -47,7 +47,8 @@ class PoseEstimator {
 
   // what the last estimatePose did (instrumentation; not in the reference)
   ndt_result lastResult;
-  double lastGridMs, lastMatchMs, lastFilterMs;
+  double lastGridMs, lastMatchMs, lastFilterMs;            // device grid kernels, device match kernel, host voxel filter
+  double lastSetSourceWallMs, lastSetTargetWallMs, lastAlignWallMs;   // host wall time of the three ABI calls
   int lastSourcePoints, lastTargetPoints;
 
   PoseEstimator();

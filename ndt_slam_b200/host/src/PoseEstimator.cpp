@@ -22,6 +22,7 @@ inline double now_ms() {
 PoseEstimator::PoseEstimator()
     : curScan(nullptr), refScan(nullptr), coeNDTCov(1.0), TransformationEpsilon(0.01), StepSize(0.1), Resolution(1.0),
       MaximumIterations(35), LeafSize(0.1), ndt(nullptr), totalError(0.0), lastGridMs(0), lastMatchMs(0), lastFilterMs(0),
+      lastSetSourceWallMs(0), lastSetTargetWallMs(0), lastAlignWallMs(0),
       lastSourcePoints(0), lastTargetPoints(0) {
   ros::param::get("coeNDTCov", coeNDTCov);
   ros::param::get("TransformationEpsilon", TransformationEpsilon);
@@ -96,10 +97,14 @@ double PoseEstimator::estimatePose(Pose2D &initPose, Pose2D &estPose, Eigen::Mat
 
   timer.start_timer();
   // ndt.setInputSource(filtered) ; ndt.setInputTarget(target_cloud) -> device grid build
+  t0 = now_ms();
   if (ndt_set_source(ndt, reinterpret_cast<const float *>(filtered.points.data()), (int64_t)filtered.points.size(), NDT_MEM_HOST) != NDT_OK)
     fail(ndt, "ndt_set_source");
+  lastSetSourceWallMs = now_ms() - t0;
+  t0 = now_ms();
   if (ndt_set_target(ndt, reinterpret_cast<const float *>(target_cloud->points.data()), (int64_t)target_cloud->points.size(), NDT_MEM_HOST) != NDT_OK)
     fail(ndt, "ndt_set_target");
+  lastSetTargetWallMs = now_ms() - t0;
   float ms = 0.f;
   ndt_last_kernel_ms(ndt, &ms);
   lastGridMs = ms;
@@ -107,7 +112,9 @@ double PoseEstimator::estimatePose(Pose2D &initPose, Pose2D &estPose, Eigen::Mat
   // ndt.align(output, Translation3f(tx, ty, 0) * AngleAxisf(DEG2RAD(th), Z)): the ABI rounds the guess through float
   const double guess[3] = {initPose.tx, initPose.ty, DEG2RAD(initPose.th)};
   ndt_result res;
+  t0 = now_ms();
   if (ndt_align(ndt, guess, &res) != NDT_OK) fail(ndt, "ndt_align");
+  lastAlignWallMs = now_ms() - t0;
   ndt_last_kernel_ms(ndt, &ms);
   lastMatchMs = ms;
   lastResult = res;

@@ -40,7 +40,7 @@ int64_t cloud_out(const pcl::PointCloud<pcl::PointXYZ> &c, float *xyzw, int64_t 
 }
 struct Slam {
   PointCloudMap pcmap; FrontEnd fe; PoseEstimator estim;
-  double ms[6] = {0, 0, 0, 0, 0, 0};    // resample, estimate, fuse, growMap, device grid kernels, device match kernel
+  double ms[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // resample, estimate, fuse, growMap, device grid, device match, host filter, set_source wall, set_target wall, align wall
   int64_t evals = 0, point_evals = 0, matches = 0;
   Slam() { fe.setPoseEstimator(&estim); fe.setPointCloudMap(&pcmap); }
 };
@@ -119,7 +119,8 @@ int host_slam_process(void *h, int sid, const double odo[3], const double *xy, i
     const ScanMatcher &sm = s->fe.matcher();
     s->ms[0] += sm.msResample; s->ms[1] += sm.msEstimate; s->ms[2] += sm.msFuse; s->ms[3] += sm.msGrowMap;
     if (sm.msEstimate > 0) {
-      s->ms[4] += s->estim.lastGridMs; s->ms[5] += s->estim.lastMatchMs;
+      s->ms[4] += s->estim.lastGridMs; s->ms[5] += s->estim.lastMatchMs; s->ms[6] += s->estim.lastFilterMs;
+      s->ms[7] += s->estim.lastSetSourceWallMs; s->ms[8] += s->estim.lastSetTargetWallMs; s->ms[9] += s->estim.lastAlignWallMs;
       s->evals += s->estim.lastResult.evals; s->point_evals += s->estim.lastResult.point_evals; s->matches += 1;
     }
     return 0;
@@ -139,9 +140,9 @@ int64_t host_slam_local_map(void *h, float *xyzw, int64_t cap) { return cloud_ou
 int64_t host_slam_global_map(void *h, float *xyzw, int64_t cap) { return cloud_out(*((Slam *)h)->pcmap.globalMap_cloud, xyzw, cap); }
 int host_slam_submaps(void *h) { return (int)((Slam *)h)->pcmap.submaps.size(); }
 // ms: resample, estimate, fuse, growMap, device grid kernels, device match kernel ; counts: matches, evals, point_evals
-void host_slam_stats(void *h, double ms6[6], int64_t counts3[3]) {
+void host_slam_stats(void *h, double ms10[10], int64_t counts3[3]) {
   Slam *s = (Slam *)h;
-  for (int i = 0; i < 6; ++i) ms6[i] = s->ms[i];
+  for (int i = 0; i < 10; ++i) ms10[i] = s->ms[i];
   counts3[0] = s->matches; counts3[1] = s->evals; counts3[2] = s->point_evals;
 }
 

@@ -155,10 +155,11 @@ class Slam:
         return self.L.host_slam_submaps(self.h)
 
     def stats(self):
-        ms = (C.c_double * 6)(); cnt = (C.c_int64 * 3)()
+        ms = (C.c_double * 10)(); cnt = (C.c_int64 * 3)()
         self.L.host_slam_stats(self.h, ms, cnt)
         return dict(resample_ms=ms[0], estimate_ms=ms[1], fuse_ms=ms[2], growmap_ms=ms[3], device_grid_ms=ms[4],
-                    device_match_ms=ms[5], matches=cnt[0], evals=cnt[1], point_evals=cnt[2])
+                    device_match_ms=ms[5], host_filter_ms=ms[6], set_source_wall_ms=ms[7], set_target_wall_ms=ms[8],
+                    align_wall_ms=ms[9], matches=cnt[0], evals=cnt[1], point_evals=cnt[2])
 
 
 def launcher_run() -> int:
@@ -178,4 +179,6 @@ def write_scan_log(path, odo_deg, scans, header_lines=("# synthetic", "# ndt_sla
         for i, (o, xy) in enumerate(zip(odo_deg, scans)):
             f.write(f"{i} {float(o[0])!r} {float(o[1])!r} {float(o[2])!r} img{i}.png\n")
             f.write(f"{xy.shape[0]} " + " ".join(f"{float(x)!r} {float(y)!r}" for x, y in xy) + " \n")
-            f.write("0 \n0 \n")
+            # left / right lidar groups (empty). The file must end right after the last token: the reader
+            # detects the end of data by hitting EOF inside the last getline (SlamLauncher.cpp:96-99).
+            f.write("0 \n0 \n" if i + 1 < len(scans) else "0 \n0")

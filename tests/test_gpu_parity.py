@@ -274,3 +274,25 @@ def test_cuda_path_matches_golden_vectors(path):
         assert np.hypot(*(res[k]["pose"][:2] - z["align_pose"][k][:2])) < POSE_M
         assert abs(res[k]["pose"][2] - z["align_pose"][k][2]) < POSE_RAD
         assert res[k]["fitness"] == pytest.approx(z["align_fitness"][k], rel=1e-4)
+
+
+def test_fitness_exact_with_dense_buckets():
+    """Dense NDT buckets switch the 1-NN of getFitnessScore to the finer lattice: the result stays exact."""
+    rng = synth.rng_for(51)
+    segs = synth.office(51, 24.0, 16.0, 8)
+    tgt = synth.to_xyzw(np.concatenate([synth.sample_walls(segs, 0.004, 0.01, rng) for _ in range(3)], axis=0))
+    scan = synth.raycast(segs, (6.0, 5.0, 0.3), rng)
+    src = oa.approx_voxel_filter(synth.to_xyzw(common.prep_scan(scan)), 0.05)
+    prm = common.params(resolution=0.5)
+    g, o = capi.Ndt(prm), oa.Oracle(prm)
+    g.set_target(tgt); g.set_source(src); o.set_target(tgt); o.set_source(src)
+    gi = g.grid_info()
+    assert gi.n_points / gi.n_leaves > 24          # dense enough to trigger the fine lattice
+    guess = [6.02, 4.97, 0.31]
+    a, b = g.align(guess), o.align(guess)
+    _assert_result_close(a, b)
+    # a source far outside the map still gets the exact answer (ring search gives up, exhaustive scan)
+    far = src.copy(); far[:, 1] += 300.0
+    g.set_source(far); o.set_source(far)
+    a, b = g.align([0.0, 0.0, 0.0]), o.align([0.0, 0.0, 0.0])
+    assert a.fitness == pytest.approx(b.fitness, rel=1e-9)

@@ -57,4 +57,4 @@ def test_scan_log_roundtrip_format(tmp_path):
     p = tmp_path / "log.txt"
     ha.write_scan_log(p, [(0.0, 0.0, 0.0), (0.1, 0.0, 1.0)], [np.array([[1.0, 2.0], [3.0, 4.0]]), np.array([[5.0, 6.0]])])
     lines = p.read_text().splitlines()
-    assert len(lines) == 4 + 2 * 4 and lines[4].startswith("0 0.0 0.0 0.0 ") and lines[5].startswith("2 1.0 2.0 3.0 4.0")
+    assert len(lines) == 4 + 2 * 4 and not p.read_text().endswith((" ", "\n")) and lines[4].startswith("0 0.0 0.0 0.0 ") and lines[5].startswith("2 1.0 2.0 3.0 4.0")
