@@ -27,7 +27,7 @@ int ensure_pinned(Handle *h, size_t bytes) {
   if (bytes <= h->pinned_cap) return 0;
   if (h->pinned) cudaFreeHost(h->pinned);
   h->pinned = nullptr; h->pinned_cap = 0;
-  size_t want = bytes + bytes / 4 + 4096;
+  size_t want = 2 * bytes + 4096;
   cudaError_t e = cudaMallocHost(&h->pinned, want);
   if (e != cudaSuccess) { set_err(h, NDT_ERR_CUDA, "cudaMallocHost", e); return 1; }
   h->pinned_cap = want;

@@ -16,8 +16,9 @@
 //   k_count     cell id per point (float32, bit-exact), warp-aggregated int atomics -> count + rank
 //   k_alloc     per dense cell: leaf ids and contiguous bucket ranges (warp-aggregated allocation)
 //   k_fill      scatter point indices into their leaf bucket
-//   k_rank      one thread per bucket entry: order every bucket by point index (rank by counting)
-//   k_finalize  one warp per leaf: accumulate in input order
+//   k_rank      one thread per bucket entry: order every bucket by point index (rank by counting) and
+//               write the points in bucket order
+//   k_finalize  one thread per leaf: walk the (contiguous) bucket in input order
 //               (fp32 centroid, fp64 sums), mean, single-pass covariance, 2x2 eigen clamp, inverse,
 //               64-byte record + cell->slot table
 #include "ndt_host.h"
@@ -104,53 +105,54 @@ __global__ void __launch_bounds__(256) k_count(const float4 *__restrict__ pts, i
   }
 }
 
-// pass 1b: walk the padded count table; every occupied cell gets a leaf id and a bucket range, and the
-// count table turns into the slot table (-1 everywhere until k_finalize fills in the tree members)
+// pass 1b: walk the padded count table row by row; every occupied cell gets a leaf id and a bucket
+// range, and the count table turns into the slot table (-1 everywhere until k_finalize fills in the tree
+// members); the probe table starts as all-NaN.
 __global__ void __launch_bounds__(256) k_alloc(int32_t *__restrict__ count_slot, float2 *__restrict__ cen, int div_x, int div_y,
                                               int32_t *__restrict__ leaf_id, int32_t *__restrict__ leaf_cell,
                                               int32_t *__restrict__ leaf_n, int32_t *__restrict__ leaf_start,
                                               int32_t *__restrict__ ctr) {
   const int lane = threadIdx.x & 31;
-  const int W = div_x + 4;
-  const int64_t n_pad = (int64_t)W * (div_y + 4);
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t n_round = ((n_pad + 31) / 32) * 32;
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_round; q += stride) {
-    int n = 0, cell = -1;
-    if (q < n_pad) {
-      const int r = (int)(q / W), c = (int)(q - (int64_t)r * W);
-      if (r >= 2 && r < div_y + 2 && c >= 2 && c < div_x + 2) {
-        cell = (r - 2) * div_x + (c - 2);
-        n = count_slot[q];
-      }
-    }
-    const bool has = n > 0;
-    const unsigned bal = __ballot_sync(0xffffffffu, has);
-    if (bal != 0u) {
-      int incl = n;
+  const int W = div_x + 4, H = div_y + 4;
+  const int warps_per_block = blockDim.x >> 5, warp_in_block = threadIdx.x >> 5;
+  const float qnan = __int_as_float(0x7fc00000);
+  for (int r = blockIdx.x; r < H; r += gridDim.x) {
+    const bool row_in = (r >= 2 && r < div_y + 2);
+    const size_t row0 = (size_t)r * W;
+    for (int c0 = warp_in_block * 32; c0 < W; c0 += warps_per_block * 32) {
+      const int c = c0 + lane;
+      const bool valid = c < W;
+      const bool interior = valid && row_in && c >= 2 && c < div_x + 2;
+      const int n = interior ? count_slot[row0 + c] : 0;
+      const bool has = n > 0;
+      const unsigned bal = __ballot_sync(0xffffffffu, has);
+      const int cell = interior ? (r - 2) * div_x + (c - 2) : -1;
+      if (bal != 0u) {
+        int incl = n;
 #pragma unroll
-      for (int dlt = 1; dlt < 32; dlt <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, dlt);
-        if (lane >= dlt) incl += t;
+        for (int dlt = 1; dlt < 32; dlt <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, dlt);
+          if (lane >= dlt) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int base_leaf = 0, base_pts = 0;
+        if (lane == 0) {
+          base_leaf = atomicAdd(ctr + CTR_LEAVES, __popc(bal));
+          base_pts = atomicAdd(ctr + CTR_PTS, total);
+        }
+        base_leaf = __shfl_sync(0xffffffffu, base_leaf, 0);
+        base_pts = __shfl_sync(0xffffffffu, base_pts, 0);
+        if (has) {
+          const int leaf = base_leaf + __popc(bal & ((1u << lane) - 1u));
+          leaf_id[cell] = leaf;
+          leaf_cell[leaf] = cell;
+          leaf_n[leaf] = n;
+          leaf_start[leaf] = base_pts + incl - n;
+        }
       }
-      const int total = __shfl_sync(0xffffffffu, incl, 31);
-      int base_leaf = 0, base_pts = 0;
-      if (lane == 0) {
-        base_leaf = atomicAdd(ctr + CTR_LEAVES, __popc(bal));
-        base_pts = atomicAdd(ctr + CTR_PTS, total);
-      }
-      base_leaf = __shfl_sync(0xffffffffu, base_leaf, 0);
-      base_pts = __shfl_sync(0xffffffffu, base_pts, 0);
-      if (has) {
-        const int leaf = base_leaf + __popc(bal & ((1u << lane) - 1u));
-        leaf_id[cell] = leaf;
-        leaf_cell[leaf] = cell;
-        leaf_n[leaf] = n;
-        leaf_start[leaf] = base_pts + incl - n;
-      }
+      if (interior && !has) leaf_id[cell] = -1;
+      if (valid) { count_slot[row0 + c] = -1; cen[row0 + c] = make_float2(qnan, qnan); }
     }
-    if (cell >= 0 && !has) leaf_id[cell] = -1;
-    if (q < n_pad) { count_slot[q] = -1; cen[q] = make_float2(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000)); }
   }
 }
 
@@ -175,7 +177,8 @@ __global__ void __launch_bounds__(256) k_rank(int64_t n, const int32_t *__restri
                                              const int32_t *__restrict__ leaf_id,
                                              const int32_t *__restrict__ leaf_start,
                                              const int32_t *__restrict__ leaf_n, const int32_t *__restrict__ list,
-                                             int32_t *__restrict__ sorted_idx, int32_t *__restrict__ ctr) {
+                                             const float4 *__restrict__ pts, int32_t *__restrict__ sorted_idx,
+                                             float2 *__restrict__ tgt_sorted, int32_t *__restrict__ ctr) {
   const int64_t n_bucketed = ctr[CTR_PTS];
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_bucketed; p += (int64_t)gridDim.x * blockDim.x) {
     const int v = list[p];
@@ -184,6 +187,8 @@ __global__ void __launch_bounds__(256) k_rank(int64_t n, const int32_t *__restri
     int r = 0;
     for (int j = 0; j < m; ++j) r += (__ldg(list + st + j) < v) ? 1 : 0;
     sorted_idx[st + r] = v;
+    const float4 pt = __ldg(pts + v);
+    tgt_sorted[st + r] = make_float2(pt.x, pt.y);     // points in bucket order: finalize and the 1-NN read them contiguously
   }
 }
 
@@ -213,45 +218,32 @@ __device__ inline void eig2(double a, double b, double d, double *lam, double *v
 
 struct FinalizeParams { int32_t min_points; double eig_mult; int32_t quirks; };
 
-// pass 2: one warp per leaf
-__global__ void __launch_bounds__(256) k_finalize(const float4 *__restrict__ pts,
-                                                 const int32_t *__restrict__ sorted_idx, float2 *__restrict__ tgt_sorted,
-                                                 int2 *__restrict__ leaf_range,
+// pass 2: one thread per leaf. The bucket is contiguous and already in input order (k_rank), so the
+// thread walks it sequentially: fp32 centroid and fp64 sums accumulate exactly like the reference's
+// pass 1, then mean, single-pass covariance, eigenvalue clamp, inverse.
+__global__ void __launch_bounds__(128) k_finalize(const float2 *__restrict__ tgt_sorted,
                                                  const int32_t *__restrict__ leaf_cell,
                                                  const int32_t *__restrict__ leaf_n,
-                                                 const int32_t *__restrict__ leaf_start,
+                                                 const int32_t *__restrict__ leaf_start, int2 *__restrict__ leaf_range,
                                                  int32_t *__restrict__ leaf_nr, double2 *__restrict__ leaf_mean,
                                                  double *__restrict__ leaf_icov, float2 *__restrict__ leaf_cen,
                                                  int32_t *__restrict__ slot, float2 *__restrict__ cen_tab,
                                                  CellRec *__restrict__ recs,
                                                  int32_t *__restrict__ ctr, FinalizeParams fp, int div_x) {
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int n_warps = (gridDim.x * blockDim.x) >> 5;
   const int n_leaves = ctr[CTR_LEAVES];
-  for (int leaf = warp; leaf < n_leaves; leaf += n_warps) {
+  for (int leaf = blockIdx.x * blockDim.x + threadIdx.x; leaf < n_leaves; leaf += gridDim.x * blockDim.x) {
     const int n = leaf_n[leaf], st = leaf_start[leaf];
-    // the bucket is already in input order (k_rank): accumulate sequentially; every lane keeps the same sums
+    leaf_range[leaf] = make_int2(st, n);
     double sx = 0, sy = 0, sxx = 0, syx = 0, syy = 0;
     float cx = 0.f, cy = 0.f;
-    for (int base = 0; base < n; base += 32) {
-      float px = 0.f, py = 0.f;
-      if (base + lane < n) {
-        const float4 p = __ldg(pts + sorted_idx[st + base + lane]);
-        px = p.x; py = p.y;
-        tgt_sorted[st + base + lane] = make_float2(px, py);
-      }
-      const int m = min(32, n - base);
-      for (int k = 0; k < m; ++k) {
-        const float x = __shfl_sync(0xffffffffu, px, k), y = __shfl_sync(0xffffffffu, py, k);
-        const double xd = (double)x, yd = (double)y;
-        sx += xd; sy += yd;
-        sxx += xd * xd; syx += yd * xd; syy += yd * yd;
-        cx = __fadd_rn(cx, x); cy = __fadd_rn(cy, y);
-      }
+    const float2 *__restrict__ bucket = tgt_sorted + st;
+    for (int k = 0; k < n; ++k) {
+      const float2 p = __ldg(bucket + k);
+      const double xd = (double)p.x, yd = (double)p.y;
+      sx += xd; sy += yd;
+      sxx += xd * xd; syx += yd * xd; syy += yd * yd;
+      cx = __fadd_rn(cx, p.x); cy = __fadd_rn(cy, p.y);
     }
-    if (lane != 0) continue;
-    leaf_range[leaf] = make_int2(st, n);
     const double nn = (double)n;
     cx = cx / (float)n; cy = cy / (float)n;
     const double psx = sx, psy = sy;
@@ -326,7 +318,7 @@ __global__ void __launch_bounds__(256) k_finalize(const float4 *__restrict__ pts
       r.cx = cx; r.cy = cy; r.nr_points = nr; r.cell = leaf_cell[leaf];
       r.mx = m0; r.my = m1; r.c00 = ic0; r.c01 = ic1; r.c10 = ic2; r.c11 = ic3;
       recs[s] = r;
-      const int cell = leaf_cell[leaf];
+      const int cell = r.cell;
       const int j = cell / div_x, i = cell - j * div_x;
       slot[(j + 2) * (div_x + 4) + i + 2] = s;
       cen_tab[(j + 2) * (div_x + 4) + i + 2] = make_float2(cx, cy);
@@ -433,8 +425,11 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace) {
   float mn[2] = {std::numeric_limits<float>::max(), std::numeric_limits<float>::max()};
   float mx[2] = {-std::numeric_limits<float>::max(), -std::numeric_limits<float>::max()};
   int64_t nfin = 0;
-  if (memspace != NDT_MEM_HOST && h->timing) cudaEventRecord(h->ev0, st);
-  if (memspace == NDT_MEM_HOST) {
+  // small host clouds are staged through pinned memory and get their bounds on the way; large ones are
+  // copied as they are and take the device bounds kernel (a scalar host pass over 10^5+ points costs more)
+  const bool stage_on_host = (memspace == NDT_MEM_HOST) && (n < 32768);
+  if (!stage_on_host && h->timing) cudaEventRecord(h->ev0, st);
+  if (stage_on_host) {
     // stage through pinned memory; bounds come for free while the points pass through the host cache
     if (ensure_pinned(h, npts * sizeof(float4))) return NDT_ERR_CUDA;
     float *stage = (float *)h->pinned;
@@ -455,7 +450,8 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace) {
     k_init_counters<<<1, 32, 0, st>>>(ctr, bounds);
     ++h->launches;
     if (n > 0) {
-      NDT_CUDA(h, cudaMemcpyAsync(gb.tgt.p, xyzw, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+      NDT_CUDA(h, cudaMemcpyAsync(gb.tgt.p, xyzw, (size_t)n * sizeof(float4),
+                                  memspace == NDT_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
       k_bounds<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(gb.tgt.as<float4>(), n, bounds, ctr);
       ++h->launches;
       int32_t hb[CTR_COUNT + 4];
@@ -515,7 +511,7 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace) {
   NDT_CUDA(h, cudaMemsetAsync(gb.slot.p, 0, npad * 4, st));
   k_count<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(gb.tgt.as<float4>(), n, d, gb.slot.as<int32_t>(),
                                                         gb.cell_of.as<int32_t>(), gb.rank_of.as<int32_t>());
-  k_alloc<<<grid_for((int64_t)npad, 256, h->sm_count), 256, 0, st>>>(gb.slot.as<int32_t>(), gb.cen.as<float2>(), gd.div_x, gd.div_y,
+  k_alloc<<<std::min(gd.div_y + 4, h->sm_count * 8), 256, 0, st>>>(gb.slot.as<int32_t>(), gb.cen.as<float2>(), gd.div_x, gd.div_y,
                                                                  gb.leaf_id.as<int32_t>(), gb.leaf_cell.as<int32_t>(),
                                                                  gb.leaf_n.as<int32_t>(), gb.leaf_start.as<int32_t>(), ctr);
   k_fill<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(n, gb.cell_of.as<int32_t>(), gb.rank_of.as<int32_t>(),
@@ -525,11 +521,11 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace) {
   const int64_t warps_needed = (int64_t)max_leaves;
   k_rank<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(n, gb.cell_of.as<int32_t>(), gb.leaf_id.as<int32_t>(),
                                                        gb.leaf_start.as<int32_t>(), gb.leaf_n.as<int32_t>(),
-                                                       gb.list.as<int32_t>(), gb.sorted_idx.as<int32_t>(), ctr);
-  k_finalize<<<grid_for(warps_needed * 32, 256, h->sm_count), 256, 0, st>>>(
-      gb.tgt.as<float4>(), gb.sorted_idx.as<int32_t>(), gb.tgt_sorted.as<float2>(),
-      gb.leaf_range.as<int2>(), gb.leaf_cell.as<int32_t>(),
-      gb.leaf_n.as<int32_t>(), gb.leaf_start.as<int32_t>(), gb.leaf_nr.as<int32_t>(), gb.leaf_mean.as<double2>(),
+                                                       gb.list.as<int32_t>(), gb.tgt.as<float4>(), gb.sorted_idx.as<int32_t>(),
+                                                       gb.tgt_sorted.as<float2>(), ctr);
+  k_finalize<<<grid_for(warps_needed, 128, h->sm_count, 16), 128, 0, st>>>(
+      gb.tgt_sorted.as<float2>(), gb.leaf_cell.as<int32_t>(),
+      gb.leaf_n.as<int32_t>(), gb.leaf_start.as<int32_t>(), gb.leaf_range.as<int2>(), gb.leaf_nr.as<int32_t>(), gb.leaf_mean.as<double2>(),
       gb.leaf_icov.as<double>(), gb.leaf_cen.as<float2>(), gb.slot.as<int32_t>(), gb.cen.as<float2>(), gb.recs.as<CellRec>(), ctr, fp, gd.div_x);
   h->launches += 5;
   NDT_CUDA(h, cudaMemcpyAsync(h->h_counters, ctr, sizeof(h->h_counters), cudaMemcpyDeviceToHost, st));

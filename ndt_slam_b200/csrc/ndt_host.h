@@ -18,7 +18,7 @@ struct DevBuf {
     if (bytes <= cap) return cudaSuccess;
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
-    size_t want = bytes + bytes / 4 + 256;
+    size_t want = 2 * bytes + 4096;     // geometric growth: a map that grows scan by scan reallocates O(log n) times
     cudaError_t e = cudaMalloc(&p, want);
     if (e == cudaSuccess) cap = want;
     return e;
