@@ -39,7 +39,7 @@ struct BlobHeader {
   uint64_t magic;
   GridDims gd;
   int32_t counters[CTR_COUNT];
-  int64_t off_slot, off_cen, off_recs, off_leaf_id, off_leaf_range, off_sorted, off_tgt, off_nn_range, off_nn_pts, total;
+  int64_t off_slot, off_cen, off_occ, off_recs, off_leaf_id, off_leaf_range, off_sorted, off_tgt, off_nn_range, off_nn_pts, total;
 };
 static constexpr uint64_t kBlobMagic = 0x4e44544232303042ull;  // "NDTB200B"
 
@@ -55,6 +55,7 @@ static BlobHeader blob_layout(const Handle *h) {
   const int64_t npad = nc > 0 ? (int64_t)(h->gd.div_x + 4) * (h->gd.div_y + 4) : 0;
   b.off_slot = o; o = align256(o + npad * 4);
   b.off_cen = o; o = align256(o + npad * 8);
+  b.off_occ = o; o = align256(o + ((npad + 31) / 32 + 1) * 4);
   b.off_recs = o; o = align256(o + nsl * (int64_t)sizeof(CellRec));
   b.off_leaf_id = o; o = align256(o + nc * 4);
   b.off_leaf_range = o; o = align256(o + nl * 8);
@@ -137,7 +138,7 @@ int ndt_destroy(ndt_handle hh) {
   GridBuffers &g = h->gb;
   DevBuf *all[] = {&g.tgt, &g.cell_of, &g.rank_of, &g.list, &g.sorted_idx, &g.slot, &g.leaf_id, &g.leaf_cell,
                    &g.leaf_n, &g.leaf_start, &g.leaf_nr, &g.leaf_mean, &g.leaf_icov, &g.leaf_cen, &g.recs,
-                   &g.counters, &g.cen, &g.nn_cnt, &g.nn_range, &g.nn_pts, &g.tgt_sorted, &g.leaf_range, &h->src, &h->scratch, &h->scratch2, &h->stage, &h->io};
+                   &g.counters, &g.cen, &g.occ, &g.nn_cnt, &g.nn_range, &g.nn_pts, &g.tgt_sorted, &g.leaf_range, &h->src, &h->scratch, &h->scratch2, &h->stage, &h->io};
   for (DevBuf *b : all) b->release();
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -454,6 +455,7 @@ int ndt_grid_export(ndt_handle hh, void *device_blob, int64_t bytes) {
   const int64_t npad = nc > 0 ? (int64_t)(h->gd.div_x + 4) * (h->gd.div_y + 4) : 0;
   NDT_CUDA(h, cp(b.off_slot, h->gb.slot, npad * 4));
   NDT_CUDA(h, cp(b.off_cen, h->gb.cen, npad * 8));
+  NDT_CUDA(h, cp(b.off_occ, h->gb.occ, npad > 0 ? ((npad + 31) / 32 + 1) * 4 : 0));
   NDT_CUDA(h, cp(b.off_recs, h->gb.recs, nsl * (int64_t)sizeof(CellRec)));
   NDT_CUDA(h, cp(b.off_leaf_id, h->gb.leaf_id, nc * 4));
   NDT_CUDA(h, cp(b.off_leaf_range, h->gb.leaf_range, nl * 8));
@@ -487,6 +489,7 @@ int ndt_grid_import(ndt_handle hh, const void *device_blob, int64_t bytes) {
   const int64_t npad = nc > 0 ? (int64_t)(h->gd.div_x + 4) * (h->gd.div_y + 4) : 0;
   NDT_CUDA(h, take(h->gb.slot, b.off_slot, npad * 4));
   NDT_CUDA(h, take(h->gb.cen, b.off_cen, npad * 8));
+  NDT_CUDA(h, take(h->gb.occ, b.off_occ, npad > 0 ? ((npad + 31) / 32 + 1) * 4 : 0));
   NDT_CUDA(h, take(h->gb.recs, b.off_recs, nsl * (int64_t)sizeof(CellRec)));
   NDT_CUDA(h, take(h->gb.leaf_id, b.off_leaf_id, nc * 4));
   NDT_CUDA(h, take(h->gb.leaf_range, b.off_leaf_range, nl * 8));

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(128) k_finalize(const float2 *__restrict__ tgt
                                                  int32_t *__restrict__ leaf_nr, double2 *__restrict__ leaf_mean,
                                                  double *__restrict__ leaf_icov, float2 *__restrict__ leaf_cen,
                                                  int32_t *__restrict__ slot, float2 *__restrict__ cen_tab,
-                                                 CellRec *__restrict__ recs,
+                                                 uint32_t *__restrict__ occ, CellRec *__restrict__ recs,
                                                  int32_t *__restrict__ ctr, FinalizeParams fp, int div_x) {
   const int n_leaves = ctr[CTR_LEAVES];
   for (int leaf = blockIdx.x * blockDim.x + threadIdx.x; leaf < n_leaves; leaf += gridDim.x * blockDim.x) {
@@ -320,8 +320,17 @@ __global__ void __launch_bounds__(128) k_finalize(const float2 *__restrict__ tgt
       recs[s] = r;
       const int cell = r.cell;
       const int j = cell / div_x, i = cell - j * div_x;
-      slot[(j + 2) * (div_x + 4) + i + 2] = s;
-      cen_tab[(j + 2) * (div_x + 4) + i + 2] = make_float2(cx, cy);
+      const int W = div_x + 4, q = (j + 2) * W + i + 2;
+      slot[q] = s;
+      cen_tab[q] = make_float2(cx, cy);
+      // dilated occupancy: every cell whose 3x3 block contains this tree cell
+#pragma unroll
+      for (int dj = -1; dj <= 1; ++dj)
+#pragma unroll
+        for (int di = -1; di <= 1; ++di) {
+          const int t = q + dj * W + di;
+          atomicOr(occ + (t >> 5), 1u << (t & 31));
+        }
     }
   }
 }
@@ -495,6 +504,9 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace) {
   const size_t npad = (size_t)(gd.div_x + 4) * (size_t)(gd.div_y + 4);
   NDT_CUDA(h, gb.slot.reserve(npad * 4));
   NDT_CUDA(h, gb.cen.reserve(npad * sizeof(float2)));
+  const size_t occ_words = (npad + 31) / 32 + 1;
+  NDT_CUDA(h, gb.occ.reserve(occ_words * 4));
+  NDT_CUDA(h, cudaMemsetAsync(gb.occ.p, 0, occ_words * 4, st));
   NDT_CUDA(h, gb.leaf_id.reserve(nc * 4));
   const size_t max_leaves = std::min(npts, nc);
   NDT_CUDA(h, gb.leaf_cell.reserve(max_leaves * 4));
@@ -526,7 +538,7 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace) {
   k_finalize<<<grid_for(warps_needed, 128, h->sm_count, 16), 128, 0, st>>>(
       gb.tgt_sorted.as<float2>(), gb.leaf_cell.as<int32_t>(),
       gb.leaf_n.as<int32_t>(), gb.leaf_start.as<int32_t>(), gb.leaf_range.as<int2>(), gb.leaf_nr.as<int32_t>(), gb.leaf_mean.as<double2>(),
-      gb.leaf_icov.as<double>(), gb.leaf_cen.as<float2>(), gb.slot.as<int32_t>(), gb.cen.as<float2>(), gb.recs.as<CellRec>(), ctr, fp, gd.div_x);
+      gb.leaf_icov.as<double>(), gb.leaf_cen.as<float2>(), gb.slot.as<int32_t>(), gb.cen.as<float2>(), gb.occ.as<uint32_t>(), gb.recs.as<CellRec>(), ctr, fp, gd.div_x);
   h->launches += 5;
   NDT_CUDA(h, cudaMemcpyAsync(h->h_counters, ctr, sizeof(h->h_counters), cudaMemcpyDeviceToHost, st));
   NDT_CUDA(h, cudaStreamSynchronize(st));
@@ -599,6 +611,7 @@ GridView grid_view(const Handle *h) {
   G.slot = gb.slot.as<int32_t>();
   G.slot_w = h->gd.div_x + 4;
   G.cen = gb.cen.as<float2>();
+  G.occ = gb.occ.as<uint32_t>();
   G.recs = gb.recs.as<CellRec>();
   G.min_bx = h->gd.min_bx; G.min_by = h->gd.min_by; G.div_x = h->gd.div_x; G.div_y = h->gd.div_y;
   G.inv_leaf = h->gd.inv_leaf; G.r2 = h->gd.r2; G.leaf = h->gd.leaf;

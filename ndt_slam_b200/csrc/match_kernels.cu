@@ -39,9 +39,10 @@ struct SmemSrc {
 // One cooperative objective pass. All threads of the group call pass<MODE>() with identical
 // arguments and leave with identical totals. Everything the hot loop touches is copied into
 // locals first (the object itself lives in local memory behind `this`).
-template <class Coop, class CenL, class SlotL, class RecL, class SrcL>
+template <class Coop, class OccL, class CenL, class SlotL, class RecL, class SrcL>
 struct Objective {
   ProbeGeom geom;
+  OccL occ;
   CenL cen;
   SlotL slot;
   RecL rec;
@@ -60,7 +61,7 @@ struct Objective {
     const PoseF pf = pose_to_float(p);
     const Coop co = coop;
     int pairs = 0;
-    accumulate_points<MODE>(geom, cen, slot, rec, src, co.rank(), co.size(), ns, pf, sse != 0, ac.cs, ac.sn, d1, d2,
+    accumulate_points<MODE>(geom, occ, cen, slot, rec, src, co.rank(), co.size(), ns, pf, sse != 0, ac.cs, ac.sn, d1, d2,
                             Q, acc, pairs);
     if (MODE == 0) co.template allreduce<13>(acc);
     else if (MODE == 1) co.template allreduce<4>(acc);
@@ -70,20 +71,22 @@ struct Objective {
   }
 };
 
-template <class Coop, class CenL, class SlotL, class RecL, class SrcL>
-__device__ __forceinline__ Objective<Coop, CenL, SlotL, RecL, SrcL> make_objective(
-    const GridView &G, const MatchParams &mp, const Coop &coop, CenL cen, SlotL slot, RecL rec, SrcL src, int ns,
+template <class Coop, class OccL, class CenL, class SlotL, class RecL, class SrcL>
+__device__ __forceinline__ Objective<Coop, OccL, CenL, SlotL, RecL, SrcL> make_objective(
+    const GridView &G, const MatchParams &mp, const Coop &coop, OccL occ, CenL cen, SlotL slot, RecL rec, SrcL src, int ns,
     HitQueue Q) {
-  return Objective<Coop, CenL, SlotL, RecL, SrcL>{probe_geom(G), cen, slot, rec, src, ns, mp.d1, mp.d2,
+  return Objective<Coop, OccL, CenL, SlotL, RecL, SrcL>{probe_geom(G), occ, cen, slot, rec, src, ns, mp.d1, mp.d2,
                                                   (mp.quirks & NDT_QUIRK_TRANSFORM_SSE_ORDER) ? 1 : 0, coop, Q};
 }
 
-// per-warp queue storage carved from static shared memory of the CTA (8 warps)
-struct QueueStore {
-  float4 xy[8][QCAP];
-  int cell[8][QCAP];
-  __device__ __forceinline__ HitQueue mine() { const int w = threadIdx.x >> 5; return HitQueue{xy[w], cell[w]}; }
-};
+// per-warp hit queues live at the start of the CTA's dynamic shared memory (8 warps per CTA)
+constexpr int QUEUE_BYTES = 8 * QUEUE_BYTES_PER_WARP;          // 51,200 B
+__device__ __forceinline__ HitQueue my_queue(unsigned char *smem) {
+  const int w = threadIdx.x >> 5;
+  float4 *xy = reinterpret_cast<float4 *>(smem) + w * QCAP;
+  int *cell = reinterpret_cast<int *>(smem + 8 * QCAP * 16) + w * QCAP;
+  return HitQueue{xy, cell};
+}
 
 template <class Coop, class SrcL>
 __device__ inline double fitness_pass(const GridView &G, const SrcL &src, int ns, const MatchParams &mp,
@@ -128,9 +131,9 @@ template <int MODE>
 __global__ void __launch_bounds__(256) k_eval_partial(GridView G, MatchParams mp, const float4 *__restrict__ src,
                                                      int ns, const double *__restrict__ poses, int slices,
                                                      double *__restrict__ partial, int *__restrict__ pairs_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double scratch[8 * NACC];
   __shared__ int s_pairs[8];
-  __shared__ QueueStore qs;
   const int pose_i = blockIdx.x / slices, slice = blockIdx.x % slices;
   const double p[3] = {poses[3 * pose_i], poses[3 * pose_i + 1], poses[3 * pose_i + 2]};
   AngleCache ac;
@@ -144,8 +147,8 @@ __global__ void __launch_bounds__(256) k_eval_partial(GridView G, MatchParams mp
   // slice s owns points [s * chunk, (s + 1) * chunk)
   const int chunk = (ns + slices - 1) / slices;
   const int lo = slice * chunk, hi = min(ns, lo + chunk);
-  accumulate_points<MODE>(probe_geom(G), GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, GlobalSrc{src},
-                          lo + (int)threadIdx.x, (int)blockDim.x, hi, pf, sse, ac.cs, ac.sn, mp.d1, mp.d2, qs.mine(),
+  accumulate_points<MODE>(probe_geom(G), GlobalOcc{G.occ}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, GlobalSrc{src},
+                          lo + (int)threadIdx.x, (int)blockDim.x, hi, pf, sse, ac.cs, ac.sn, mp.d1, mp.d2, my_queue(smem_raw),
                           acc, pairs);
   BlockCoop coop{scratch};
   coop.allreduce<NACC>(acc);
@@ -190,7 +193,6 @@ __global__ void __launch_bounds__(256) k_align_block(GridView G, MatchParams mp,
                                                     ndt_result *__restrict__ out, int n_slots, int n_cells) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double scratch[8 * NACC];
-  __shared__ QueueStore qs;
   BlockCoop coop{scratch};
   const int job = blockIdx.x;
   const double guess[3] = {guesses[3 * job], guesses[3 * job + 1], guesses[3 * job + 2]};
@@ -198,18 +200,20 @@ __global__ void __launch_bounds__(256) k_align_block(GridView G, MatchParams mp,
   MatchOut mo;
   if (TILE) {
     // stage the local map tile (here: the whole grid) in shared memory: records first (64-B aligned), then slots
-    CellRec *s_recs = reinterpret_cast<CellRec *>(smem_raw);
-    float2 *s_cen = reinterpret_cast<float2 *>(smem_raw + (size_t)n_slots * sizeof(CellRec));
+    CellRec *s_recs = reinterpret_cast<CellRec *>(smem_raw + QUEUE_BYTES);
+    float2 *s_cen = reinterpret_cast<float2 *>(smem_raw + QUEUE_BYTES + (size_t)n_slots * sizeof(CellRec));
     int32_t *s_slot = reinterpret_cast<int32_t *>(s_cen + n_cells);
+    uint32_t *s_occ = reinterpret_cast<uint32_t *>(s_slot + n_cells);
+    for (int i = threadIdx.x; i < (n_cells + 31) / 32 + 1; i += blockDim.x) s_occ[i] = __ldg(G.occ + i);
     const int4 *gr = reinterpret_cast<const int4 *>(G.recs);
     int4 *sr = reinterpret_cast<int4 *>(s_recs);
     for (int i = threadIdx.x; i < n_slots * 4; i += blockDim.x) sr[i] = __ldg(gr + i);
     for (int i = threadIdx.x; i < n_cells; i += blockDim.x) { s_cen[i] = __ldg(G.cen + i); s_slot[i] = __ldg(G.slot + i); }
     __syncthreads();
-    auto obj = make_objective(G, mp, coop, SmemCen{s_cen}, SmemSlot{s_slot}, SmemRec{s_recs}, gsrc, ns, qs.mine());
+    auto obj = make_objective(G, mp, coop, SmemOcc{s_occ}, SmemCen{s_cen}, SmemSlot{s_slot}, SmemRec{s_recs}, gsrc, ns, my_queue(smem_raw));
     match_device(obj, mp, guess, mo);
   } else {
-    auto obj = make_objective(G, mp, coop, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, qs.mine());
+    auto obj = make_objective(G, mp, coop, GlobalOcc{G.occ}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, my_queue(smem_raw));
     match_device(obj, mp, guess, mo);
   }
   double fsum = 0.0;
@@ -248,16 +252,16 @@ struct ClusterCoop {
 __global__ void __launch_bounds__(256) k_align_cluster(GridView G, MatchParams mp, const float4 *__restrict__ src,
                                                       int ns, const double *__restrict__ guesses,
                                                       ndt_result *__restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double scratch[8 * NACC];
   __shared__ double xchg[NACC];
-  __shared__ QueueStore qs;
   cg::cluster_group cluster = cg::this_cluster();
   ClusterCoop coop{scratch, xchg, (int)cluster.block_rank(), (int)cluster.num_blocks()};
   const int job = blockIdx.x / coop.csize;
   const double guess[3] = {guesses[3 * job], guesses[3 * job + 1], guesses[3 * job + 2]};
   const GlobalSrc gsrc{src};
   MatchOut mo;
-  auto obj = make_objective(G, mp, coop, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, qs.mine());
+  auto obj = make_objective(G, mp, coop, GlobalOcc{G.occ}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, my_queue(smem_raw));
   match_device(obj, mp, guess, mo);
   double fsum = 0.0;
   if (mp.want_fitness) fsum = fitness_pass(G, gsrc, ns, mp, mo.p, coop);
@@ -274,17 +278,20 @@ template <bool SRC_SMEM>
 __global__ void __launch_bounds__(256, NDT_WARP_KERNEL_MIN_CTAS) k_align_warp(GridView G, MatchParams mp, const float4 *__restrict__ src,
                                                    int ns, const double *__restrict__ guesses,
                                                    ndt_result *__restrict__ out, int64_t n_jobs,
-                                                   int32_t *__restrict__ job_counter) {
+                                                   int32_t *__restrict__ job_counter, int occ_words) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ QueueStore qs;
-  float2 *s_src = reinterpret_cast<float2 *>(smem_raw);
+  // dynamic shared memory: hit queues | occupancy bitmap (occ_words, 0 = left in global) | source points
+  uint32_t *s_occ = reinterpret_cast<uint32_t *>(smem_raw + QUEUE_BYTES);
+  for (int i = threadIdx.x; i < occ_words; i += blockDim.x) s_occ[i] = __ldg(G.occ + i);
+  const uint32_t *occ_ptr = occ_words > 0 ? s_occ : G.occ;
+  float2 *s_src = reinterpret_cast<float2 *>(smem_raw + QUEUE_BYTES + ((occ_words * 4 + 15) & ~15));
   if (SRC_SMEM) {
     for (int i = threadIdx.x; i < ns; i += blockDim.x) {
       const float4 v = __ldg(src + i);
       s_src[i] = make_float2(v.x, v.y);
     }
-    __syncthreads();
   }
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   WarpCoop coop{lane};
   const GlobalSrc gsrc{src};
@@ -298,11 +305,11 @@ __global__ void __launch_bounds__(256, NDT_WARP_KERNEL_MIN_CTAS) k_align_warp(Gr
     MatchOut mo;
     double fsum = 0.0;
     if (SRC_SMEM) {
-      auto obj = make_objective(G, mp, coop, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, ssrc, ns, qs.mine());
+      auto obj = make_objective(G, mp, coop, SmemOcc{occ_ptr}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, ssrc, ns, my_queue(smem_raw));
       match_device(obj, mp, guess, mo);
       if (mp.want_fitness) fsum = fitness_pass(G, ssrc, ns, mp, mo.p, coop);
     } else {
-      auto obj = make_objective(G, mp, coop, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, qs.mine());
+      auto obj = make_objective(G, mp, coop, SmemOcc{occ_ptr}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, my_queue(smem_raw));
       match_device(obj, mp, guess, mo);
       if (mp.want_fitness) fsum = fitness_pass(G, gsrc, ns, mp, mo.p, coop);
     }
@@ -401,10 +408,12 @@ int launch_eval(Handle *h, const double *d_poses, int64_t n, int want_hessian, d
   const MatchParams mp = match_params(h, false);
   const float4 *src = h->src.as<float4>();
   if (h->timing) cudaEventRecord(h->ev0, st);
+  NDT_CUDA(h, cudaFuncSetAttribute(k_eval_partial<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, QUEUE_BYTES));
+  NDT_CUDA(h, cudaFuncSetAttribute(k_eval_partial<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, QUEUE_BYTES));
   if (want_hessian)
-    k_eval_partial<0><<<(unsigned)blocks, 256, 0, st>>>(G, mp, src, ns, d_poses, slices, h->scratch.as<double>(), h->scratch2.as<int>());
+    k_eval_partial<0><<<(unsigned)blocks, 256, QUEUE_BYTES, st>>>(G, mp, src, ns, d_poses, slices, h->scratch.as<double>(), h->scratch2.as<int>());
   else
-    k_eval_partial<1><<<(unsigned)blocks, 256, 0, st>>>(G, mp, src, ns, d_poses, slices, h->scratch.as<double>(), h->scratch2.as<int>());
+    k_eval_partial<1><<<(unsigned)blocks, 256, QUEUE_BYTES, st>>>(G, mp, src, ns, d_poses, slices, h->scratch.as<double>(), h->scratch2.as<int>());
   k_eval_final<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(h->scratch.as<double>(), h->scratch2.as<int>(), slices, n, d_out14, d_pairs);
   h->launches += 2;
   if (h->timing) cudaEventRecord(h->ev1, st);
@@ -425,15 +434,19 @@ int launch_align(Handle *h, const double *d_guesses, int64_t n, ndt_result *d_re
     // batch: persistent CTAs, one warp per match
     NDT_CUDA(h, cudaMemsetAsync(ctr + CTR_JOB, 0, sizeof(int32_t), st));
     const bool src_smem = (size_t)ns * sizeof(float2) <= 64 * 1024;
-    const size_t smem = src_smem ? (size_t)ns * sizeof(float2) : 0;
+    const int64_t npad = h->gd.n_cells > 0 ? (int64_t)(h->gd.div_x + 4) * (h->gd.div_y + 4) : 0;
+    int occ_words = (int)((npad + 31) / 32 + 1);
+    if ((size_t)occ_words * 4 > 64 * 1024) occ_words = 0;          // large grids: bitmap stays in global memory / L1
+    const size_t smem = QUEUE_BYTES + (((size_t)occ_words * 4 + 15) & ~size_t(15)) + (src_smem ? (size_t)ns * sizeof(float2) : 0);
     const int ctas_per_sm = NDT_WARP_KERNEL_MIN_CTAS;
     int64_t grid = (int64_t)h->sm_count * ctas_per_sm;
     grid = std::min<int64_t>(grid, (n + 7) / 8);
     if (src_smem) {
       NDT_CUDA(h, cudaFuncSetAttribute(k_align_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_align_warp<true><<<(unsigned)grid, 256, smem, st>>>(G, mp, src, ns, d_guesses, d_results, n, ctr + CTR_JOB);
+      k_align_warp<true><<<(unsigned)grid, 256, smem, st>>>(G, mp, src, ns, d_guesses, d_results, n, ctr + CTR_JOB, occ_words);
     } else {
-      k_align_warp<false><<<(unsigned)grid, 256, 0, st>>>(G, mp, src, ns, d_guesses, d_results, n, ctr + CTR_JOB);
+      NDT_CUDA(h, cudaFuncSetAttribute(k_align_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_align_warp<false><<<(unsigned)grid, 256, smem, st>>>(G, mp, src, ns, d_guesses, d_results, n, ctr + CTR_JOB, occ_words);
     }
   } else if (ns > 4096) {
     // large source cloud: spread one match over a thread-block cluster (DSMEM reduction)
@@ -445,7 +458,8 @@ int launch_align(Handle *h, const double *d_guesses, int64_t n, ndt_result *d_re
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(n * csize));
     cfg.blockDim = dim3(256);
-    cfg.dynamicSmemBytes = 0;
+    NDT_CUDA(h, cudaFuncSetAttribute(k_align_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, QUEUE_BYTES));
+    cfg.dynamicSmemBytes = QUEUE_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -455,13 +469,14 @@ int launch_align(Handle *h, const double *d_guesses, int64_t n, ndt_result *d_re
   } else {
     const int n_slots = h->h_counters[CTR_SLOTS];
     const int n_cells = h->gd.n_cells > 0 ? (h->gd.div_x + 4) * (h->gd.div_y + 4) : 0;   // padded table
-    const size_t tile = (size_t)n_slots * sizeof(CellRec) + (size_t)n_cells * (sizeof(float2) + sizeof(int32_t));
-    const size_t budget = (size_t)h->max_smem_optin > 4096 ? (size_t)h->max_smem_optin - 4096 : 0;
+    const size_t tile = (size_t)n_slots * sizeof(CellRec) + (size_t)n_cells * (sizeof(float2) + sizeof(int32_t)) + ((size_t)(n_cells + 31) / 32 + 1) * 4;
+    const size_t budget = (size_t)h->max_smem_optin > 4096 + QUEUE_BYTES ? (size_t)h->max_smem_optin - 4096 - QUEUE_BYTES : 0;
     if (tile > 0 && tile <= budget) {
-      NDT_CUDA(h, cudaFuncSetAttribute(k_align_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile));
-      k_align_block<true><<<(unsigned)n, 256, tile, st>>>(G, mp, src, ns, d_guesses, d_results, n_slots, n_cells);
+      NDT_CUDA(h, cudaFuncSetAttribute(k_align_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(tile + QUEUE_BYTES)));
+      k_align_block<true><<<(unsigned)n, 256, tile + QUEUE_BYTES, st>>>(G, mp, src, ns, d_guesses, d_results, n_slots, n_cells);
     } else {
-      k_align_block<false><<<(unsigned)n, 256, 0, st>>>(G, mp, src, ns, d_guesses, d_results, n_slots, n_cells);
+      NDT_CUDA(h, cudaFuncSetAttribute(k_align_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, QUEUE_BYTES));
+      k_align_block<false><<<(unsigned)n, 256, QUEUE_BYTES, st>>>(G, mp, src, ns, d_guesses, d_results, n_slots, n_cells);
     }
   }
   ++h->launches;

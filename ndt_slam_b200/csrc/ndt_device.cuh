@@ -37,6 +37,8 @@ struct GridView {
   const int32_t *__restrict__ slot;     // [(div_x + 4) * (div_y + 4)] padded by 2 cells of -1 on every side:
                                         // cell (i, j) lives at (j + 2) * slot_w + i + 2; value = record index or -1
   int32_t slot_w;                       // div_x + 4
+  const uint32_t *__restrict__ occ;     // 1 bit per padded cell: some tree cell lies in the 3x3 block around it
+                                        // (dilated occupancy: a clear bit means the point cannot hit anything)
   const float2 *__restrict__ cen;       // same padded indexing: float32 centroid of tree cells, NaN elsewhere
                                         // (the probe is one load + a float compare: NaN < r2 is false)
   const CellRec *__restrict__ recs;     // compact records of cells with n >= min_points
@@ -120,7 +122,8 @@ __device__ __forceinline__ float dist2f(float ax, float ay, float bx, float by) 
 //          with a handful of active lanes (k = 0.3 .. 2 hits per point spread over 9 positions).
 // ------------------------------------------------------------------------------------------------
 constexpr int NACC = 13;
-constexpr int QCAP = 128;           // per-warp queue capacity: < 32 queued before a row is probed, a row adds <= 96
+constexpr int QCAP = 320;           // per-warp ring capacity: < 32 queued before a step is probed, a step adds <= 9 * 32
+constexpr int QUEUE_BYTES_PER_WARP = QCAP * (16 + 4);
 
 struct HitQueue {
   float4 *xy;     // [QCAP] xt, yt (transformed, float32), xf, yf (original)
@@ -182,76 +185,99 @@ __device__ __forceinline__ ProbeGeom probe_geom(const GridView &G) {
 // is lane-contiguous inside a warp (first = warp_first + lane): every lane of a warp iterates the same
 // number of times. acc must be a register array of the caller. pairs: warp-uniform hit count.
 //
-// Written as a small warp-uniform state machine so that the probe code and the fp64 hit path each
-// exist exactly once in the instruction stream (the matcher is instruction-cache sensitive).
-template <int MODE, class CenL, class SlotL, class RecL, class SrcL>
-__device__ __forceinline__ void accumulate_points(const ProbeGeom g, const CenL cen_at, const SlotL slot_at,
+// One warp step = 32 points. Probe: all nine centroid loads are issued back to back (no bounds checks:
+// padded table; no emptiness branch: NaN centroids fail the compare), giving a 9-bit hit mask per lane;
+// one warp prefix scan turns the per-lane hit counts into ring offsets. Drain: see above. The loop is a
+// warp-uniform state machine with a single drain site, so the fp64 hit path exists once in the
+// instruction stream (the matcher is instruction-cache sensitive).
+template <int MODE, class OccL, class CenL, class SlotL, class RecL, class SrcL>
+__device__ __forceinline__ void accumulate_points(const ProbeGeom g, const OccL occ_at, const CenL cen_at, const SlotL slot_at,
                                                   const RecL rec_at, const SrcL src, const int first,
                                                   const int stride, const int hi, const PoseF pf,
                                                   const bool sse_order, const double cs, const double sn,
                                                   const double d1, const double d2, const HitQueue Q, double *acc,
                                                   int &pairs) {
   const int lane = threadIdx.x & 31;
-  const unsigned lt = (1u << lane) - 1u;
   int qhead = 0, qn = 0;
   int i0 = first - lane;
-  int row = 3;                       // 3: fetch the next point; 0..2: probe that row of the 3x3 block
-  int base = 0;                      // padded-table index of the point's own cell (0 = a border cell: all NaN)
-  float xt = 0.f, yt = 0.f, xf = 0.f, yf = 0.f;
   for (;;) {
-    const bool done = (row == 3) && (i0 >= hi);
+    const bool done = (i0 >= hi);
     if (qn >= 32 || (done && qn > 0)) {
       // drain: every lane pops one queued (point, cell) hit and runs the fp64 hit path converged
       const int n = min(qn, 32);
       __syncwarp();
       if (lane < n) {
-        const int pos = (qhead + lane) & (QCAP - 1);
+        int pos = qhead + lane;
+        if (pos >= QCAP) pos -= QCAP;
         hit_path<MODE>(rec_at, Q.xy[pos], slot_at(Q.cell[pos]), cs, sn, d1, d2, acc);
       }
       __syncwarp();
-      qhead = (qhead + n) & (QCAP - 1);
+      qhead += n;
+      if (qhead >= QCAP) qhead -= QCAP;
       qn -= n;
       pairs += n;
       continue;
     }
     if (done) break;
-    if (row == 3) {
-      const int i = i0 + lane;
-      i0 += stride;
-      row = 0;
-      base = g.W + 1;                // (1, 1) of the padded table: its 3x3 block is all border (NaN)
-      if (i < hi) {
-        const float2 xy = src(i);
-        xf = xy.x; yf = xy.y;
-        xform(pf, sse_order, xf, yf, xt, yt);
-        const int ci = cell_coord(xt, g.inv_leaf, g.min_bx);
-        const int cj = cell_coord(yt, g.inv_leaf, g.min_by);
-        if (ci >= -1 && cj >= -1 && ci <= g.div_x && cj <= g.div_y) base = (cj + 2) * g.W + ci + 2;
+    // ---- probe one warp step ----
+    const int i = i0 + lane;
+    i0 += stride;
+    int base = 0;
+    bool cand = false;               // can this point hit anything at all? (dilated occupancy bit of its own cell)
+    float xt = 0.f, yt = 0.f, xf = 0.f, yf = 0.f;
+    if (i < hi) {
+      const float2 xy = src(i);
+      xf = xy.x; yf = xy.y;
+      xform(pf, sse_order, xf, yf, xt, yt);
+      const int ci = cell_coord(xt, g.inv_leaf, g.min_bx);
+      const int cj = cell_coord(yt, g.inv_leaf, g.min_by);
+      if (ci >= -1 && cj >= -1 && ci <= g.div_x && cj <= g.div_y) {
+        base = (cj + 2) * g.W + ci + 2;
+        cand = (occ_at(base >> 5) >> (base & 31)) & 1u;
       }
     }
-    // probe one row of the 3x3 block: three adjacent centroids, branch-free (NaN = not a tree cell)
-    const int r = base + (row - 1) * g.W;
-    const float2 c0 = cen_at(r - 1), c1 = cen_at(r), c2 = cen_at(r + 1);
-    ++row;
-    const bool h0 = dist2f(xt, yt, c0.x, c0.y) < g.r2;
-    const bool h1 = dist2f(xt, yt, c1.x, c1.y) < g.r2;
-    const bool h2 = dist2f(xt, yt, c2.x, c2.y) < g.r2;
-    const unsigned m0 = __ballot_sync(0xffffffffu, h0);
-    const unsigned m1 = __ballot_sync(0xffffffffu, h1);
-    const unsigned m2 = __ballot_sync(0xffffffffu, h2);
-    if ((m0 | m1 | m2) != 0u) {
-      const int n0 = __popc(m0), n1 = __popc(m1);
-      const int b0 = qhead + qn;
-      if (h0) { const int pos = (b0 + __popc(m0 & lt)) & (QCAP - 1); Q.xy[pos] = make_float4(xt, yt, xf, yf); Q.cell[pos] = r - 1; }
-      if (h1) { const int pos = (b0 + n0 + __popc(m1 & lt)) & (QCAP - 1); Q.xy[pos] = make_float4(xt, yt, xf, yf); Q.cell[pos] = r; }
-      if (h2) { const int pos = (b0 + n0 + n1 + __popc(m2 & lt)) & (QCAP - 1); Q.xy[pos] = make_float4(xt, yt, xf, yf); Q.cell[pos] = r + 1; }
-      qn += n0 + n1 + __popc(m2);
+    if (!__any_sync(0xffffffffu, cand)) continue;      // open space for all 32 points: nothing to probe
+    unsigned mask = 0u;
+    if (cand) {
+      float2 c[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) c[k] = cen_at(base + (k / 3 - 1) * g.W + (k % 3 - 1));
+#pragma unroll
+      for (int k = 0; k < 9; ++k) mask |= (dist2f(xt, yt, c[k].x, c[k].y) < g.r2) ? (1u << k) : 0u;
+    }
+    if (__any_sync(0xffffffffu, mask != 0u)) {
+      const int cnt = __popc(mask);
+      int incl = cnt;
+#pragma unroll
+      for (int dlt = 1; dlt < 32; dlt <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, dlt);
+        if (lane >= dlt) incl += t;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      int pos = qhead + qn + incl - cnt;
+      if (pos >= QCAP) pos -= QCAP;
+      while (mask) {
+        const int k = __ffs(mask) - 1;
+        mask &= mask - 1u;
+        Q.xy[pos] = make_float4(xt, yt, xf, yf);
+        Q.cell[pos] = base + (k / 3 - 1) * g.W + (k % 3 - 1);
+        if (++pos == QCAP) pos = 0;
+      }
+      qn += total;
     }
   }
   __syncwarp();
 }
 
 // global-memory accessors (read-only path, L1/L2 cached)
+struct GlobalOcc {
+  const uint32_t *__restrict__ p;
+  __device__ __forceinline__ uint32_t operator()(int w) const { return __ldg(p + w); }
+};
+struct SmemOcc {
+  const uint32_t *p;
+  __device__ __forceinline__ uint32_t operator()(int w) const { return p[w]; }
+};
 struct GlobalCen {
   const float2 *__restrict__ p;
   __device__ __forceinline__ float2 operator()(int i) const { return __ldg(p + i); }

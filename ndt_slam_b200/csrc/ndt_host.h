@@ -43,6 +43,7 @@ struct GridBuffers {
   DevBuf nn_pts;       // float2[n]       target (x, y) in fine-bucket order
   DevBuf slot;         // int32[padded]   count during the build, then cell -> record slot
   DevBuf cen;          // float2[padded]  probe table: float32 centroid of tree cells, NaN elsewhere
+  DevBuf occ;          // uint32[padded/32] dilated occupancy bitmap (3x3 block contains a tree cell)
   DevBuf leaf_id;      // int32[n_cells]  cell -> leaf or -1
   DevBuf leaf_cell;    // int32[n]        per leaf: cell index
   DevBuf leaf_n;       // int32[n]
