@@ -57,7 +57,7 @@ static BlobHeader blob_layout(const Handle *h) {
   b.off_cen = o; o = align256(o + npad * 8);
   b.off_occ = o; o = align256(o + ((npad + 31) / 32 + 1) * 4);
   b.off_recs = o; o = align256(o + nsl * (int64_t)sizeof(CellRec));
-  b.off_leaf_id = o; o = align256(o + nc * 4);
+  b.off_leaf_id = o; o = align256(o + npad * 4);
   b.off_leaf_range = o; o = align256(o + nl * 8);
   b.off_sorted = o; o = align256(o + nt * 8);
   b.off_tgt = o; o = align256(o + nt * (int64_t)sizeof(float4));
@@ -138,7 +138,7 @@ int ndt_destroy(ndt_handle hh) {
   GridBuffers &g = h->gb;
   DevBuf *all[] = {&g.tgt, &g.cell_of, &g.rank_of, &g.list, &g.sorted_idx, &g.slot, &g.leaf_id, &g.leaf_cell,
                    &g.leaf_n, &g.leaf_start, &g.leaf_nr, &g.leaf_mean, &g.leaf_icov, &g.leaf_cen, &g.recs,
-                   &g.counters, &g.cen, &g.occ, &g.nn_cnt, &g.nn_range, &g.nn_pts, &g.tgt_sorted, &g.leaf_range, &h->src, &h->scratch, &h->scratch2, &h->stage, &h->io};
+                   &g.counters, &g.leaf_pair, &g.dims, &g.pair_off, &g.cen, &g.occ, &g.nn_cnt, &g.nn_range, &g.nn_pts, &g.tgt_sorted, &g.leaf_range, &h->src, &h->scratch, &h->scratch2, &h->stage, &h->io};
   for (DevBuf *b : all) b->release();
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -189,6 +189,11 @@ int ndt_grid_readback(ndt_handle hh, int64_t cap, int32_t *cell_idx, int32_t *nr
   NDT_CUDA(h, cudaMemcpyAsync(icov.data(), h->gb.leaf_icov.p, nl * 32, cudaMemcpyDeviceToHost, st));
   NDT_CUDA(h, cudaMemcpyAsync(cen.data(), h->gb.leaf_cen.p, nl * 8, cudaMemcpyDeviceToHost, st));
   NDT_CUDA(h, cudaStreamSynchronize(st));
+  // leaves are stored by their position in the padded table: convert to PCL's ijk0 + ijk1 * div_x
+  {
+    const int W = h->gd.div_x + 4, dx = h->gd.div_x;
+    for (int64_t k = 0; k < nl; ++k) { const int q = cell[k], r = q / W, c = q - r * W; cell[k] = (r - 2) * dx + (c - 2); }
+  }
   // PCL keeps leaves in a std::map keyed by cell index: report in that order
   std::vector<int64_t> order(nl);
   std::iota(order.begin(), order.end(), 0);
@@ -457,7 +462,7 @@ int ndt_grid_export(ndt_handle hh, void *device_blob, int64_t bytes) {
   NDT_CUDA(h, cp(b.off_cen, h->gb.cen, npad * 8));
   NDT_CUDA(h, cp(b.off_occ, h->gb.occ, npad > 0 ? ((npad + 31) / 32 + 1) * 4 : 0));
   NDT_CUDA(h, cp(b.off_recs, h->gb.recs, nsl * (int64_t)sizeof(CellRec)));
-  NDT_CUDA(h, cp(b.off_leaf_id, h->gb.leaf_id, nc * 4));
+  NDT_CUDA(h, cp(b.off_leaf_id, h->gb.leaf_id, npad * 4));
   NDT_CUDA(h, cp(b.off_leaf_range, h->gb.leaf_range, nl * 8));
   NDT_CUDA(h, cp(b.off_sorted, h->gb.tgt_sorted, nt * 8));
   NDT_CUDA(h, cp(b.off_tgt, h->gb.tgt, nt * (int64_t)sizeof(float4)));
@@ -491,7 +496,7 @@ int ndt_grid_import(ndt_handle hh, const void *device_blob, int64_t bytes) {
   NDT_CUDA(h, take(h->gb.cen, b.off_cen, npad * 8));
   NDT_CUDA(h, take(h->gb.occ, b.off_occ, npad > 0 ? ((npad + 31) / 32 + 1) * 4 : 0));
   NDT_CUDA(h, take(h->gb.recs, b.off_recs, nsl * (int64_t)sizeof(CellRec)));
-  NDT_CUDA(h, take(h->gb.leaf_id, b.off_leaf_id, nc * 4));
+  NDT_CUDA(h, take(h->gb.leaf_id, b.off_leaf_id, npad * 4));
   NDT_CUDA(h, take(h->gb.leaf_range, b.off_leaf_range, nl * 8));
   NDT_CUDA(h, take(h->gb.tgt_sorted, b.off_sorted, nt * 8));
   NDT_CUDA(h, take(h->gb.tgt, b.off_tgt, nt * (int64_t)sizeof(float4)));

@@ -74,59 +74,78 @@ __global__ void __launch_bounds__(256) k_bounds(const float4 *__restrict__ pts, 
 
 struct Dims { int32_t min_bx, min_by, div_x, div_y; float inv_leaf; };
 
-// pass 1a: cell of each point + a unique rank inside the cell (warp-aggregated int atomics)
-__global__ void __launch_bounds__(256) k_count(const float4 *__restrict__ pts, int64_t n, Dims d,
+// Which grid does point i belong to? (batched scan pairs: point ranges per pair; one grid: always 0)
+__device__ __forceinline__ int pair_of(const int64_t *__restrict__ off, int n_pairs, int64_t i) {
+  if (n_pairs <= 1) return 0;
+  int lo = 0, hi = n_pairs;               // off[lo] <= i < off[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(off + mid) <= i) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// pass 1a: cell of each point + a unique rank inside the cell (warp-aggregated int atomics).
+// All grids share one padded table; grid g owns entries [dims[g].base, dims[g].base + W*H).
+__global__ void __launch_bounds__(256) k_count(const float4 *__restrict__ pts, int64_t n,
+                                              const int64_t *__restrict__ off, int n_pairs,
+                                              const PairDims *__restrict__ dims, float inv_leaf,
                                               int32_t *__restrict__ count, int32_t *__restrict__ cell_of,
                                               int32_t *__restrict__ rank_of) {
   const int lane = threadIdx.x & 31;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t n_round = ((n + 31) / 32) * 32;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-    int cell = -1, pcell = -1;
+    int pcell = -1;
     if (i < n) {
       const float4 p = __ldg(pts + i);
       if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
-        const int i0 = cell_coord(p.x, d.inv_leaf, d.min_bx);
-        const int i1 = cell_coord(p.y, d.inv_leaf, d.min_by);
-        cell = i0 + i1 * d.div_x;
-        pcell = (i1 + 2) * (d.div_x + 4) + i0 + 2;     // position in the padded count / slot table
+        const PairDims d = dims[pair_of(off, n_pairs, i)];
+        if (d.div_x > 0) {
+          const int i0 = cell_coord(p.x, inv_leaf, d.min_bx);
+          const int i1 = cell_coord(p.y, inv_leaf, d.min_by);
+          pcell = d.base + (i1 + 2) * d.W + i0 + 2;     // position in the shared padded count / slot table
+        }
       }
     }
     // lanes of this warp that hit the same cell share one atomic
-    const unsigned grp = __match_any_sync(0xffffffffu, cell);
+    const unsigned grp = __match_any_sync(0xffffffffu, pcell);
     const int leader = __ffs(grp) - 1;
     int base = 0;
-    if (cell >= 0 && lane == leader) base = atomicAdd(count + pcell, __popc(grp));
+    if (pcell >= 0 && lane == leader) base = atomicAdd(count + pcell, __popc(grp));
     base = __shfl_sync(0xffffffffu, base, leader);
     if (i < n) {
-      cell_of[i] = cell;
+      cell_of[i] = pcell;
       rank_of[i] = base + __popc(grp & ((1u << lane) - 1u));
     }
   }
 }
 
-// pass 1b: walk the padded count table row by row; every occupied cell gets a leaf id and a bucket
-// range, and the count table turns into the slot table (-1 everywhere until k_finalize fills in the tree
-// members); the probe table starts as all-NaN.
-__global__ void __launch_bounds__(256) k_alloc(int32_t *__restrict__ count_slot, float2 *__restrict__ cen, int div_x, int div_y,
+// pass 1b: walk the padded count tables row by row (blockIdx.x = grid * chunks + chunk); every occupied
+// cell gets a leaf id and a bucket range, the count table turns into the slot table (-1 everywhere until
+// k_finalize fills in the tree members), the probe table starts as all-NaN and leaf_id as all -1.
+__global__ void __launch_bounds__(256) k_alloc(int32_t *__restrict__ count_slot, float2 *__restrict__ cen,
+                                              const PairDims *__restrict__ dims, int chunks,
                                               int32_t *__restrict__ leaf_id, int32_t *__restrict__ leaf_cell,
-                                              int32_t *__restrict__ leaf_n, int32_t *__restrict__ leaf_start,
-                                              int32_t *__restrict__ ctr) {
+                                              int32_t *__restrict__ leaf_pair, int32_t *__restrict__ leaf_n,
+                                              int32_t *__restrict__ leaf_start, int32_t *__restrict__ ctr) {
   const int lane = threadIdx.x & 31;
-  const int W = div_x + 4, H = div_y + 4;
+  const int pair = blockIdx.x / chunks, chunk = blockIdx.x - pair * chunks;
+  const PairDims d = dims[pair];
+  const int W = d.W, H = d.H;
   const int warps_per_block = blockDim.x >> 5, warp_in_block = threadIdx.x >> 5;
   const float qnan = __int_as_float(0x7fc00000);
-  for (int r = blockIdx.x; r < H; r += gridDim.x) {
-    const bool row_in = (r >= 2 && r < div_y + 2);
-    const size_t row0 = (size_t)r * W;
+  for (int r = chunk; r < H; r += chunks) {
+    const bool row_in = (r >= 2 && r < d.div_y + 2);
+    const size_t row0 = (size_t)d.base + (size_t)r * W;
     for (int c0 = warp_in_block * 32; c0 < W; c0 += warps_per_block * 32) {
       const int c = c0 + lane;
       const bool valid = c < W;
-      const bool interior = valid && row_in && c >= 2 && c < div_x + 2;
+      const bool interior = valid && row_in && c >= 2 && c < d.div_x + 2;
       const int n = interior ? count_slot[row0 + c] : 0;
       const bool has = n > 0;
       const unsigned bal = __ballot_sync(0xffffffffu, has);
-      const int cell = interior ? (r - 2) * div_x + (c - 2) : -1;
+      int leaf = -1;
       if (bal != 0u) {
         int incl = n;
 #pragma unroll
@@ -143,15 +162,18 @@ __global__ void __launch_bounds__(256) k_alloc(int32_t *__restrict__ count_slot,
         base_leaf = __shfl_sync(0xffffffffu, base_leaf, 0);
         base_pts = __shfl_sync(0xffffffffu, base_pts, 0);
         if (has) {
-          const int leaf = base_leaf + __popc(bal & ((1u << lane) - 1u));
-          leaf_id[cell] = leaf;
-          leaf_cell[leaf] = cell;
+          leaf = base_leaf + __popc(bal & ((1u << lane) - 1u));
+          leaf_cell[leaf] = (int32_t)(row0 + c);
+          leaf_pair[leaf] = pair;
           leaf_n[leaf] = n;
           leaf_start[leaf] = base_pts + incl - n;
         }
       }
-      if (interior && !has) leaf_id[cell] = -1;
-      if (valid) { count_slot[row0 + c] = -1; cen[row0 + c] = make_float2(qnan, qnan); }
+      if (valid) {
+        leaf_id[row0 + c] = leaf;
+        count_slot[row0 + c] = -1;
+        cen[row0 + c] = make_float2(qnan, qnan);
+      }
     }
   }
 }
@@ -229,7 +251,9 @@ __global__ void __launch_bounds__(128) k_finalize(const float2 *__restrict__ tgt
                                                  double *__restrict__ leaf_icov, float2 *__restrict__ leaf_cen,
                                                  int32_t *__restrict__ slot, float2 *__restrict__ cen_tab,
                                                  uint32_t *__restrict__ occ, CellRec *__restrict__ recs,
-                                                 int32_t *__restrict__ ctr, FinalizeParams fp, int div_x) {
+                                                 int32_t *__restrict__ ctr, FinalizeParams fp,
+                                                 const int32_t *__restrict__ leaf_pair,
+                                                 const PairDims *__restrict__ dims) {
   const int n_leaves = ctr[CTR_LEAVES];
   for (int leaf = blockIdx.x * blockDim.x + threadIdx.x; leaf < n_leaves; leaf += gridDim.x * blockDim.x) {
     const int n = leaf_n[leaf], st = leaf_start[leaf];
@@ -318,9 +342,8 @@ __global__ void __launch_bounds__(128) k_finalize(const float2 *__restrict__ tgt
       r.cx = cx; r.cy = cy; r.nr_points = nr; r.cell = leaf_cell[leaf];
       r.mx = m0; r.my = m1; r.c00 = ic0; r.c01 = ic1; r.c10 = ic2; r.c11 = ic3;
       recs[s] = r;
-      const int cell = r.cell;
-      const int j = cell / div_x, i = cell - j * div_x;
-      const int W = div_x + 4, q = (j + 2) * W + i + 2;
+      const int q = r.cell;                               // position in the shared padded tables
+      const int W = dims[leaf_pair[leaf]].W;
       slot[q] = s;
       cen_tab[q] = make_float2(cx, cy);
       // dilated occupancy: every cell whose 3x3 block contains this tree cell
@@ -412,6 +435,67 @@ inline int grid_for(int64_t work, int threads, int sm_count, int per_sm = 8) {
 
 }  // namespace
 
+// Build every table from the points in gb.tgt for n_grids grids laid out back to back.
+int grid_build_tables(Handle *h, int64_t n, int n_grids, int64_t total_pad, int max_h) {
+  GridBuffers &gb = h->gb;
+  cudaStream_t st = h->stream;
+  int32_t *ctr = gb.counters.as<int32_t>();
+  const size_t npts = (size_t)(n > 0 ? n : 1);
+  const size_t npad = (size_t)total_pad;
+  NDT_CUDA(h, gb.cell_of.reserve(npts * 4));
+  NDT_CUDA(h, gb.rank_of.reserve(npts * 4));
+  NDT_CUDA(h, gb.list.reserve(npts * 4));
+  NDT_CUDA(h, gb.sorted_idx.reserve(npts * 4));
+  NDT_CUDA(h, gb.tgt_sorted.reserve(npts * sizeof(float2)));
+  NDT_CUDA(h, gb.slot.reserve(npad * 4));
+  NDT_CUDA(h, gb.cen.reserve(npad * sizeof(float2)));
+  NDT_CUDA(h, gb.leaf_id.reserve(npad * 4));
+  const size_t occ_words = (npad + 31) / 32 + 1;
+  NDT_CUDA(h, gb.occ.reserve(occ_words * 4));
+  const size_t max_leaves = std::min(npts, npad);
+  NDT_CUDA(h, gb.leaf_cell.reserve(max_leaves * 4));
+  NDT_CUDA(h, gb.leaf_pair.reserve(max_leaves * 4));
+  NDT_CUDA(h, gb.leaf_n.reserve(max_leaves * 4));
+  NDT_CUDA(h, gb.leaf_start.reserve(max_leaves * 4));
+  NDT_CUDA(h, gb.leaf_range.reserve(max_leaves * sizeof(int2)));
+  NDT_CUDA(h, gb.leaf_nr.reserve(max_leaves * 4));
+  NDT_CUDA(h, gb.leaf_mean.reserve(max_leaves * sizeof(double2)));
+  NDT_CUDA(h, gb.leaf_icov.reserve(max_leaves * 4 * sizeof(double)));
+  NDT_CUDA(h, gb.leaf_cen.reserve(max_leaves * sizeof(float2)));
+  NDT_CUDA(h, gb.recs.reserve(max_leaves * sizeof(CellRec)));
+
+  const PairDims *dims = gb.dims.as<PairDims>();
+  const int64_t *off = gb.pair_off.as<int64_t>();
+  NDT_CUDA(h, cudaMemsetAsync(gb.occ.p, 0, occ_words * 4, st));
+  NDT_CUDA(h, cudaMemsetAsync(gb.slot.p, 0, npad * 4, st));
+  k_count<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(gb.tgt.as<float4>(), n, off, n_grids, dims, h->gd.inv_leaf,
+                                                        gb.slot.as<int32_t>(), gb.cell_of.as<int32_t>(),
+                                                        gb.rank_of.as<int32_t>());
+  // enough CTAs to fill the machine: several row chunks per grid when there are few grids
+  int chunks = 1;
+  if (n_grids < h->sm_count * 8) chunks = std::max(1, std::min(max_h, (h->sm_count * 8) / std::max(n_grids, 1)));
+  k_alloc<<<(unsigned)((int64_t)n_grids * chunks), 256, 0, st>>>(gb.slot.as<int32_t>(), gb.cen.as<float2>(), dims, chunks,
+                                                                gb.leaf_id.as<int32_t>(), gb.leaf_cell.as<int32_t>(),
+                                                                gb.leaf_pair.as<int32_t>(), gb.leaf_n.as<int32_t>(),
+                                                                gb.leaf_start.as<int32_t>(), ctr);
+  k_fill<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(n, gb.cell_of.as<int32_t>(), gb.rank_of.as<int32_t>(),
+                                                       gb.leaf_id.as<int32_t>(), gb.leaf_start.as<int32_t>(),
+                                                       gb.list.as<int32_t>());
+  k_rank<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(n, gb.cell_of.as<int32_t>(), gb.leaf_id.as<int32_t>(),
+                                                       gb.leaf_start.as<int32_t>(), gb.leaf_n.as<int32_t>(),
+                                                       gb.list.as<int32_t>(), gb.tgt.as<float4>(), gb.sorted_idx.as<int32_t>(),
+                                                       gb.tgt_sorted.as<float2>(), ctr);
+  FinalizeParams fp{h->prm.min_points, h->prm.eig_mult, h->prm.quirks};
+  k_finalize<<<grid_for((int64_t)max_leaves, 128, h->sm_count, 16), 128, 0, st>>>(
+      gb.tgt_sorted.as<float2>(), gb.leaf_cell.as<int32_t>(), gb.leaf_n.as<int32_t>(), gb.leaf_start.as<int32_t>(),
+      gb.leaf_range.as<int2>(), gb.leaf_nr.as<int32_t>(), gb.leaf_mean.as<double2>(), gb.leaf_icov.as<double>(),
+      gb.leaf_cen.as<float2>(), gb.slot.as<int32_t>(), gb.cen.as<float2>(), gb.occ.as<uint32_t>(), gb.recs.as<CellRec>(), ctr,
+      fp, gb.leaf_pair.as<int32_t>(), dims);
+  h->launches += 5;
+  NDT_CUDA(h, cudaGetLastError());
+  return NDT_OK;
+}
+
 int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace) {
   GridBuffers &gb = h->gb;
   GridDims &gd = h->gd;
@@ -422,6 +506,8 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace) {
   const size_t npts = (size_t)(n > 0 ? n : 1);
   NDT_CUDA(h, gb.tgt.reserve(npts * sizeof(float4)));
   NDT_CUDA(h, gb.counters.reserve((CTR_COUNT + 4) * sizeof(int32_t)));
+  NDT_CUDA(h, gb.dims.reserve(sizeof(PairDims)));
+  NDT_CUDA(h, gb.pair_off.reserve(2 * sizeof(int64_t)));
   int32_t *ctr = gb.counters.as<int32_t>();
   int32_t *bounds = ctr + CTR_COUNT;
   gd = GridDims();
@@ -434,33 +520,36 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace) {
   float mn[2] = {std::numeric_limits<float>::max(), std::numeric_limits<float>::max()};
   float mx[2] = {-std::numeric_limits<float>::max(), -std::numeric_limits<float>::max()};
   int64_t nfin = 0;
-  // small host clouds are staged through pinned memory and get their bounds on the way; large ones are
-  // copied as they are and take the device bounds kernel (a scalar host pass over 10^5+ points costs more)
-  const bool stage_on_host = (memspace == NDT_MEM_HOST) && (n < 32768);
-  if (!stage_on_host && h->timing) cudaEventRecord(h->ev0, st);
-  if (stage_on_host) {
-    // stage through pinned memory; bounds come for free while the points pass through the host cache
-    if (ensure_pinned(h, npts * sizeof(float4))) return NDT_ERR_CUDA;
+  // Host clouds always go through the pinned stage (a copy from pageable memory is several times slower).
+  // Small ones get their bounds in the same host pass; large ones are memcpy'd and take the bounds kernel.
+  const bool host_in = (memspace == NDT_MEM_HOST);
+  const bool host_bounds = host_in && (n < 32768);
+  const void *copy_from = xyzw;
+  if (host_in && n > 0) {
+    if (ensure_pinned(h, npts * sizeof(float4) + 256)) return NDT_ERR_CUDA;
     float *stage = (float *)h->pinned;
-    for (int64_t i = 0; i < n; ++i) {
-      const float x = xyzw[4 * i], y = xyzw[4 * i + 1], z = xyzw[4 * i + 2];
-      stage[4 * i] = x; stage[4 * i + 1] = y; stage[4 * i + 2] = z; stage[4 * i + 3] = xyzw[4 * i + 3];
-      if (std::isfinite(x) && std::isfinite(y) && std::isfinite(z)) {
-        mn[0] = std::min(mn[0], x); mn[1] = std::min(mn[1], y);
-        mx[0] = std::max(mx[0], x); mx[1] = std::max(mx[1], y);
-        ++nfin;
+    if (host_bounds) {
+      for (int64_t i = 0; i < n; ++i) {
+        const float x = xyzw[4 * i], y = xyzw[4 * i + 1], z = xyzw[4 * i + 2];
+        stage[4 * i] = x; stage[4 * i + 1] = y; stage[4 * i + 2] = z; stage[4 * i + 3] = xyzw[4 * i + 3];
+        if (std::isfinite(x) && std::isfinite(y) && std::isfinite(z)) {
+          mn[0] = std::min(mn[0], x); mn[1] = std::min(mn[1], y);
+          mx[0] = std::max(mx[0], x); mx[1] = std::max(mx[1], y);
+          ++nfin;
+        }
       }
+    } else {
+      std::memcpy(stage, xyzw, (size_t)n * sizeof(float4));
     }
-    if (h->timing) cudaEventRecord(h->ev0, st);     // device time only: the host staging loop is not in it
-    k_init_counters<<<1, 32, 0, st>>>(ctr, bounds);
-    ++h->launches;
-    if (n > 0) NDT_CUDA(h, cudaMemcpyAsync(gb.tgt.p, stage, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, st));
-  } else {
-    k_init_counters<<<1, 32, 0, st>>>(ctr, bounds);
-    ++h->launches;
-    if (n > 0) {
-      NDT_CUDA(h, cudaMemcpyAsync(gb.tgt.p, xyzw, (size_t)n * sizeof(float4),
-                                  memspace == NDT_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+    copy_from = stage;
+  }
+  if (h->timing) cudaEventRecord(h->ev0, st);       // device time only: host staging is not in it
+  k_init_counters<<<1, 32, 0, st>>>(ctr, bounds);
+  ++h->launches;
+  if (n > 0) {
+    NDT_CUDA(h, cudaMemcpyAsync(gb.tgt.p, copy_from, (size_t)n * sizeof(float4),
+                                host_in ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+    if (!host_bounds) {
       k_bounds<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(gb.tgt.as<float4>(), n, bounds, ctr);
       ++h->launches;
       int32_t hb[CTR_COUNT + 4];
@@ -471,6 +560,7 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace) {
         mn[0] = ord_float(hb[CTR_COUNT + 0]); mn[1] = ord_float(hb[CTR_COUNT + 1]);
         mx[0] = ord_float(hb[CTR_COUNT + 2]); mx[1] = ord_float(hb[CTR_COUNT + 3]);
       }
+      NDT_CUDA(h, cudaMemsetAsync(ctr + CTR_NFIN, 0, 4, st));
     }
   }
   bool empty = (nfin == 0);
@@ -485,7 +575,8 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace) {
     gd.min_bx = min_bx; gd.min_by = min_by;
     gd.div_x = max_bx - min_bx + 1; gd.div_y = max_by - min_by + 1;
     gd.n_cells = (int64_t)gd.div_x * gd.div_y;
-    if (gd.n_cells > (int64_t)INT_MAX) return set_err(h, NDT_ERR_CAPACITY, "ndt_set_target: grid exceeds 2^31-1 cells");
+    if ((int64_t)(gd.div_x + 4) * (gd.div_y + 4) > (int64_t)INT_MAX)
+      return set_err(h, NDT_ERR_CAPACITY, "ndt_set_target: grid exceeds 2^31-1 cells");
   }
   if (empty) {
     gd.div_x = gd.div_y = 0; gd.n_cells = 0;
@@ -495,51 +586,13 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace) {
     if (h->timing) cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
     return NDT_OK;
   }
-  const size_t nc = (size_t)gd.n_cells;
-  NDT_CUDA(h, gb.cell_of.reserve(npts * 4));
-  NDT_CUDA(h, gb.rank_of.reserve(npts * 4));
-  NDT_CUDA(h, gb.list.reserve(npts * 4));
-  NDT_CUDA(h, gb.sorted_idx.reserve(npts * 4));
-  NDT_CUDA(h, gb.tgt_sorted.reserve(npts * sizeof(float2)));
-  const size_t npad = (size_t)(gd.div_x + 4) * (size_t)(gd.div_y + 4);
-  NDT_CUDA(h, gb.slot.reserve(npad * 4));
-  NDT_CUDA(h, gb.cen.reserve(npad * sizeof(float2)));
-  const size_t occ_words = (npad + 31) / 32 + 1;
-  NDT_CUDA(h, gb.occ.reserve(occ_words * 4));
-  NDT_CUDA(h, cudaMemsetAsync(gb.occ.p, 0, occ_words * 4, st));
-  NDT_CUDA(h, gb.leaf_id.reserve(nc * 4));
-  const size_t max_leaves = std::min(npts, nc);
-  NDT_CUDA(h, gb.leaf_cell.reserve(max_leaves * 4));
-  NDT_CUDA(h, gb.leaf_n.reserve(max_leaves * 4));
-  NDT_CUDA(h, gb.leaf_start.reserve(max_leaves * 4));
-  NDT_CUDA(h, gb.leaf_range.reserve(max_leaves * sizeof(int2)));
-  NDT_CUDA(h, gb.leaf_nr.reserve(max_leaves * 4));
-  NDT_CUDA(h, gb.leaf_mean.reserve(max_leaves * sizeof(double2)));
-  NDT_CUDA(h, gb.leaf_icov.reserve(max_leaves * 4 * sizeof(double)));
-  NDT_CUDA(h, gb.leaf_cen.reserve(max_leaves * sizeof(float2)));
-  NDT_CUDA(h, gb.recs.reserve(max_leaves * sizeof(CellRec)));
-
-  Dims d{gd.min_bx, gd.min_by, gd.div_x, gd.div_y, gd.inv_leaf};
-  NDT_CUDA(h, cudaMemsetAsync(gb.slot.p, 0, npad * 4, st));
-  k_count<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(gb.tgt.as<float4>(), n, d, gb.slot.as<int32_t>(),
-                                                        gb.cell_of.as<int32_t>(), gb.rank_of.as<int32_t>());
-  k_alloc<<<std::min(gd.div_y + 4, h->sm_count * 8), 256, 0, st>>>(gb.slot.as<int32_t>(), gb.cen.as<float2>(), gd.div_x, gd.div_y,
-                                                                 gb.leaf_id.as<int32_t>(), gb.leaf_cell.as<int32_t>(),
-                                                                 gb.leaf_n.as<int32_t>(), gb.leaf_start.as<int32_t>(), ctr);
-  k_fill<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(n, gb.cell_of.as<int32_t>(), gb.rank_of.as<int32_t>(),
-                                                       gb.leaf_id.as<int32_t>(), gb.leaf_start.as<int32_t>(),
-                                                       gb.list.as<int32_t>());
-  FinalizeParams fp{h->prm.min_points, h->prm.eig_mult, h->prm.quirks};
-  const int64_t warps_needed = (int64_t)max_leaves;
-  k_rank<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(n, gb.cell_of.as<int32_t>(), gb.leaf_id.as<int32_t>(),
-                                                       gb.leaf_start.as<int32_t>(), gb.leaf_n.as<int32_t>(),
-                                                       gb.list.as<int32_t>(), gb.tgt.as<float4>(), gb.sorted_idx.as<int32_t>(),
-                                                       gb.tgt_sorted.as<float2>(), ctr);
-  k_finalize<<<grid_for(warps_needed, 128, h->sm_count, 16), 128, 0, st>>>(
-      gb.tgt_sorted.as<float2>(), gb.leaf_cell.as<int32_t>(),
-      gb.leaf_n.as<int32_t>(), gb.leaf_start.as<int32_t>(), gb.leaf_range.as<int2>(), gb.leaf_nr.as<int32_t>(), gb.leaf_mean.as<double2>(),
-      gb.leaf_icov.as<double>(), gb.leaf_cen.as<float2>(), gb.slot.as<int32_t>(), gb.cen.as<float2>(), gb.occ.as<uint32_t>(), gb.recs.as<CellRec>(), ctr, fp, gd.div_x);
-  h->launches += 5;
+  // one grid: a single PairDims at base 0
+  PairDims pd{};
+  pd.min_bx = gd.min_bx; pd.min_by = gd.min_by; pd.div_x = gd.div_x; pd.div_y = gd.div_y;
+  pd.W = gd.div_x + 4; pd.H = gd.div_y + 4; pd.base = 0; pd.ns = 0; pd.src_off = 0; pd.tgt_off = 0; pd.nt = n;
+  NDT_CUDA(h, cudaMemcpyAsync(gb.dims.p, &pd, sizeof(pd), cudaMemcpyHostToDevice, st));
+  const int64_t npad_total = (int64_t)pd.W * pd.H;
+  if (int rc = grid_build_tables(h, n, 1, npad_total, pd.H)) return rc;
   NDT_CUDA(h, cudaMemcpyAsync(h->h_counters, ctr, sizeof(h->h_counters), cudaMemcpyDeviceToHost, st));
   NDT_CUDA(h, cudaStreamSynchronize(st));
   NDT_CUDA(h, cudaGetLastError());
@@ -610,6 +663,7 @@ GridView grid_view(const Handle *h) {
   const GridBuffers &gb = h->gb;
   G.slot = gb.slot.as<int32_t>();
   G.slot_w = h->gd.div_x + 4;
+  G.table_base = 0;
   G.cen = gb.cen.as<float2>();
   G.occ = gb.occ.as<uint32_t>();
   G.recs = gb.recs.as<CellRec>();

@@ -37,6 +37,8 @@ struct GridView {
   const int32_t *__restrict__ slot;     // [(div_x + 4) * (div_y + 4)] padded by 2 cells of -1 on every side:
                                         // cell (i, j) lives at (j + 2) * slot_w + i + 2; value = record index or -1
   int32_t slot_w;                       // div_x + 4
+  int32_t table_base;                   // offset of this grid inside the shared tables (0 for a single grid;
+                                        // batched scan-pair matching packs one padded table per pair back to back)
   const uint32_t *__restrict__ occ;     // 1 bit per padded cell: some tree cell lies in the 3x3 block around it
                                         // (dilated occupancy: a clear bit means the point cannot hit anything)
   const float2 *__restrict__ cen;       // same padded indexing: float32 centroid of tree cells, NaN elsewhere
@@ -47,7 +49,7 @@ struct GridView {
   float r2;                             // (float)((double)leaf * leaf)
   float leaf;
   // 1-NN buckets (fitness): every occupied cell
-  const int32_t *__restrict__ leaf_id;  // [div_x * div_y] -> leaf index or -1
+  const int32_t *__restrict__ leaf_id;  // same padded indexing -> leaf index or -1
   const int2 *__restrict__ leaf_range;  // per leaf: (start, n) into tgt_sorted
   const float2 *__restrict__ tgt_sorted;// target (x, y) in bucket order (cell by cell, input order inside a cell)
   const float4 *__restrict__ tgt;       // target points, input order
@@ -59,6 +61,17 @@ struct GridView {
   float nn_inv_leaf, nn_leaf;
   const int2 *__restrict__ nn_range;    // [nn_div_x * nn_div_y]
   const float2 *__restrict__ nn_pts;    // target (x, y) in fine-bucket order
+};
+
+// geometry of one grid inside the shared padded tables (one entry for ndt_set_target, one per pair for
+// ndt_match_pairs); for the batched matcher it also names the pair's point ranges
+struct PairDims {
+  int32_t min_bx, min_by, div_x, div_y;
+  int32_t W, H;            // padded extents: div + 4
+  int32_t base;            // first entry of this grid in the shared tables
+  int32_t ns;              // pairs: number of (filtered) source points
+  int64_t src_off, tgt_off;// pairs: first source / target point
+  int64_t nt;              // pairs: number of target points
 };
 
 struct MatchParams {
@@ -174,11 +187,11 @@ __device__ __forceinline__ void hit_path(const RecL &rec_at, const float4 e, con
 
 // the scalars of the grid the probe loop needs, held in registers (not re-read through a struct pointer)
 struct ProbeGeom {
-  int W, div_x, div_y, min_bx, min_by;
+  int W, div_x, div_y, min_bx, min_by, base;
   float inv_leaf, r2;
 };
 __device__ __forceinline__ ProbeGeom probe_geom(const GridView &G) {
-  return ProbeGeom{G.slot_w, G.div_x, G.div_y, G.min_bx, G.min_by, G.inv_leaf, G.r2};
+  return ProbeGeom{G.slot_w, G.div_x, G.div_y, G.min_bx, G.min_by, G.table_base, G.inv_leaf, G.r2};
 }
 
 // Accumulate the objective over points i = first + k * stride (k = 0, 1, ...), i < hi, where `first`
@@ -232,7 +245,7 @@ __device__ __forceinline__ void accumulate_points(const ProbeGeom g, const OccL 
       const int ci = cell_coord(xt, g.inv_leaf, g.min_bx);
       const int cj = cell_coord(yt, g.inv_leaf, g.min_by);
       if (ci >= -1 && cj >= -1 && ci <= g.div_x && cj <= g.div_y) {
-        base = (cj + 2) * g.W + ci + 2;
+        base = g.base + (cj + 2) * g.W + ci + 2;
         cand = (occ_at(base >> 5) >> (base & 31)) & 1u;
       }
     }
@@ -620,7 +633,7 @@ __device__ __forceinline__ void nn_scan(const GridView &G, int lf, float xt, flo
 }
 __device__ __forceinline__ int nn_leaf(const GridView &G, int a, int b) {
   if (a < 0 || a >= G.div_x || b < 0 || b >= G.div_y) return -1;
-  return __ldg(G.leaf_id + (size_t)b * G.div_x + a);
+  return __ldg(G.leaf_id + G.table_base + (b + 2) * G.slot_w + a + 2);
 }
 __device__ __forceinline__ void nn_visit(const GridView &G, int a, int b, float xt, float yt, float &best) {
   nn_scan(G, nn_leaf(G, a, b), xt, yt, best);

@@ -45,7 +45,10 @@ struct GridBuffers {
   DevBuf cen;          // float2[padded]  probe table: float32 centroid of tree cells, NaN elsewhere
   DevBuf occ;          // uint32[padded/32] dilated occupancy bitmap (3x3 block contains a tree cell)
   DevBuf leaf_id;      // int32[n_cells]  cell -> leaf or -1
-  DevBuf leaf_cell;    // int32[n]        per leaf: cell index
+  DevBuf leaf_cell;    // int32[n]        per leaf: position in the shared padded tables
+  DevBuf leaf_pair;    // int32[n]        per leaf: which grid it belongs to
+  DevBuf dims;         // PairDims[n_grids]
+  DevBuf pair_off;     // int64[n_grids+1] target point ranges (batched pairs)
   DevBuf leaf_n;       // int32[n]
   DevBuf leaf_start;   // int32[n]
   DevBuf leaf_nr;      // int32[n]        PCL nr_points after pass 2 (n or -1)
@@ -98,6 +101,11 @@ struct Handle {
 
 // grid_build.cu
 int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace);
+// shared by ndt_set_target (one grid) and ndt_match_pairs (one grid per pair): target points are in gb.tgt,
+// geometry in gb.dims (device), point ranges in gb.pair_off (device, n_grids + 1 entries; unused for one grid)
+int grid_build_tables(Handle *h, int64_t n, int n_grids, int64_t total_pad, int max_h);
+int pairs_prepare(Handle *h, const int64_t *d_tgt_off, const int64_t *d_src_off, const int32_t *d_src_cnt, int64_t n_pairs,
+                  int64_t *total_pad, int *max_h);
 int grid_cell_index(Handle *h, const float *xyzw, int64_t n, int memspace, int32_t *idx_out);
 GridView grid_view(const Handle *h);
 MatchParams match_params(const Handle *h, bool want_fitness);
