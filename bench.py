@@ -39,6 +39,7 @@ UNIT = "point-evals/s"
 HYP_PER_GPU = 65_536
 LAUNCH = dict(space=0.05, space_thre=0.25, leaf=0.05)     # ndt_mapping.launch:15-16, 36
 RESOLUTION = 0.5
+C5_PAIRS = 8_192
 
 
 def log(*a):
@@ -187,6 +188,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--c2-scans", type=int, default=300)
     ap.add_argument("--no-cpu-baseline", action="store_true", help="profiling runs only")
+    ap.add_argument("--c5-pairs", type=int, default=C5_PAIRS, help="scan pairs of the C5 figure in total (0 = skip)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -331,6 +333,13 @@ def main():
     bi_local, best_local = g.best_of(d_res.data_ptr(), n=n_h, space=capi.MEM_DEVICE)
     b_score = best_local.score if bi_local >= 0 else -np.inf
     g_score, g_index, g_pose, g_owner = best_over_ranks(b_score, lo + max(bi_local, 0), list(best_local.pose), device="cuda")
+    c5_line = None
+    if args.c5_pairs > 0:
+        try:
+            c5_line = run_c5(prm, capi, torch, dist, stream, rank, world, args.c5_pairs, max(K // 2, 2), 2,
+                             cpu_baseline=not args.no_cpu_baseline)
+        except Exception as ex:       # reported, never hidden
+            c5_line = {"error": repr(ex)}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -398,11 +407,138 @@ def main():
         "cpu_baseline": cpu_baseline,
         "grid_build_ms": t_build, "grid_broadcast_ms": bcast_ms,
         "reloc_best_error_m": reloc_err, "reloc_best": {"score": g_score, "hypothesis": g_index, "owner_rank": g_owner},
+        "c5": c5_line,
         "extras": extras,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def build_c5(lo: int, hi: int):
+    """Scan pairs [lo, hi) of C5 (seeds 1000 + i): resampled target / source clouds packed back to back."""
+    from ndt_slam_b200 import synth
+    from oracle import oracle_api as oa   # data preparation only (resampler restatement)
+
+    srcs, tgts, offs = [], [], []
+    for i in range(lo, hi):
+        d = synth.c5_pair(i)
+        tgts.append(synth.to_xyzw(oa.resample(d["scan_a"], LAUNCH["space"], LAUNCH["space_thre"])))
+        srcs.append(synth.to_xyzw(oa.resample(d["scan_b"], LAUNCH["space"], LAUNCH["space_thre"])))
+        offs.append(d["offset"])
+
+    def pack(cl):
+        off = np.zeros(len(cl) + 1, np.int64)
+        off[1:] = np.cumsum([c.shape[0] for c in cl])
+        return np.ascontiguousarray(np.concatenate(cl, axis=0), dtype=np.float32), off
+
+    src, so = pack(srcs)
+    tgt, to = pack(tgts)
+    return dict(src=src, so=so, tgt=tgt, to=to, truth=np.array(offs), srcs=srcs, tgts=tgts)
+
+
+def run_c5(prm, capi, torch, dist, stream, rank, world, n_total, K, W, cpu_baseline=True):
+    """C5: loop-closure verification, n_total independent scan-pair matches (filter + grid build + match +
+    fitness per pair) sharded across the ranks, no collective on the data path. Strong scaling."""
+    from ndt_slam_b200.sharding import shard_range
+
+    lo, hi = shard_range(n_total, rank, world)
+    n = hi - lo
+    c5 = build_c5(lo, hi)
+    g = capi.Ndt(prm)
+    guesses = np.zeros((n, 3))
+    d_src, d_tgt = torch.from_numpy(c5["src"]).cuda(), torch.from_numpy(c5["tgt"]).cuda()
+    d_g = torch.from_numpy(guesses).cuda()
+    d_res = torch.zeros(n * capi.RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def step_device():
+        g.match_pairs(d_src.data_ptr(), c5["so"], d_tgt.data_ptr(), c5["to"], d_g.data_ptr(), n, source_leaf=LAUNCH["leaf"],
+                      space=capi.MEM_DEVICE, out=d_res.data_ptr())
+
+    for _ in range(W):
+        step_device()
+    torch.cuda.synchronize()
+    res = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype=capi.RESULT_DTYPE)
+    pe = int(res["point_evals"].sum())
+    l0 = g.launch_count()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(K):
+        flush.zero_()
+        a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+        a.record(stream); step_device(); b.record(stream)
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    launches = g.launch_count() - l0
+    ms = float(sum(a.elapsed_time(b) for a, b in evs))
+    # end to end: pinned host clouds in, results out
+    h_src, h_tgt = torch.from_numpy(c5["src"]).pin_memory(), torch.from_numpy(c5["tgt"]).pin_memory()
+    h_res = torch.zeros(n * capi.RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    h_res_np = h_res.numpy().view(capi.RESULT_DTYPE)
+
+    def step_e2e():
+        g.match_pairs(h_src.numpy(), c5["so"], h_tgt.numpy(), c5["to"], guesses, n, source_leaf=LAUNCH["leaf"],
+                      space=capi.MEM_HOST, out=h_res_np)
+
+    step_e2e()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        step_e2e()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
+    c = torch.tensor([float(n), float(pe)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    ms_max, e2e_max = float(t[0].item()), float(t[1].item())
+    n_all, pe_all = float(c[0].item()), float(c[1].item())
+    err = np.hypot(res["pose"][:, 0] - c5["truth"][:, 0], res["pose"][:, 1] - c5["truth"][:, 1])
+    out = {"workload": "C5: %d independent scan-pair matches (resampled 1081-beam scans, source filter + grid build + "
+                       "match + fitness per pair), sharded x%d" % (int(n_all), world),
+           "scaling": "strong", "pairs_total": int(n_all), "matches_per_sec": n_all / (ms_max / K * 1e-3),
+           "ms_per_step": ms_max / K, "point_evals_per_sec": pe_all / (ms_max / K * 1e-3),
+           "evals_per_match": float(res["evals"].mean()), "gpu_launches_per_step": launches / K,
+           "e2e": {"matches_per_sec": n_all * K / e2e_max, "h2d_bytes_per_step": int(c5["src"].nbytes + c5["tgt"].nbytes + n * 24),
+                   "d2h_bytes_per_step": int(n * capi.RESULT_DTYPE.itemsize)},
+           "source_points_total_rank0": int(c5["src"].shape[0]), "target_points_total_rank0": int(c5["tgt"].shape[0]),
+           "rank0_within_5cm_of_truth": float(np.mean(err < 0.05))}
+    if rank == 0 and cpu_baseline:
+        out["cpu_baseline"] = cpu_pairs(prm, c5, min(n, 8192), os.cpu_count() or 1)
+    return out
+
+
+def cpu_pairs(prm, c5, n_sample, threads):
+    """The oracle on host cores over a sample of the same pairs: filter + grid build + match + fitness per pair."""
+    from oracle import oracle_api as oa
+
+    ids = list(range(n_sample))
+    lock = threading.Lock()
+
+    def work(_):
+        o = oa.Oracle(prm)
+        pe = nm = 0
+        while True:
+            with lock:
+                if not ids:
+                    break
+                k = ids.pop()
+            o.set_target(c5["tgts"][k]); o.set_source(oa.approx_voxel_filter(c5["srcs"][k], LAUNCH["leaf"]))
+            r = o.align([0.0, 0.0, 0.0])
+            pe += r.point_evals; nm += 1
+        return pe, nm
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        outs = list(ex.map(work, range(threads)))
+    sec = time.perf_counter() - t0
+    return {"matches_per_sec": sum(o[1] for o in outs) / sec, "point_evals_per_sec": sum(o[0] for o in outs) / sec,
+            "cores": threads, "kind": "port", "sample": f"{n_sample} pairs of this workload, {threads} threads, {sec:.1f} s"}
 
 
 def run_extras(g, prm, capi, torch, c2_scans=300, c3=True):

@@ -150,7 +150,13 @@ int ndt_best_of(ndt_handle h, const ndt_result *results, int64_t n, int memspace
 
 /* n independent scan-pair matches (loop-closure verification): pair i matches
  * src[src_off[i] .. src_off[i+1]) against a grid built from tgt[tgt_off[i] .. tgt_off[i+1]).
- * source_leaf > 0 applies the ApproximateVoxelGrid source filter first (as estimatePose does). */
+ * source_leaf > 0 applies the ApproximateVoxelGrid source filter first (as estimatePose does).
+ * This is n_pairs x PoseEstimator::estimatePose [REF src/PoseEstimator.cpp:4-69] in one call: all grids are
+ * built by one pass of the grid-build kernels (one shared padded table, one slice per pair) and one
+ * persistent kernel matches every pair (one warp per pair); results carry the fitness score.
+ * src_off / tgt_off (n_pairs + 1 entries, starting at 0) are always HOST arrays; the points, guesses and
+ * results live in `memspace`. The handle's own target / source (ndt_set_target / ndt_set_source) are
+ * overwritten by this call. */
 int ndt_match_pairs(ndt_handle h, const float *src_xyzw, const int64_t *src_off,
                     const float *tgt_xyzw, const int64_t *tgt_off, const double *guesses,
                     int64_t n_pairs, float source_leaf, int memspace, ndt_result *results);

@@ -401,35 +401,65 @@ int ndt_match_pairs(ndt_handle hh, const float *src_xyzw, const int64_t *src_off
                     const int64_t *tgt_off, const double *guesses, int64_t n_pairs, float source_leaf,
                     int memspace, ndt_result *results) {
   H_OR_FAIL(hh);
-  if (n_pairs < 0 || (n_pairs > 0 && (!src_xyzw || !src_off || !tgt_xyzw || !tgt_off || !guesses || !results)))
+  if (n_pairs < 0 || (n_pairs > 0 && (!src_off || !tgt_off || !guesses || !results)))
     return set_err(h, NDT_ERR_ARG, "ndt_match_pairs: bad argument");
-  if (memspace != NDT_MEM_HOST) return set_err(h, NDT_ERR_ARG, "ndt_match_pairs: device buffers not supported yet");
-  // Round-1 formulation: every pair runs the full device path (grid build kernels + persistent
-  // matcher) back to back on this handle's stream. A fused one-CTA-per-pair kernel is the next step.
-  cudaStream_t st = h->stream;
-  float total_ms = 0.f;
-  std::vector<float> filtered;
+  if (n_pairs == 0) return NDT_OK;
+  if (n_pairs > (int64_t)(1 << 30)) return set_err(h, NDT_ERR_CAPACITY, "ndt_match_pairs: too many pairs");
+  // the offset arrays are host metadata (like the point counts of the single-match calls)
+  const int64_t ns_total = src_off[n_pairs] - src_off[0], nt_total = tgt_off[n_pairs] - tgt_off[0];
+  if (src_off[0] != 0 || tgt_off[0] != 0) return set_err(h, NDT_ERR_ARG, "ndt_match_pairs: offsets must start at 0");
   for (int64_t i = 0; i < n_pairs; ++i) {
-    const int64_t ns = src_off[i + 1] - src_off[i], nt = tgt_off[i + 1] - tgt_off[i];
-    int rc = grid_build(h, tgt_xyzw + 4 * tgt_off[i], nt, NDT_MEM_HOST);
-    if (rc) return rc;
-    total_ms += h->last_ms;
-    const float *sp = src_xyzw + 4 * src_off[i];
-    int64_t m = ns;
-    if (source_leaf > 0.f && ns > 0) {
-      filtered.resize((size_t)ns * 4);
-      rc = ndt_approx_voxel_filter(hh, sp, ns, source_leaf, NDT_MEM_HOST, filtered.data(), &m);
-      if (rc) return rc;
-      sp = filtered.data();
-    }
-    rc = ndt_set_source(hh, sp, m, NDT_MEM_HOST);
-    if (rc) return rc;
-    rc = ndt_align(hh, guesses + 3 * i, results + i);
-    if (rc) return rc;
-    total_ms += h->last_ms;
+    if (src_off[i + 1] < src_off[i] || tgt_off[i + 1] < tgt_off[i]) return set_err(h, NDT_ERR_ARG, "ndt_match_pairs: offsets must be non-decreasing");
+    if (src_off[i + 1] - src_off[i] > 0x7fffffffLL) return set_err(h, NDT_ERR_CAPACITY, "ndt_match_pairs: source cloud too large");
   }
-  (void)st;
-  h->last_ms = total_ms;
+  if ((ns_total > 0 && !src_xyzw) || (nt_total > 0 && !tgt_xyzw)) return set_err(h, NDT_ERR_ARG, "ndt_match_pairs: null points");
+  if (nt_total > (int64_t)INT32_MAX) return set_err(h, NDT_ERR_CAPACITY, "ndt_match_pairs: more than 2^31-1 target points");
+  cudaStream_t st = h->stream;
+  GridBuffers &gb = h->gb;
+  GridDims &gd = h->gd;
+  h->have_grid = false; h->have_src = false;          // the handle's single grid / source are overwritten
+  gd = GridDims();
+  gd.leaf = h->prm.resolution; gd.inv_leaf = 1.0f / gd.leaf; gd.r2 = (float)((double)gd.leaf * (double)gd.leaf);
+  std::memset(h->h_counters, 0, sizeof(h->h_counters));
+  const bool host = (memspace == NDT_MEM_HOST);
+  const cudaMemcpyKind in_kind = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  const size_t nt_b = (size_t)std::max<int64_t>(nt_total, 1) * sizeof(float4), ns_b = (size_t)std::max<int64_t>(ns_total, 1) * sizeof(float4);
+  NDT_CUDA(h, gb.tgt.reserve(nt_b));
+  NDT_CUDA(h, h->src.reserve(ns_b));
+  NDT_CUDA(h, h->scratch.reserve(ns_b));
+  NDT_CUDA(h, gb.pair_off.reserve(2 * ((size_t)n_pairs + 1) * sizeof(int64_t)));
+  const size_t gbytes = (size_t)n_pairs * 3 * sizeof(double), rbytes = (size_t)n_pairs * sizeof(ndt_result);
+  const double *d_g = guesses;
+  ndt_result *d_r = results;
+  if (host) {
+    NDT_CUDA(h, h->io.reserve(gbytes + rbytes + 256));
+    d_g = h->io.as<double>();
+    d_r = (ndt_result *)((char *)h->io.p + ((gbytes + 255) & ~size_t(255)));
+    NDT_CUDA(h, cudaMemcpyAsync(h->io.p, guesses, gbytes, cudaMemcpyHostToDevice, st));
+  }
+  int64_t *d_off = gb.pair_off.as<int64_t>();
+  NDT_CUDA(h, cudaMemcpyAsync(d_off, tgt_off, ((size_t)n_pairs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  NDT_CUDA(h, cudaMemcpyAsync(d_off + n_pairs + 1, src_off, ((size_t)n_pairs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  if (nt_total > 0) NDT_CUDA(h, cudaMemcpyAsync(gb.tgt.p, tgt_xyzw, (size_t)nt_total * sizeof(float4), in_kind, st));
+  // raw source clouds: device inputs are filtered straight from the caller's buffer
+  const float4 *d_raw = reinterpret_cast<const float4 *>(src_xyzw);
+  if (host && ns_total > 0) {
+    NDT_CUDA(h, cudaMemcpyAsync(h->scratch.p, src_xyzw, (size_t)ns_total * sizeof(float4), cudaMemcpyHostToDevice, st));
+    d_raw = h->scratch.as<float4>();
+  }
+  if (h->timing) cudaEventRecord(h->ev0, st);
+  int64_t total_pad = 0;
+  int max_h = 0;
+  if (int rc = pairs_prepare(h, n_pairs, &total_pad, &max_h)) return rc;          // one 16-byte read-back
+  if (int rc = launch_pairs_filter(h, d_raw, h->src.as<float4>(), n_pairs, source_leaf)) return rc;
+  gd.n_tgt = nt_total;
+  if (int rc = grid_build_tables(h, nt_total, (int)n_pairs, total_pad, max_h)) return rc;
+  if (int rc = launch_align_pairs(h, h->src.as<float4>(), d_g, n_pairs, d_r, /*want_fitness=*/true)) return rc;
+  if (h->timing) cudaEventRecord(h->ev1, st);
+  if (!host) { h->ms_pending = true; return NDT_OK; }
+  NDT_CUDA(h, cudaMemcpyAsync(results, d_r, rbytes, cudaMemcpyDeviceToHost, st));
+  NDT_CUDA(h, cudaStreamSynchronize(st));
+  if (h->timing) cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
   h->ms_pending = false;
   return NDT_OK;
 }

@@ -37,6 +37,7 @@ __device__ __forceinline__ int float_ord(float f) {
   const int i = __float_as_int(f);
   return i >= 0 ? i : i ^ 0x7fffffff;
 }
+__device__ __forceinline__ float ord_to_float(int o) { return __int_as_float(o >= 0 ? o : o ^ 0x7fffffff); }
 inline float ord_float(int o) {
   int i = o >= 0 ? o : o ^ 0x7fffffff;
   float f;
@@ -425,6 +426,87 @@ __global__ void __launch_bounds__(256) k_cell_index(const float4 *__restrict__ p
   }
 }
 
+// ---- batched scan pairs: geometry of every pair's grid, computed on the device ----
+// One warp per pair: getMinMax3D over the pair's finite target points, then the same float32 bounding-box
+// arithmetic as the single-grid host code in grid_build() (VoxelGridCovariance::applyFilter).
+// An empty / degenerate target gets a 4 x 4 all-empty table so the matcher needs no special case.
+__global__ void __launch_bounds__(256) k_pair_bounds(const float4 *__restrict__ tgt, const int64_t *__restrict__ tgt_off,
+                                                    const int64_t *__restrict__ src_off, int n_pairs, float inv_leaf,
+                                                    PairDims *__restrict__ dims, int64_t *__restrict__ pad) {
+  const int lane = threadIdx.x & 31;
+  const int pair = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pair >= n_pairs) return;
+  const int64_t t0 = tgt_off[pair], t1 = tgt_off[pair + 1];
+  int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN, nf = 0;
+  for (int64_t i = t0 + lane; i < t1; i += 32) {
+    const float4 p = __ldg(tgt + i);
+    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+      const int ox = float_ord(p.x), oy = float_ord(p.y);
+      mnx = min(mnx, ox); mny = min(mny, oy); mxx = max(mxx, ox); mxy = max(mxy, oy);
+      ++nf;
+    }
+  }
+  mnx = __reduce_min_sync(0xffffffffu, mnx); mny = __reduce_min_sync(0xffffffffu, mny);
+  mxx = __reduce_max_sync(0xffffffffu, mxx); mxy = __reduce_max_sync(0xffffffffu, mxy);
+  nf = __reduce_add_sync(0xffffffffu, nf);
+  if (lane != 0) return;
+  PairDims d{};
+  d.src_off = src_off[pair]; d.tgt_off = t0; d.nt = t1 - t0;
+  d.ns = (int32_t)(src_off[pair + 1] - src_off[pair]);
+  bool empty = (nf == 0);
+  if (!empty) {
+    const float fx0 = ord_to_float(mnx), fy0 = ord_to_float(mny), fx1 = ord_to_float(mxx), fy1 = ord_to_float(mxy);
+    const int64_t dx = (int64_t)((fx1 - fx0) * inv_leaf) + 1;
+    const int64_t dy = (int64_t)((fy1 - fy0) * inv_leaf) + 1;
+    if (dx * dy > (int64_t)INT_MAX) empty = true;          // PCL: "leaf size too small", empty grid
+    if (!empty) {
+      d.min_bx = (int)floorf(fx0 * inv_leaf); d.min_by = (int)floorf(fy0 * inv_leaf);
+      d.div_x = (int)floorf(fx1 * inv_leaf) - d.min_bx + 1;
+      d.div_y = (int)floorf(fy1 * inv_leaf) - d.min_by + 1;
+    }
+  }
+  if (empty) { d.min_bx = d.min_by = 0; d.div_x = d.div_y = 0; }
+  d.W = d.div_x + 4; d.H = d.div_y + 4;
+  dims[pair] = d;
+  pad[pair] = (int64_t)d.W * d.H;
+}
+
+// exclusive scan of the padded table sizes -> PairDims::base; out[0] = total entries, out[1] = tallest table
+__global__ void __launch_bounds__(1024) k_pair_scan(PairDims *__restrict__ dims, const int64_t *__restrict__ pad, int n_pairs,
+                                                   int64_t *__restrict__ out) {
+  __shared__ int64_t s_sum[32];
+  __shared__ int s_max[32];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int chunk = (n_pairs + 1023) / 1024;
+  const int lo = min(n_pairs, t * chunk), hi = min(n_pairs, lo + chunk);
+  int64_t mine = 0;
+  int mh = 0;
+  for (int i = lo; i < hi; ++i) { mine += pad[i]; mh = max(mh, dims[i].H); }
+  int64_t incl = mine;
+#pragma unroll
+  for (int dlt = 1; dlt < 32; dlt <<= 1) {
+    const int64_t v = __shfl_up_sync(0xffffffffu, incl, dlt);
+    if (lane >= dlt) incl += v;
+  }
+  mh = __reduce_max_sync(0xffffffffu, mh);
+  if (lane == 31) s_sum[w] = incl;
+  if (lane == 0) s_max[w] = mh;
+  __syncthreads();
+  int64_t before = 0;
+  for (int k = 0; k < w; ++k) before += s_sum[k];
+  int64_t run = before + incl - mine;
+  for (int i = lo; i < hi; ++i) {
+    dims[i].base = (int32_t)min(run, (int64_t)INT_MAX);   // the host rejects totals beyond int32 before any table is touched
+    run += pad[i];
+  }
+  if (t == 1023) {
+    out[0] = before + incl;
+    int m = 0;
+    for (int k = 0; k < 32; ++k) m = max(m, s_max[k]);
+    out[1] = m;
+  }
+}
+
 inline int grid_for(int64_t work, int threads, int sm_count, int per_sm = 8) {
   int64_t b = (work + threads - 1) / threads;
   const int64_t cap = (int64_t)sm_count * per_sm;
@@ -493,6 +575,32 @@ int grid_build_tables(Handle *h, int64_t n, int n_grids, int64_t total_pad, int 
       fp, gb.leaf_pair.as<int32_t>(), dims);
   h->launches += 5;
   NDT_CUDA(h, cudaGetLastError());
+  return NDT_OK;
+}
+
+// Batched scan pairs: gb.tgt holds every pair's target points back to back, gb.pair_off the device copies of
+// the target offsets [0, n_pairs] followed by the source offsets [n_pairs + 1, 2 n_pairs + 1]. Computes every
+// pair's grid geometry (gb.dims) and its place in the shared tables; one 16-byte read-back sizes the tables.
+int pairs_prepare(Handle *h, int64_t n_pairs, int64_t *total_pad, int *max_h) {
+  GridBuffers &gb = h->gb;
+  cudaStream_t st = h->stream;
+  NDT_CUDA(h, gb.dims.reserve((size_t)n_pairs * sizeof(PairDims)));
+  NDT_CUDA(h, h->scratch2.reserve(((size_t)n_pairs + 2) * sizeof(int64_t)));
+  NDT_CUDA(h, gb.counters.reserve((CTR_COUNT + 4) * sizeof(int32_t)));
+  if (ensure_pinned(h, 256)) return NDT_ERR_CUDA;
+  int64_t *pad = h->scratch2.as<int64_t>(), *out = pad + n_pairs;
+  const int64_t *off = gb.pair_off.as<int64_t>();
+  k_init_counters<<<1, 32, 0, st>>>(gb.counters.as<int32_t>(), gb.counters.as<int32_t>() + CTR_COUNT);
+  k_pair_bounds<<<(unsigned)((n_pairs + 7) / 8), 256, 0, st>>>(gb.tgt.as<float4>(), off, off + n_pairs + 1, (int)n_pairs,
+                                                              h->gd.inv_leaf, gb.dims.as<PairDims>(), pad);
+  k_pair_scan<<<1, 1024, 0, st>>>(gb.dims.as<PairDims>(), pad, (int)n_pairs, out);
+  h->launches += 3;
+  int64_t *hp = (int64_t *)h->pinned;
+  NDT_CUDA(h, cudaMemcpyAsync(hp, out, 16, cudaMemcpyDeviceToHost, st));
+  NDT_CUDA(h, cudaStreamSynchronize(st));
+  *total_pad = hp[0];
+  *max_h = (int)hp[1];
+  if (*total_pad > (int64_t)INT_MAX) return set_err(h, NDT_ERR_CAPACITY, "ndt_match_pairs: the pairs' grids exceed 2^31-1 cells in total");
   return NDT_OK;
 }
 
@@ -580,6 +688,10 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace) {
   }
   if (empty) {
     gd.div_x = gd.div_y = 0; gd.n_cells = 0;
+    // a 4 x 4 all-empty padded table (clear occupancy bits): a match against an empty target probes nothing
+    NDT_CUDA(h, gb.occ.reserve(64)); NDT_CUDA(h, gb.slot.reserve(64)); NDT_CUDA(h, gb.cen.reserve(128)); NDT_CUDA(h, gb.leaf_id.reserve(64));
+    NDT_CUDA(h, cudaMemsetAsync(gb.occ.p, 0, 64, st)); NDT_CUDA(h, cudaMemsetAsync(gb.slot.p, 0xff, 64, st));
+    NDT_CUDA(h, cudaMemsetAsync(gb.cen.p, 0xff, 128, st)); NDT_CUDA(h, cudaMemsetAsync(gb.leaf_id.p, 0xff, 64, st));
     h->have_grid = true;
     if (h->timing) { cudaEventRecord(h->ev1, st); }
     NDT_CUDA(h, cudaStreamSynchronize(st));

@@ -386,6 +386,80 @@ __global__ void k_voxel_filter(const float4 *__restrict__ in, int64_t n, float l
   *n_out = op;
 }
 
+// the same filter for a batch of scan pairs: one CTA per pair (thread 0 walks the cloud, the history lives in
+// shared memory); pair i reads in[src_off .. src_off + ns) and writes its centroids to out at the same offset
+// (the filter never grows a cloud), then records the new count in PairDims::ns. leaf <= 0: plain copy.
+__global__ void __launch_bounds__(32) k_voxel_filter_pairs(const float4 *__restrict__ in, float4 *__restrict__ out,
+                                                          PairDims *__restrict__ dims, float leaf) {
+  __shared__ HistEntry he[512];
+  const int pair = blockIdx.x;
+  const int64_t off = dims[pair].src_off;
+  const int n = dims[pair].ns;
+  if (!(leaf > 0.f)) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) out[off + i] = __ldg(in + off + i);
+    return;
+  }
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) { he[i].count = 0; he[i].cx = he[i].cy = he[i].cz = 0.f; he[i].ix = he[i].iy = he[i].iz = 0; }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const float inv = __fdiv_rn(1.0f, leaf);
+  int op = 0;
+  float4 *o = out + off;
+  for (int i = 0; i < n; ++i) {
+    const float4 p = __ldg(in + off + i);
+    const int ix = (int)floorf(__fmul_rn(p.x, inv)), iy = (int)floorf(__fmul_rn(p.y, inv)), iz = (int)floorf(__fmul_rn(p.z, inv));
+    const unsigned hash = ((unsigned)ix * 7171u + (unsigned)iy * 3079u + (unsigned)iz * 4231u) & 511u;
+    HistEntry &e = he[hash];
+    if (e.count && (ix != e.ix || iy != e.iy || iz != e.iz)) {
+      const float c = (float)e.count;
+      o[op++] = make_float4(__fdiv_rn(e.cx, c), __fdiv_rn(e.cy, c), __fdiv_rn(e.cz, c), 0.f);
+      e.count = 0; e.cx = e.cy = e.cz = 0.f;
+    }
+    e.ix = ix; e.iy = iy; e.iz = iz; e.count++;
+    e.cx = __fadd_rn(e.cx, p.x); e.cy = __fadd_rn(e.cy, p.y); e.cz = __fadd_rn(e.cz, p.z);
+  }
+  for (int k = 0; k < 512; ++k) {
+    HistEntry &e = he[k];
+    if (e.count) {
+      const float c = (float)e.count;
+      o[op++] = make_float4(__fdiv_rn(e.cx, c), __fdiv_rn(e.cy, c), __fdiv_rn(e.cz, c), 0.f);
+    }
+  }
+  dims[pair].ns = op;
+}
+
+// ---------------------------------------------------------------------------------------------
+// persistent scan-pair matcher (loop-closure verification): one warp per pair pulled from an atomic work
+// counter. Every pair has its own grid inside the shared padded tables (PairDims) and its own source cloud.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, NDT_WARP_KERNEL_MIN_CTAS) k_align_pairs(GridView G0, MatchParams mp,
+                                                    const PairDims *__restrict__ dims, const float4 *__restrict__ src_all,
+                                                    const double *__restrict__ guesses, ndt_result *__restrict__ out,
+                                                    int64_t n_jobs, int32_t *__restrict__ job_counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  WarpCoop coop{lane};
+  for (;;) {
+    int job = 0;
+    if (lane == 0) job = atomicAdd(job_counter, 1);
+    job = __shfl_sync(0xffffffffu, job, 0);
+    if (job >= n_jobs) break;
+    const PairDims d = dims[job];
+    GridView G = G0;
+    G.min_bx = d.min_bx; G.min_by = d.min_by; G.div_x = d.div_x; G.div_y = d.div_y;
+    G.slot_w = d.W; G.table_base = d.base;
+    G.tgt = G0.tgt + d.tgt_off; G.n_tgt = d.nt; G.nn_f = 0;
+    const double guess[3] = {guesses[3 * (size_t)job], guesses[3 * (size_t)job + 1], guesses[3 * (size_t)job + 2]};
+    const GlobalSrc gsrc{src_all + d.src_off};
+    MatchOut mo;
+    auto obj = make_objective(G, mp, coop, GlobalOcc{G.occ}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, d.ns, my_queue(smem_raw));
+    match_device(obj, mp, guess, mo);
+    double fsum = 0.0;
+    if (mp.want_fitness) fsum = fitness_pass(G, gsrc, d.ns, mp, mo.p, coop);
+    if (lane == 0) write_result(out + job, mo, d.ns, fsum, mp.want_fitness != 0, G.n_tgt);
+  }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -481,6 +555,33 @@ int launch_align(Handle *h, const double *d_guesses, int64_t n, ndt_result *d_re
   }
   ++h->launches;
   if (h->timing) cudaEventRecord(h->ev1, st);
+  NDT_CUDA(h, cudaGetLastError());
+  return NDT_OK;
+}
+
+int launch_pairs_filter(Handle *h, const float4 *d_in, float4 *d_out, int64_t n_pairs, float leaf) {
+  if (n_pairs <= 0) return NDT_OK;
+  k_voxel_filter_pairs<<<(unsigned)n_pairs, 32, 0, h->stream>>>(d_in, d_out, h->gb.dims.as<PairDims>(), leaf);
+  ++h->launches;
+  NDT_CUDA(h, cudaGetLastError());
+  return NDT_OK;
+}
+
+int launch_align_pairs(Handle *h, const float4 *d_src, const double *d_guesses, int64_t n_pairs, ndt_result *d_results,
+                       bool want_fitness) {
+  if (n_pairs <= 0) return NDT_OK;
+  cudaStream_t st = h->stream;
+  GridView G = grid_view(h);        // shared tables; the per-pair geometry comes from PairDims inside the kernel
+  G.nn_f = 0;
+  const MatchParams mp = match_params(h, want_fitness);
+  int32_t *ctr = h->gb.counters.as<int32_t>();
+  NDT_CUDA(h, cudaMemsetAsync(ctr + CTR_JOB, 0, sizeof(int32_t), st));
+  int64_t grid = (int64_t)h->sm_count * NDT_WARP_KERNEL_MIN_CTAS;
+  grid = std::min<int64_t>(grid, (n_pairs + 7) / 8);
+  NDT_CUDA(h, cudaFuncSetAttribute(k_align_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, QUEUE_BYTES));
+  k_align_pairs<<<(unsigned)grid, 256, QUEUE_BYTES, st>>>(G, mp, h->gb.dims.as<PairDims>(), d_src, d_guesses, d_results,
+                                                         n_pairs, ctr + CTR_JOB);
+  ++h->launches;
   NDT_CUDA(h, cudaGetLastError());
   return NDT_OK;
 }

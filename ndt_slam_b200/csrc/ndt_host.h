@@ -104,8 +104,7 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace);
 // shared by ndt_set_target (one grid) and ndt_match_pairs (one grid per pair): target points are in gb.tgt,
 // geometry in gb.dims (device), point ranges in gb.pair_off (device, n_grids + 1 entries; unused for one grid)
 int grid_build_tables(Handle *h, int64_t n, int n_grids, int64_t total_pad, int max_h);
-int pairs_prepare(Handle *h, const int64_t *d_tgt_off, const int64_t *d_src_off, const int32_t *d_src_cnt, int64_t n_pairs,
-                  int64_t *total_pad, int *max_h);
+int pairs_prepare(Handle *h, int64_t n_pairs, int64_t *total_pad, int *max_h);
 int grid_cell_index(Handle *h, const float *xyzw, int64_t n, int memspace, int32_t *idx_out);
 GridView grid_view(const Handle *h);
 MatchParams match_params(const Handle *h, bool want_fitness);
@@ -115,6 +114,10 @@ int launch_eval(Handle *h, const double *d_poses, int64_t n, int want_hessian, d
 int launch_align(Handle *h, const double *d_guesses, int64_t n, ndt_result *d_results, bool want_fitness);
 int launch_best_of(Handle *h, const ndt_result *d_results, int64_t n, int64_t *d_best_index, ndt_result *d_best);
 int launch_voxel_filter(Handle *h, const float4 *d_in, int64_t n, float leaf, float4 *d_out, int32_t *d_nout);
+// batched scan pairs: per-pair source filter (writes PairDims::ns) and the persistent warp-per-pair matcher
+int launch_pairs_filter(Handle *h, const float4 *d_in, float4 *d_out, int64_t n_pairs, float leaf);
+int launch_align_pairs(Handle *h, const float4 *d_src, const double *d_guesses, int64_t n_pairs, ndt_result *d_results,
+                       bool want_fitness);
 
 // helpers (capi.cu)
 int set_err(Handle *h, int code, const char *what, cudaError_t e = cudaSuccess);

@@ -21,6 +21,7 @@ src = ha.voxel_filter(synth.to_xyzw(ha.resample(seq["scans"][n])), 0.05)
 guess = np.array([poses[-1, 0], poses[-1, 1], np.deg2rad(poses[-1, 2])])
 print("target", tgt.shape, "source", src.shape, "stats", slam.stats())
 g = capi.Ndt(capi.default_params(resolution=0.5))
+torch.cuda.cudart().cudaProfilerStart()      # ncu --profile-from-start off: only the state benchmark below
 d_t = torch.from_numpy(tgt).cuda()
 def timeit(f, k=10):
     f(); torch.cuda.synchronize(); t0 = time.perf_counter()
@@ -32,3 +33,12 @@ gi = g.grid_info(); print("leaves", gi.n_leaves, "tree", gi.n_slots, "cells", li
 rb = g.grid_readback(); print("bucket sizes: max", np.abs(rb["nr_points"]).max(), "mean", np.abs(rb["nr_points"]).mean())
 print("set_source        wall ms", timeit(lambda: g.set_source(src)))
 print("align             wall ms", timeit(lambda: g.align(guess)), "kernel ms", g.last_kernel_ms(), "evals", g.align(guess).evals)
+# sporadic launches (one per 8 ms, like the per-scan loop): does the device time change when the GPU idles in between?
+import subprocess
+for gap in (0.0, 0.002, 0.008, 0.03):
+    ms = []
+    for _ in range(40):
+        time.sleep(gap)
+        g.set_target(tgt); ms.append(g.last_kernel_ms())
+    clk = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.mem,pstate,power.draw", "--format=csv,noheader"], capture_output=True, text=True).stdout.strip()
+    print(f"gap {gap*1e3:.0f} ms: set_target device ms median {np.median(ms):.3f} min {np.min(ms):.3f} max {np.max(ms):.3f} | {clk}")

@@ -296,3 +296,75 @@ def test_fitness_exact_with_dense_buckets():
     g.set_source(far); o.set_source(far)
     a, b = g.align([0.0, 0.0, 0.0]), o.align([0.0, 0.0, 0.0])
     assert a.fitness == pytest.approx(b.fitness, rel=1e-9)
+
+
+def _c5_batch(ids):
+    """Scan pairs as ndt_match_pairs takes them: raw (resampled) source clouds, target clouds, offsets."""
+    srcs, tgts = [], []
+    for i in ids:
+        d = synth.c5_pair(i)
+        tgts.append(synth.to_xyzw(common.prep_scan(d["scan_a"])))
+        srcs.append(synth.to_xyzw(common.prep_scan(d["scan_b"])))
+    return srcs, tgts
+
+
+def _pack(clouds):
+    off = np.zeros(len(clouds) + 1, np.int64)
+    off[1:] = np.cumsum([c.shape[0] for c in clouds])
+    pts = np.concatenate(clouds, axis=0) if off[-1] > 0 else np.zeros((0, 4), np.float32)
+    return np.ascontiguousarray(pts, dtype=np.float32), off
+
+
+def test_match_pairs_parity_with_oracle_per_pair():
+    """C5 (loop-closure verification): one batched call == n x (filter, grid build, match, fitness) of the oracle.
+    Includes ragged sizes, an empty target, an empty source and a single-point target."""
+    prm = common.params(resolution=0.5)
+    srcs, tgts = _c5_batch(range(70))
+    tgts[5] = np.zeros((0, 4), np.float32)            # empty target
+    srcs[9] = np.zeros((0, 4), np.float32)            # empty source
+    tgts[11] = tgts[11][:1]                            # one target point: a grid with no tree cell
+    srcs[13] = srcs[13][:40]; tgts[17] = tgts[17][:100]
+    n = len(srcs)
+    src, so = _pack(srcs); tgt, to = _pack(tgts)
+    guesses = np.zeros((n, 3))
+    g = capi.Ndt(prm)
+    res = g.match_pairs(src, so, tgt, to, guesses, n, source_leaf=common.LAUNCH["leaf"])
+    o = oa.Oracle(prm)
+    worst_t = 0.0
+    for k in range(n):
+        fs = oa.approx_voxel_filter(srcs[k], common.LAUNCH["leaf"]) if srcs[k].shape[0] else srcs[k]
+        o.set_target(tgts[k]); o.set_source(fs)
+        b = o.align(guesses[k])
+        r = res[k]
+        assert r["converged"] == b.converged and r["iters"] == b.iters and r["evals"] == b.evals, k
+        assert r["point_evals"] == b.evals * fs.shape[0], k           # identical filtered source size
+        assert np.hypot(r["pose"][0] - b.pose[0], r["pose"][1] - b.pose[1]) < POSE_M, k
+        assert abs(r["pose"][2] - b.pose[2]) < POSE_RAD, k
+        assert r["score"] == pytest.approx(b.score, rel=REL_EVAL, abs=1e-12), k
+        if fs.shape[0] and tgts[k].shape[0]:
+            assert r["fitness"] == pytest.approx(b.fitness, rel=1e-9), k
+        worst_t = max(worst_t, float(np.hypot(r["pose"][0] - b.pose[0], r["pose"][1] - b.pose[1])))
+    # the batched call agrees with the single-match entry points of the same library (different reduction tree:
+    # one CTA per match there, one warp per pair here)
+    for k in (0, 3, 33):
+        g1 = capi.Ndt(prm)
+        g1.set_target(tgts[k]); g1.set_source(g1.approx_voxel_filter(srcs[k], common.LAUNCH["leaf"]))
+        a = g1.align(guesses[k])
+        assert np.allclose(a.pose, res[k]["pose"], rtol=0, atol=1e-9) and a.score == pytest.approx(res[k]["score"], rel=1e-10)
+        assert a.iters == res[k]["iters"] and a.evals == res[k]["evals"]
+    # device-resident inputs / outputs give the same bytes
+    d_src, d_tgt = torch.from_numpy(src).cuda(), torch.from_numpy(tgt).cuda()
+    d_g = torch.from_numpy(guesses).cuda()
+    d_res = torch.zeros(n * capi.RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    g.match_pairs(d_src.data_ptr(), so, d_tgt.data_ptr(), to, d_g.data_ptr(), n, source_leaf=common.LAUNCH["leaf"],
+                  space=capi.MEM_DEVICE, out=d_res.data_ptr())
+    g.synchronize()
+    res2 = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype=capi.RESULT_DTYPE)
+    assert np.array_equal(res2["pose"], res["pose"]) and np.array_equal(res2["score"], res["score"])
+    # recovery of the true offset for ordinary pairs
+    ok = 0
+    for k in range(20, 70):
+        off = synth.c5_pair(k)["offset"]
+        if res[k]["converged"] and np.hypot(res[k]["pose"][0] - off[0], res[k]["pose"][1] - off[1]) < 0.05:
+            ok += 1
+    assert ok >= 35
