@@ -79,13 +79,13 @@ __device__ __forceinline__ Objective<Coop, OccL, CenL, SlotL, RecL, SrcL> make_o
                                                   (mp.quirks & NDT_QUIRK_TRANSFORM_SSE_ORDER) ? 1 : 0, coop, Q};
 }
 
-// per-warp hit queues live at the start of the CTA's dynamic shared memory (8 warps per CTA)
-constexpr int QUEUE_BYTES = 8 * QUEUE_BYTES_PER_WARP;          // 51,200 B
+// per-warp rings live at the start of the CTA's dynamic shared memory (8 warps per CTA): [8][QCAP] int2 hits | [8][CQCAP] int2 candidates
+constexpr int QUEUE_BYTES = 8 * QUEUE_BYTES_PER_WARP;          // 24,576 B
 __device__ __forceinline__ HitQueue my_queue(unsigned char *smem) {
   const int w = threadIdx.x >> 5;
-  float4 *xy = reinterpret_cast<float4 *>(smem) + w * QCAP;
-  int *cell = reinterpret_cast<int *>(smem + 8 * QCAP * 16) + w * QCAP;
-  return HitQueue{xy, cell};
+  int2 *hit = reinterpret_cast<int2 *>(smem) + w * QCAP;
+  int2 *cand = reinterpret_cast<int2 *>(smem + 8 * QCAP * 8) + w * CQCAP;
+  return HitQueue{hit, cand};
 }
 
 template <class Coop, class SrcL>

@@ -126,21 +126,20 @@ __device__ __forceinline__ float dist2f(float ax, float ay, float bx, float by) 
 // MODE 0: score + gradient + Hessian; 1: score + gradient; 2: Hessian only (computeHessian)
 // acc layout: [0] score, [1..3] gradient, [4..12] Hessian row-major
 //
-// Two phases per warp step (32 source points):
-//   probe  each lane transforms its point (float32, bit-exact), reads the 3x3 block of the
-//          cell->slot table and runs the float32 centroid radius test; every (point, cell) hit is
-//          pushed into a per-warp ring queue in shared memory (ballot + popc offsets);
-//   drain  whenever 32 hits are queued, all 32 lanes pop one hit each and run the fp64 hit path
-//          fully converged. Without the queue the hit path would run once per neighbour position
-//          with a handful of active lanes (k = 0.3 .. 2 hits per point spread over 9 positions).
+// accumulate_points() below runs it as three compacted stages (transform -> probe -> fp64 hit path) linked by
+// two per-warp rings in shared memory.
 // ------------------------------------------------------------------------------------------------
 constexpr int NACC = 13;
-constexpr int QCAP = 320;           // per-warp ring capacity: < 32 queued before a step is probed, a step adds <= 9 * 32
-constexpr int QUEUE_BYTES_PER_WARP = QCAP * (16 + 4);
+constexpr int QCAP = 320;           // hit ring per warp: < 32 queued before a probe, a probe adds <= 9 * 32
+constexpr int CQCAP = 128;          // candidate ring per warp: < 32 queued before a double step, which adds <= 64
+constexpr int QUEUE_BYTES_PER_WARP = (QCAP + CQCAP) * 8;
 
+// Ring entries are 8 bytes: the source point index plus a table position. The float32 transform of a point is
+// eight flops, so stages B and C redo it from the (shared-memory) source point instead of carrying 16 more bytes
+// per entry -- the rings of a CTA then take 24 KB and three CTAs fit on an SM.
 struct HitQueue {
-  float4 *xy;     // [QCAP] xt, yt (transformed, float32), xf, yf (original)
-  int *cell;      // [QCAP] padded-table index of the hit cell
+  int2 *hit;      // [QCAP]  (source point index, padded-table index of the hit cell)
+  int2 *cand;     // [CQCAP] (source point index, padded-table index of the point's own cell)
 };
 
 template <int MODE, class RecL>
@@ -198,11 +197,35 @@ __device__ __forceinline__ ProbeGeom probe_geom(const GridView &G) {
 // is lane-contiguous inside a warp (first = warp_first + lane): every lane of a warp iterates the same
 // number of times. acc must be a register array of the caller. pairs: warp-uniform hit count.
 //
-// One warp step = 32 points. Probe: all nine centroid loads are issued back to back (no bounds checks:
-// padded table; no emptiness branch: NaN centroids fail the compare), giving a 9-bit hit mask per lane;
-// one warp prefix scan turns the per-lane hit counts into ring offsets. Drain: see above. The loop is a
-// warp-uniform state machine with a single drain site, so the fp64 hit path exists once in the
-// instruction stream (the matcher is instruction-cache sensitive).
+// Three stages, each run by a full warp on compacted work (a warp-uniform state machine; every stage
+// exists once in the instruction stream -- the matcher is instruction-cache sensitive):
+//   A  transform  2 x 32 source points: float32 transform (bit-exact), own cell, dilated-occupancy bit. Points
+//                 that can hit something (typically a third of a scan against a building-sized map) are
+//                 pushed into the per-warp candidate ring (ballot + popc offsets).
+//   B  probe      whenever 32 candidates are queued: nine centroid loads each, issued back to back (no
+//                 bounds checks: padded table; no emptiness branch: NaN centroids fail the compare), the
+//                 float32 radius test gives a 9-bit hit mask per lane, one warp prefix scan turns the
+//                 per-lane hit counts into offsets in the hit ring.
+//   C  drain      whenever 32 hits are queued: every lane pops one (point, cell) hit and runs the fp64
+//                 hit path fully converged.
+// Without the rings the probe would run for every point (all 32 lanes pay when one is a candidate) and the
+// hit path once per neighbour position with a handful of active lanes.
+// stage A for one point: padded-table index of its own cell if the point can hit anything, else -1
+template <class OccL, class SrcL>
+__device__ __forceinline__ int candidate_cell(const ProbeGeom &g, const OccL &occ_at, const SrcL &src, const int i,
+                                              const bool valid, const PoseF &pf, const bool sse_order) {
+  const float2 xy = src(i);
+  float xt, yt;
+  xform(pf, sse_order, xy.x, xy.y, xt, yt);
+  const int ci = cell_coord(xt, g.inv_leaf, g.min_bx);
+  const int cj = cell_coord(yt, g.inv_leaf, g.min_by);
+  // -1 <= ci <= div_x and -1 <= cj <= div_y: the cells whose 3x3 block can touch the grid
+  const bool in = valid && (unsigned)(ci + 1) <= (unsigned)(g.div_x + 1) && (unsigned)(cj + 1) <= (unsigned)(g.div_y + 1);
+  const int base = in ? (g.base + (cj + 2) * g.W + ci + 2) : 0;
+  const unsigned word = occ_at(base >> 5);
+  return (in && ((word >> (base & 31)) & 1u)) ? base : -1;
+}
+
 template <int MODE, class OccL, class CenL, class SlotL, class RecL, class SrcL>
 __device__ __forceinline__ void accumulate_points(const ProbeGeom g, const OccL occ_at, const CenL cen_at, const SlotL slot_at,
                                                   const RecL rec_at, const SrcL src, const int first,
@@ -211,73 +234,85 @@ __device__ __forceinline__ void accumulate_points(const ProbeGeom g, const OccL 
                                                   const double d1, const double d2, const HitQueue Q, double *acc,
                                                   int &pairs) {
   const int lane = threadIdx.x & 31;
-  int qhead = 0, qn = 0;
+  const unsigned lt = (1u << lane) - 1u;
+  int qhead = 0, qn = 0;           // hit ring
+  int chead = 0, cn = 0;           // candidate ring
   int i0 = first - lane;
   for (;;) {
+    // ---- A: transform source points two warp steps at a time until 32 candidates are queued ----
+    while (cn < 32 && i0 < hi) {
+      const int ia = i0 + lane, ib = ia + stride;
+      i0 += 2 * stride;
+      const int ba = candidate_cell(g, occ_at, src, min(ia, hi - 1), ia < hi, pf, sse_order);
+      const int bb = candidate_cell(g, occ_at, src, min(ib, hi - 1), ib < hi, pf, sse_order);
+      const unsigned bal_a = __ballot_sync(0xffffffffu, ba >= 0);
+      const unsigned bal_b = __ballot_sync(0xffffffffu, bb >= 0);
+      const int na = __popc(bal_a);
+      if (ba >= 0) Q.cand[(chead + cn + __popc(bal_a & lt)) & (CQCAP - 1)] = make_int2(ia, ba);
+      if (bb >= 0) Q.cand[(chead + cn + na + __popc(bal_b & lt)) & (CQCAP - 1)] = make_int2(ib, bb);
+      cn += na + __popc(bal_b);
+    }
     const bool done = (i0 >= hi);
-    if (qn >= 32 || (done && qn > 0)) {
-      // drain: every lane pops one queued (point, cell) hit and runs the fp64 hit path converged
+    if (cn >= 32 || (done && cn > 0)) {
+      // ---- B: probe up to 32 queued candidates ----
+      const int n = min(cn, 32);
+      __syncwarp();
+      unsigned mask = 0u;
+      int2 cd = make_int2(0, 0);
+      if (lane < n) {
+        cd = Q.cand[(chead + lane) & (CQCAP - 1)];
+        float2 c[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) c[k] = cen_at(cd.y + (k / 3 - 1) * g.W + (k % 3 - 1));
+        const float2 xy = src(cd.x);
+        float xt, yt;
+        xform(pf, sse_order, xy.x, xy.y, xt, yt);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) mask |= (dist2f(xt, yt, c[k].x, c[k].y) < g.r2) ? (1u << k) : 0u;
+      }
+      chead = (chead + n) & (CQCAP - 1);
+      cn -= n;
+      if (__any_sync(0xffffffffu, mask != 0u)) {
+        const int cnt = __popc(mask);
+        int incl = cnt;
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, dlt);
+          if (lane >= dlt) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int pos = qhead + qn + incl - cnt;
+        if (pos >= QCAP) pos -= QCAP;
+        while (mask) {
+          const int k = __ffs(mask) - 1;
+          mask &= mask - 1u;
+          Q.hit[pos] = make_int2(cd.x, cd.y + (k / 3 - 1) * g.W + (k % 3 - 1));
+          if (++pos == QCAP) pos = 0;
+        }
+        qn += total;
+      }
+    }
+    // ---- C: every lane pops one queued (point, cell) hit and runs the fp64 hit path converged ----
+    while (qn >= 32 || (done && cn == 0 && qn > 0)) {
       const int n = min(qn, 32);
       __syncwarp();
       if (lane < n) {
         int pos = qhead + lane;
         if (pos >= QCAP) pos -= QCAP;
-        hit_path<MODE>(rec_at, Q.xy[pos], slot_at(Q.cell[pos]), cs, sn, d1, d2, acc);
+        const int2 h = Q.hit[pos];
+        const float2 xy = src(h.x);
+        float4 e;
+        e.z = xy.x; e.w = xy.y;
+        xform(pf, sse_order, xy.x, xy.y, e.x, e.y);
+        hit_path<MODE>(rec_at, e, slot_at(h.y), cs, sn, d1, d2, acc);
       }
       __syncwarp();
       qhead += n;
       if (qhead >= QCAP) qhead -= QCAP;
       qn -= n;
       pairs += n;
-      continue;
     }
-    if (done) break;
-    // ---- probe one warp step ----
-    const int i = i0 + lane;
-    i0 += stride;
-    int base = 0;
-    bool cand = false;               // can this point hit anything at all? (dilated occupancy bit of its own cell)
-    float xt = 0.f, yt = 0.f, xf = 0.f, yf = 0.f;
-    if (i < hi) {
-      const float2 xy = src(i);
-      xf = xy.x; yf = xy.y;
-      xform(pf, sse_order, xf, yf, xt, yt);
-      const int ci = cell_coord(xt, g.inv_leaf, g.min_bx);
-      const int cj = cell_coord(yt, g.inv_leaf, g.min_by);
-      if (ci >= -1 && cj >= -1 && ci <= g.div_x && cj <= g.div_y) {
-        base = g.base + (cj + 2) * g.W + ci + 2;
-        cand = (occ_at(base >> 5) >> (base & 31)) & 1u;
-      }
-    }
-    if (!__any_sync(0xffffffffu, cand)) continue;      // open space for all 32 points: nothing to probe
-    unsigned mask = 0u;
-    if (cand) {
-      float2 c[9];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) c[k] = cen_at(base + (k / 3 - 1) * g.W + (k % 3 - 1));
-#pragma unroll
-      for (int k = 0; k < 9; ++k) mask |= (dist2f(xt, yt, c[k].x, c[k].y) < g.r2) ? (1u << k) : 0u;
-    }
-    if (__any_sync(0xffffffffu, mask != 0u)) {
-      const int cnt = __popc(mask);
-      int incl = cnt;
-#pragma unroll
-      for (int dlt = 1; dlt < 32; dlt <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, dlt);
-        if (lane >= dlt) incl += t;
-      }
-      const int total = __shfl_sync(0xffffffffu, incl, 31);
-      int pos = qhead + qn + incl - cnt;
-      if (pos >= QCAP) pos -= QCAP;
-      while (mask) {
-        const int k = __ffs(mask) - 1;
-        mask &= mask - 1u;
-        Q.xy[pos] = make_float4(xt, yt, xf, yf);
-        Q.cell[pos] = base + (k / 3 - 1) * g.W + (k % 3 - 1);
-        if (++pos == QCAP) pos = 0;
-      }
-      qn += total;
-    }
+    if (done && cn == 0) break;       // the drain loop above has emptied the hit ring
   }
   __syncwarp();
 }
