@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(256) k_bounds(const float4 *__restrict__ pts, 
 }
 
 struct Dims { int32_t min_bx, min_by, div_x, div_y; float inv_leaf; };
+constexpr int FINALIZE_BIG_LEAF = 96;     // leaves with more points are reduced by a warp instead of a thread
 
 // Which grid does point i belong to? (batched scan pairs: point ranges per pair; one grid: always 0)
 __device__ __forceinline__ int pair_of(const int64_t *__restrict__ off, int n_pairs, int64_t i) {
@@ -129,7 +130,8 @@ __global__ void __launch_bounds__(256) k_alloc(int32_t *__restrict__ count_slot,
                                               const PairDims *__restrict__ dims, int chunks,
                                               int32_t *__restrict__ leaf_id, int32_t *__restrict__ leaf_cell,
                                               int32_t *__restrict__ leaf_pair, int32_t *__restrict__ leaf_n,
-                                              int32_t *__restrict__ leaf_start, int32_t *__restrict__ ctr) {
+                                              int32_t *__restrict__ leaf_start, int32_t *__restrict__ big_list,
+                                              int32_t *__restrict__ ctr) {
   const int lane = threadIdx.x & 31;
   const int pair = blockIdx.x / chunks, chunk = blockIdx.x - pair * chunks;
   const PairDims d = dims[pair];
@@ -168,6 +170,7 @@ __global__ void __launch_bounds__(256) k_alloc(int32_t *__restrict__ count_slot,
           leaf_pair[leaf] = pair;
           leaf_n[leaf] = n;
           leaf_start[leaf] = base_pts + incl - n;
+          if (n > FINALIZE_BIG_LEAF) big_list[atomicAdd(ctr + CTR_BIG, 1)] = leaf;   // dense leaves get a warp in k_finalize
         }
       }
       if (valid) {
@@ -241,34 +244,29 @@ __device__ inline void eig2(double a, double b, double d, double *lam, double *v
 
 struct FinalizeParams { int32_t min_points; double eig_mult; int32_t quirks; };
 
-// pass 2: one thread per leaf. The bucket is contiguous and already in input order (k_rank), so the
-// thread walks it sequentially: fp32 centroid and fp64 sums accumulate exactly like the reference's
-// pass 1, then mean, single-pass covariance, eigenvalue clamp, inverse.
-__global__ void __launch_bounds__(128) k_finalize(const float2 *__restrict__ tgt_sorted,
-                                                 const int32_t *__restrict__ leaf_cell,
-                                                 const int32_t *__restrict__ leaf_n,
-                                                 const int32_t *__restrict__ leaf_start, int2 *__restrict__ leaf_range,
-                                                 int32_t *__restrict__ leaf_nr, double2 *__restrict__ leaf_mean,
-                                                 double *__restrict__ leaf_icov, float2 *__restrict__ leaf_cen,
-                                                 int32_t *__restrict__ slot, float2 *__restrict__ cen_tab,
-                                                 uint32_t *__restrict__ occ, CellRec *__restrict__ recs,
-                                                 int32_t *__restrict__ ctr, FinalizeParams fp,
-                                                 const int32_t *__restrict__ leaf_pair,
-                                                 const PairDims *__restrict__ dims) {
-  const int n_leaves = ctr[CTR_LEAVES];
-  for (int leaf = blockIdx.x * blockDim.x + threadIdx.x; leaf < n_leaves; leaf += gridDim.x * blockDim.x) {
-    const int n = leaf_n[leaf], st = leaf_start[leaf];
+// pass 2. The bucket of a leaf is contiguous and already in input order (k_rank); its sums must be taken in that
+// order (fp32 centroid and fp64 sums accumulate exactly like the reference's pass 1: bit-identical results), so a
+// leaf is one sequential chain of adds. Sparse leaves (C3: ~7 points) take one thread each. A dense leaf (C2 local
+// map: thousands of points in a 0.5 m cell) takes a warp: coalesced 32-point loads, then every lane replays the
+// same chain from register shuffles -- the chain then runs at add latency instead of one memory round trip per point.
+struct LeafSums { double sx, sy, sxx, syx, syy; float cx, cy; };
+
+struct FinalizeOut {
+  int2 *__restrict__ leaf_range; int32_t *__restrict__ leaf_nr; double2 *__restrict__ leaf_mean; double *__restrict__ leaf_icov;
+  float2 *__restrict__ leaf_cen; int32_t *__restrict__ slot; float2 *__restrict__ cen_tab; uint32_t *__restrict__ occ;
+  CellRec *__restrict__ recs; int32_t *__restrict__ ctr;
+  const int32_t *__restrict__ leaf_cell; const int32_t *__restrict__ leaf_pair; const PairDims *__restrict__ dims;
+};
+
+__device__ __forceinline__ void finish_leaf(const int leaf, const int n, const int st, const LeafSums sums, const FinalizeParams fp,
+                                            const FinalizeOut &o) {
+    int2 *leaf_range = o.leaf_range; int32_t *leaf_nr = o.leaf_nr; double2 *leaf_mean = o.leaf_mean; double *leaf_icov = o.leaf_icov;
+    float2 *leaf_cen = o.leaf_cen; int32_t *slot = o.slot; float2 *cen_tab = o.cen_tab; uint32_t *occ = o.occ; CellRec *recs = o.recs;
+    int32_t *ctr = o.ctr; const int32_t *leaf_cell = o.leaf_cell; const int32_t *leaf_pair = o.leaf_pair; const PairDims *dims = o.dims;
     leaf_range[leaf] = make_int2(st, n);
-    double sx = 0, sy = 0, sxx = 0, syx = 0, syy = 0;
-    float cx = 0.f, cy = 0.f;
-    const float2 *__restrict__ bucket = tgt_sorted + st;
-    for (int k = 0; k < n; ++k) {
-      const float2 p = __ldg(bucket + k);
-      const double xd = (double)p.x, yd = (double)p.y;
-      sx += xd; sy += yd;
-      sxx += xd * xd; syx += yd * xd; syy += yd * yd;
-      cx = __fadd_rn(cx, p.x); cy = __fadd_rn(cy, p.y);
-    }
+    double sx = sums.sx, sy = sums.sy;
+    const double sxx = sums.sxx, syx = sums.syx, syy = sums.syy;
+    float cx = sums.cx, cy = sums.cy;
     const double nn = (double)n;
     cx = cx / (float)n; cy = cy / (float)n;
     const double psx = sx, psy = sy;
@@ -356,6 +354,48 @@ __global__ void __launch_bounds__(128) k_finalize(const float2 *__restrict__ tgt
           atomicOr(occ + (t >> 5), 1u << (t & 31));
         }
     }
+}
+
+__global__ void __launch_bounds__(128) k_finalize(const float2 *__restrict__ tgt_sorted, const int32_t *__restrict__ leaf_n,
+                                                 const int32_t *__restrict__ leaf_start, const int32_t *__restrict__ big_list,
+                                                 FinalizeParams fp, FinalizeOut o) {
+  const int n_leaves = o.ctr[CTR_LEAVES];
+  // sparse leaves: one thread each
+  for (int leaf = blockIdx.x * blockDim.x + threadIdx.x; leaf < n_leaves; leaf += gridDim.x * blockDim.x) {
+    const int n = leaf_n[leaf], st = leaf_start[leaf];
+    if (n > FINALIZE_BIG_LEAF) continue;
+    LeafSums a{0, 0, 0, 0, 0, 0.f, 0.f};
+    const float2 *__restrict__ bucket = tgt_sorted + st;
+    for (int k = 0; k < n; ++k) {
+      const float2 p = __ldg(bucket + k);
+      const double xd = (double)p.x, yd = (double)p.y;
+      a.sx += xd; a.sy += yd;
+      a.sxx += xd * xd; a.syx += yd * xd; a.syy += yd * yd;
+      a.cx = __fadd_rn(a.cx, p.x); a.cy = __fadd_rn(a.cy, p.y);
+    }
+    finish_leaf(leaf, n, st, a, fp, o);
+  }
+  // dense leaves (listed by k_alloc): one warp each
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  const int n_big = o.ctr[CTR_BIG];
+  for (int b = warp; b < n_big; b += n_warps) {
+    const int leaf = big_list[b];
+    const int n = leaf_n[leaf], st = leaf_start[leaf];
+    LeafSums a{0, 0, 0, 0, 0, 0.f, 0.f};
+    const float2 *__restrict__ bucket = tgt_sorted + st;
+    for (int c = 0; c < n; c += 32) {
+      const float2 mp = (c + lane < n) ? __ldg(bucket + c + lane) : make_float2(0.f, 0.f);
+      const int m = min(32, n - c);
+      for (int k = 0; k < m; ++k) {
+        const float px = __shfl_sync(0xffffffffu, mp.x, k), py = __shfl_sync(0xffffffffu, mp.y, k);
+        const double xd = (double)px, yd = (double)py;
+        a.sx += xd; a.sy += yd;
+        a.sxx += xd * xd; a.syx += yd * xd; a.syy += yd * yd;
+        a.cx = __fadd_rn(a.cx, px); a.cy = __fadd_rn(a.cy, py);
+      }
+    }
+    if (lane == 0) finish_leaf(leaf, n, st, a, fp, o);
   }
 }
 
@@ -537,6 +577,7 @@ int grid_build_tables(Handle *h, int64_t n, int n_grids, int64_t total_pad, int 
   const size_t max_leaves = std::min(npts, npad);
   NDT_CUDA(h, gb.leaf_cell.reserve(max_leaves * 4));
   NDT_CUDA(h, gb.leaf_pair.reserve(max_leaves * 4));
+  NDT_CUDA(h, gb.big_list.reserve((npts / FINALIZE_BIG_LEAF + 1) * 4));
   NDT_CUDA(h, gb.leaf_n.reserve(max_leaves * 4));
   NDT_CUDA(h, gb.leaf_start.reserve(max_leaves * 4));
   NDT_CUDA(h, gb.leaf_range.reserve(max_leaves * sizeof(int2)));
@@ -559,7 +600,7 @@ int grid_build_tables(Handle *h, int64_t n, int n_grids, int64_t total_pad, int 
   k_alloc<<<(unsigned)((int64_t)n_grids * chunks), 256, 0, st>>>(gb.slot.as<int32_t>(), gb.cen.as<float2>(), dims, chunks,
                                                                 gb.leaf_id.as<int32_t>(), gb.leaf_cell.as<int32_t>(),
                                                                 gb.leaf_pair.as<int32_t>(), gb.leaf_n.as<int32_t>(),
-                                                                gb.leaf_start.as<int32_t>(), ctr);
+                                                                gb.leaf_start.as<int32_t>(), gb.big_list.as<int32_t>(), ctr);
   k_fill<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(n, gb.cell_of.as<int32_t>(), gb.rank_of.as<int32_t>(),
                                                        gb.leaf_id.as<int32_t>(), gb.leaf_start.as<int32_t>(),
                                                        gb.list.as<int32_t>());
@@ -568,11 +609,11 @@ int grid_build_tables(Handle *h, int64_t n, int n_grids, int64_t total_pad, int 
                                                        gb.list.as<int32_t>(), gb.tgt.as<float4>(), gb.sorted_idx.as<int32_t>(),
                                                        gb.tgt_sorted.as<float2>(), ctr);
   FinalizeParams fp{h->prm.min_points, h->prm.eig_mult, h->prm.quirks};
-  k_finalize<<<grid_for((int64_t)max_leaves, 128, h->sm_count, 16), 128, 0, st>>>(
-      gb.tgt_sorted.as<float2>(), gb.leaf_cell.as<int32_t>(), gb.leaf_n.as<int32_t>(), gb.leaf_start.as<int32_t>(),
-      gb.leaf_range.as<int2>(), gb.leaf_nr.as<int32_t>(), gb.leaf_mean.as<double2>(), gb.leaf_icov.as<double>(),
-      gb.leaf_cen.as<float2>(), gb.slot.as<int32_t>(), gb.cen.as<float2>(), gb.occ.as<uint32_t>(), gb.recs.as<CellRec>(), ctr,
-      fp, gb.leaf_pair.as<int32_t>(), dims);
+  FinalizeOut fo{gb.leaf_range.as<int2>(), gb.leaf_nr.as<int32_t>(), gb.leaf_mean.as<double2>(), gb.leaf_icov.as<double>(),
+                 gb.leaf_cen.as<float2>(), gb.slot.as<int32_t>(), gb.cen.as<float2>(), gb.occ.as<uint32_t>(), gb.recs.as<CellRec>(), ctr,
+                 gb.leaf_cell.as<int32_t>(), gb.leaf_pair.as<int32_t>(), dims};
+  k_finalize<<<std::max(grid_for((int64_t)max_leaves, 128, h->sm_count, 16), 2 * h->sm_count), 128, 0, st>>>(gb.tgt_sorted.as<float2>(), gb.leaf_n.as<int32_t>(),
+                                                                                  gb.leaf_start.as<int32_t>(), gb.big_list.as<int32_t>(), fp, fo);
   h->launches += 5;
   NDT_CUDA(h, cudaGetLastError());
   return NDT_OK;

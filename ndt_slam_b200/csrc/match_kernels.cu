@@ -53,18 +53,17 @@ struct Objective {
   Coop coop;
   HitQueue Q;          // this warp's hit queue (shared memory)
 
-  template <int MODE>
-  __device__ __noinline__ void pass(const double *p, const AngleCache &ac, double *out) {
+  __device__ __noinline__ void pass(const int mode, const double *p, const AngleCache &ac, double *out) {
     double acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
     const PoseF pf = pose_to_float(p);
     const Coop co = coop;
     int pairs = 0;
-    accumulate_points<MODE>(geom, occ, cen, slot, rec, src, co.rank(), co.size(), ns, pf, sse != 0, ac.cs, ac.sn, d1, d2,
-                            Q, acc, pairs);
-    if (MODE == 0) co.template allreduce<13>(acc);
-    else if (MODE == 1) co.template allreduce<4>(acc);
+    accumulate_points(mode, geom, occ, cen, slot, rec, src, co.rank(), co.size(), ns, pf, sse != 0, ac.cs, ac.sn, d1, d2,
+                      Q, acc, pairs);
+    if (mode == 0) co.template allreduce<13>(acc);
+    else if (mode == 1) co.template allreduce<4>(acc);
     else co.template allreduce<9>(acc + 4);
 #pragma unroll
     for (int k = 0; k < NACC; ++k) out[k] = acc[k];
@@ -79,12 +78,12 @@ __device__ __forceinline__ Objective<Coop, OccL, CenL, SlotL, RecL, SrcL> make_o
                                                   (mp.quirks & NDT_QUIRK_TRANSFORM_SSE_ORDER) ? 1 : 0, coop, Q};
 }
 
-// per-warp rings live at the start of the CTA's dynamic shared memory (8 warps per CTA): [8][QCAP] int2 hits | [8][CQCAP] int2 candidates
-constexpr int QUEUE_BYTES = 8 * QUEUE_BYTES_PER_WARP;          // 24,576 B
+// per-warp rings live at the start of the CTA's dynamic shared memory: [nw][QCAP] int2 hits | [nw][CQCAP] int2 candidates
+constexpr int QUEUE_BYTES = 8 * QUEUE_BYTES_PER_WARP;          // 8 warps per CTA: 28,672 B
 __device__ __forceinline__ HitQueue my_queue(unsigned char *smem) {
-  const int w = threadIdx.x >> 5;
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   int2 *hit = reinterpret_cast<int2 *>(smem) + w * QCAP;
-  int2 *cand = reinterpret_cast<int2 *>(smem + 8 * QCAP * 8) + w * CQCAP;
+  int2 *cand = reinterpret_cast<int2 *>(smem + nw * QCAP * 8) + w * CQCAP;
   return HitQueue{hit, cand};
 }
 
@@ -147,7 +146,7 @@ __global__ void __launch_bounds__(256) k_eval_partial(GridView G, MatchParams mp
   // slice s owns points [s * chunk, (s + 1) * chunk)
   const int chunk = (ns + slices - 1) / slices;
   const int lo = slice * chunk, hi = min(ns, lo + chunk);
-  accumulate_points<MODE>(probe_geom(G), GlobalOcc{G.occ}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, GlobalSrc{src},
+  accumulate_points(MODE, probe_geom(G), GlobalOcc{G.occ}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, GlobalSrc{src},
                           lo + (int)threadIdx.x, (int)blockDim.x, hi, pf, sse, ac.cs, ac.sn, mp.d1, mp.d2, my_queue(smem_raw),
                           acc, pairs);
   BlockCoop coop{scratch};
@@ -274,17 +273,22 @@ __global__ void __launch_bounds__(256) k_align_cluster(GridView G, MatchParams m
 #ifndef NDT_WARP_KERNEL_MIN_CTAS
 #define NDT_WARP_KERNEL_MIN_CTAS 2
 #endif
+#ifndef NDT_WARP_KERNEL_THREADS
+#define NDT_WARP_KERNEL_THREADS 256
+#endif
+constexpr int WK_THREADS = NDT_WARP_KERNEL_THREADS, WK_WARPS = WK_THREADS / 32;
+constexpr int WK_QUEUE_BYTES = WK_WARPS * QUEUE_BYTES_PER_WARP;
 template <bool SRC_SMEM>
-__global__ void __launch_bounds__(256, NDT_WARP_KERNEL_MIN_CTAS) k_align_warp(GridView G, MatchParams mp, const float4 *__restrict__ src,
+__global__ void __launch_bounds__(WK_THREADS, NDT_WARP_KERNEL_MIN_CTAS) k_align_warp(GridView G, MatchParams mp, const float4 *__restrict__ src,
                                                    int ns, const double *__restrict__ guesses,
                                                    ndt_result *__restrict__ out, int64_t n_jobs,
                                                    int32_t *__restrict__ job_counter, int occ_words) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // dynamic shared memory: hit queues | occupancy bitmap (occ_words, 0 = left in global) | source points
-  uint32_t *s_occ = reinterpret_cast<uint32_t *>(smem_raw + QUEUE_BYTES);
+  uint32_t *s_occ = reinterpret_cast<uint32_t *>(smem_raw + WK_QUEUE_BYTES);
   for (int i = threadIdx.x; i < occ_words; i += blockDim.x) s_occ[i] = __ldg(G.occ + i);
   const uint32_t *occ_ptr = occ_words > 0 ? s_occ : G.occ;
-  float2 *s_src = reinterpret_cast<float2 *>(smem_raw + QUEUE_BYTES + ((occ_words * 4 + 15) & ~15));
+  float2 *s_src = reinterpret_cast<float2 *>(smem_raw + WK_QUEUE_BYTES + ((occ_words * 4 + 15) & ~15));
   if (SRC_SMEM) {
     for (int i = threadIdx.x; i < ns; i += blockDim.x) {
       const float4 v = __ldg(src + i);
@@ -511,16 +515,16 @@ int launch_align(Handle *h, const double *d_guesses, int64_t n, ndt_result *d_re
     const int64_t npad = h->gd.n_cells > 0 ? (int64_t)(h->gd.div_x + 4) * (h->gd.div_y + 4) : 0;
     int occ_words = (int)((npad + 31) / 32 + 1);
     if ((size_t)occ_words * 4 > 64 * 1024) occ_words = 0;          // large grids: bitmap stays in global memory / L1
-    const size_t smem = QUEUE_BYTES + (((size_t)occ_words * 4 + 15) & ~size_t(15)) + (src_smem ? (size_t)ns * sizeof(float2) : 0);
+    const size_t smem = WK_QUEUE_BYTES + (((size_t)occ_words * 4 + 15) & ~size_t(15)) + (src_smem ? (size_t)ns * sizeof(float2) : 0);
     const int ctas_per_sm = NDT_WARP_KERNEL_MIN_CTAS;
     int64_t grid = (int64_t)h->sm_count * ctas_per_sm;
-    grid = std::min<int64_t>(grid, (n + 7) / 8);
+    grid = std::min<int64_t>(grid, (n + WK_WARPS - 1) / WK_WARPS);
     if (src_smem) {
       NDT_CUDA(h, cudaFuncSetAttribute(k_align_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_align_warp<true><<<(unsigned)grid, 256, smem, st>>>(G, mp, src, ns, d_guesses, d_results, n, ctr + CTR_JOB, occ_words);
+      k_align_warp<true><<<(unsigned)grid, WK_THREADS, smem, st>>>(G, mp, src, ns, d_guesses, d_results, n, ctr + CTR_JOB, occ_words);
     } else {
       NDT_CUDA(h, cudaFuncSetAttribute(k_align_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_align_warp<false><<<(unsigned)grid, 256, smem, st>>>(G, mp, src, ns, d_guesses, d_results, n, ctr + CTR_JOB, occ_words);
+      k_align_warp<false><<<(unsigned)grid, WK_THREADS, smem, st>>>(G, mp, src, ns, d_guesses, d_results, n, ctr + CTR_JOB, occ_words);
     }
   } else if (ns > 4096) {
     // large source cloud: spread one match over a thread-block cluster (DSMEM reduction)

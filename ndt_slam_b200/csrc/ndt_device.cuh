@@ -95,11 +95,14 @@ __device__ __forceinline__ int cell_coord(float v, float inv, int min_b) {
   return (int)__fsub_rn(floorf(__fmul_rn(v, inv)), (float)min_b);
 }
 
+// fp64 sincos carries a long slow path; one out-of-line copy serves every call site of a kernel
+static __device__ __noinline__ void sincos_once(double a, double *s, double *c) { sincos(a, s, c); }
+
 __device__ __forceinline__ PoseF pose_to_float(const double p[3]) {
   PoseF f;
   const float yaw = (float)p[2];
   double sd, cd;
-  sincos((double)yaw, &sd, &cd);
+  sincos_once((double)yaw, &sd, &cd);
   f.c = (float)cd; f.s = (float)sd;
   f.tx = (float)p[0]; f.ty = (float)p[1];
   return f;
@@ -123,7 +126,9 @@ __device__ __forceinline__ float dist2f(float ax, float ay, float bx, float by) 
 
 // ------------------------------------------------------------------------------------------------
 // objective
-// MODE 0: score + gradient + Hessian; 1: score + gradient; 2: Hessian only (computeHessian)
+// MODE 0: score + gradient + Hessian; 1: score + gradient; 2: Hessian only (computeHessian). The mode is a run-time,
+// warp-uniform value: the three stages exist once in the instruction stream of the persistent matchers (they are
+// instruction-cache bound when every warp of an SM sits in a different pass of a different match).
 // acc layout: [0] score, [1..3] gradient, [4..12] Hessian row-major
 //
 // accumulate_points() below runs it as three compacted stages (transform -> probe -> fp64 hit path) linked by
@@ -142,8 +147,8 @@ struct HitQueue {
   int2 *cand;     // [CQCAP] (source point index, padded-table index of the point's own cell)
 };
 
-template <int MODE, class RecL>
-__device__ __forceinline__ void hit_path(const RecL &rec_at, const float4 e, const int s, const double cs,
+template <class RecL>
+__device__ __forceinline__ void hit_path(const int MODE, const RecL &rec_at, const float4 e, const int s, const double cs,
                                          const double sn, const double d1, const double d2, double *acc) {
   double2 m, r0, r1;
   rec_at.body(s, m, r0, r1);
@@ -226,8 +231,8 @@ __device__ __forceinline__ int candidate_cell(const ProbeGeom &g, const OccL &oc
   return (in && ((word >> (base & 31)) & 1u)) ? base : -1;
 }
 
-template <int MODE, class OccL, class CenL, class SlotL, class RecL, class SrcL>
-__device__ __forceinline__ void accumulate_points(const ProbeGeom g, const OccL occ_at, const CenL cen_at, const SlotL slot_at,
+template <class OccL, class CenL, class SlotL, class RecL, class SrcL>
+__device__ __forceinline__ void accumulate_points(const int MODE, const ProbeGeom g, const OccL occ_at, const CenL cen_at, const SlotL slot_at,
                                                   const RecL rec_at, const SrcL src, const int first,
                                                   const int stride, const int hi, const PoseF pf,
                                                   const bool sse_order, const double cs, const double sn,
@@ -304,7 +309,7 @@ __device__ __forceinline__ void accumulate_points(const ProbeGeom g, const OccL 
         float4 e;
         e.z = xy.x; e.w = xy.y;
         xform(pf, sse_order, xy.x, xy.y, e.x, e.y);
-        hit_path<MODE>(rec_at, e, slot_at(h.y), cs, sn, d1, d2, acc);
+        hit_path(MODE, rec_at, e, slot_at(h.y), cs, sn, d1, d2, acc);
       }
       __syncwarp();
       qhead += n;
@@ -411,7 +416,9 @@ struct BlockCoop {            // one CTA per match; scratch = [nwarps][NACC] dou
 // 3x3 solve like Eigen::JacobiSVD(H).solve(b): one-sided Jacobi SVD + pseudo-inverse with Eigen's
 // default rank threshold (diagSize * epsilon * sigma_max, diagSize = 6 in PCL's 6x6 solve)
 // ------------------------------------------------------------------------------------------------
-__device__ inline void svd_solve3(const double *Hin, const double *b, double *x) {
+static __device__ __noinline__ void svd_solve3_jacobi(const double *Hin, const double *b, double *x);
+
+__device__ __forceinline__ void svd_solve3(const double *Hin, const double *b, double *x) {
   {
     // Fast path: a well-conditioned H has full rank under Eigen's threshold, and the pseudo-inverse
     // solution is H^-1 b. Adjugate solve (one division); the condition estimate
@@ -434,6 +441,10 @@ __device__ inline void svd_solve3(const double *Hin, const double *b, double *x)
       return;
     }
   }
+  svd_solve3_jacobi(Hin, b, x);
+}
+
+static __device__ __noinline__ void svd_solve3_jacobi(const double *Hin, const double *b, double *x) {
   double A[3][3], V[3][3];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
@@ -485,7 +496,7 @@ __device__ inline void svd_solve3(const double *Hin, const double *b, double *x)
 // ------------------------------------------------------------------------------------------------
 // More-Thuente helpers
 // ------------------------------------------------------------------------------------------------
-__device__ inline double mt_trial_value(double a_l, double f_l, double g_l, double a_u, double f_u, double g_u,
+static __device__ __noinline__ double mt_trial_value(double a_l, double f_l, double g_l, double a_u, double f_u, double g_u,
                                         double a_t, double f_t, double g_t) {
   if (f_t > f_l) {
     const double z = 3 * (f_t - f_l) / (a_t - a_l) - g_t - g_l;
@@ -530,7 +541,7 @@ __device__ __forceinline__ double std_max(double a, double b) { return (a < b) ?
 
 // ------------------------------------------------------------------------------------------------
 // the matcher: Newton direction + More-Thuente line search, entirely on device.
-// `Obj` evaluates one objective pass cooperatively: obj.template pass<MODE>(p, cs, sn, out13)
+// `Obj` evaluates one objective pass cooperatively: obj.pass(mode, p, angle_cache, out13)
 // (MODE 2 must not touch score/gradient). All threads of the cooperating group call this with
 // identical arguments and receive identical results.
 // ------------------------------------------------------------------------------------------------
@@ -538,7 +549,7 @@ struct AngleCache { double cs, sn; };
 
 __device__ __forceinline__ void angle_terms(const MatchParams &mp, double yaw, AngleCache &ac) {
   if ((mp.quirks & NDT_QUIRK_ANGLE_SNAP) && fabs(yaw) < 10e-5) { ac.cs = 1.0; ac.sn = 0.0; }
-  else { sincos(yaw, &ac.sn, &ac.cs); }
+  else { sincos_once(yaw, &ac.sn, &ac.cs); }
 }
 
 struct MatchOut {
@@ -576,7 +587,7 @@ __device__ inline double step_length_mt(Obj &obj, const MatchParams &mp, const d
 #pragma unroll
   for (int k = 0; k < 3; ++k) x_t[k] = x[k] + dir[k] * a_t;
   angle_terms(mp, x_t[2], ac);
-  obj.template pass<0>(x_t, ac, acc); ++evals;
+  obj.pass(0, x_t, ac, acc); ++evals;
   score = acc[0]; g[0] = acc[1]; g[1] = acc[2]; g[2] = acc[3];
 #pragma unroll
   for (int k = 0; k < 9; ++k) H[k] = acc[4 + k];
@@ -586,14 +597,13 @@ __device__ inline double step_length_mt(Obj &obj, const MatchParams &mp, const d
   double d_psi_t = d_phi_t - mu * d_phi_0;
   while (!interval_converged && step_iterations < max_step_iterations &&
          !(psi_t <= 0 && d_phi_t <= -nu * d_phi_0)) {
-    if (open_interval) a_t = mt_trial_value(a_l, f_l, g_l, a_u, f_u, g_u, a_t, psi_t, d_psi_t);
-    else a_t = mt_trial_value(a_l, f_l, g_l, a_u, f_u, g_u, a_t, phi_t, d_phi_t);
+    a_t = mt_trial_value(a_l, f_l, g_l, a_u, f_u, g_u, a_t, open_interval ? psi_t : phi_t, open_interval ? d_psi_t : d_phi_t);
     a_t = std_min(a_t, step_max);
     a_t = std_max(a_t, step_min);
 #pragma unroll
     for (int k = 0; k < 3; ++k) x_t[k] = x[k] + dir[k] * a_t;
     angle_terms(mp, x_t[2], ac);
-    obj.template pass<1>(x_t, ac, acc); ++evals;
+    obj.pass(1, x_t, ac, acc); ++evals;
     score = acc[0]; g[0] = acc[1]; g[1] = acc[2]; g[2] = acc[3];
     phi_t = -score;
     d_phi_t = -(g[0] * dir[0] + g[1] * dir[1] + g[2] * dir[2]);
@@ -604,13 +614,13 @@ __device__ inline double step_length_mt(Obj &obj, const MatchParams &mp, const d
       f_l = f_l + phi_0 - mu * d_phi_0 * a_l; g_l = g_l + mu * d_phi_0;
       f_u = f_u + phi_0 - mu * d_phi_0 * a_u; g_u = g_u + mu * d_phi_0;
     }
-    if (open_interval) interval_converged = mt_update_interval(a_l, f_l, g_l, a_u, f_u, g_u, a_t, psi_t, d_psi_t);
-    else interval_converged = mt_update_interval(a_l, f_l, g_l, a_u, f_u, g_u, a_t, phi_t, d_phi_t);
+    interval_converged = mt_update_interval(a_l, f_l, g_l, a_u, f_u, g_u, a_t, open_interval ? psi_t : phi_t,
+                                            open_interval ? d_psi_t : d_phi_t);
     step_iterations++;
   }
   if (step_iterations) {
     // computeHessian: Hessian only, angle terms as cached by the last computeDerivatives (same x_t)
-    obj.template pass<2>(x_t, ac, acc); ++evals;
+    obj.pass(2, x_t, ac, acc); ++evals;
 #pragma unroll
     for (int k = 0; k < 9; ++k) H[k] = acc[4 + k];
   }
@@ -626,7 +636,7 @@ __device__ inline void match_device(Obj &obj, const MatchParams &mp, const doubl
   int evals = 0, nr_iterations = 0;
   bool converged = false;
   angle_terms(mp, p[2], ac);
-  obj.template pass<0>(p, ac, acc); ++evals;
+  obj.pass(0, p, ac, acc); ++evals;
   score = acc[0]; g[0] = acc[1]; g[1] = acc[2]; g[2] = acc[3];
 #pragma unroll
   for (int k = 0; k < 9; ++k) H[k] = acc[4 + k];

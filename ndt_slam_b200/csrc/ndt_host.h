@@ -28,7 +28,7 @@ struct DevBuf {
 };
 
 // device-side counters written by the build kernels
-enum { CTR_LEAVES = 0, CTR_PTS = 1, CTR_SLOTS = 2, CTR_VALID = 3, CTR_NFIN = 4, CTR_JOB = 5, CTR_COUNT = 8 };
+enum { CTR_LEAVES = 0, CTR_PTS = 1, CTR_SLOTS = 2, CTR_VALID = 3, CTR_NFIN = 4, CTR_JOB = 5, CTR_BIG = 6, CTR_COUNT = 8 };
 
 struct GridBuffers {
   DevBuf tgt;          // float4[n]       target points (device copy or alias source)
@@ -47,6 +47,7 @@ struct GridBuffers {
   DevBuf leaf_id;      // int32[n_cells]  cell -> leaf or -1
   DevBuf leaf_cell;    // int32[n]        per leaf: position in the shared padded tables
   DevBuf leaf_pair;    // int32[n]        per leaf: which grid it belongs to
+  DevBuf big_list;     // int32[]         leaves with more than FINALIZE_BIG_LEAF points (reduced by a warp each)
   DevBuf dims;         // PairDims[n_grids]
   DevBuf pair_off;     // int64[n_grids+1] target point ranges (batched pairs)
   DevBuf leaf_n;       // int32[n]
