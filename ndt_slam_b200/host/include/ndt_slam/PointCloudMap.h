@@ -15,6 +15,7 @@
 #include "Pose2D.h"
 #include "Scan2D.h"
 #include "Timer.h"
+#include "VoxelFilter.h"
 
 class Submap {
  public:
@@ -40,7 +41,24 @@ class Submap {
   pcl::PointCloud<pcl::PointXYZ>::Ptr filterPoints();
   void makeMap();
 
+  // Thinned view of p_cloud as (prefix, tail): `prefix` = centroids the filter has already emitted for good (it only
+  // grows while p_cloud grows at its end), `tail` = the end-of-cloud flush (<= 512 points, changes every scan).
+  // filterPoints() == prefix + tail. Lets makeLocalMap update localMap_cloud in O(new points).
+  const std::vector<pcl::PointXYZ> &thinnedPrefix();
+  void thinnedTail(std::vector<pcl::PointXYZ> &tail) const { thin.append_live(tail); }
+
  private:
+  // Incremental state (not in the reference, which rebuilds p_cloud and re-filters it from scratch every scan --
+  // quadratic over a sub-map's life). Without moving-object removal a sub-map only ever appends whole scans, so both
+  // the concatenation and the order-dependent voxel filter can continue from where they stopped; the clouds produced
+  // are bit-identical to the from-scratch ones.
+  size_t appended_scans = 0;                 // scans[first .. appended_scans) are already in p_cloud
+  const void *appended_into = nullptr;       // the p_cloud object they were appended to
+  size_t appended_points = 0;
+  ndt_host::IncrementalVoxelGrid thin;
+  const void *thin_of = nullptr;             // the p_cloud object `thin` has consumed a prefix of
+  void syncThin();
+
   void readParams() {
     ros::param::get("removeMoving", removeMoving);
     ros::param::get("LeafSize", LeafSize);
@@ -88,6 +106,12 @@ class PointCloudMap {
   void addPoints(const std::vector<LPoint2D> &lps);
   void makeGlobalMap();
   void makeLocalMap();
+
+ private:
+  // makeLocalMap keeps localMap_cloud = [previous sub-map][current sub-map's thinned prefix][tail] and only rewrites
+  // what changed since the last call (same content as rebuilding it from scratch)
+  const void *lm_prev = nullptr, *lm_cur = nullptr;
+  size_t lm_prev_points = 0, lm_prefix_points = 0, lm_fixed = 0;
 };
 
 // PCD v0.7 ASCII writer for x y z float clouds (what pcl::io::savePCDFileASCII emits)

@@ -1,6 +1,7 @@
 // PointCloudMap.cpp -- sub-map bookkeeping [REF src/PointCloudMap.cpp:4-134; PointCloudMap.h:124-136].
 #include "ndt_slam/PointCloudMap.h"
 
+#include <algorithm>
 #include <cmath>
 #include <fstream>
 #include <iomanip>
@@ -10,9 +11,30 @@
 
 typedef pcl::PointCloud<pcl::PointXYZ> Cloud;
 
+// Bring the incremental filter up to date with p_cloud. Anything other than "the same cloud object grew at its end"
+// (a new cloud object, a shorter cloud, a different leaf size, moving-object removal rebuilding the cloud) restarts it.
+void Submap::syncThin() {
+  const float leaf = static_cast<float>(LeafSize);
+  if (thin_of != p_cloud.get() || p_cloud->points.size() < thin.consumed || thin.leaf != leaf || removeMoving) {
+    thin.reset(leaf);
+    thin_of = p_cloud.get();
+  }
+  thin.feed(p_cloud->points.data(), p_cloud->points.size());
+}
+
+const std::vector<pcl::PointXYZ> &Submap::thinnedPrefix() {
+  syncThin();
+  return thin.emitted;
+}
+
 Cloud::Ptr Submap::filterPoints() {
   Cloud::Ptr thinned = std::make_shared<Cloud>();
-  ndt_host::approximate_voxel_grid(*p_cloud, static_cast<float>(LeafSize), *thinned);
+  syncThin();
+  thinned->points.assign(thin.emitted.begin(), thin.emitted.end());
+  thin.append_live(thinned->points);
+  thinned->width = static_cast<uint32_t>(thinned->points.size());
+  thinned->height = 1;
+  thinned->is_dense = false;
   return thinned;
 }
 
@@ -21,11 +43,12 @@ Cloud::Ptr Submap::filterPoints() {
 //                voxels seen only by i+1 and not by {i, i+2}; the first sub-map also keeps its first scan
 //                and the newest sub-map its latest scan unfiltered.
 //  otherwise:    plain concatenation; sub-maps after the first skip the two scans carried over from their
-//                predecessor.
+//                predecessor. Only the scans added since the last call are appended (same cloud as clearing
+//                and re-concatenating everything).
 void Submap::makeMap() {
-  p_cloud->clear();
   const int n = static_cast<int>(scans.size());
   if (removeMoving) {
+    p_cloud->clear();
     if (cntS == 0) *p_cloud += *scans[0];
     for (int i = 0; i + 2 < n; ++i) {
       Cloud::Ptr outer = std::make_shared<Cloud>();
@@ -37,7 +60,16 @@ void Submap::makeMap() {
     if (newest) *p_cloud += *scans[n - 1];
     return;
   }
-  for (int i = (cntS == 0 ? 0 : 2); i < n; ++i) *p_cloud += *scans[i];
+  const size_t first = (cntS == 0 ? 0 : 2);
+  if (appended_into != p_cloud.get() || appended_points != p_cloud->points.size() || appended_scans < first ||
+      appended_scans > static_cast<size_t>(n)) {
+    p_cloud->clear();                              // someone else touched the cloud: start over
+    appended_scans = first;
+    appended_into = p_cloud.get();
+  }
+  for (size_t i = appended_scans; i < static_cast<size_t>(n); ++i) *p_cloud += *scans[i];
+  appended_scans = std::max(appended_scans, static_cast<size_t>(n));
+  appended_points = p_cloud->points.size();
 }
 
 void PointCloudMap::addPose(const Pose2D &p) {
@@ -100,9 +132,27 @@ void PointCloudMap::makeGlobalMap() {
 }
 
 void PointCloudMap::makeLocalMap() {
-  localMap_cloud->clear();
-  if (submaps.size() >= 2) *localMap_cloud += *submaps[submaps.size() - 2].p_cloud;   // previous sub-map only
-  *localMap_cloud += *submaps.back().filterPoints();
+  const Cloud *prev = submaps.size() >= 2 ? submaps[submaps.size() - 2].p_cloud.get() : nullptr;   // previous sub-map only
+  Submap &cur = submaps.back();
+  const std::vector<pcl::PointXYZ> &prefix = cur.thinnedPrefix();
+  const size_t prev_points = prev ? prev->points.size() : 0;
+  std::vector<pcl::PointXYZ> &lm = localMap_cloud->points;
+  const bool same_layout = lm_cur == cur.p_cloud.get() && lm_prev == prev && lm_prev_points == prev_points &&
+                           lm_prefix_points <= prefix.size() && lm_fixed == prev_points + lm_prefix_points && lm.size() >= lm_fixed;
+  if (!same_layout) {
+    lm.clear();
+    if (prev) lm.insert(lm.end(), prev->points.begin(), prev->points.end());
+    lm_prev = prev; lm_prev_points = prev_points; lm_cur = cur.p_cloud.get(); lm_prefix_points = 0;
+  } else {
+    lm.resize(lm_fixed);                           // drop the old tail
+  }
+  lm.insert(lm.end(), prefix.begin() + lm_prefix_points, prefix.end());
+  lm_prefix_points = prefix.size();
+  lm_fixed = lm.size();
+  cur.thinnedTail(lm);
+  localMap_cloud->width = static_cast<uint32_t>(lm.size());
+  localMap_cloud->height = 1;
+  localMap_cloud->is_dense = false;
 }
 
 int savePCDFileASCII(const std::string &path, const Cloud &cloud) {

@@ -146,6 +146,37 @@ void host_slam_stats(void *h, double ms10[10], int64_t counts3[3]) {
   counts3[0] = s->matches; counts3[1] = s->evals; counts3[2] = s->point_evals;
 }
 
+// PointCloudMap on its own (no device): feed map-frame scans + poses like ScanMatcher::growMap does
+// (addPose, addPoints, makeLocalMap per scan; makeGlobalMap at the end) and return both clouds.
+// check_every > 0 additionally compares, every check_every scans, the incrementally maintained local map with one
+// rebuilt from scratch by the one-shot filter (returns -(scan+1) at the first difference).
+int64_t host_map_replay(const double *poses3, const double *xy, const int64_t *off, int n_scans, int check_every,
+                        float *local_out, int64_t lcap, int64_t *n_local, float *global_out, int64_t gcap, int64_t *n_global) {
+  PointCloudMap pcmap;
+  for (int s = 0; s < n_scans; ++s) {
+    pcmap.addPose(Pose2D(poses3[3 * s], poses3[3 * s + 1], poses3[3 * s + 2]));
+    std::vector<LPoint2D> lps(off[s + 1] - off[s]);
+    for (int64_t i = off[s]; i < off[s + 1]; ++i) lps[i - off[s]].setData(s, xy[2 * i], xy[2 * i + 1]);
+    pcmap.addPoints(lps);
+    pcmap.makeLocalMap();
+    if (check_every > 0 && (s + 1) % check_every == 0) {
+      pcl::PointCloud<pcl::PointXYZ> expect, thinned;
+      if (pcmap.submaps.size() >= 2) expect += *pcmap.submaps[pcmap.submaps.size() - 2].p_cloud;
+      const Submap &cur = pcmap.submaps.back();
+      ndt_host::approximate_voxel_grid(*cur.p_cloud, static_cast<float>(cur.LeafSize), thinned);
+      expect += thinned;
+      const auto &got = pcmap.localMap_cloud->points;
+      if (got.size() != expect.points.size()) return -(int64_t)(s + 1);
+      for (size_t i = 0; i < got.size(); ++i)
+        if (std::memcmp(&got[i], &expect.points[i], 12) != 0) return -(int64_t)(s + 1);
+    }
+  }
+  pcmap.makeGlobalMap();
+  *n_local = cloud_out(*pcmap.localMap_cloud, local_out, lcap);
+  *n_global = cloud_out(*pcmap.globalMap_cloud, global_out, gcap);
+  return (int64_t)pcmap.submaps.size();
+}
+
 // SlamLauncher: run a text scan log end to end (parameters filename_in / poses_name / map_name ... must be set)
 int host_launcher_run() {
   try {

@@ -49,6 +49,7 @@ def load():
     L.host_slam_submaps.argtypes = [vp]; L.host_slam_submaps.restype = C.c_int
     L.host_slam_stats.argtypes = [vp, dp, C.POINTER(C.c_int64)]
     L.host_launcher_run.restype = C.c_int
+    L.host_map_replay.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, i64, vp, vp, i64, vp]; L.host_map_replay.restype = i64
     _lib = L
     return L
 
@@ -85,6 +86,24 @@ def voxel_filter(xyzw, leaf):
     out = np.zeros_like(xyzw)
     m = L.host_voxel_filter(_p(xyzw), xyzw.shape[0], leaf, _p(out))
     return np.ascontiguousarray(out[:m])
+
+
+def map_replay(poses_deg, scans_map_xy, check_every=0):
+    """PointCloudMap alone: (addPose, addPoints, makeLocalMap) per scan, makeGlobalMap at the end.
+    Returns (n_submaps, local_map xyzw, global_map xyzw). Raises if the incremental local map ever differs from a
+    from-scratch rebuild (check_every > 0)."""
+    L = load()
+    poses = np.ascontiguousarray(poses_deg, np.float64)
+    off = np.zeros(len(scans_map_xy) + 1, np.int64)
+    off[1:] = np.cumsum([s.shape[0] for s in scans_map_xy])
+    xy = np.ascontiguousarray(np.concatenate(scans_map_xy, axis=0), np.float64)
+    cap = int(off[-1]) + 1024
+    lo, go = np.zeros((cap, 4), np.float32), np.zeros((cap, 4), np.float32)
+    nl, ng = C.c_int64(), C.c_int64()
+    ns = L.host_map_replay(_p(poses), _p(xy), _p(off), len(scans_map_xy), check_every, _p(lo), cap, C.byref(nl), _p(go), cap, C.byref(ng))
+    if ns < 0:
+        raise RuntimeError(f"incremental local map differs from the from-scratch rebuild at scan {-ns - 1}")
+    return int(ns), np.ascontiguousarray(lo[: nl.value]), np.ascontiguousarray(go[: ng.value])
 
 
 def cal_motion(cur, prev):

@@ -54,6 +54,7 @@ def load():
     L.ref_slam_local_map.argtypes = [vp, vp, i64]; L.ref_slam_local_map.restype = i64
     L.ref_slam_global_map.argtypes = [vp, vp, i64]; L.ref_slam_global_map.restype = i64
     L.ref_slam_submaps.argtypes = [vp]; L.ref_slam_submaps.restype = C.c_int
+    L.ref_map_replay.argtypes = [vp, vp, vp, C.c_int, vp, i64, vp, vp, i64, vp]; L.ref_map_replay.restype = i64
     _lib = L
     return L
 
@@ -91,6 +92,20 @@ def voxel_filter(xyzw, leaf):
     out = np.zeros_like(xyzw)
     m = L.ref_voxel_filter(_p(xyzw), xyzw.shape[0], leaf, _p(out))
     return np.ascontiguousarray(out[:m])
+
+
+def map_replay(poses_deg, scans_map_xy):
+    """The reference's PointCloudMap alone (same driver as ndt_slam_b200.host_api.map_replay)."""
+    L = load()
+    poses = np.ascontiguousarray(poses_deg, np.float64)
+    off = np.zeros(len(scans_map_xy) + 1, np.int64)
+    off[1:] = np.cumsum([s.shape[0] for s in scans_map_xy])
+    xy = np.ascontiguousarray(np.concatenate(scans_map_xy, axis=0), np.float64)
+    cap = int(off[-1]) + 1024
+    lo, go = np.zeros((cap, 4), np.float32), np.zeros((cap, 4), np.float32)
+    nl, ng = C.c_int64(), C.c_int64()
+    ns = L.ref_map_replay(_p(poses), _p(xy), _p(off), len(scans_map_xy), _p(lo), cap, C.byref(nl), _p(go), cap, C.byref(ng))
+    return int(ns), np.ascontiguousarray(lo[: nl.value]), np.ascontiguousarray(go[: ng.value])
 
 
 def fuse_pose(pred, est, motion, last, last_cov, Q):

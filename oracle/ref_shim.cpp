@@ -194,4 +194,27 @@ int64_t ref_slam_global_map(void *h, float *xyzw, int64_t cap) {
 }
 int ref_slam_submaps(void *h) { return (int)((Slam *)h)->pcmap.submaps.size(); }
 
+// The reference's own PointCloudMap on its own: same driver as host_map_replay in the product's harness.
+int64_t ref_map_replay(const double *poses3, const double *xy, const int64_t *off, int n_scans,
+                       float *local_out, int64_t lcap, int64_t *n_local, float *global_out, int64_t gcap, int64_t *n_global) {
+  Quiet q;
+  PointCloudMap pcmap;
+  for (int s = 0; s < n_scans; ++s) {
+    pcmap.addPose(Pose2D(poses3[3 * s], poses3[3 * s + 1], poses3[3 * s + 2]));
+    std::vector<LPoint2D> lps(off[s + 1] - off[s]);
+    for (int64_t i = off[s]; i < off[s + 1]; ++i) lps[i - off[s]].setData(s, xy[2 * i], xy[2 * i + 1]);
+    pcmap.addPoints(lps);
+    pcmap.makeLocalMap();
+  }
+  pcmap.makeGlobalMap();
+  auto dump = [](const pcl::PointCloud<pcl::PointXYZ> &c, float *o, int64_t cap) {
+    const int64_t m = std::min<int64_t>(cap, (int64_t)c.points.size());
+    for (int64_t i = 0; i < m; ++i) { o[4 * i] = c.points[i].x; o[4 * i + 1] = c.points[i].y; o[4 * i + 2] = c.points[i].z; o[4 * i + 3] = 0.f; }
+    return (int64_t)c.points.size();
+  };
+  *n_local = dump(*pcmap.localMap_cloud, local_out, lcap);
+  *n_global = dump(*pcmap.globalMap_cloud, global_out, gcap);
+  return (int64_t)pcmap.submaps.size();
+}
+
 }  // extern "C"

@@ -11,7 +11,7 @@ ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
 import ndt_common as common  # noqa: E402
 from ndt_slam_b200 import synth  # noqa: E402
-from oracle import ref_api as ra  # noqa: E402
+from oracle import oracle_api as oa, ref_api as ra  # noqa: E402
 
 OUT = Path(__file__).resolve().parent
 
@@ -84,6 +84,25 @@ def sequence_vectors(n_scans=60):
                         n_submaps=slam.submaps(), truth=seq["traj"][:n_scans])
 
 
+def map_replay_inputs(n_scans=150):
+    """Map-frame scans along the C2 ground-truth trajectory (the inputs of PointCloudMap::addPose / addPoints)."""
+    seq = synth.c2_sequence(seed=2, n_scans=2000)
+    traj = seq["traj"][:n_scans]
+    poses = np.column_stack([traj[:, 0], traj[:, 1], np.rad2deg(traj[:, 2])])
+    scans = [synth.transform(oa.resample(seq["scans"][i], 0.05, 0.25), traj[i]) for i in range(n_scans)]
+    return poses, scans
+
+
+def map_vectors():
+    """The reference's own PointCloudMap (src/PointCloudMap.cpp, compiled unmodified) driven scan by scan: sub-map
+    splitting, concatenation, ApproximateVoxelGrid thinning, local and global map."""
+    poses, scans = map_replay_inputs()
+    ra.set_params(sepThre=1.0, LeafSize=0.2)
+    n_sub, local, glob = ra.map_replay(poses, scans)
+    ra.set_params()
+    np.savez_compressed(OUT / "map_replay_sep1_leaf0.2.npz", n_submaps=n_sub, local_map=local[:, :2].copy(), global_map=glob[:, :2].copy())
+
+
 if __name__ == "__main__":
     if not ra.available():
         raise SystemExit("oracle/_ref is not built (needs /root/reference): run `make -C oracle`")
@@ -92,5 +111,6 @@ if __name__ == "__main__":
     c1_vectors(3, 1.0)
     host_vectors()
     sequence_vectors()
+    map_vectors()
     for p in sorted(OUT.glob("*.npz")):
         print(p.name, p.stat().st_size)
