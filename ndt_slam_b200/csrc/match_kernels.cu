@@ -11,7 +11,7 @@
 //   k_align_cluster one thread-block cluster per match, DSMEM reduction (large source clouds)
 //   k_align_warp    persistent CTAs, one warp per match pulled from an atomic work counter (batches)
 //   k_best_of       arg-max of the batch results
-//   k_voxel_filter  ApproximateVoxelGrid, one thread per cloud (sequential hash history)
+//   k_voxel_filter(_pairs)  ApproximateVoxelGrid, one warp per cloud (slot-parallel replay of the hash history)
 #include "ndt_host.h"
 
 #include <cooperative_groups.h>
@@ -354,82 +354,96 @@ __global__ void __launch_bounds__(1024) k_best_of(const ndt_result *__restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
-// pcl::ApproximateVoxelGrid<PointXYZ>::applyFilter: inherently sequential
-// (order-dependent 512-entry hash history), so one thread walks one cloud.
+// pcl::ApproximateVoxelGrid<PointXYZ>::applyFilter: an order-dependent 512-entry hash history.
+// A point only ever touches the history slot its voxel hashes to, so points with different hashes commute; only the
+// order *within a slot* and the order of the emitted centroids matter. A warp takes 32 consecutive points: lanes with
+// the same hash are serialised in lane order (__match_any_sync groups, one round per group member), lanes with
+// different hashes update their slots in parallel, and the centroids flushed by the chunk are written in lane order
+// (ballot + popc) -- exactly the sequential output, bit for bit.
 // ---------------------------------------------------------------------------------------------
-struct HistEntry { int ix, iy, iz, count; float cx, cy, cz; };
+struct VfTable { int ix[512], iy[512], iz[512], n[512]; float sx[512], sy[512], sz[512]; };   // 14,336 B per warp
 
-__global__ void k_voxel_filter(const float4 *__restrict__ in, int64_t n, float leaf, float4 *__restrict__ out,
-                               int32_t *__restrict__ n_out) {
-  __shared__ HistEntry he[512];
-  for (int i = threadIdx.x; i < 512; i += blockDim.x) { he[i].count = 0; he[i].cx = he[i].cy = he[i].cz = 0.f; he[i].ix = he[i].iy = he[i].iz = 0; }
-  __syncthreads();
-  if (threadIdx.x != 0) return;
+__device__ __forceinline__ int voxel_filter_warp(const float4 *__restrict__ in, const int n, const float leaf,
+                                                 float4 *__restrict__ o, VfTable &T) {
+  const int lane = threadIdx.x & 31;
+  for (int k = lane; k < 512; k += 32) { T.n[k] = 0; T.sx[k] = T.sy[k] = T.sz[k] = 0.f; T.ix[k] = T.iy[k] = T.iz[k] = 0; }
+  __syncwarp();
   const float inv = __fdiv_rn(1.0f, leaf);
+  const unsigned lt = (1u << lane) - 1u;
   int op = 0;
-  for (int64_t i = 0; i < n; ++i) {
-    const float4 p = __ldg(in + i);
-    const int ix = (int)floorf(__fmul_rn(p.x, inv)), iy = (int)floorf(__fmul_rn(p.y, inv)), iz = (int)floorf(__fmul_rn(p.z, inv));
-    const unsigned hash = ((unsigned)ix * 7171u + (unsigned)iy * 3079u + (unsigned)iz * 4231u) & 511u;
-    HistEntry &e = he[hash];
-    if (e.count && (ix != e.ix || iy != e.iy || iz != e.iz)) {
-      const float c = (float)e.count;
-      out[op++] = make_float4(__fdiv_rn(e.cx, c), __fdiv_rn(e.cy, c), __fdiv_rn(e.cz, c), 0.f);
-      e.count = 0; e.cx = e.cy = e.cz = 0.f;
+  for (int c = 0; c < n; c += 32) {
+    const int i = c + lane;
+    const bool valid = i < n;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    int ix = 0, iy = 0, iz = 0, hash = -1 - lane;           // invalid lanes: unique negative keys (groups of one, never active)
+    if (valid) {
+      p = __ldg(in + i);
+      ix = (int)floorf(__fmul_rn(p.x, inv)); iy = (int)floorf(__fmul_rn(p.y, inv)); iz = (int)floorf(__fmul_rn(p.z, inv));
+      hash = (int)(((unsigned)ix * 7171u + (unsigned)iy * 3079u + (unsigned)iz * 4231u) & 511u);
     }
-    e.ix = ix; e.iy = iy; e.iz = iz; e.count++;
-    e.cx = __fadd_rn(e.cx, p.x); e.cy = __fadd_rn(e.cy, p.y); e.cz = __fadd_rn(e.cz, p.z);
-  }
-  for (int k = 0; k < 512; ++k) {
-    HistEntry &e = he[k];
-    if (e.count) {
-      const float c = (float)e.count;
-      out[op++] = make_float4(__fdiv_rn(e.cx, c), __fdiv_rn(e.cy, c), __fdiv_rn(e.cz, c), 0.f);
+    const unsigned grp = __match_any_sync(0xffffffffu, hash);
+    const int rank = __popc(grp & lt);
+    const int rounds = __reduce_max_sync(0xffffffffu, valid ? __popc(grp) : 0);
+    bool flushed = false;
+    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < rounds; ++r) {
+      if (valid && rank == r) {
+        int cnt = T.n[hash];
+        float sx = T.sx[hash], sy = T.sy[hash], sz = T.sz[hash];
+        if (cnt && (ix != T.ix[hash] || iy != T.iy[hash] || iz != T.iz[hash])) {      // a different voxel claims the slot
+          const float cf = (float)cnt;
+          f = make_float4(__fdiv_rn(sx, cf), __fdiv_rn(sy, cf), __fdiv_rn(sz, cf), 0.f);
+          flushed = true;
+          cnt = 0; sx = sy = sz = 0.f;
+        }
+        T.ix[hash] = ix; T.iy[hash] = iy; T.iz[hash] = iz; T.n[hash] = cnt + 1;
+        T.sx[hash] = __fadd_rn(sx, p.x); T.sy[hash] = __fadd_rn(sy, p.y); T.sz[hash] = __fadd_rn(sz, p.z);
+      }
+      __syncwarp();
     }
+    const unsigned bal = __ballot_sync(0xffffffffu, flushed);
+    if (flushed) o[op + __popc(bal & lt)] = f;
+    op += __popc(bal);
   }
-  *n_out = op;
+  // end-of-cloud flush in slot order
+  for (int k0 = 0; k0 < 512; k0 += 32) {
+    const int k = k0 + lane;
+    const int cnt = T.n[k];
+    const unsigned bal = __ballot_sync(0xffffffffu, cnt != 0);
+    if (cnt) {
+      const float cf = (float)cnt;
+      o[op + __popc(bal & lt)] = make_float4(__fdiv_rn(T.sx[k], cf), __fdiv_rn(T.sy[k], cf), __fdiv_rn(T.sz[k], cf), 0.f);
+    }
+    op += __popc(bal);
+  }
+  return op;
 }
 
-// the same filter for a batch of scan pairs: one CTA per pair (thread 0 walks the cloud, the history lives in
-// shared memory); pair i reads in[src_off .. src_off + ns) and writes its centroids to out at the same offset
-// (the filter never grows a cloud), then records the new count in PairDims::ns. leaf <= 0: plain copy.
-__global__ void __launch_bounds__(32) k_voxel_filter_pairs(const float4 *__restrict__ in, float4 *__restrict__ out,
-                                                          PairDims *__restrict__ dims, float leaf) {
-  __shared__ HistEntry he[512];
-  const int pair = blockIdx.x;
+// one cloud (ndt_approx_voxel_filter): one warp
+__global__ void __launch_bounds__(32) k_voxel_filter(const float4 *__restrict__ in, int64_t n, float leaf, float4 *__restrict__ out,
+                                                     int32_t *__restrict__ n_out) {
+  __shared__ VfTable tab;
+  const int op = voxel_filter_warp(in, (int)n, leaf, out, tab);
+  if (threadIdx.x == 0) *n_out = op;
+}
+
+// a batch of scan pairs, one warp per pair: pair i reads in[src_off .. src_off + ns) and writes its centroids to out at
+// the same offset (the filter never grows a cloud), then records the new count in PairDims::ns. leaf <= 0: plain copy.
+constexpr int VF_WARPS = 2;
+__global__ void __launch_bounds__(32 * VF_WARPS) k_voxel_filter_pairs(const float4 *__restrict__ in, float4 *__restrict__ out,
+                                                                      PairDims *__restrict__ dims, int n_pairs, float leaf) {
+  __shared__ VfTable tabs[VF_WARPS];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int pair = blockIdx.x * VF_WARPS + w;
+  if (pair >= n_pairs) return;
   const int64_t off = dims[pair].src_off;
   const int n = dims[pair].ns;
   if (!(leaf > 0.f)) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) out[off + i] = __ldg(in + off + i);
+    for (int i = lane; i < n; i += 32) out[off + i] = __ldg(in + off + i);
     return;
   }
-  for (int i = threadIdx.x; i < 512; i += blockDim.x) { he[i].count = 0; he[i].cx = he[i].cy = he[i].cz = 0.f; he[i].ix = he[i].iy = he[i].iz = 0; }
-  __syncthreads();
-  if (threadIdx.x != 0) return;
-  const float inv = __fdiv_rn(1.0f, leaf);
-  int op = 0;
-  float4 *o = out + off;
-  for (int i = 0; i < n; ++i) {
-    const float4 p = __ldg(in + off + i);
-    const int ix = (int)floorf(__fmul_rn(p.x, inv)), iy = (int)floorf(__fmul_rn(p.y, inv)), iz = (int)floorf(__fmul_rn(p.z, inv));
-    const unsigned hash = ((unsigned)ix * 7171u + (unsigned)iy * 3079u + (unsigned)iz * 4231u) & 511u;
-    HistEntry &e = he[hash];
-    if (e.count && (ix != e.ix || iy != e.iy || iz != e.iz)) {
-      const float c = (float)e.count;
-      o[op++] = make_float4(__fdiv_rn(e.cx, c), __fdiv_rn(e.cy, c), __fdiv_rn(e.cz, c), 0.f);
-      e.count = 0; e.cx = e.cy = e.cz = 0.f;
-    }
-    e.ix = ix; e.iy = iy; e.iz = iz; e.count++;
-    e.cx = __fadd_rn(e.cx, p.x); e.cy = __fadd_rn(e.cy, p.y); e.cz = __fadd_rn(e.cz, p.z);
-  }
-  for (int k = 0; k < 512; ++k) {
-    HistEntry &e = he[k];
-    if (e.count) {
-      const float c = (float)e.count;
-      o[op++] = make_float4(__fdiv_rn(e.cx, c), __fdiv_rn(e.cy, c), __fdiv_rn(e.cz, c), 0.f);
-    }
-  }
-  dims[pair].ns = op;
+  const int op = voxel_filter_warp(in + off, n, leaf, out + off, tabs[w]);
+  if (lane == 0) dims[pair].ns = op;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -565,7 +579,8 @@ int launch_align(Handle *h, const double *d_guesses, int64_t n, ndt_result *d_re
 
 int launch_pairs_filter(Handle *h, const float4 *d_in, float4 *d_out, int64_t n_pairs, float leaf) {
   if (n_pairs <= 0) return NDT_OK;
-  k_voxel_filter_pairs<<<(unsigned)n_pairs, 32, 0, h->stream>>>(d_in, d_out, h->gb.dims.as<PairDims>(), leaf);
+  k_voxel_filter_pairs<<<(unsigned)((n_pairs + VF_WARPS - 1) / VF_WARPS), 32 * VF_WARPS, 0, h->stream>>>(d_in, d_out, h->gb.dims.as<PairDims>(),
+                                                                                                       (int)n_pairs, leaf);
   ++h->launches;
   NDT_CUDA(h, cudaGetLastError());
   return NDT_OK;
@@ -598,7 +613,7 @@ int launch_best_of(Handle *h, const ndt_result *d_results, int64_t n, int64_t *d
 }
 
 int launch_voxel_filter(Handle *h, const float4 *d_in, int64_t n, float leaf, float4 *d_out, int32_t *d_nout) {
-  k_voxel_filter<<<1, 128, 0, h->stream>>>(d_in, n, leaf, d_out, d_nout);
+  k_voxel_filter<<<1, 32, 0, h->stream>>>(d_in, n, leaf, d_out, d_nout);
   ++h->launches;
   NDT_CUDA(h, cudaGetLastError());
   return NDT_OK;
