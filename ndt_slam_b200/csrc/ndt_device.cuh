@@ -135,7 +135,11 @@ __device__ __forceinline__ float dist2f(float ax, float ay, float bx, float by) 
 // two per-warp rings in shared memory.
 // ------------------------------------------------------------------------------------------------
 constexpr int NACC = 13;
-constexpr int QCAP = 320;           // hit ring per warp: < 32 queued before a probe, a probe adds <= 9 * 32
+#ifndef NDT_HITS_PER_LANE
+#define NDT_HITS_PER_LANE 2
+#endif
+constexpr int HITS_PER_LANE = NDT_HITS_PER_LANE;   // hits a lane evaluates side by side in one drain
+constexpr int QCAP = 32 * HITS_PER_LANE + 288;   // hit ring per warp: < 32 * HITS_PER_LANE queued before a probe, a probe adds <= 9 * 32
 constexpr int CQCAP = 128;          // candidate ring per warp: < 32 queued before a double step, which adds <= 64
 constexpr int QUEUE_BYTES_PER_WARP = (QCAP + CQCAP) * 8;
 
@@ -147,45 +151,62 @@ struct HitQueue {
   int2 *cand;     // [CQCAP] (source point index, padded-table index of the point's own cell)
 };
 
-template <class RecL>
-__device__ __forceinline__ void hit_path(const int MODE, const RecL &rec_at, const float4 e, const int s, const double cs,
-                                         const double sn, const double d1, const double d2, double *acc) {
-  double2 m, r0, r1;
-  rec_at.body(s, m, r0, r1);
-  const double x = (double)e.z, y = (double)e.w;
-  const double dx = (double)e.x - m.x, dy = (double)e.y - m.y;
-  const double c00 = r0.x, c01 = r0.y, c10 = r1.x, c11 = r1.y;
-  const double Cdx = c00 * dx + c01 * dy, Cdy = c10 * dx + c11 * dy;
-  const double q = dx * Cdx + dy * Cdy;
-  double ex = exp(-d2 * q / 2.0);
-  const double score_inc = -d1 * ex;
-  ex = d2 * ex;
-  if (ex > 1.0 || ex < 0.0 || ex != ex) return;
-  ex *= d1;
-  const double Jx = -sn * x - cs * y, Jy = cs * x - sn * y;
-  // cov_dxd_pi = C * J_i for i = x, y, yaw ; a_i = d . (C J_i)
-  const double CJ2x = c00 * Jx + c01 * Jy, CJ2y = c10 * Jx + c11 * Jy;
-  const double a0 = dx * c00 + dy * c10;
-  const double a1 = dx * c01 + dy * c11;
-  const double a2 = dx * CJ2x + dy * CJ2y;
-  if (MODE != 2) {
-    acc[0] += score_inc;
-    acc[1] += a0 * ex; acc[2] += a1 * ex; acc[3] += a2 * ex;
+// NH hits per lane, evaluated side by side: the code is straight-line (the reference's guard on e turns into
+// selects), so the independent dependency chains of the hits interleave and hide each other's fp64 latency.
+// valid[u] = the lane really holds hit u; a lane without a hit computes on a clamped copy and adds exact zeros.
+template <int NH, class RecL>
+__device__ __forceinline__ void hit_path(const int MODE, const RecL &rec_at, const float4 *e, const int *s, const bool *valid,
+                                         const double cs, const double sn, const double d1, const double d2, double *acc) {
+  double dx[NH], dy[NH], x[NH], y[NH], c00[NH], c01[NH], c10[NH], c11[NH], ex[NH], sc[NH];
+#pragma unroll
+  for (int u = 0; u < NH; ++u) {
+    double2 m, r0, r1;
+    rec_at.body(s[u], m, r0, r1);
+    x[u] = (double)e[u].z; y[u] = (double)e[u].w;
+    dx[u] = (double)e[u].x - m.x; dy[u] = (double)e[u].y - m.y;
+    c00[u] = r0.x; c01[u] = r0.y; c10[u] = r1.x; c11[u] = r1.y;
   }
-  if (MODE != 1) {
-    const double Hx = -cs * x + sn * y, Hy = -sn * x - cs * y;
-    const double dCH = dx * (c00 * Hx + c01 * Hy) + dy * (c10 * Hx + c11 * Hy);
-    const double k0 = -d2 * a0, k1 = -d2 * a1, k2 = -d2 * a2;
-    // H(i,j) += e * (-d2 a_i a_j + J_j . (C J_i) [+ d.(C H_yawyaw) for i = j = yaw])
-    acc[4]  += ex * (k0 * a0 + c00);
-    acc[5]  += ex * (k0 * a1 + c10);
-    acc[6]  += ex * (k0 * a2 + (Jx * c00 + Jy * c10));
-    acc[7]  += ex * (k1 * a0 + c01);
-    acc[8]  += ex * (k1 * a1 + c11);
-    acc[9]  += ex * (k1 * a2 + (Jx * c01 + Jy * c11));
-    acc[10] += ex * (k2 * a0 + CJ2x);
-    acc[11] += ex * (k2 * a1 + CJ2y);
-    acc[12] += ex * (k2 * a2 + (Jx * CJ2x + Jy * CJ2y) + dCH);
+#pragma unroll
+  for (int u = 0; u < NH; ++u) {
+    const double Cdx = c00[u] * dx[u] + c01[u] * dy[u], Cdy = c10[u] * dx[u] + c11[u] * dy[u];
+    const double q = dx[u] * Cdx + dy[u] * Cdy;
+    ex[u] = exp(-d2 * q / 2.0);
+  }
+#pragma unroll
+  for (int u = 0; u < NH; ++u) {
+    sc[u] = valid[u] ? -d1 * ex[u] : 0.0;            // the score term is added before the guard
+    const double t = d2 * ex[u];
+    const bool ok = valid[u] && !(t > 1.0 || t < 0.0 || t != t);
+    ex[u] = ok ? t * d1 : 0.0;
+    dx[u] = ok ? dx[u] : 0.0; dy[u] = ok ? dy[u] : 0.0;      // keep a rejected term finite: its contributions are exact zeros
+  }
+#pragma unroll
+  for (int u = 0; u < NH; ++u) {
+    const double Jx = -sn * x[u] - cs * y[u], Jy = cs * x[u] - sn * y[u];
+    // cov_dxd_pi = C * J_i for i = x, y, yaw ; a_i = d . (C J_i)
+    const double CJ2x = c00[u] * Jx + c01[u] * Jy, CJ2y = c10[u] * Jx + c11[u] * Jy;
+    const double a0 = dx[u] * c00[u] + dy[u] * c10[u];
+    const double a1 = dx[u] * c01[u] + dy[u] * c11[u];
+    const double a2 = dx[u] * CJ2x + dy[u] * CJ2y;
+    if (MODE != 2) {
+      acc[0] += sc[u];
+      acc[1] += a0 * ex[u]; acc[2] += a1 * ex[u]; acc[3] += a2 * ex[u];
+    }
+    if (MODE != 1) {
+      const double Hx = -cs * x[u] + sn * y[u], Hy = -sn * x[u] - cs * y[u];
+      const double dCH = dx[u] * (c00[u] * Hx + c01[u] * Hy) + dy[u] * (c10[u] * Hx + c11[u] * Hy);
+      const double k0 = -d2 * a0, k1 = -d2 * a1, k2 = -d2 * a2;
+      // H(i,j) += e * (-d2 a_i a_j + J_j . (C J_i) [+ d.(C H_yawyaw) for i = j = yaw])
+      acc[4]  += ex[u] * (k0 * a0 + c00[u]);
+      acc[5]  += ex[u] * (k0 * a1 + c10[u]);
+      acc[6]  += ex[u] * (k0 * a2 + (Jx * c00[u] + Jy * c10[u]));
+      acc[7]  += ex[u] * (k1 * a0 + c01[u]);
+      acc[8]  += ex[u] * (k1 * a1 + c11[u]);
+      acc[9]  += ex[u] * (k1 * a2 + (Jx * c01[u] + Jy * c11[u]));
+      acc[10] += ex[u] * (k2 * a0 + CJ2x);
+      acc[11] += ex[u] * (k2 * a1 + CJ2y);
+      acc[12] += ex[u] * (k2 * a2 + (Jx * CJ2x + Jy * CJ2y) + dCH);
+    }
   }
 }
 
@@ -297,20 +318,26 @@ __device__ __forceinline__ void accumulate_points(const int MODE, const ProbeGeo
         qn += total;
       }
     }
-    // ---- C: every lane pops one queued (point, cell) hit and runs the fp64 hit path converged ----
-    while (qn >= 32 || (done && cn == 0 && qn > 0)) {
-      const int n = min(qn, 32);
+    // ---- C: every lane pops HITS_PER_LANE queued (point, cell) hits and runs the fp64 hit path converged ----
+    while (qn >= 32 * HITS_PER_LANE || (done && cn == 0 && qn > 0)) {
+      const int n = min(qn, 32 * HITS_PER_LANE);
       __syncwarp();
-      if (lane < n) {
-        int pos = qhead + lane;
+      float4 e[HITS_PER_LANE];
+      int sl[HITS_PER_LANE];
+      bool valid[HITS_PER_LANE];
+#pragma unroll
+      for (int u = 0; u < HITS_PER_LANE; ++u) {
+        const int k = lane + 32 * u;
+        valid[u] = k < n;
+        int pos = qhead + (valid[u] ? k : 0);      // a lane without a hit recomputes the first one with weight zero
         if (pos >= QCAP) pos -= QCAP;
         const int2 h = Q.hit[pos];
         const float2 xy = src(h.x);
-        float4 e;
-        e.z = xy.x; e.w = xy.y;
-        xform(pf, sse_order, xy.x, xy.y, e.x, e.y);
-        hit_path(MODE, rec_at, e, slot_at(h.y), cs, sn, d1, d2, acc);
+        e[u].z = xy.x; e[u].w = xy.y;
+        xform(pf, sse_order, xy.x, xy.y, e[u].x, e[u].y);
+        sl[u] = slot_at(h.y);
       }
+      hit_path<HITS_PER_LANE>(MODE, rec_at, e, sl, valid, cs, sn, d1, d2, acc);
       __syncwarp();
       qhead += n;
       if (qhead >= QCAP) qhead -= QCAP;
