@@ -423,11 +423,6 @@ int ndt_match_pairs(ndt_handle hh, const float *src_xyzw, const int64_t *src_off
   std::memset(h->h_counters, 0, sizeof(h->h_counters));
   const bool host = (memspace == NDT_MEM_HOST);
   const cudaMemcpyKind in_kind = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
-  const size_t nt_b = (size_t)std::max<int64_t>(nt_total, 1) * sizeof(float4), ns_b = (size_t)std::max<int64_t>(ns_total, 1) * sizeof(float4);
-  NDT_CUDA(h, gb.tgt.reserve(nt_b));
-  NDT_CUDA(h, h->src.reserve(ns_b));
-  NDT_CUDA(h, h->scratch.reserve(ns_b));
-  NDT_CUDA(h, gb.pair_off.reserve(2 * ((size_t)n_pairs + 1) * sizeof(int64_t)));
   const size_t gbytes = (size_t)n_pairs * 3 * sizeof(double), rbytes = (size_t)n_pairs * sizeof(ndt_result);
   const double *d_g = guesses;
   ndt_result *d_r = results;
@@ -437,24 +432,43 @@ int ndt_match_pairs(ndt_handle hh, const float *src_xyzw, const int64_t *src_off
     d_r = (ndt_result *)((char *)h->io.p + ((gbytes + 255) & ~size_t(255)));
     NDT_CUDA(h, cudaMemcpyAsync(h->io.p, guesses, gbytes, cudaMemcpyHostToDevice, st));
   }
-  int64_t *d_off = gb.pair_off.as<int64_t>();
-  NDT_CUDA(h, cudaMemcpyAsync(d_off, tgt_off, ((size_t)n_pairs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-  NDT_CUDA(h, cudaMemcpyAsync(d_off + n_pairs + 1, src_off, ((size_t)n_pairs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-  if (nt_total > 0) NDT_CUDA(h, cudaMemcpyAsync(gb.tgt.p, tgt_xyzw, (size_t)nt_total * sizeof(float4), in_kind, st));
-  // raw source clouds: device inputs are filtered straight from the caller's buffer
-  const float4 *d_raw = reinterpret_cast<const float4 *>(src_xyzw);
-  if (host && ns_total > 0) {
-    NDT_CUDA(h, cudaMemcpyAsync(h->scratch.p, src_xyzw, (size_t)ns_total * sizeof(float4), cudaMemcpyHostToDevice, st));
-    d_raw = h->scratch.as<float4>();
-  }
+  // Pairs go through the pipeline in batches of at most `batch_points` target points: bounds the size of the shared
+  // tables for very large inputs. (Measured on C5: smaller, L2-sized batches are slower -- a pair is matched by one warp
+  // in ~1 ms, so every batch ends with a latency tail; see DESIGN.md.)
+  int64_t batch_points = 32000000;                     // NDT_B200_PAIRS_BATCH_POINTS overrides (tuning / tests)
+  if (const char *e = getenv("NDT_B200_PAIRS_BATCH_POINTS")) { const int64_t v = atoll(e); if (v > 0) batch_points = v; }
   if (h->timing) cudaEventRecord(h->ev0, st);
-  int64_t total_pad = 0;
-  int max_h = 0;
-  if (int rc = pairs_prepare(h, n_pairs, &total_pad, &max_h)) return rc;          // one 16-byte read-back
-  if (int rc = launch_pairs_filter(h, d_raw, h->src.as<float4>(), n_pairs, source_leaf)) return rc;
-  gd.n_tgt = nt_total;
-  if (int rc = grid_build_tables(h, nt_total, (int)n_pairs, total_pad, max_h)) return rc;
-  if (int rc = launch_align_pairs(h, h->src.as<float4>(), d_g, n_pairs, d_r, /*want_fitness=*/true)) return rc;
+  std::vector<int64_t> off_stage;
+  for (int64_t p0 = 0; p0 < n_pairs;) {
+    int64_t p1 = p0 + 1;
+    while (p1 < n_pairs && tgt_off[p1 + 1] - tgt_off[p0] <= batch_points && src_off[p1 + 1] - src_off[p0] <= 2 * batch_points) ++p1;
+    const int64_t nb = p1 - p0, nt = tgt_off[p1] - tgt_off[p0], ns = src_off[p1] - src_off[p0];
+    NDT_CUDA(h, gb.tgt.reserve((size_t)std::max<int64_t>(nt, 1) * sizeof(float4)));
+    NDT_CUDA(h, h->src.reserve((size_t)std::max<int64_t>(ns, 1) * sizeof(float4)));
+    NDT_CUDA(h, gb.pair_off.reserve(2 * ((size_t)nb + 1) * sizeof(int64_t)));
+    off_stage.resize(2 * ((size_t)nb + 1));
+    for (int64_t i = 0; i <= nb; ++i) {
+      off_stage[i] = tgt_off[p0 + i] - tgt_off[p0];
+      off_stage[nb + 1 + i] = src_off[p0 + i] - src_off[p0];
+    }
+    NDT_CUDA(h, cudaMemcpyAsync(gb.pair_off.p, off_stage.data(), off_stage.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    if (nt > 0) NDT_CUDA(h, cudaMemcpyAsync(gb.tgt.p, tgt_xyzw + 4 * tgt_off[p0], (size_t)nt * sizeof(float4), in_kind, st));
+    // raw source clouds: device inputs are filtered straight from the caller's buffer
+    const float4 *d_raw = reinterpret_cast<const float4 *>(src_xyzw) + src_off[p0];
+    if (host) {
+      NDT_CUDA(h, h->scratch.reserve((size_t)std::max<int64_t>(ns, 1) * sizeof(float4)));
+      if (ns > 0) NDT_CUDA(h, cudaMemcpyAsync(h->scratch.p, src_xyzw + 4 * src_off[p0], (size_t)ns * sizeof(float4), cudaMemcpyHostToDevice, st));
+      d_raw = h->scratch.as<float4>();
+    }
+    int64_t total_pad = 0;
+    int max_h = 0;
+    if (int rc = pairs_prepare(h, nb, &total_pad, &max_h)) return rc;          // one 16-byte read-back (also fences off_stage)
+    if (int rc = launch_pairs_filter(h, d_raw, h->src.as<float4>(), nb, source_leaf)) return rc;
+    gd.n_tgt = nt;
+    if (int rc = grid_build_tables(h, nt, (int)nb, total_pad, max_h)) return rc;
+    if (int rc = launch_align_pairs(h, h->src.as<float4>(), d_g + 3 * p0, nb, d_r + p0, /*want_fitness=*/true)) return rc;
+    p0 = p1;
+  }
   if (h->timing) cudaEventRecord(h->ev1, st);
   if (!host) { h->ms_pending = true; return NDT_OK; }
   NDT_CUDA(h, cudaMemcpyAsync(results, d_r, rbytes, cudaMemcpyDeviceToHost, st));

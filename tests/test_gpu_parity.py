@@ -352,6 +352,14 @@ def test_match_pairs_parity_with_oracle_per_pair():
         a = g1.align(guesses[k])
         assert np.allclose(a.pose, res[k]["pose"], rtol=0, atol=1e-9) and a.score == pytest.approx(res[k]["score"], rel=1e-10)
         assert a.iters == res[k]["iters"] and a.evals == res[k]["evals"]
+    # small batches (several grid-build + match rounds inside one call) give the same bytes
+    import os
+    os.environ["NDT_B200_PAIRS_BATCH_POINTS"] = "9000"
+    try:
+        res_b = g.match_pairs(src, so, tgt, to, guesses, n, source_leaf=common.LAUNCH["leaf"])
+    finally:
+        del os.environ["NDT_B200_PAIRS_BATCH_POINTS"]
+    assert np.array_equal(res_b["pose"], res["pose"]) and np.array_equal(res_b["fitness"], res["fitness"])
     # device-resident inputs / outputs give the same bytes
     d_src, d_tgt = torch.from_numpy(src).cuda(), torch.from_numpy(tgt).cuda()
     d_g = torch.from_numpy(guesses).cuda()
