@@ -237,8 +237,11 @@ __device__ __forceinline__ ProbeGeom probe_geom(const GridView &G) {
 // Without the rings the probe would run for every point (all 32 lanes pay when one is a candidate) and the
 // hit path once per neighbour position with a handful of active lanes.
 // stage A for one point: padded-table index of its own cell if the point can hit anything, else -1
-template <class OccL, class SrcL>
-__device__ __forceinline__ int candidate_cell(const ProbeGeom &g, const OccL &occ_at, const SrcL &src, const int i,
+#ifndef NDT_PREFETCH_CEN
+#define NDT_PREFETCH_CEN 0      // measured: an L1 prefetch of the centroid rows at candidate time is slower (C4 13.2 -> 14.4 ms)
+#endif
+template <class OccL, class CenL, class SrcL>
+__device__ __forceinline__ int candidate_cell(const ProbeGeom &g, const OccL &occ_at, const CenL &cen_at, const SrcL &src, const int i,
                                               const bool valid, const PoseF &pf, const bool sse_order) {
   const float2 xy = src(i);
   float xt, yt;
@@ -249,7 +252,11 @@ __device__ __forceinline__ int candidate_cell(const ProbeGeom &g, const OccL &oc
   const bool in = valid && (unsigned)(ci + 1) <= (unsigned)(g.div_x + 1) && (unsigned)(cj + 1) <= (unsigned)(g.div_y + 1);
   const int base = in ? (g.base + (cj + 2) * g.W + ci + 2) : 0;
   const unsigned word = occ_at(base >> 5);
-  return (in && ((word >> (base & 31)) & 1u)) ? base : -1;
+  const bool cand = in && ((word >> (base & 31)) & 1u);
+#if NDT_PREFETCH_CEN
+  if (cand) cen_at.prefetch(base, g.W);        // stage B reads these nine centroids a few hundred cycles from now
+#endif
+  return cand ? base : -1;
 }
 
 template <class OccL, class CenL, class SlotL, class RecL, class SrcL>
@@ -269,8 +276,8 @@ __device__ __forceinline__ void accumulate_points(const int MODE, const ProbeGeo
     while (cn < 32 && i0 < hi) {
       const int ia = i0 + lane, ib = ia + stride;
       i0 += 2 * stride;
-      const int ba = candidate_cell(g, occ_at, src, min(ia, hi - 1), ia < hi, pf, sse_order);
-      const int bb = candidate_cell(g, occ_at, src, min(ib, hi - 1), ib < hi, pf, sse_order);
+      const int ba = candidate_cell(g, occ_at, cen_at, src, min(ia, hi - 1), ia < hi, pf, sse_order);
+      const int bb = candidate_cell(g, occ_at, cen_at, src, min(ib, hi - 1), ib < hi, pf, sse_order);
       const unsigned bal_a = __ballot_sync(0xffffffffu, ba >= 0);
       const unsigned bal_b = __ballot_sync(0xffffffffu, bb >= 0);
       const int na = __popc(bal_a);
@@ -361,10 +368,17 @@ struct SmemOcc {
 struct GlobalCen {
   const float2 *__restrict__ p;
   __device__ __forceinline__ float2 operator()(int i) const { return __ldg(p + i); }
+  // L1 prefetch of the three rows of the 3x3 block around entry i (each row: 24 contiguous bytes)
+  __device__ __forceinline__ void prefetch(int i, int W) const {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p + i - W - 1));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p + i - 1));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p + i + W - 1));
+  }
 };
 struct SmemCen {
   const float2 *p;
   __device__ __forceinline__ float2 operator()(int i) const { return p[i]; }
+  __device__ __forceinline__ void prefetch(int, int) const {}
 };
 struct GlobalSlot {
   const int32_t *__restrict__ p;
