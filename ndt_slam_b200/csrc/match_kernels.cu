@@ -93,11 +93,15 @@ __device__ inline double fitness_pass(const GridView &G, const SrcL &src, int ns
   const PoseF pf = pose_to_float(p);
   const bool sse = (mp.quirks & NDT_QUIRK_TRANSFORM_SSE_ORDER) != 0;
   double sum[1] = {0.0};
-  for (int i = coop.rank(); i < ns; i += coop.size()) {
-    const float2 xy = src(i);
+  const int lane = threadIdx.x & 31;
+  for (int i0 = coop.rank() - lane; i0 < ns; i0 += coop.size()) {        // warp-uniform trip count: the 1-NN is warp-collective
+    const int i = i0 + lane;
+    const bool valid = i < ns;
+    const float2 xy = src(valid ? i : ns - 1);
     float xt, yt;
     xform(pf, sse, xy.x, xy.y, xt, yt);
-    sum[0] += (double)nn_dist2(G, xt, yt, 48);
+    const float d = nn_dist2_warp(G, xt, yt, valid);
+    if (valid) sum[0] += (double)d;
   }
   coop.template allreduce<1>(sum);
   return sum[0];

@@ -704,78 +704,144 @@ __device__ inline void match_device(Obj &obj, const MatchParams &mp, const doubl
 }
 
 // ------------------------------------------------------------------------------------------------
-// Registration::getFitnessScore: exact float 1-NN squared distance via ring search over the cell
-// buckets built with the grid; exhaustive scan if nothing is found within `max_rings`.
+// Registration::getFitnessScore: exact float32 1-NN squared distance from a transformed source point to the
+// target cloud (PCL: a second kd-tree over all target points). Here: ring search over the cell buckets built with
+// the grid (the NDT cells, or a finer lattice when those are dense), exact because a ring is only trusted once every
+// point outside the rings visited so far is provably farther than the best found.
+//   stage 1  one query per lane, a few rings; the bucket descriptors of a ring are fetched eight at a time so the
+//            loads of a ring overlap instead of forming one dependent chain per cell;
+//   stage 2  queries stage 1 could not certify (points far from the map) are finished by the whole warp: one cell of
+//            the ring per lane, one warp-min per ring; exhaustive scan (lanes stride over the cloud) as last resort.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void nn_scan(const GridView &G, int lf, float xt, float yt, float &best) {
-  if (lf < 0) return;
-  const int2 rg = __ldg(G.leaf_range + lf);
-  const float2 *__restrict__ p = G.tgt_sorted + rg.x;
-  for (int k = 0; k < rg.y; ++k) {
-    const float2 t = __ldg(p + k);
-    const float dd = dist2f(xt, yt, t.x, t.y);
-    if (dd < best) best = dd;
-  }
-}
-__device__ __forceinline__ int nn_leaf(const GridView &G, int a, int b) {
-  if (a < 0 || a >= G.div_x || b < 0 || b >= G.div_y) return -1;
-  return __ldg(G.leaf_id + G.table_base + (b + 2) * G.slot_w + a + 2);
-}
-__device__ __forceinline__ void nn_visit(const GridView &G, int a, int b, float xt, float yt, float &best) {
-  nn_scan(G, nn_leaf(G, a, b), xt, yt, best);
+constexpr int NN_STAGE1_RINGS_FINE = 6, NN_STAGE1_RINGS_COARSE = 3, NN_MAX_RINGS = 48;
+
+// t-th cell of ring r around (0, 0), t in [0, 8r) (r = 0: the centre)
+__device__ __forceinline__ void ring_cell(int r, int t, int &di, int &dj) {
+  const int w = 2 * r + 1;
+  if (t < w) { di = t - r; dj = -r; }
+  else if (t < 2 * w) { di = t - w - r; dj = r; }
+  else { const int u = t - 2 * w; dj = (u >> 1) - r + 1; di = (u & 1) ? r : -r; }
 }
 
-// fine-lattice variant: same ring search, direct (start, n) table
-__device__ __forceinline__ void nn_scan_fine(const GridView &G, int a, int b, float xt, float yt, float &best) {
-  if (a < 0 || a >= G.nn_div_x || b < 0 || b >= G.nn_div_y) return;
-  const int2 rg = __ldg(G.nn_range + (size_t)b * G.nn_div_x + a);
-  const float2 *__restrict__ p = G.nn_pts + rg.x;
-  for (int k = 0; k < rg.y; ++k) {
-    const float2 t = __ldg(p + k);
-    const float dd = dist2f(xt, yt, t.x, t.y);
-    if (dd < best) best = dd;
+template <bool FINE>
+__device__ __forceinline__ int2 nn_bucket(const GridView &G, int a, int b) {
+  if (FINE) {
+    if (a < 0 || a >= G.nn_div_x || b < 0 || b >= G.nn_div_y) return make_int2(0, 0);
+    return __ldg(G.nn_range + (size_t)b * G.nn_div_x + a);
   }
+  if (a < 0 || a >= G.div_x || b < 0 || b >= G.div_y) return make_int2(0, 0);
+  const int lf = __ldg(G.leaf_id + G.table_base + (b + 2) * G.slot_w + a + 2);
+  return lf >= 0 ? __ldg(G.leaf_range + lf) : make_int2(0, 0);
 }
 
-__device__ inline float nn_dist2(const GridView &G, float xt, float yt, int max_rings) {
-  float best = FLT_MAX;
-  const bool fine = G.nn_f > 0;
-  const int dvx = fine ? G.nn_div_x : G.div_x, dvy = fine ? G.nn_div_y : G.div_y;
-  const float inv = fine ? G.nn_inv_leaf : G.inv_leaf;
-  const double leaf = fine ? (double)G.nn_leaf : (double)G.leaf;
-  if (dvx > 0) {
-    const int ci = cell_coord(xt, inv, fine ? G.nn_min_bx : G.min_bx);
-    const int cj = cell_coord(yt, inv, fine ? G.nn_min_by : G.min_by);
-    // rings that lie entirely outside the lattice hold nothing: start at the first ring that touches it
-    int ox = 0, oy = 0;
-    if (ci < 0) ox = -ci; else if (ci >= dvx) ox = ci - (dvx - 1);
-    if (cj < 0) oy = -cj; else if (cj >= dvy) oy = cj - (dvy - 1);
-    const int r_start = max(ox, oy);
-    if (fine) max_rings *= G.nn_f;
-    for (int ring = r_start; ring <= r_start + max_rings; ++ring) {
-      if (ring == 0) {
-        if (fine) nn_scan_fine(G, ci, cj, xt, yt, best); else nn_visit(G, ci, cj, xt, yt, best);
-      } else {
-        for (int di = -ring; di <= ring; ++di) {
-          if (fine) { nn_scan_fine(G, ci + di, cj - ring, xt, yt, best); nn_scan_fine(G, ci + di, cj + ring, xt, yt, best); }
-          else { nn_visit(G, ci + di, cj - ring, xt, yt, best); nn_visit(G, ci + di, cj + ring, xt, yt, best); }
-        }
-        for (int dj = -ring + 1; dj <= ring - 1; ++dj) {
-          if (fine) { nn_scan_fine(G, ci - ring, cj + dj, xt, yt, best); nn_scan_fine(G, ci + ring, cj + dj, xt, yt, best); }
-          else { nn_visit(G, ci - ring, cj + dj, xt, yt, best); nn_visit(G, ci + ring, cj + dj, xt, yt, best); }
-        }
-        // every point outside rings 0..ring is at least (ring - 0.01) cells away
-        const double lim = ((double)ring - 0.01) * leaf;
-        if ((double)best < lim * lim) return best;
+// one ring, one query per lane
+template <bool FINE>
+__device__ __forceinline__ void nn_ring(const GridView &G, int ci, int cj, int r, float xt, float yt, float &best) {
+  const float2 *__restrict__ pts = FINE ? G.nn_pts : G.tgt_sorted;
+  const int ncell = r == 0 ? 1 : 8 * r;
+  for (int t0 = 0; t0 < ncell; t0 += 8) {
+    int2 rg[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int di = 0, dj = 0;
+      if (r > 0) ring_cell(r, min(t0 + k, ncell - 1), di, dj);
+      rg[k] = (t0 + k < ncell) ? nn_bucket<FINE>(G, ci + di, cj + dj) : make_int2(0, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float2 *__restrict__ q = pts + rg[k].x;
+      for (int j = 0; j < rg[k].y; ++j) {
+        const float2 t = __ldg(q + j);
+        const float dd = dist2f(xt, yt, t.x, t.y);
+        if (dd < best) best = dd;
       }
     }
   }
+}
+
+// rings that lie entirely outside the lattice hold nothing: the first ring that touches it
+__device__ __forceinline__ int first_ring(int ci, int cj, int dvx, int dvy) {
+  int ox = 0, oy = 0;
+  if (ci < 0) ox = -ci; else if (ci >= dvx) ox = ci - (dvx - 1);
+  if (cj < 0) oy = -cj; else if (cj >= dvy) oy = cj - (dvy - 1);
+  return max(ox, oy);
+}
+
+// every point outside rings 0..ring is at least (ring - 0.01) cells away
+__device__ __forceinline__ bool ring_certifies(int ring, double leaf, float best) {
+  const double lim = ((double)ring - 0.01) * leaf;
+  return ring >= 1 && (double)best < lim * lim;
+}
+
+// stage 1: returns true when `best` is the exact answer
+__device__ __forceinline__ bool nn_stage1(const GridView &G, float xt, float yt, float &best) {
+  best = FLT_MAX;
+  if (G.div_x <= 0) return false;
+  if (G.nn_f > 0) {
+    const int ci = cell_coord(xt, G.nn_inv_leaf, G.nn_min_bx), cj = cell_coord(yt, G.nn_inv_leaf, G.nn_min_by);
+    const int r0 = first_ring(ci, cj, G.nn_div_x, G.nn_div_y);
+    if (r0 > 2 * NN_STAGE1_RINGS_FINE) return false;
+    for (int ring = r0; ring <= r0 + NN_STAGE1_RINGS_FINE; ++ring) {
+      nn_ring<true>(G, ci, cj, ring, xt, yt, best);
+      if (ring_certifies(ring, (double)G.nn_leaf, best)) return true;
+    }
+    return false;
+  }
+  const int ci = cell_coord(xt, G.inv_leaf, G.min_bx), cj = cell_coord(yt, G.inv_leaf, G.min_by);
+  const int r0 = first_ring(ci, cj, G.div_x, G.div_y);
+  if (r0 > 2 * NN_STAGE1_RINGS_COARSE) return false;
+  for (int ring = r0; ring <= r0 + NN_STAGE1_RINGS_COARSE; ++ring) {
+    nn_ring<false>(G, ci, cj, ring, xt, yt, best);
+    if (ring_certifies(ring, (double)G.leaf, best)) return true;
+  }
+  return false;
+}
+
+// stage 2: the whole warp finishes one query (all lanes pass the same xt, yt, best); returns the exact answer
+__device__ inline float nn_stage2_warp(const GridView &G, float xt, float yt, float best) {
+  const int lane = threadIdx.x & 31;
+  if (G.div_x > 0) {
+    const int ci = cell_coord(xt, G.inv_leaf, G.min_bx), cj = cell_coord(yt, G.inv_leaf, G.min_by);
+    const int r0 = first_ring(ci, cj, G.div_x, G.div_y);
+    for (int ring = r0; ring <= r0 + NN_MAX_RINGS; ++ring) {
+      const int ncell = ring == 0 ? 1 : 8 * ring;
+      for (int t = lane; t < ncell; t += 32) {                       // one cell of the ring per lane
+        int di = 0, dj = 0;
+        if (ring > 0) ring_cell(ring, t, di, dj);
+        const int2 rg = nn_bucket<false>(G, ci + di, cj + dj);
+        const float2 *__restrict__ q = G.tgt_sorted + rg.x;
+        for (int j = 0; j < rg.y; ++j) {
+          const float2 p = __ldg(q + j);
+          const float dd = dist2f(xt, yt, p.x, p.y);
+          if (dd < best) best = dd;
+        }
+      }
+      best = __int_as_float(__reduce_min_sync(0xffffffffu, __float_as_int(best)));   // best >= 0: int order == float order
+      if (ring_certifies(ring, (double)G.leaf, best)) return best;
+    }
+  }
   // exhaustive fallback (query far from every occupied cell): still exact
-  for (int64_t j = 0; j < G.n_tgt; ++j) {
+  for (int64_t j = lane; j < G.n_tgt; j += 32) {
     const float4 t = __ldg(G.tgt + j);
     if (!isfinite(t.x) || !isfinite(t.y) || !isfinite(t.z)) continue;
     const float dd = dist2f(xt, yt, t.x, t.y);
     if (dd < best) best = dd;
+  }
+  return __int_as_float(__reduce_min_sync(0xffffffffu, __float_as_int(best)));
+}
+
+// Warp-collective: every lane of the warp must call this (valid = false for lanes without a query). Returns the
+// squared distance for this lane's query.
+__device__ inline float nn_dist2_warp(const GridView &G, float xt, float yt, bool valid) {
+  float best = FLT_MAX;
+  const bool sure = valid ? nn_stage1(G, xt, yt, best) : true;
+  unsigned todo = __ballot_sync(0xffffffffu, !sure);
+  while (todo) {
+    const int l = __ffs(todo) - 1;
+    todo &= todo - 1u;
+    const float qx = __shfl_sync(0xffffffffu, xt, l), qy = __shfl_sync(0xffffffffu, yt, l), qb = __shfl_sync(0xffffffffu, best, l);
+    const float r = nn_stage2_warp(G, qx, qy, qb);
+    if ((int)(threadIdx.x & 31) == l) best = r;
   }
   return best;
 }

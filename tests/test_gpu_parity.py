@@ -184,6 +184,29 @@ def test_align_parity_many_guesses_block_and_warp_kernels(c1):
     assert best.score == many["score"][bi]
 
 
+def test_align_small_source_one_cta_kernel(c1):
+    """Sources below the cluster threshold (600 points) take k_align_block: whole-grid tile in shared memory when it fits
+    (C1-sized grid), global tables otherwise (a grid too large for the tile)."""
+    pb, g, o = c1
+    small = np.ascontiguousarray(pb["src"][::3])
+    assert small.shape[0] < 600
+    g.set_source(small); o.set_source(small)
+    rng = synth.rng_for(29)
+    for k in range(6):
+        guess = pb["guess"] + rng.normal(0, [0.1, 0.1, 0.02])
+        _assert_result_close(g.align(guess), o.align(guess))
+    g.set_source(pb["src"]); o.set_source(pb["src"])
+    # large grid: the tile does not fit in shared memory
+    prm = common.params(resolution=0.5)
+    g2, o2 = capi.Ndt(prm), oa.Oracle(prm)
+    big = common.random_cloud(31, 60000, extent=400.0)
+    sub = np.ascontiguousarray(big[1000:1400])
+    c, s_ = np.cos(0.01), np.sin(0.01)
+    srcp = sub.copy(); srcp[:, 0] = c * sub[:, 0] + s_ * sub[:, 1] - 0.05; srcp[:, 1] = -s_ * sub[:, 0] + c * sub[:, 1] + 0.04
+    g2.set_target(big); o2.set_target(big); g2.set_source(srcp); o2.set_source(srcp)
+    _assert_result_close(g2.align([0.0, 0.0, 0.0]), o2.align([0.0, 0.0, 0.0]))
+
+
 def test_align_empty_overlap(c1):
     pb, g, o = c1
     far = pb["src"].copy(); far[:, 0] += 500.0
