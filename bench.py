@@ -356,19 +356,25 @@ def main():
     bytes_per_eval = 160.0 + 48.0 * kbar
     kern_ms = float(np.mean(step_ms))                 # one launch per step: step time == kernel time
     achieved = pe_step * bytes_per_eval / (kern_ms * 1e-3) / 1e9
-    traffic = None
-    tp = ROOT / "profiles" / "traffic.json"
+    traffic, ncu_facts = None, None
+    tp = ROOT / "profiles" / "traffic.json"       # written by profiles/make_summary.py from the committed ncu --set full capture
     if tp.exists():
         try:
-            traffic = json.loads(tp.read_text()).get("k_align_warp_C4_bytes_per_launch")
+            tj = json.loads(tp.read_text())
+            traffic = tj.get("k_align_warp_C4_bytes_per_launch")
+            ncu_facts = {k: tj.get(k) for k in ("dram_read_bytes", "dram_write_bytes", "issue_slots_busy_pct", "fp64_pipe_pct",
+                                                "l1_hit_pct", "l2_hit_pct", "source")}
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
                 "kernel": "k_align_warp", "bytes_per_point_eval": bytes_per_eval, "kbar": kbar,
-                "note": "C4 grid (%.1f MB) is L2-resident: the HBM-equivalent fraction is an algorithmic-bytes figure, "
-                        "the kernel is fp64-issue / L1-L2 latency bound (see DESIGN.md)" %
-                        ((gi.n_slots * 64 + gi.div_b[0] * gi.div_b[1] * 4) / 1e6)}
+                "algorithmic_bytes_per_launch": pe_step * bytes_per_eval, "kernel_ms": kern_ms, "ncu": ncu_facts,
+                "note": "C4's probe tables (%.1f MB) and source scan are L2 / L1 / shared-memory resident, so the algorithmic bytes "
+                        "(SURVEY 8d: 160 + 48 k per point-eval) never reach HBM: frac > 1 is an HBM-equivalent figure, DRAM traffic "
+                        "per launch is `traffic` (mostly write-back of spilled optimiser state). What bounds the kernel is issue "
+                        "slots (`ncu.issue_slots_busy_pct`) and L1/L2 load latency at 16 warps/SM (DESIGN.md 4.2)" %
+                        ((gi.n_slots * 64 + (gi.div_b[0] + 4) * (gi.div_b[1] + 4) * 12) / 1e6)}
 
     # ---- CPU baseline on this box's host cores (bounded sample of the same workload) --------------
     cores = os.cpu_count() or 1
