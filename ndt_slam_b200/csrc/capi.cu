@@ -122,6 +122,7 @@ int ndt_create(const ndt_params *p, ndt_handle *out) {
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
   cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+  { int coop = 0; cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device); h->coop_launch = coop != 0; }
   if ((e = h->gb.counters.reserve((CTR_COUNT + 4) * sizeof(int32_t))) != cudaSuccess ||
       (e = h->stage.reserve(4096)) != cudaSuccess) {
     set_err(nullptr, NDT_ERR_CUDA, "cudaMalloc", e); delete h; return NDT_ERR_CUDA;

@@ -8,7 +8,8 @@
 // Kernels
 //   k_eval_partial / k_eval_final  one objective pass for n poses (parity hook, relocalisation sweep)
 //   k_align_block   one CTA per match, optional shared-memory tile of the whole grid (single scans)
-//   k_align_cluster one thread-block cluster per match, DSMEM reduction (large source clouds)
+//   k_align_cluster one thread-block cluster per match, DSMEM reduction (single scans)
+//   k_align_grid    one match on every SM, cooperative launch + grid-wide reduction (very large source clouds)
 //   k_align_warp    persistent CTAs, one warp per match pulled from an atomic work counter (batches)
 //   k_best_of       arg-max of the batch results
 //   k_voxel_filter(_pairs)  ApproximateVoxelGrid, one warp per cloud (slot-parallel replay of the hash history)
@@ -272,6 +273,61 @@ __global__ void __launch_bounds__(256) k_align_cluster(GridView G, MatchParams m
 }
 
 // ---------------------------------------------------------------------------------------------
+// one match on the whole GPU (very large source clouds, C3): cooperative launch, one grid-wide barrier per objective
+// pass. Every CTA publishes its 13 block partials, grid.sync(), then every CTA sums all partials in the same fixed order
+// -- all threads of the grid hold bit-identical totals and run the optimiser redundantly, like the other matchers.
+// ---------------------------------------------------------------------------------------------
+struct GridCoop {
+  double *scratch;       // [16 * 16] block scratch (shared memory)
+  double *gpart;         // [2][gridDim.x][16] partials of every CTA (global), double-buffered
+  int *epoch;            // this thread's count of reductions so far (selects the buffer)
+  __device__ __forceinline__ int rank() const { return blockIdx.x * blockDim.x + threadIdx.x; }
+  __device__ __forceinline__ int size() const { return gridDim.x * blockDim.x; }
+  template <int N> __device__ __forceinline__ void allreduce(double *v) const {
+    BlockCoop b{scratch};
+    b.allreduce<N>(v);
+    double *buf = gpart + (size_t)((*epoch) & 1) * gridDim.x * 16;
+    ++(*epoch);
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      if (threadIdx.x == k) buf[blockIdx.x * 16 + k] = v[k];
+    __threadfence();
+    cg::this_grid().sync();
+    // thread (k, j): component k over CTAs j, j + 16, ... ; then the 16 strided sums are added in order
+    const int k = threadIdx.x & 15, j = threadIdx.x >> 4;
+    double s = 0.0;
+    if (k < N) for (int c = j; c < (int)gridDim.x; c += 16) s += __ldcg(buf + c * 16 + k);
+    scratch[j * 16 + k] = s;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+      double t = scratch[q];
+#pragma unroll
+      for (int i = 1; i < 16; ++i) t += scratch[i * 16 + q];
+      v[q] = t;
+    }
+    __syncthreads();
+  }
+};
+
+__global__ void __launch_bounds__(256, 2) k_align_grid(GridView G, MatchParams mp, const float4 *__restrict__ src, int ns,
+                                                    const double *__restrict__ guess3, ndt_result *__restrict__ out,
+                                                    double *__restrict__ gpart) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double scratch[16 * 16];
+  int epoch = 0;
+  GridCoop coop{scratch, gpart, &epoch};
+  const double guess[3] = {guess3[0], guess3[1], guess3[2]};
+  const GlobalSrc gsrc{src};
+  MatchOut mo;
+  auto obj = make_objective(G, mp, coop, GlobalOcc{G.occ}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, my_queue(smem_raw));
+  match_device(obj, mp, guess, mo);
+  double fsum = 0.0;
+  if (mp.want_fitness) fsum = fitness_pass(G, gsrc, ns, mp, mo.p, coop);
+  if (blockIdx.x == 0 && threadIdx.x == 0) write_result(out, mo, ns, fsum, mp.want_fitness != 0, G.n_tgt);
+}
+
+// ---------------------------------------------------------------------------------------------
 // persistent batch matcher: one warp per match, work pulled from an atomic counter
 // ---------------------------------------------------------------------------------------------
 #ifndef NDT_WARP_KERNEL_MIN_CTAS
@@ -520,6 +576,9 @@ int launch_eval(Handle *h, const double *d_poses, int64_t n, int want_hessian, d
   return NDT_OK;
 }
 
+#ifndef NDT_GRID_MIN_NS
+#define NDT_GRID_MIN_NS 16384     // above this one match takes the whole GPU (cooperative launch)
+#endif
 #ifndef NDT_CLUSTER_MIN_NS
 #define NDT_CLUSTER_MIN_NS 600      // measured on C1 (855 points): 8-CTA cluster 0.090 ms vs one CTA 0.113 ms
 #endif
@@ -549,6 +608,23 @@ int launch_align(Handle *h, const double *d_guesses, int64_t n, ndt_result *d_re
     } else {
       NDT_CUDA(h, cudaFuncSetAttribute(k_align_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_align_warp<false><<<(unsigned)grid, WK_THREADS, smem, st>>>(G, mp, src, ns, d_guesses, d_results, n, ctr + CTR_JOB, occ_words);
+    }
+  } else if (ns > NDT_GRID_MIN_NS && h->coop_launch) {
+    // very large source cloud: one match at a time on every SM (cooperative launch, grid-wide reduction)
+    int per_sm = 0;
+    NDT_CUDA(h, cudaFuncSetAttribute(k_align_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, QUEUE_BYTES));
+    NDT_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_align_grid, 256, QUEUE_BYTES));
+    int grid = h->sm_count * std::max(1, std::min(per_sm, 2));
+    grid = (int)std::min<int64_t>(grid, (ns + 255) / 256);
+    NDT_CUDA(h, h->scratch.reserve((size_t)2 * grid * 16 * sizeof(double)));
+    double *gpart = h->scratch.as<double>();
+    for (int64_t i = 0; i < n; ++i) {
+      const double *gi = d_guesses + 3 * i;
+      ndt_result *ri = d_results + i;
+      int ns_arg = ns;
+      void *args[] = {(void *)&G, (void *)&mp, (void *)&src, (void *)&ns_arg, (void *)&gi, (void *)&ri, (void *)&gpart};
+      NDT_CUDA(h, cudaLaunchCooperativeKernel((const void *)k_align_grid, dim3(grid), dim3(256), args, QUEUE_BYTES, st));
+      if (i > 0) ++h->launches;
     }
   } else if (ns > NDT_CLUSTER_MIN_NS) {
     // large source cloud: spread one match over a thread-block cluster (DSMEM reduction)

@@ -80,6 +80,7 @@ struct Handle {
   float last_ms = 0.f;
   int sm_count = 148;
   int max_smem_optin = 0;
+  bool coop_launch = false;      // cudaDevAttrCooperativeLaunch
 
   GridBuffers gb;
   GridDims gd;

@@ -227,8 +227,9 @@ def test_voxel_filter_device_matches_oracle():
             assert np.array_equal(g.approx_voxel_filter(xyzw, leaf), oa.approx_voxel_filter(xyzw, leaf))
 
 
-def test_large_source_cluster_kernel():
-    """> 4096 source points: the thread-block-cluster matcher (DSMEM reduction)."""
+def test_large_source_cluster_and_whole_gpu_kernels():
+    """20,000 source points: the cooperative whole-GPU matcher (grid-wide reduction); the first 9,000 of them: the
+    thread-block-cluster matcher (DSMEM reduction)."""
     rng = synth.rng_for(31)
     segs = synth.office(31, 60.0, 40.0, 20)
     tgt_xy = synth.sample_walls(segs, 0.005, 0.01, rng)
@@ -245,6 +246,13 @@ def test_large_source_cluster_kernel():
     a, b = g.align([0.0, 0.0, 0.0]), o.align([0.0, 0.0, 0.0])
     _assert_result_close(a, b)
     assert np.hypot(a.pose[0] - true[0], a.pose[1] - true[1]) < 0.02
+    a2 = g.align([0.0, 0.0, 0.0])                       # run-to-run determinism of the grid-wide reduction
+    assert list(a2.pose) == list(a.pose) and a2.score == a.score
+    few = g.align_batch(np.array([[0.0, 0.0, 0.0], [0.02, -0.01, 0.001]]))      # two matches, one cooperative launch each
+    assert np.allclose(few[0]["pose"], a.pose, rtol=0, atol=0) and few[1]["converged"] == 1
+    part = np.ascontiguousarray(src[:9000])
+    g.set_source(part); o.set_source(part)
+    _assert_result_close(g.align([0.0, 0.0, 0.0]), o.align([0.0, 0.0, 0.0]))
 
 
 def test_grid_export_import_roundtrip(c1):
