@@ -123,61 +123,72 @@ __global__ void __launch_bounds__(256) k_count(const float4 *__restrict__ pts, i
   }
 }
 
-// pass 1b: walk the padded count tables row by row (blockIdx.x = grid * chunks + chunk); every occupied
-// cell gets a leaf id and a bucket range, the count table turns into the slot table (-1 everywhere until
-// k_finalize fills in the tree members), the probe table starts as all-NaN and leaf_id as all -1.
-__global__ void __launch_bounds__(256) k_alloc(int32_t *__restrict__ count_slot, float2 *__restrict__ cen,
-                                              const PairDims *__restrict__ dims, int chunks,
-                                              int32_t *__restrict__ leaf_id, int32_t *__restrict__ leaf_cell,
-                                              int32_t *__restrict__ leaf_pair, int32_t *__restrict__ leaf_n,
-                                              int32_t *__restrict__ leaf_start, int32_t *__restrict__ big_list,
-                                              int32_t *__restrict__ ctr) {
+// pass 1b: walk the padded count tables row by row (blockIdx.x = grid * chunks + chunk); every occupied cell gets a leaf
+// id and a bucket range and its count turns into leaf id + 1 in place (0 stays "empty"). Only occupied cells are written:
+// the probe table was NaN-filled and the count table zeroed by memsets (a C3 grid has 16.8 M cells for 0.6 M leaves), and
+// the slot table needs no initialisation at all -- it is only ever read for cells whose centroid is not NaN.
+__global__ void __launch_bounds__(256) k_alloc(int32_t *__restrict__ count_leaf, const PairDims *__restrict__ dims, int chunks,
+                                              int32_t *__restrict__ leaf_cell, int32_t *__restrict__ leaf_pair,
+                                              int32_t *__restrict__ leaf_n, int32_t *__restrict__ leaf_start,
+                                              int32_t *__restrict__ big_list, int32_t *__restrict__ ctr) {
+  __shared__ int s_leaves[8], s_pts[8], s_base[2];
   const int lane = threadIdx.x & 31;
   const int pair = blockIdx.x / chunks, chunk = blockIdx.x - pair * chunks;
   const PairDims d = dims[pair];
-  const int W = d.W, H = d.H;
+  const int W = d.W;
   const int warps_per_block = blockDim.x >> 5, warp_in_block = threadIdx.x >> 5;
-  const float qnan = __int_as_float(0x7fc00000);
-  for (int r = chunk; r < H; r += chunks) {
-    const bool row_in = (r >= 2 && r < d.div_y + 2);
+  // sweep 1: how many leaves / points does this warp own? One pair of global atomics per CTA (577 k leaves at C3 would
+  // otherwise serialise on two addresses).
+  int my_pts = 0, wl = 0;
+  for (int r = 2 + chunk; r < d.div_y + 2; r += chunks) {           // interior rows only: the padding holds no points
     const size_t row0 = (size_t)d.base + (size_t)r * W;
     for (int c0 = warp_in_block * 32; c0 < W; c0 += warps_per_block * 32) {
       const int c = c0 + lane;
-      const bool valid = c < W;
-      const bool interior = valid && row_in && c >= 2 && c < d.div_x + 2;
-      const int n = interior ? count_slot[row0 + c] : 0;
+      const int n = (c < W) ? count_leaf[row0 + c] : 0;
+      my_pts += n;
+      wl += __popc(__ballot_sync(0xffffffffu, n > 0));
+    }
+  }
+  const int wp = __reduce_add_sync(0xffffffffu, my_pts);
+  if (lane == 0) { s_leaves[warp_in_block] = wl; s_pts[warp_in_block] = wp; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tl = 0, tp = 0;
+    for (int w = 0; w < warps_per_block; ++w) { tl += s_leaves[w]; tp += s_pts[w]; }
+    s_base[0] = tl ? atomicAdd(ctr + CTR_LEAVES, tl) : 0;
+    s_base[1] = tp ? atomicAdd(ctr + CTR_PTS, tp) : 0;
+  }
+  __syncthreads();
+  int run_leaf = s_base[0], run_pts = s_base[1];
+  for (int w = 0; w < warp_in_block; ++w) { run_leaf += s_leaves[w]; run_pts += s_pts[w]; }
+  if (wl == 0) return;
+  // sweep 2: same walk, ids and bucket ranges from the warp's running offsets
+  for (int r = 2 + chunk; r < d.div_y + 2; r += chunks) {
+    const size_t row0 = (size_t)d.base + (size_t)r * W;
+    for (int c0 = warp_in_block * 32; c0 < W; c0 += warps_per_block * 32) {
+      const int c = c0 + lane;
+      const int n = (c < W) ? count_leaf[row0 + c] : 0;
       const bool has = n > 0;
       const unsigned bal = __ballot_sync(0xffffffffu, has);
-      int leaf = -1;
-      if (bal != 0u) {
-        int incl = n;
+      if (bal == 0u) continue;
+      int incl = n;
 #pragma unroll
-        for (int dlt = 1; dlt < 32; dlt <<= 1) {
-          const int t = __shfl_up_sync(0xffffffffu, incl, dlt);
-          if (lane >= dlt) incl += t;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        int base_leaf = 0, base_pts = 0;
-        if (lane == 0) {
-          base_leaf = atomicAdd(ctr + CTR_LEAVES, __popc(bal));
-          base_pts = atomicAdd(ctr + CTR_PTS, total);
-        }
-        base_leaf = __shfl_sync(0xffffffffu, base_leaf, 0);
-        base_pts = __shfl_sync(0xffffffffu, base_pts, 0);
-        if (has) {
-          leaf = base_leaf + __popc(bal & ((1u << lane) - 1u));
-          leaf_cell[leaf] = (int32_t)(row0 + c);
-          leaf_pair[leaf] = pair;
-          leaf_n[leaf] = n;
-          leaf_start[leaf] = base_pts + incl - n;
-          if (n > FINALIZE_BIG_LEAF) big_list[atomicAdd(ctr + CTR_BIG, 1)] = leaf;   // dense leaves get a warp in k_finalize
-        }
+      for (int dlt = 1; dlt < 32; dlt <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, dlt);
+        if (lane >= dlt) incl += t;
       }
-      if (valid) {
-        leaf_id[row0 + c] = leaf;
-        count_slot[row0 + c] = -1;
-        cen[row0 + c] = make_float2(qnan, qnan);
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      if (has) {
+        const int leaf = run_leaf + __popc(bal & ((1u << lane) - 1u));
+        leaf_cell[leaf] = (int32_t)(row0 + c);
+        leaf_pair[leaf] = pair;
+        leaf_n[leaf] = n;
+        leaf_start[leaf] = run_pts + incl - n;
+        count_leaf[row0 + c] = leaf + 1;
+        if (n > FINALIZE_BIG_LEAF) big_list[atomicAdd(ctr + CTR_BIG, 1)] = leaf;   // dense leaves get a warp in k_finalize
       }
+      run_leaf += __popc(bal);
+      run_pts += total;
     }
   }
 }
@@ -190,7 +201,7 @@ __global__ void __launch_bounds__(256) k_fill(int64_t n, const int32_t *__restri
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int cell = cell_of[i];
     if (cell < 0) continue;
-    const int leaf = __ldg(leaf_id + cell);
+    const int leaf = __ldg(leaf_id + cell) - 1;
     list[__ldg(leaf_start + leaf) + rank_of[i]] = (int32_t)i;
   }
 }
@@ -208,7 +219,7 @@ __global__ void __launch_bounds__(256) k_rank(int64_t n, const int32_t *__restri
   const int64_t n_bucketed = ctr[CTR_PTS];
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_bucketed; p += (int64_t)gridDim.x * blockDim.x) {
     const int v = list[p];
-    const int leaf = __ldg(leaf_id + cell_of[v]);
+    const int leaf = __ldg(leaf_id + cell_of[v]) - 1;
     const int st = __ldg(leaf_start + leaf), m = __ldg(leaf_n + leaf);
     int r = 0;
     for (int j = 0; j < m; ++j) r += (__ldg(list + st + j) < v) ? 1 : 0;
@@ -590,15 +601,15 @@ int grid_build_tables(Handle *h, int64_t n, int n_grids, int64_t total_pad, int 
   const PairDims *dims = gb.dims.as<PairDims>();
   const int64_t *off = gb.pair_off.as<int64_t>();
   NDT_CUDA(h, cudaMemsetAsync(gb.occ.p, 0, occ_words * 4, st));
-  NDT_CUDA(h, cudaMemsetAsync(gb.slot.p, 0, npad * 4, st));
+  NDT_CUDA(h, cudaMemsetAsync(gb.leaf_id.p, 0, npad * 4, st));               // per-cell counts, then leaf id + 1
+  NDT_CUDA(h, cudaMemsetAsync(gb.cen.p, 0xff, npad * sizeof(float2), st));   // all-ones is a NaN: "no tree cell here"
   k_count<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(gb.tgt.as<float4>(), n, off, n_grids, dims, h->gd.inv_leaf,
-                                                        gb.slot.as<int32_t>(), gb.cell_of.as<int32_t>(),
+                                                        gb.leaf_id.as<int32_t>(), gb.cell_of.as<int32_t>(),
                                                         gb.rank_of.as<int32_t>());
   // enough CTAs to fill the machine: several row chunks per grid when there are few grids
   int chunks = 1;
   if (n_grids < h->sm_count * 8) chunks = std::max(1, std::min(max_h, (h->sm_count * 8) / std::max(n_grids, 1)));
-  k_alloc<<<(unsigned)((int64_t)n_grids * chunks), 256, 0, st>>>(gb.slot.as<int32_t>(), gb.cen.as<float2>(), dims, chunks,
-                                                                gb.leaf_id.as<int32_t>(), gb.leaf_cell.as<int32_t>(),
+  k_alloc<<<(unsigned)((int64_t)n_grids * chunks), 256, 0, st>>>(gb.leaf_id.as<int32_t>(), dims, chunks, gb.leaf_cell.as<int32_t>(),
                                                                 gb.leaf_pair.as<int32_t>(), gb.leaf_n.as<int32_t>(),
                                                                 gb.leaf_start.as<int32_t>(), gb.big_list.as<int32_t>(), ctr);
   k_fill<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(n, gb.cell_of.as<int32_t>(), gb.rank_of.as<int32_t>(),
@@ -732,7 +743,7 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace) {
     // a 4 x 4 all-empty padded table (clear occupancy bits): a match against an empty target probes nothing
     NDT_CUDA(h, gb.occ.reserve(64)); NDT_CUDA(h, gb.slot.reserve(64)); NDT_CUDA(h, gb.cen.reserve(128)); NDT_CUDA(h, gb.leaf_id.reserve(64));
     NDT_CUDA(h, cudaMemsetAsync(gb.occ.p, 0, 64, st)); NDT_CUDA(h, cudaMemsetAsync(gb.slot.p, 0xff, 64, st));
-    NDT_CUDA(h, cudaMemsetAsync(gb.cen.p, 0xff, 128, st)); NDT_CUDA(h, cudaMemsetAsync(gb.leaf_id.p, 0xff, 64, st));
+    NDT_CUDA(h, cudaMemsetAsync(gb.cen.p, 0xff, 128, st)); NDT_CUDA(h, cudaMemsetAsync(gb.leaf_id.p, 0, 64, st));
     h->have_grid = true;
     if (h->timing) { cudaEventRecord(h->ev1, st); }
     NDT_CUDA(h, cudaStreamSynchronize(st));

@@ -34,7 +34,7 @@ struct __align__(16) CellRec {   // 64 bytes
 static_assert(sizeof(CellRec) == 64, "CellRec must be 64 bytes");
 
 struct GridView {
-  const int32_t *__restrict__ slot;     // [(div_x + 4) * (div_y + 4)] padded by 2 cells of -1 on every side:
+  const int32_t *__restrict__ slot;     // [(div_x + 4) * (div_y + 4)] padded by 2 cells on every side (defined only where cen is not NaN):
                                         // cell (i, j) lives at (j + 2) * slot_w + i + 2; value = record index or -1
   int32_t slot_w;                       // div_x + 4
   int32_t table_base;                   // offset of this grid inside the shared tables (0 for a single grid;
@@ -49,7 +49,7 @@ struct GridView {
   float r2;                             // (float)((double)leaf * leaf)
   float leaf;
   // 1-NN buckets (fitness): every occupied cell
-  const int32_t *__restrict__ leaf_id;  // same padded indexing -> leaf index or -1
+  const int32_t *__restrict__ leaf_id;  // same padded indexing -> leaf index + 1, 0 for an empty cell
   const int2 *__restrict__ leaf_range;  // per leaf: (start, n) into tgt_sorted
   const float2 *__restrict__ tgt_sorted;// target (x, y) in bucket order (cell by cell, input order inside a cell)
   const float4 *__restrict__ tgt;       // target points, input order
@@ -730,8 +730,8 @@ __device__ __forceinline__ int2 nn_bucket(const GridView &G, int a, int b) {
     return __ldg(G.nn_range + (size_t)b * G.nn_div_x + a);
   }
   if (a < 0 || a >= G.div_x || b < 0 || b >= G.div_y) return make_int2(0, 0);
-  const int lf = __ldg(G.leaf_id + G.table_base + (b + 2) * G.slot_w + a + 2);
-  return lf >= 0 ? __ldg(G.leaf_range + lf) : make_int2(0, 0);
+  const int lf = __ldg(G.leaf_id + G.table_base + (b + 2) * G.slot_w + a + 2);      // leaf id + 1, 0 = empty cell
+  return lf > 0 ? __ldg(G.leaf_range + lf - 1) : make_int2(0, 0);
 }
 
 // one ring, one query per lane

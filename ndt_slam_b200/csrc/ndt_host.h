@@ -41,10 +41,10 @@ struct GridBuffers {
   DevBuf nn_cnt;       // int32[nn cells] fine nearest-neighbour lattice: counts (build only)
   DevBuf nn_range;     // int2[nn cells]  (start, n)
   DevBuf nn_pts;       // float2[n]       target (x, y) in fine-bucket order
-  DevBuf slot;         // int32[padded]   count during the build, then cell -> record slot
+  DevBuf slot;         // int32[padded]   cell -> record slot (written for tree cells only; never initialised elsewhere)
   DevBuf cen;          // float2[padded]  probe table: float32 centroid of tree cells, NaN elsewhere
   DevBuf occ;          // uint32[padded/32] dilated occupancy bitmap (3x3 block contains a tree cell)
-  DevBuf leaf_id;      // int32[n_cells]  cell -> leaf or -1
+  DevBuf leaf_id;      // int32[padded]   per-cell point count during the build, then leaf id + 1 (0 = empty)
   DevBuf leaf_cell;    // int32[n]        per leaf: position in the shared padded tables
   DevBuf leaf_pair;    // int32[n]        per leaf: which grid it belongs to
   DevBuf big_list;     // int32[]         leaves with more than FINALIZE_BIG_LEAF points (reduced by a warp each)
