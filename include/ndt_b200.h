@@ -114,6 +114,11 @@ const char *ndt_version(void);
 
 /* ---- grid build: ndt.setInputTarget(target_cloud)  (PoseEstimator.cpp:19) --------------- */
 int ndt_set_target(ndt_handle h, const float *xyzw, int64_t n, int memspace);
+/* Same, for a target that only changed at its end since the previous ndt_set_target* call on this handle (a map that
+ * grows scan by scan: PointCloudMap::makeLocalMap [REF src/PointCloudMap.cpp:119-134]): the caller promises that the
+ * first n_same points are identical to the previous call's, so only points [n_same, n) are staged and copied to the
+ * device; the grid itself is rebuilt in full and is identical to ndt_set_target's. n_same = 0 is ndt_set_target. */
+int ndt_set_target_prefix(ndt_handle h, const float *xyzw, int64_t n, int64_t n_same, int memspace);
 int ndt_get_grid_info(ndt_handle h, ndt_grid_info *info);
 /* Leaves in ascending cell-index order (the std::map order of PCL's leaves_), for parity
  * checks: cell index, nr_points (-1 = failed eigen check), mean[2], icov[4] (xx,xy,yx,yy),

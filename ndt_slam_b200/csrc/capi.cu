@@ -159,6 +159,11 @@ int ndt_set_target(ndt_handle hh, const float *xyzw, int64_t n, int memspace) {
   return grid_build(h, xyzw, n, memspace);
 }
 
+int ndt_set_target_prefix(ndt_handle hh, const float *xyzw, int64_t n, int64_t n_same, int memspace) {
+  H_OR_FAIL(hh);
+  return grid_build(h, xyzw, n, memspace, n_same);
+}
+
 int ndt_get_grid_info(ndt_handle hh, ndt_grid_info *info) {
   H_OR_FAIL(hh);
   if (!info) return NDT_ERR_ARG;
@@ -419,6 +424,7 @@ int ndt_match_pairs(ndt_handle hh, const float *src_xyzw, const int64_t *src_off
   GridBuffers &gb = h->gb;
   GridDims &gd = h->gd;
   h->have_grid = false; h->have_src = false;          // the handle's single grid / source are overwritten
+  h->tgt_on_device = 0;
   gd = GridDims();
   gd.leaf = h->prm.resolution; gd.inv_leaf = 1.0f / gd.leaf; gd.r2 = (float)((double)gd.leaf * (double)gd.leaf);
   std::memset(h->h_counters, 0, sizeof(h->h_counters));
@@ -527,6 +533,7 @@ int ndt_grid_import(ndt_handle hh, const void *device_blob, int64_t bytes) {
   NDT_CUDA(h, cudaStreamSynchronize(st));
   if (b.magic != kBlobMagic || b.total > bytes) return set_err(h, NDT_ERR_ARG, "ndt_grid_import: not a grid blob");
   h->have_grid = false;
+  h->tgt_on_device = 0;
   h->gd = b.gd;
   std::memcpy(h->h_counters, b.counters, sizeof(b.counters));
   const int64_t nc = h->gd.n_cells, nl = h->h_counters[CTR_LEAVES], nsl = h->h_counters[CTR_SLOTS], nt = h->gd.n_tgt;

@@ -23,11 +23,14 @@
 //               64-byte record + cell->slot table
 #include "ndt_host.h"
 
+#include <cooperative_groups.h>
 #include <climits>
 #include <cmath>
 #include <cstring>
 #include <limits>
 #include <vector>
+
+namespace cg = cooperative_groups;
 
 namespace ndt {
 
@@ -346,8 +349,13 @@ __device__ __forceinline__ void finish_leaf(const int leaf, const int n, const i
     leaf_icov[4 * (size_t)leaf + 2] = ic2; leaf_icov[4 * (size_t)leaf + 3] = ic3;
     leaf_cen[leaf] = make_float2(cx, cy);
     if (in_tree) {
-      const int s = atomicAdd(ctr + CTR_SLOTS, 1);
-      if (nr > 0) atomicAdd(ctr + CTR_VALID, 1);
+      // warp-aggregated slot allocation (one atomic per group of lanes that got here together)
+      cg::coalesced_group act = cg::coalesced_threads();
+      int s = 0;
+      if (act.thread_rank() == 0) s = atomicAdd(ctr + CTR_SLOTS, (int)act.size());
+      s = act.shfl(s, 0) + (int)act.thread_rank();
+      const unsigned okm = act.ballot(nr > 0);
+      if (act.thread_rank() == 0 && okm) atomicAdd(ctr + CTR_VALID, __popc(okm));
       CellRec r;
       r.cx = cx; r.cy = cy; r.nr_points = nr; r.cell = leaf_cell[leaf];
       r.mx = m0; r.my = m1; r.c00 = ic0; r.c01 = ic1; r.c10 = ic2; r.c11 = ic3;
@@ -656,15 +664,19 @@ int pairs_prepare(Handle *h, int64_t n_pairs, int64_t *total_pad, int *max_h) {
   return NDT_OK;
 }
 
-int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace) {
+int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace, int64_t n_same) {
   GridBuffers &gb = h->gb;
   GridDims &gd = h->gd;
   cudaStream_t st = h->stream;
   h->have_grid = false;
+  // n_same: the caller promises that the first n_same points equal the first n_same points of the previous target of
+  // this handle (a map that only changed at its end). They are still on the device: only the rest is staged and copied.
+  if (n_same < 0 || n_same > n || n_same > h->tgt_on_device || memspace != NDT_MEM_HOST) n_same = 0;
+  h->tgt_on_device = 0;
   if (n < 0 || (n > 0 && !xyzw)) return set_err(h, NDT_ERR_ARG, "ndt_set_target: bad points");
   if (n > (int64_t)INT_MAX) return set_err(h, NDT_ERR_CAPACITY, "ndt_set_target: more than 2^31-1 points");
   const size_t npts = (size_t)(n > 0 ? n : 1);
-  NDT_CUDA(h, gb.tgt.reserve(npts * sizeof(float4)));
+  NDT_CUDA(h, gb.tgt.reserve(npts * sizeof(float4), (size_t)n_same * sizeof(float4), st));
   NDT_CUDA(h, gb.counters.reserve((CTR_COUNT + 4) * sizeof(int32_t)));
   NDT_CUDA(h, gb.dims.reserve(sizeof(PairDims)));
   NDT_CUDA(h, gb.pair_off.reserve(2 * sizeof(int64_t)));
@@ -683,12 +695,14 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace) {
   // Host clouds always go through the pinned stage (a copy from pageable memory is several times slower).
   // Small ones get their bounds in the same host pass; large ones are memcpy'd and take the bounds kernel.
   const bool host_in = (memspace == NDT_MEM_HOST);
-  const bool host_bounds = host_in && (n < 32768);
+  const bool host_bounds = host_in && (n < 32768) && n_same == 0;
   const void *copy_from = xyzw;
   if (host_in && n > 0) {
-    if (ensure_pinned(h, npts * sizeof(float4) + 256)) return NDT_ERR_CUDA;
+    if (ensure_pinned(h, (npts - (size_t)n_same) * sizeof(float4) + 256)) return NDT_ERR_CUDA;
     float *stage = (float *)h->pinned;
-    if (host_bounds) {
+    if (n_same > 0) {
+      std::memcpy(stage, xyzw + 4 * n_same, (size_t)(n - n_same) * sizeof(float4));      // the changed tail only
+    } else if (host_bounds) {
       for (int64_t i = 0; i < n; ++i) {
         const float x = xyzw[4 * i], y = xyzw[4 * i + 1], z = xyzw[4 * i + 2];
         stage[4 * i] = x; stage[4 * i + 1] = y; stage[4 * i + 2] = z; stage[4 * i + 3] = xyzw[4 * i + 3];
@@ -707,8 +721,9 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace) {
   k_init_counters<<<1, 32, 0, st>>>(ctr, bounds);
   ++h->launches;
   if (n > 0) {
-    NDT_CUDA(h, cudaMemcpyAsync(gb.tgt.p, copy_from, (size_t)n * sizeof(float4),
-                                host_in ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+    if (n > n_same)
+      NDT_CUDA(h, cudaMemcpyAsync(gb.tgt.as<float4>() + n_same, copy_from, (size_t)(n - n_same) * sizeof(float4),
+                                  host_in ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
     if (!host_bounds) {
       k_bounds<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(gb.tgt.as<float4>(), n, bounds, ctr);
       ++h->launches;
@@ -799,6 +814,7 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace) {
   }
   NDT_CUDA(h, cudaGetLastError());
   h->have_grid = true;
+  h->tgt_on_device = n;
   return NDT_OK;
 }
 

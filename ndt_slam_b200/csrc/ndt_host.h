@@ -14,13 +14,19 @@ namespace ndt {
 struct DevBuf {
   void *p = nullptr;
   size_t cap = 0;
-  cudaError_t reserve(size_t bytes) {
+  // keep > 0: the first `keep` bytes survive a reallocation (copied on `st`)
+  cudaError_t reserve(size_t bytes, size_t keep = 0, cudaStream_t st = nullptr) {
     if (bytes <= cap) return cudaSuccess;
+    const size_t want = 2 * bytes + 4096;     // geometric growth: a map that grows scan by scan reallocates O(log n) times
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, want);
+    if (e != cudaSuccess) return e;
+    if (p && keep > 0) {
+      e = cudaMemcpyAsync(q, p, keep < cap ? keep : cap, cudaMemcpyDeviceToDevice, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
     if (p) cudaFree(p);
-    p = nullptr; cap = 0;
-    size_t want = 2 * bytes + 4096;     // geometric growth: a map that grows scan by scan reallocates O(log n) times
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e == cudaSuccess) cap = want;
+    p = q; cap = want;
     return e;
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
@@ -85,6 +91,7 @@ struct Handle {
   GridBuffers gb;
   GridDims gd;
   bool have_grid = false;
+  int64_t tgt_on_device = 0;     // leading points of gb.tgt that still hold the last ndt_set_target cloud (0: unknown)
   int32_t h_counters[CTR_COUNT] = {0};   // host copy after the last build
 
   DevBuf src;          // float4[ns]
@@ -102,7 +109,7 @@ struct Handle {
 };
 
 // grid_build.cu
-int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace);
+int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace, int64_t n_same = 0);
 // shared by ndt_set_target (one grid) and ndt_match_pairs (one grid per pair): target points are in gb.tgt,
 // geometry in gb.dims (device), point ranges in gb.pair_off (device, n_grids + 1 entries; unused for one grid)
 int grid_build_tables(Handle *h, int64_t n, int n_grids, int64_t total_pad, int max_h);

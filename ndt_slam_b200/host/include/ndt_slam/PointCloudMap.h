@@ -85,6 +85,11 @@ class PointCloudMap {
   std::vector<pcl::PointCloud<pcl::PointXYZ>::Ptr> maps;
   std::string map_name, separated_map_name;
 
+  // not in the reference: makeLocalMap number `localMapEpoch` left the first `localMapStablePrefix` points of
+  // localMap_cloud exactly as call localMapEpoch - 1 had them (lets the matcher upload only the changed tail)
+  uint64_t localMapEpoch = 0;
+  size_t localMapStablePrefix = 0;
+
   PointCloudMap() : startFrame(0), sepThre(30), atd(0) {
     ros::param::get("start_frame", startFrame);
     ros::param::get("sepThre", sepThre);

@@ -36,6 +36,10 @@ class PoseEstimator {
 
   double LeafSize;
 
+  uint64_t hintEpoch = 0, uploadedEpoch = 0;     // see hintTargetPrefix
+  size_t hintPrefix = 0;
+  const void *uploadedCloud = nullptr;
+
   ndt_handle ndt;       // stands where the reference has  pcl::NDT<pcl::PointXYZ, pcl::PointXYZ> ndt;
   Timer timer;
 
@@ -55,6 +59,11 @@ class PoseEstimator {
   ~PoseEstimator();
   PoseEstimator(const PoseEstimator &) = delete;
   PoseEstimator &operator=(const PoseEstimator &) = delete;
+
+  // Optional hint (not in the reference): the reference cloud handed to the next estimatePose is version `epoch` of a
+  // cloud whose first `stablePoints` points did not change since version epoch - 1. When the previous estimatePose
+  // uploaded exactly that previous version, only the changed tail is copied to the device (ndt_set_target_prefix).
+  void hintTargetPrefix(uint64_t epoch, size_t stablePoints) { hintEpoch = epoch; hintPrefix = stablePoints; }
 
   void setScanPair(const Scan2D *curScan, pcl::PointCloud<pcl::PointXYZ>::Ptr refScan);
   void setScanPair(const Scan2D *curScan, const Scan2D *refScan);

@@ -139,6 +139,8 @@ void PointCloudMap::makeLocalMap() {
   std::vector<pcl::PointXYZ> &lm = localMap_cloud->points;
   const bool same_layout = lm_cur == cur.p_cloud.get() && lm_prev == prev && lm_prev_points == prev_points &&
                            lm_prefix_points <= prefix.size() && lm_fixed == prev_points + lm_prefix_points && lm.size() >= lm_fixed;
+  ++localMapEpoch;
+  localMapStablePrefix = same_layout ? lm_fixed : 0;
   if (!same_layout) {
     lm.clear();
     if (prev) lm.insert(lm.end(), prev->points.begin(), prev->points.end());

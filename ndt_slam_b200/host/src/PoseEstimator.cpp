@@ -1,6 +1,7 @@
 // PoseEstimator.cpp -- estimatePose on the B200 through the C ABI [REF src/PoseEstimator.cpp:4-69].
 #include "ndt_slam/PoseEstimator.h"
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -102,8 +103,15 @@ double PoseEstimator::estimatePose(Pose2D &initPose, Pose2D &estPose, Eigen::Mat
     fail(ndt, "ndt_set_source");
   lastSetSourceWallMs = now_ms() - t0;
   t0 = now_ms();
-  if (ndt_set_target(ndt, reinterpret_cast<const float *>(target_cloud->points.data()), (int64_t)target_cloud->points.size(), NDT_MEM_HOST) != NDT_OK)
+  // a local map that only changed at its end since the cloud uploaded last time: copy the tail only
+  int64_t n_same = 0;
+  if (hintEpoch != 0 && uploadedEpoch != 0 && hintEpoch == uploadedEpoch + 1 && uploadedCloud == target_cloud.get())
+    n_same = (int64_t)std::min(hintPrefix, target_cloud->points.size());
+  if (ndt_set_target_prefix(ndt, reinterpret_cast<const float *>(target_cloud->points.data()), (int64_t)target_cloud->points.size(), n_same,
+                            NDT_MEM_HOST) != NDT_OK)
     fail(ndt, "ndt_set_target");
+  uploadedEpoch = hintEpoch; uploadedCloud = target_cloud.get();
+  hintEpoch = 0; hintPrefix = 0;
   lastSetTargetWallMs = now_ms() - t0;
   float ms = 0.f;
   ndt_last_kernel_ms(ndt, &ms);

@@ -83,6 +83,27 @@ def test_grid_device_resident_input_and_nonfinite_points():
     assert g.grid_info().n_points == tgt.shape[0] - 2
 
 
+def test_set_target_prefix_uploads_only_the_tail():
+    """ndt_set_target_prefix: a cloud that only changed at its end (a local map growing scan by scan). The grid must be
+    the one ndt_set_target builds from the whole cloud, across device-buffer reallocations."""
+    prm = common.params(resolution=0.5)
+    g, o = capi.Ndt(prm), oa.Oracle(prm)
+    full = common.random_cloud(41, 120000, extent=60.0)
+    n_prev, cloud = 0, None
+    for n in (900, 2500, 2600, 40000, 40010, 120000):
+        stable = max(n_prev - 300, 0)                      # the last 300 points of the previous version were replaced
+        cloud = full[:n].copy()
+        cloud[stable:n_prev, 0] += 0.013                  # ... by different ones
+        full[stable:n_prev] = cloud[stable:n_prev]
+        g.set_target(cloud, n_same=stable)
+        o.set_target(cloud)
+        _assert_grid_equal(g, o)
+        n_prev = n
+    # a stale or oversized promise degrades to a full upload
+    g.set_target(cloud[:5000], n_same=10**9); o.set_target(cloud[:5000])
+    _assert_grid_equal(g, o)
+
+
 def test_grid_edge_cases():
     prm = common.params(resolution=0.5)
     g, o = capi.Ndt(prm), oa.Oracle(prm)
