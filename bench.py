@@ -186,6 +186,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--hyp-per-gpu", type=int, default=HYP_PER_GPU)
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--extras-only", action="store_true", help="print the C1/C2/C3 figures as one JSON object (used by the main run)")
     ap.add_argument("--c2-scans", type=int, default=300)
     ap.add_argument("--no-cpu-baseline", action="store_true", help="profiling runs only")
     ap.add_argument("--c5-pairs", type=int, default=C5_PAIRS, help="scan pairs of the C5 figure in total (0 = skip)")
@@ -203,6 +204,11 @@ def main():
 
     if args.impl == "reference":
         return reference_arm(args, rank, n_gpus, K, W)
+    if args.extras_only:
+        import torch
+        from ndt_slam_b200 import capi
+        print(json.dumps(run_extras(None, capi.default_params(resolution=RESOLUTION), capi, torch, c2_scans=args.c2_scans)), flush=True)
+        return
 
     import torch
     import torch.distributed as dist
@@ -387,10 +393,15 @@ def main():
                     "sample": f"{nm_c} of {n_h} hypotheses of this workload, full matches, {cores} threads, {sec_c:.1f} s",
                     "matches_per_sec": nm_c / sec_c}
 
+    # Secondary single-GPU figures run in a fresh process: they are latency measurements of single matches / a per-scan
+    # loop, and inside this process (16 CPU-baseline threads just finished, 256 MiB flush buffer, pinned staging, a second
+    # CUDA stream) the same C2 loop measured 2-7x slower than on its own.
     extras = {}
     if not args.no_extras and world == 1:
         try:
-            extras = run_extras(g, prm, capi, torch, c2_scans=args.c2_scans)
+            cp = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--extras-only", "--c2-scans", str(args.c2_scans)],
+                                capture_output=True, text=True, timeout=900)
+            extras = json.loads(cp.stdout.strip().splitlines()[-1]) if cp.returncode == 0 else {"error": cp.stderr[-400:]}
         except Exception as ex:       # reported, never hidden
             extras = {"error": repr(ex)}
 
