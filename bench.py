@@ -210,6 +210,18 @@ def main():
         print(json.dumps(run_extras(None, capi.default_params(resolution=RESOLUTION), capi, torch, c2_scans=args.c2_scans)), flush=True)
         return
 
+    # Secondary single-GPU figures (C1 / C2 / C3) run first, in a fresh process, before this one creates its CUDA context:
+    # they are latency measurements of single matches and of a per-scan loop, and with a second context alive on the GPU
+    # (or inside this process after the batched runs) the same C2 loop measures 2-7x slower than on its own.
+    extras = {}
+    if not args.no_extras and world == 1:
+        try:
+            cp = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--extras-only", "--c2-scans", str(args.c2_scans)],
+                                capture_output=True, text=True, timeout=900)
+            extras = json.loads(cp.stdout.strip().splitlines()[-1]) if cp.returncode == 0 else {"error": cp.stderr[-400:]}
+        except Exception as ex:       # reported, never hidden
+            extras = {"error": repr(ex)}
+
     import torch
     import torch.distributed as dist
 
@@ -392,18 +404,6 @@ def main():
     cpu_baseline = {"value": pe_c / sec_c, "unit": UNIT, "cores": cores, "kind": kind,
                     "sample": f"{nm_c} of {n_h} hypotheses of this workload, full matches, {cores} threads, {sec_c:.1f} s",
                     "matches_per_sec": nm_c / sec_c}
-
-    # Secondary single-GPU figures run in a fresh process: they are latency measurements of single matches / a per-scan
-    # loop, and inside this process (16 CPU-baseline threads just finished, 256 MiB flush buffer, pinned staging, a second
-    # CUDA stream) the same C2 loop measured 2-7x slower than on its own.
-    extras = {}
-    if not args.no_extras and world == 1:
-        try:
-            cp = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--extras-only", "--c2-scans", str(args.c2_scans)],
-                                capture_output=True, text=True, timeout=900)
-            extras = json.loads(cp.stdout.strip().splitlines()[-1]) if cp.returncode == 0 else {"error": cp.stderr[-400:]}
-        except Exception as ex:       # reported, never hidden
-            extras = {"error": repr(ex)}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
