@@ -120,6 +120,7 @@ int ndt_create(const ndt_params *p, ndt_handle *out) {
     h->own_stream = true;
   }
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
+  cudaMallocHost((void **)&h->pinned_ctr, 256);
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
   cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
   { int coop = 0; cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device); h->coop_launch = coop != 0; }
@@ -142,6 +143,7 @@ int ndt_destroy(ndt_handle hh) {
                    &g.counters, &g.leaf_pair, &g.big_list, &g.dims, &g.pair_off, &g.cen, &g.occ, &g.nn_cnt, &g.nn_range, &g.nn_pts, &g.tgt_sorted, &g.leaf_range, &h->src, &h->scratch, &h->scratch2, &h->stage, &h->io};
   for (DevBuf *b : all) b->release();
   if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->pinned_ctr) cudaFreeHost(h->pinned_ctr);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);

@@ -58,12 +58,18 @@ __global__ void k_init_counters(int32_t *ctr, int32_t *bounds) {
 __global__ void __launch_bounds__(256) k_bounds(const float4 *__restrict__ pts, int64_t n, int32_t *bounds,
                                                int32_t *ctr) {
   int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN, nf = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float4 p = __ldg(pts + i);
-    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
-      const int ox = float_ord(p.x), oy = float_ord(p.y);
-      mnx = min(mnx, ox); mny = min(mny, oy); mxx = max(mxx, ox); mxy = max(mxy, oy);
-      ++nf;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 4 * stride) {
+    float4 p[4];                                    // four independent 16-byte loads in flight per thread
+#pragma unroll
+    for (int u = 0; u < 4; ++u) p[u] = (i + u * stride < n) ? __ldg(pts + i + u * stride) : make_float4(NAN, NAN, NAN, 0.f);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (isfinite(p[u].x) && isfinite(p[u].y) && isfinite(p[u].z)) {
+        const int ox = float_ord(p[u].x), oy = float_ord(p[u].y);
+        mnx = min(mnx, ox); mny = min(mny, oy); mxx = max(mxx, ox); mxy = max(mxy, oy);
+        ++nf;
+      }
     }
   }
   mnx = __reduce_min_sync(0xffffffffu, mnx); mny = __reduce_min_sync(0xffffffffu, mny);
@@ -727,8 +733,8 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace, int64_t n_
     if (!host_bounds) {
       k_bounds<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(gb.tgt.as<float4>(), n, bounds, ctr);
       ++h->launches;
-      int32_t hb[CTR_COUNT + 4];
-      NDT_CUDA(h, cudaMemcpyAsync(hb, ctr, sizeof(hb), cudaMemcpyDeviceToHost, st));
+      int32_t *hb = h->pinned_ctr;                  // pinned: a pageable destination makes this a staged, slower copy
+      NDT_CUDA(h, cudaMemcpyAsync(hb, ctr, (CTR_COUNT + 4) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
       NDT_CUDA(h, cudaStreamSynchronize(st));
       nfin = hb[CTR_NFIN];
       if (nfin > 0) {
@@ -772,8 +778,9 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace, int64_t n_
   NDT_CUDA(h, cudaMemcpyAsync(gb.dims.p, &pd, sizeof(pd), cudaMemcpyHostToDevice, st));
   const int64_t npad_total = (int64_t)pd.W * pd.H;
   if (int rc = grid_build_tables(h, n, 1, npad_total, pd.H)) return rc;
-  NDT_CUDA(h, cudaMemcpyAsync(h->h_counters, ctr, sizeof(h->h_counters), cudaMemcpyDeviceToHost, st));
+  NDT_CUDA(h, cudaMemcpyAsync(h->pinned_ctr, ctr, sizeof(h->h_counters), cudaMemcpyDeviceToHost, st));
   NDT_CUDA(h, cudaStreamSynchronize(st));
+  std::memcpy(h->h_counters, h->pinned_ctr, sizeof(h->h_counters));
   NDT_CUDA(h, cudaGetLastError());
   h->h_counters[CTR_NFIN] = (int32_t)nfin;
 

@@ -103,6 +103,7 @@ struct Handle {
   DevBuf stage;        // 4 KB persistent staging (single pose / single result)
   DevBuf io;           // host<->device staging of batched poses / results
   bool ms_pending = false;  // last_ms not yet resolved (async device-space call)
+  int32_t *pinned_ctr = nullptr; // 256 B of pinned host memory for the small counter read-backs of the grid build
   void *pinned = nullptr;       // pinned host staging
   size_t pinned_cap = 0;
   bool timing = true;           // record ev0/ev1 around kernels
