@@ -250,7 +250,7 @@ __device__ __forceinline__ int candidate_cell(const ProbeGeom &g, const OccL &oc
   const int cj = cell_coord(yt, g.inv_leaf, g.min_by);
   // -1 <= ci <= div_x and -1 <= cj <= div_y: the cells whose 3x3 block can touch the grid
   const bool in = valid && (unsigned)(ci + 1) <= (unsigned)(g.div_x + 1) && (unsigned)(cj + 1) <= (unsigned)(g.div_y + 1);
-  const int base = in ? (g.base + (cj + 2) * g.W + ci + 2) : 0;
+  const int base = in ? (g.base + (cj + 2) * g.W + ci + 2) : g.base;      // out of range: any valid entry of this grid (unused)
   const unsigned word = occ_at(base >> 5);
   const bool cand = in && ((word >> (base & 31)) & 1u);
 #if NDT_PREFETCH_CEN

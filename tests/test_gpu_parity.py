@@ -376,6 +376,7 @@ def test_match_pairs_parity_with_oracle_per_pair():
     srcs[9] = np.zeros((0, 4), np.float32)            # empty source
     tgts[11] = tgts[11][:1]                            # one target point: a grid with no tree cell
     srcs[13] = srcs[13][:40]; tgts[17] = tgts[17][:100]
+    srcs[21] = np.concatenate([srcs[21], srcs[21][::2] + np.float32(0.003), srcs[21][::3] - np.float32(0.002)])   # > 1152 points: not staged in smem
     n = len(srcs)
     src, so = _pack(srcs); tgt, to = _pack(tgts)
     guesses = np.zeros((n, 3))
