@@ -333,6 +333,9 @@ __global__ void __launch_bounds__(256, 2) k_align_grid(GridView G, MatchParams m
 #ifndef NDT_WARP_KERNEL_MIN_CTAS
 #define NDT_WARP_KERNEL_MIN_CTAS 2
 #endif
+#ifndef NDT_WARP_OCC_SMEM_MAX
+#define NDT_WARP_OCC_SMEM_MAX (64 * 1024)
+#endif
 #ifndef NDT_WARP_KERNEL_THREADS
 #define NDT_WARP_KERNEL_THREADS 256
 #endif
@@ -597,7 +600,7 @@ int launch_align(Handle *h, const double *d_guesses, int64_t n, ndt_result *d_re
     const bool src_smem = (size_t)ns * sizeof(float2) <= 64 * 1024;
     const int64_t npad = h->gd.n_cells > 0 ? (int64_t)(h->gd.div_x + 4) * (h->gd.div_y + 4) : 0;
     int occ_words = (int)((npad + 31) / 32 + 1);
-    if ((size_t)occ_words * 4 > 64 * 1024) occ_words = 0;          // large grids: bitmap stays in global memory / L1
+    if ((size_t)occ_words * 4 > NDT_WARP_OCC_SMEM_MAX) occ_words = 0;          // large grids: bitmap stays in global memory / L1
     const size_t smem = WK_QUEUE_BYTES + (((size_t)occ_words * 4 + 15) & ~size_t(15)) + (src_smem ? (size_t)ns * sizeof(float2) : 0);
     const int ctas_per_sm = NDT_WARP_KERNEL_MIN_CTAS;
     int64_t grid = (int64_t)h->sm_count * ctas_per_sm;
