@@ -251,6 +251,7 @@ def main():
     # ---- grid: built once on rank 0, replicated once, no collective afterwards -------------------
     t_build = None
     bcast_ms = None
+    bcast_bytes = 0
     if rank == 0:
         g.set_target(wl["tgt"])
         t_build = g.last_kernel_ms()
@@ -267,6 +268,7 @@ def main():
         e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
         e0.record(); dist.broadcast(blob, 0); e1.record(); torch.cuda.synchronize()
         bcast_ms = e0.elapsed_time(e1)
+        bcast_bytes = nbytes
         if rank != 0:
             g.grid_import(blob.data_ptr(), nbytes)
         del blob
@@ -422,7 +424,8 @@ def main():
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
-        "grid_build_ms": t_build, "grid_broadcast_ms": bcast_ms,
+        "grid_build_ms": t_build, "grid_broadcast_ms": bcast_ms, "grid_blob_bytes": int(bcast_bytes),
+        "grid_broadcast_gbs": (bcast_bytes / (bcast_ms * 1e-3) / 1e9) if bcast_ms else None,
         "reloc_best_error_m": reloc_err, "reloc_best": {"score": g_score, "hypothesis": g_index, "owner_rank": g_owner},
         "c5": c5_line,
         "extras": extras,

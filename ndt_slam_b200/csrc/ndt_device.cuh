@@ -140,7 +140,11 @@ constexpr int NACC = 13;
 #endif
 constexpr int HITS_PER_LANE = NDT_HITS_PER_LANE;   // hits a lane evaluates side by side in one drain
 constexpr int QCAP = 32 * HITS_PER_LANE + 288;   // hit ring per warp: < 32 * HITS_PER_LANE queued before a probe, a probe adds <= 9 * 32
-constexpr int CQCAP = 128;          // candidate ring per warp: < 32 queued before a double step, which adds <= 64
+#ifndef NDT_A_STEPS
+#define NDT_A_STEPS 3      // measured on C4: 1 -> 13.9 ms, 2 -> 13.4, 3 -> 13.1, 4 -> 13.3
+#endif
+constexpr int A_STEPS = NDT_A_STEPS;      // warp steps (32 points each) stage A transforms per iteration
+constexpr int CQCAP = A_STEPS <= 3 ? 128 : 256;   // candidate ring per warp: < 32 queued before an iteration, which adds <= 32 * A_STEPS
 constexpr int QUEUE_BYTES_PER_WARP = (QCAP + CQCAP) * 8;
 
 // Ring entries are 8 bytes: the source point index plus a table position. The float32 transform of a point is
@@ -272,18 +276,23 @@ __device__ __forceinline__ void accumulate_points(const int MODE, const ProbeGeo
   int chead = 0, cn = 0;           // candidate ring
   int i0 = first - lane;
   for (;;) {
-    // ---- A: transform source points two warp steps at a time until 32 candidates are queued ----
+    // ---- A: transform source points A_STEPS warp steps at a time until 32 candidates are queued ----
     while (cn < 32 && i0 < hi) {
-      const int ia = i0 + lane, ib = ia + stride;
-      i0 += 2 * stride;
-      const int ba = candidate_cell(g, occ_at, cen_at, src, min(ia, hi - 1), ia < hi, pf, sse_order);
-      const int bb = candidate_cell(g, occ_at, cen_at, src, min(ib, hi - 1), ib < hi, pf, sse_order);
-      const unsigned bal_a = __ballot_sync(0xffffffffu, ba >= 0);
-      const unsigned bal_b = __ballot_sync(0xffffffffu, bb >= 0);
-      const int na = __popc(bal_a);
-      if (ba >= 0) Q.cand[(chead + cn + __popc(bal_a & lt)) & (CQCAP - 1)] = make_int2(ia, ba);
-      if (bb >= 0) Q.cand[(chead + cn + na + __popc(bal_b & lt)) & (CQCAP - 1)] = make_int2(ib, bb);
-      cn += na + __popc(bal_b);
+      int b[A_STEPS];
+#pragma unroll
+      for (int u = 0; u < A_STEPS; ++u) {
+        const int i = i0 + lane + u * stride;
+        b[u] = candidate_cell(g, occ_at, cen_at, src, min(i, hi - 1), i < hi, pf, sse_order);
+      }
+      int at = chead + cn;
+#pragma unroll
+      for (int u = 0; u < A_STEPS; ++u) {
+        const unsigned bal = __ballot_sync(0xffffffffu, b[u] >= 0);
+        if (b[u] >= 0) Q.cand[(at + __popc(bal & lt)) & (CQCAP - 1)] = make_int2(i0 + lane + u * stride, b[u]);
+        at += __popc(bal);
+      }
+      cn = at - chead;
+      i0 += A_STEPS * stride;
     }
     const bool done = (i0 >= hi);
     if (cn >= 32 || (done && cn > 0)) {
