@@ -75,7 +75,16 @@ __global__ void __launch_bounds__(256) k_bounds(const float4 *__restrict__ pts, 
   mnx = __reduce_min_sync(0xffffffffu, mnx); mny = __reduce_min_sync(0xffffffffu, mny);
   mxx = __reduce_max_sync(0xffffffffu, mxx); mxy = __reduce_max_sync(0xffffffffu, mxy);
   nf = __reduce_add_sync(0xffffffffu, nf);
+  // one set of global atomics per CTA, not per warp: they all hit the same five addresses
+  __shared__ int s_b[5];
+  if (threadIdx.x == 0) { s_b[0] = INT_MAX; s_b[1] = INT_MAX; s_b[2] = INT_MIN; s_b[3] = INT_MIN; s_b[4] = 0; }
+  __syncthreads();
   if ((threadIdx.x & 31) == 0 && nf > 0) {
+    atomicMin(s_b + 0, mnx); atomicMin(s_b + 1, mny); atomicMax(s_b + 2, mxx); atomicMax(s_b + 3, mxy); atomicAdd(s_b + 4, nf);
+  }
+  __syncthreads();
+  mnx = s_b[0]; mny = s_b[1]; mxx = s_b[2]; mxy = s_b[3]; nf = s_b[4];
+  if (threadIdx.x == 0 && nf > 0) {
     atomicMin(bounds + 0, mnx); atomicMin(bounds + 1, mny);
     atomicMax(bounds + 2, mxx); atomicMax(bounds + 3, mxy);
     atomicAdd(ctr + CTR_NFIN, nf);
@@ -400,8 +409,13 @@ __global__ void __launch_bounds__(128) k_finalize(const float2 *__restrict__ tgt
     }
     finish_leaf(leaf, n, st, a, fp, o);
   }
-  // dense leaves (listed by k_alloc): one warp each
-  const int lane = threadIdx.x & 31;
+  // dense leaves (listed by k_alloc): one warp each. Per 32-point chunk every lane converts its own point and forms its
+  // three products (the same IEEE operations the sequential code performs per point), parks the seven terms in shared
+  // memory, and the add chain then runs over broadcast shared-memory reads: nothing but the adds is left in the serial
+  // part, and the next chunk's global loads are already in flight.
+  __shared__ double s_d[4][32][5];
+  __shared__ float s_f[4][32][2];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
   const int n_big = o.ctr[CTR_BIG];
   for (int b = warp; b < n_big; b += n_warps) {
@@ -409,16 +423,23 @@ __global__ void __launch_bounds__(128) k_finalize(const float2 *__restrict__ tgt
     const int n = leaf_n[leaf], st = leaf_start[leaf];
     LeafSums a{0, 0, 0, 0, 0, 0.f, 0.f};
     const float2 *__restrict__ bucket = tgt_sorted + st;
+    float2 nxt = (lane < n) ? __ldg(bucket + lane) : make_float2(0.f, 0.f);
     for (int c = 0; c < n; c += 32) {
-      const float2 mp = (c + lane < n) ? __ldg(bucket + c + lane) : make_float2(0.f, 0.f);
+      const float2 mp = nxt;
+      if (c + 32 + lane < n) nxt = __ldg(bucket + c + 32 + lane);
+      const double xd = (double)mp.x, yd = (double)mp.y;
+      s_d[wib][lane][0] = xd; s_d[wib][lane][1] = yd;
+      s_d[wib][lane][2] = xd * xd; s_d[wib][lane][3] = yd * xd; s_d[wib][lane][4] = yd * yd;
+      s_f[wib][lane][0] = mp.x; s_f[wib][lane][1] = mp.y;
+      __syncwarp();
       const int m = min(32, n - c);
+#pragma unroll 8
       for (int k = 0; k < m; ++k) {
-        const float px = __shfl_sync(0xffffffffu, mp.x, k), py = __shfl_sync(0xffffffffu, mp.y, k);
-        const double xd = (double)px, yd = (double)py;
-        a.sx += xd; a.sy += yd;
-        a.sxx += xd * xd; a.syx += yd * xd; a.syy += yd * yd;
-        a.cx = __fadd_rn(a.cx, px); a.cy = __fadd_rn(a.cy, py);
+        a.sx += s_d[wib][k][0]; a.sy += s_d[wib][k][1];
+        a.sxx += s_d[wib][k][2]; a.syx += s_d[wib][k][3]; a.syy += s_d[wib][k][4];
+        a.cx = __fadd_rn(a.cx, s_f[wib][k][0]); a.cy = __fadd_rn(a.cy, s_f[wib][k][1]);
       }
+      __syncwarp();
     }
     if (lane == 0) finish_leaf(leaf, n, st, a, fp, o);
   }
