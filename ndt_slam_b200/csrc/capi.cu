@@ -97,6 +97,14 @@ int ndt_params_default(ndt_params *p) {
   return NDT_OK;
 }
 
+static void all_buffers(Handle *h, std::vector<DevBuf *> &v) {
+  GridBuffers &g = h->gb;
+  v = {&g.tgt, &g.cell_of, &g.rank_of, &g.list, &g.sorted_idx, &g.slot, &g.leaf_id, &g.leaf_cell,
+       &g.leaf_n, &g.leaf_start, &g.leaf_nr, &g.leaf_mean, &g.leaf_icov, &g.leaf_cen, &g.recs,
+       &g.counters, &g.leaf_pair, &g.big_list, &g.dims, &g.pair_off, &g.cen, &g.occ, &g.nn_cnt, &g.nn_range, &g.nn_pts,
+       &g.tgt_sorted, &g.leaf_range, &h->src, &h->scratch, &h->scratch2, &h->stage, &h->io};
+}
+
 int ndt_create(const ndt_params *p, ndt_handle *out) {
   if (!p || !out) return NDT_ERR_ARG;
   *out = nullptr;
@@ -121,6 +129,25 @@ int ndt_create(const ndt_params *p, ndt_handle *out) {
   }
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
   cudaMallocHost((void **)&h->pinned_ctr, 256);
+  {
+    // private stream-ordered pool that keeps what it is given back (no trimming at synchronisation points)
+    int pools = 0;
+    cudaDeviceGetAttribute(&pools, cudaDevAttrMemoryPoolsSupported, h->device);
+    if (pools) {
+      cudaMemPoolProps props{};
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = h->device;
+      if (cudaMemPoolCreate(&h->pool, &props) == cudaSuccess) {
+        uint64_t keep_all = UINT64_MAX;
+        cudaMemPoolSetAttribute(h->pool, cudaMemPoolAttrReleaseThreshold, &keep_all);
+      } else { h->pool = nullptr; (void)cudaGetLastError(); }
+    }
+    std::vector<DevBuf *> bufs;
+    all_buffers(h, bufs);
+    for (DevBuf *b : bufs) b->bind(h->stream, h->pool);
+  }
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
   cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
   { int coop = 0; cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device); h->coop_launch = coop != 0; }
@@ -137,11 +164,11 @@ int ndt_destroy(ndt_handle hh) {
   if (!h) return NDT_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  GridBuffers &g = h->gb;
-  DevBuf *all[] = {&g.tgt, &g.cell_of, &g.rank_of, &g.list, &g.sorted_idx, &g.slot, &g.leaf_id, &g.leaf_cell,
-                   &g.leaf_n, &g.leaf_start, &g.leaf_nr, &g.leaf_mean, &g.leaf_icov, &g.leaf_cen, &g.recs,
-                   &g.counters, &g.leaf_pair, &g.big_list, &g.dims, &g.pair_off, &g.cen, &g.occ, &g.nn_cnt, &g.nn_range, &g.nn_pts, &g.tgt_sorted, &g.leaf_range, &h->src, &h->scratch, &h->scratch2, &h->stage, &h->io};
-  for (DevBuf *b : all) b->release();
+  std::vector<DevBuf *> bufs;
+  all_buffers(h, bufs);
+  for (DevBuf *b : bufs) b->release();
+  cudaStreamSynchronize(h->stream);
+  if (h->pool) cudaMemPoolDestroy(h->pool);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->pinned_ctr) cudaFreeHost(h->pinned_ctr);
   if (h->ev0) cudaEventDestroy(h->ev0);

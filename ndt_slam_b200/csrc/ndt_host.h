@@ -10,26 +10,35 @@
 
 namespace ndt {
 
-// growable device buffer (capacity only ever grows; no cudaMalloc on the steady-state path)
+// growable device buffer (capacity only ever grows). Buffers of a handle are bound to the handle's stream and to a private
+// stream-ordered memory pool (cudaMallocFromPoolAsync / cudaFreeAsync): growing a buffer neither synchronises the device
+// nor unmaps memory -- freed blocks stay in the pool and are stitched into the next, larger request. A map that grows scan
+// by scan reallocates ~25 buffers O(log n) times; with cudaMalloc / cudaFree those scans cost tens of milliseconds.
 struct DevBuf {
   void *p = nullptr;
   size_t cap = 0;
-  // keep > 0: the first `keep` bytes survive a reallocation (copied on `st`)
-  cudaError_t reserve(size_t bytes, size_t keep = 0, cudaStream_t st = nullptr) {
+  cudaStream_t st = nullptr;
+  cudaMemPool_t pool = nullptr;      // null: plain cudaMalloc / cudaFree
+  void bind(cudaStream_t s, cudaMemPool_t m) { st = s; pool = m; }
+  // keep > 0: the first `keep` bytes survive a reallocation (stream-ordered copy)
+  cudaError_t reserve(size_t bytes, size_t keep = 0, cudaStream_t /*unused*/ = nullptr) {
     if (bytes <= cap) return cudaSuccess;
-    const size_t want = 2 * bytes + 4096;     // geometric growth: a map that grows scan by scan reallocates O(log n) times
+    const size_t want = 2 * bytes + 4096;     // geometric growth
     void *q = nullptr;
-    cudaError_t e = cudaMalloc(&q, want);
+    cudaError_t e = pool ? cudaMallocFromPoolAsync(&q, want, pool, st) : cudaMalloc(&q, want);
     if (e != cudaSuccess) return e;
     if (p && keep > 0) {
       e = cudaMemcpyAsync(q, p, keep < cap ? keep : cap, cudaMemcpyDeviceToDevice, st);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e == cudaSuccess && !pool) e = cudaStreamSynchronize(st);
     }
-    if (p) cudaFree(p);
+    if (p) { if (pool) cudaFreeAsync(p, st); else cudaFree(p); }
     p = q; cap = want;
     return e;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  void release() {
+    if (p) { if (pool) cudaFreeAsync(p, st); else cudaFree(p); }
+    p = nullptr; cap = 0;
+  }
   template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
@@ -87,6 +96,7 @@ struct Handle {
   int sm_count = 148;
   int max_smem_optin = 0;
   bool coop_launch = false;      // cudaDevAttrCooperativeLaunch
+  cudaMemPool_t pool = nullptr;  // private stream-ordered pool behind every DevBuf of this handle
 
   GridBuffers gb;
   GridDims gd;
