@@ -240,7 +240,20 @@ __global__ void __launch_bounds__(256) k_rank(int64_t n, const int32_t *__restri
     const int leaf = __ldg(leaf_id + cell_of[v]) - 1;
     const int st = __ldg(leaf_start + leaf), m = __ldg(leaf_n + leaf);
     int r = 0;
-    for (int j = 0; j < m; ++j) r += (__ldg(list + st + j) < v) ? 1 : 0;
+    // head up to a 16-byte boundary, then four indices per load (the loads of a warp are broadcasts: its threads mostly
+    // share a bucket), tail
+    const int32_t *__restrict__ bk = list + st;
+    int j = 0;
+    const int head = min(m, (int)((4 - (st & 3)) & 3));
+    for (; j < head; ++j) r += (__ldg(bk + j) < v) ? 1 : 0;
+    const int4 *__restrict__ bk4 = reinterpret_cast<const int4 *>(bk + j);
+    const int n4 = (m - j) >> 2;
+#pragma unroll 4
+    for (int q = 0; q < n4; ++q) {
+      const int4 t = __ldg(bk4 + q);
+      r += (t.x < v) + (t.y < v) + (t.z < v) + (t.w < v);
+    }
+    for (j += 4 * n4; j < m; ++j) r += (__ldg(bk + j) < v) ? 1 : 0;
     sorted_idx[st + r] = v;
     const float4 pt = __ldg(pts + v);
     tgt_sorted[st + r] = make_float2(pt.x, pt.y);     // points in bucket order: finalize and the 1-NN read them contiguously
