@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) k_eval_partial(GridView G, MatchParams mp
                                                      int ns, const double *__restrict__ poses, int slices,
                                                      double *__restrict__ partial, int *__restrict__ pairs_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ double scratch[8 * NACC];
+  __shared__ double scratch[9 * NACC];
   __shared__ int s_pairs[8];
   const int pose_i = blockIdx.x / slices, slice = blockIdx.x % slices;
   const double p[3] = {poses[3 * pose_i], poses[3 * pose_i + 1], poses[3 * pose_i + 2]};
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(256) k_align_block(GridView G, MatchParams mp,
                                                     int ns, const double *__restrict__ guesses,
                                                     ndt_result *__restrict__ out, int n_slots, int n_cells) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ double scratch[8 * NACC];
+  __shared__ double scratch[9 * NACC];
   BlockCoop coop{scratch};
   const int job = blockIdx.x;
   const double guess[3] = {guesses[3 * job], guesses[3 * job + 1], guesses[3 * job + 2]};
@@ -229,27 +229,41 @@ __global__ void __launch_bounds__(256) k_align_block(GridView G, MatchParams mp,
 // one thread-block cluster per match: block reduction, then a DSMEM exchange of the 13 partials
 // ---------------------------------------------------------------------------------------------
 struct ClusterCoop {
-  double *scratch;       // [8 * NACC] block scratch
-  double *xchg;          // [NACC] this CTA's partial, read by every CTA of the cluster through DSMEM
+  double *scratch;       // [9 * NACC] block scratch (one row per warp + the block totals)
+  double *xchg;          // [2][16] this CTA's partial (double-buffered), read by every CTA of the cluster through DSMEM
+  int *epoch;            // reductions so far (selects the exchange buffer)
   int crank, csize;
   __device__ __forceinline__ int rank() const { return crank * blockDim.x + threadIdx.x; }
   __device__ __forceinline__ int size() const { return csize * blockDim.x; }
+  // One cluster barrier per reduction: thread k forms the block partial of component k, publishes it, and after the
+  // barrier adds the partials of all CTAs in rank order (the same order everywhere: bit-identical totals). The exchange
+  // buffer alternates, so a CTA can run ahead into the next reduction while a neighbour still reads this one.
   template <int N> __device__ __forceinline__ void allreduce(double *v) const {
     cg::cluster_group cluster = cg::this_cluster();
-    BlockCoop b{scratch};
-    b.allreduce<N>(v);
+    warp_allreduce<N>(v);
+    const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double *total = scratch + nw * NACC;
+    double *xb = xchg + ((*epoch) & 1) * 16;
+    ++(*epoch);
+    if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-    for (int k = 0; k < N; ++k)
-      if (threadIdx.x == k) xchg[k] = v[k];
-    cluster.sync();
-#pragma unroll
-    for (int k = 0; k < N; ++k) v[k] = 0.0;
-    for (int r = 0; r < csize; ++r) {
-      const double *remote = cluster.map_shared_rank(xchg, r);
-#pragma unroll
-      for (int k = 0; k < N; ++k) v[k] += remote[k];
+      for (int k = 0; k < N; ++k) scratch[w * NACC + k] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < N) {
+      double s = scratch[threadIdx.x];
+      for (int i = 1; i < nw; ++i) s += scratch[i * NACC + threadIdx.x];
+      xb[threadIdx.x] = s;
     }
     cluster.sync();
+    if (threadIdx.x < N) {
+      double t = 0.0;
+      for (int r = 0; r < csize; ++r) t += cluster.map_shared_rank(xb, r)[threadIdx.x];
+      total[threadIdx.x] = t;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = total[k];
   }
 };
 
@@ -257,10 +271,11 @@ __global__ void __launch_bounds__(256) k_align_cluster(GridView G, MatchParams m
                                                       int ns, const double *__restrict__ guesses,
                                                       ndt_result *__restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ double scratch[8 * NACC];
-  __shared__ double xchg[NACC];
+  __shared__ double scratch[9 * NACC];
+  __shared__ double xchg[2 * 16];
+  int epoch = 0;
   cg::cluster_group cluster = cg::this_cluster();
-  ClusterCoop coop{scratch, xchg, (int)cluster.block_rank(), (int)cluster.num_blocks()};
+  ClusterCoop coop{scratch, xchg, &epoch, (int)cluster.block_rank(), (int)cluster.num_blocks()};
   const int job = blockIdx.x / coop.csize;
   const double guess[3] = {guesses[3 * job], guesses[3 * job + 1], guesses[3 * job + 2]};
   const GlobalSrc gsrc{src};
@@ -270,6 +285,7 @@ __global__ void __launch_bounds__(256) k_align_cluster(GridView G, MatchParams m
   double fsum = 0.0;
   if (mp.want_fitness) fsum = fitness_pass(G, gsrc, ns, mp, mo.p, coop);
   if (coop.crank == 0 && threadIdx.x == 0) write_result(out + job, mo, ns, fsum, mp.want_fitness != 0, G.n_tgt);
+  cluster.sync();        // no CTA may retire while a neighbour can still read its exchange buffer through DSMEM
 }
 
 // ---------------------------------------------------------------------------------------------

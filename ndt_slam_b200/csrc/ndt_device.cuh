@@ -439,25 +439,29 @@ struct WarpCoop {             // one warp per match
   __device__ __forceinline__ void sync() const { __syncwarp(); }
 };
 
-struct BlockCoop {            // one CTA per match; scratch = [nwarps][NACC] doubles in shared memory
+struct BlockCoop {            // one CTA per match; scratch = [nwarps + 1][NACC] doubles in shared memory
   double *scratch;
   __device__ __forceinline__ int rank() const { return threadIdx.x; }
   __device__ __forceinline__ int size() const { return blockDim.x; }
+  // warp butterflies -> one row per warp -> thread k adds column k over the warps in fixed order -> everyone reads the
+  // N totals (broadcast loads). Two barriers, 8 + N shared loads per thread.
   template <int N> __device__ __forceinline__ void allreduce(double *v) const {
     warp_allreduce<N>(v);
     const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double *total = scratch + nw * NACC;
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
       for (int k = 0; k < N; ++k) scratch[w * NACC + k] = v[k];
     }
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-      double s = scratch[k];
-      for (int i = 1; i < nw; ++i) s += scratch[i * NACC + k];
-      v[k] = s;
+    if (threadIdx.x < N) {
+      double s = scratch[threadIdx.x];
+      for (int i = 1; i < nw; ++i) s += scratch[i * NACC + threadIdx.x];
+      total[threadIdx.x] = s;
     }
     __syncthreads();
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = total[k];
   }
   __device__ __forceinline__ void sync() const { __syncthreads(); }
 };
