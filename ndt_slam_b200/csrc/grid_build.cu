@@ -823,8 +823,8 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace, int64_t n_
   const int64_t n_leaves = h->h_counters[CTR_LEAVES];
   if (n_leaves > 0 && nfin / n_leaves > 24) {
     int f = 2;
-    while (f < 16 && nfin / (n_leaves * f) > 12) f *= 2;
-    while (f > 1 && (int64_t)gd.div_x * f * ((int64_t)gd.div_y * f) > (int64_t)64 * 1024 * 1024) f /= 2;
+    while (f < 64 && nfin / (n_leaves * f) > 12) f *= 2;                   // walls: points per fine cell fall like 1 / f
+    while (f > 1 && (int64_t)gd.div_x * f * ((int64_t)gd.div_y * f) > (int64_t)8 * 1024 * 1024) f /= 2;   // lattice <= 64 MB
     if (f > 1) {
       gd.nn_f = f;
       gd.nn_leaf = gd.leaf / (float)f;

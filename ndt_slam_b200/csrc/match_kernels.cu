@@ -598,6 +598,9 @@ int launch_eval(Handle *h, const double *d_poses, int64_t n, int want_hessian, d
 #ifndef NDT_GRID_MIN_NS
 #define NDT_GRID_MIN_NS 16384     // above this one match takes the whole GPU (cooperative launch)
 #endif
+#ifndef NDT_CLUSTER_SIZE
+#define NDT_CLUSTER_SIZE 8
+#endif
 #ifndef NDT_CLUSTER_MIN_NS
 #define NDT_CLUSTER_MIN_NS 600      // measured on C1 (855 points): 8-CTA cluster 0.090 ms vs one CTA 0.113 ms
 #endif
@@ -647,10 +650,10 @@ int launch_align(Handle *h, const double *d_guesses, int64_t n, ndt_result *d_re
     }
   } else if (ns > NDT_CLUSTER_MIN_NS) {
     // large source cloud: spread one match over a thread-block cluster (DSMEM reduction)
-    int csize = 8;
-    if (ns > 16384) {
+    int csize = NDT_CLUSTER_SIZE;
+    if (csize > 8) {
       cudaError_t e = cudaFuncSetAttribute(k_align_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-      if (e == cudaSuccess) csize = 16; else (void)cudaGetLastError();
+      if (e != cudaSuccess) { csize = 8; (void)cudaGetLastError(); }
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(n * csize));

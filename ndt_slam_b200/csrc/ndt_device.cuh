@@ -724,7 +724,8 @@ __device__ inline void match_device(Obj &obj, const MatchParams &mp, const doubl
 //   stage 1  one query per lane, a few rings; the bucket descriptors of a ring are fetched eight at a time so the
 //            loads of a ring overlap instead of forming one dependent chain per cell;
 //   stage 2  queries stage 1 could not certify (points far from the map) are finished by the whole warp: one cell of
-//            the ring per lane, one warp-min per ring; exhaustive scan (lanes stride over the cloud) as last resort.
+//            the ring per lane (sparse buckets) or all lanes striding over each bucket's points (dense buckets), one
+//            warp-min per ring; exhaustive scan (lanes stride over the cloud) as last resort.
 // ------------------------------------------------------------------------------------------------
 constexpr int NN_STAGE1_RINGS_FINE = 6, NN_STAGE1_RINGS_COARSE = 3, NN_MAX_RINGS = 48;
 
@@ -780,10 +781,18 @@ __device__ __forceinline__ int first_ring(int ci, int cj, int dvx, int dvy) {
   return max(ox, oy);
 }
 
-// every point outside rings 0..ring is at least (ring - 0.01) cells away
-__device__ __forceinline__ bool ring_certifies(int ring, double leaf, float best) {
-  const double lim = ((double)ring - 0.01) * leaf;
-  return ring >= 1 && (double)best < lim * lim;
+// Every point outside rings 0..ring is at least ring cells plus the query's distance to the wall of its own cell away;
+// 0.01 cell of slack covers the float rounding of the cell assignment (x * inv_leaf). margin = that distance in cells
+// (0 for the warp-cooperative stage, which does not track it).
+__device__ __forceinline__ bool ring_certifies(int ring, double leaf, float best, float margin = 0.f) {
+  const double lim = ((double)ring + (double)margin - 0.01) * leaf;
+  return lim > 0.0 && (double)best < lim * lim;
+}
+// distance (in cells) from a coordinate to the nearer wall of its own cell, by the same float arithmetic as cell_coord
+__device__ __forceinline__ float cell_margin(float v, float inv) {
+  const float t = __fmul_rn(v, inv);
+  const float f = __fsub_rn(t, floorf(t));
+  return fminf(f, 1.0f - f);
 }
 
 // stage 1: returns true when `best` is the exact answer
@@ -794,18 +803,20 @@ __device__ __forceinline__ bool nn_stage1(const GridView &G, float xt, float yt,
     const int ci = cell_coord(xt, G.nn_inv_leaf, G.nn_min_bx), cj = cell_coord(yt, G.nn_inv_leaf, G.nn_min_by);
     const int r0 = first_ring(ci, cj, G.nn_div_x, G.nn_div_y);
     if (r0 > 2 * NN_STAGE1_RINGS_FINE) return false;
+    const float margin = r0 == 0 ? fminf(cell_margin(xt, G.nn_inv_leaf), cell_margin(yt, G.nn_inv_leaf)) : 0.f;
     for (int ring = r0; ring <= r0 + NN_STAGE1_RINGS_FINE; ++ring) {
       nn_ring<true>(G, ci, cj, ring, xt, yt, best);
-      if (ring_certifies(ring, (double)G.nn_leaf, best)) return true;
+      if (ring_certifies(ring, (double)G.nn_leaf, best, margin)) return true;
     }
     return false;
   }
   const int ci = cell_coord(xt, G.inv_leaf, G.min_bx), cj = cell_coord(yt, G.inv_leaf, G.min_by);
   const int r0 = first_ring(ci, cj, G.div_x, G.div_y);
   if (r0 > 2 * NN_STAGE1_RINGS_COARSE) return false;
+  const float margin = r0 == 0 ? fminf(cell_margin(xt, G.inv_leaf), cell_margin(yt, G.inv_leaf)) : 0.f;
   for (int ring = r0; ring <= r0 + NN_STAGE1_RINGS_COARSE; ++ring) {
     nn_ring<false>(G, ci, cj, ring, xt, yt, best);
-    if (ring_certifies(ring, (double)G.leaf, best)) return true;
+    if (ring_certifies(ring, (double)G.leaf, best, margin)) return true;
   }
   return false;
 }
@@ -816,17 +827,41 @@ __device__ inline float nn_stage2_warp(const GridView &G, float xt, float yt, fl
   if (G.div_x > 0) {
     const int ci = cell_coord(xt, G.inv_leaf, G.min_bx), cj = cell_coord(yt, G.inv_leaf, G.min_by);
     const int r0 = first_ring(ci, cj, G.div_x, G.div_y);
+    const bool dense = G.nn_f > 0;          // dense NDT buckets (hundreds of points): lanes share a bucket instead of a ring
     for (int ring = r0; ring <= r0 + NN_MAX_RINGS; ++ring) {
       const int ncell = ring == 0 ? 1 : 8 * ring;
-      for (int t = lane; t < ncell; t += 32) {                       // one cell of the ring per lane
-        int di = 0, dj = 0;
-        if (ring > 0) ring_cell(ring, t, di, dj);
-        const int2 rg = nn_bucket<false>(G, ci + di, cj + dj);
-        const float2 *__restrict__ q = G.tgt_sorted + rg.x;
-        for (int j = 0; j < rg.y; ++j) {
-          const float2 p = __ldg(q + j);
-          const float dd = dist2f(xt, yt, p.x, p.y);
-          if (dd < best) best = dd;
+      if (dense) {
+        // lanes fetch the bucket descriptors of 32 ring cells at once, then all lanes stride over the points of every
+        // non-empty one (a ring of a building-sized map is mostly empty cells)
+        for (int t0 = 0; t0 < ncell; t0 += 32) {
+          int di = 0, dj = 0;
+          const int t = t0 + lane;
+          if (ring > 0 && t < ncell) ring_cell(ring, t, di, dj);
+          const int2 mine = (t < ncell) ? nn_bucket<false>(G, ci + di, cj + dj) : make_int2(0, 0);
+          unsigned full = __ballot_sync(0xffffffffu, mine.y > 0);
+          while (full) {
+            const int k = __ffs(full) - 1;
+            full &= full - 1u;
+            const int start = __shfl_sync(0xffffffffu, mine.x, k), cnt = __shfl_sync(0xffffffffu, mine.y, k);
+            const float2 *__restrict__ q = G.tgt_sorted + start;
+            for (int j = lane; j < cnt; j += 32) {
+              const float2 p = __ldg(q + j);
+              const float dd = dist2f(xt, yt, p.x, p.y);
+              if (dd < best) best = dd;
+            }
+          }
+        }
+      } else {
+        for (int t = lane; t < ncell; t += 32) {                       // one cell of the ring per lane
+          int di = 0, dj = 0;
+          if (ring > 0) ring_cell(ring, t, di, dj);
+          const int2 rg = nn_bucket<false>(G, ci + di, cj + dj);
+          const float2 *__restrict__ q = G.tgt_sorted + rg.x;
+          for (int j = 0; j < rg.y; ++j) {
+            const float2 p = __ldg(q + j);
+            const float dd = dist2f(xt, yt, p.x, p.y);
+            if (dd < best) best = dd;
+          }
         }
       }
       best = __int_as_float(__reduce_min_sync(0xffffffffu, __float_as_int(best)));   // best >= 0: int order == float order
