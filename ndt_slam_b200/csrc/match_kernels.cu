@@ -17,6 +17,7 @@
 
 #include <cooperative_groups.h>
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace cg = cooperative_groups;
@@ -529,6 +530,9 @@ __global__ void __launch_bounds__(32 * VF_WARPS) k_voxel_filter_pairs(const floa
 // persistent scan-pair matcher (loop-closure verification): one warp per pair pulled from an atomic work
 // counter. Every pair has its own grid inside the shared padded tables (PairDims) and its own source cloud.
 // ---------------------------------------------------------------------------------------------
+#ifndef NDT_PAIRS_BLOCK_BELOW
+#define NDT_PAIRS_BLOCK_BELOW 7000          // pairs per call below which one CTA (not one warp) matches a pair (measured: 1024 pairs 1.70 -> 1.02 ms, 2048 2.09 -> 1.59, 8192 equal)
+#endif
 #ifndef NDT_PAIRS_KERNEL_MIN_CTAS
 #define NDT_PAIRS_KERNEL_MIN_CTAS 2
 #endif
@@ -557,6 +561,75 @@ __global__ void __launch_bounds__(256, NDT_PAIRS_KERNEL_MIN_CTAS) k_align_pairs(
     double fsum = 0.0;
     if (mp.want_fitness) fsum = fitness_pass(G, gsrc, d.ns, mp, mo.p, coop);
     if (lane == 0) write_result(out + job, mo, d.ns, fsum, mp.want_fitness != 0, G.n_tgt);
+  }
+}
+
+// The same workload with one CTA per pair (persistent CTAs, block reduction per objective pass). A pair matched by one
+// warp takes ~1.3 ms however many warps the GPU has to spare; eight warps finish it in ~0.15 ms, so whenever pairs are not
+// plentiful compared with the warp slots of the GPU (sharded batches!) this is the lower-latency schedule.
+// The CTA first stages what stages A and B read -- the pair's source cloud (as float2), its slice of the occupancy bitmap
+// and of the centroid table -- in shared memory with coalesced loads; a pair too large for the staging area is read in
+// place. The accessors take generic pointers, so both cases run the same code.
+constexpr int PB_SRC_CAP = 1280, PB_CEN_CAP = 2560, PB_OCC_CAP = PB_CEN_CAP / 32 + 2;
+constexpr int PB_STAGE_BYTES = PB_SRC_CAP * 8 + PB_CEN_CAP * 8 + PB_OCC_CAP * 4;
+struct AnyOcc {
+  const uint32_t *p; int w0;
+  __device__ __forceinline__ uint32_t operator()(int w) const { return p[w - w0]; }
+};
+struct AnyCen {
+  const float2 *p; int i0;
+  __device__ __forceinline__ float2 operator()(int i) const { return p[i - i0]; }
+  __device__ __forceinline__ void prefetch(int, int) const {}
+};
+struct AnySrc {
+  const float *p; int stride;      // floats between consecutive points (2: staged float2, 4: the caller's float4)
+  __device__ __forceinline__ float2 operator()(int i) const { return *reinterpret_cast<const float2 *>(p + (size_t)i * stride); }
+};
+
+__global__ void __launch_bounds__(256, NDT_PAIRS_KERNEL_MIN_CTAS) k_align_pairs_block(GridView G0, MatchParams mp,
+                                                    const PairDims *__restrict__ dims, const float4 *__restrict__ src_all,
+                                                    const double *__restrict__ guesses, ndt_result *__restrict__ out,
+                                                    int64_t n_jobs, int32_t *__restrict__ job_counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double scratch[9 * NACC];
+  __shared__ int s_job;
+  float2 *s_src = reinterpret_cast<float2 *>(smem_raw + QUEUE_BYTES);
+  float2 *s_cen = s_src + PB_SRC_CAP;
+  uint32_t *s_occ = reinterpret_cast<uint32_t *>(s_cen + PB_CEN_CAP);
+  BlockCoop coop{scratch};
+  for (;;) {
+    if (threadIdx.x == 0) s_job = atomicAdd(job_counter, 1);
+    __syncthreads();
+    const int job = s_job;
+    __syncthreads();
+    if (job >= n_jobs) break;
+    const PairDims d = dims[job];
+    GridView G = G0;
+    G.min_bx = d.min_bx; G.min_by = d.min_by; G.div_x = d.div_x; G.div_y = d.div_y;
+    G.slot_w = d.W; G.table_base = d.base;
+    G.tgt = G0.tgt + d.tgt_off; G.n_tgt = d.nt; G.nn_f = 0;
+    const double guess[3] = {guesses[3 * (size_t)job], guesses[3 * (size_t)job + 1], guesses[3 * (size_t)job + 2]};
+    const int ncell = d.W * d.H, w0 = d.base >> 5, nw = ((d.base + ncell + 31) >> 5) - w0 + 1;
+    AnySrc asrc{reinterpret_cast<const float *>(src_all + d.src_off), 4};
+    AnyCen acen{G.cen, 0};
+    AnyOcc aocc{G.occ, 0};
+    if (d.ns <= PB_SRC_CAP) {
+      for (int i = threadIdx.x; i < d.ns; i += blockDim.x) { const float4 v = __ldg(src_all + d.src_off + i); s_src[i] = make_float2(v.x, v.y); }
+      asrc = AnySrc{reinterpret_cast<const float *>(s_src), 2};
+    }
+    if (ncell <= PB_CEN_CAP) {
+      for (int i = threadIdx.x; i < ncell; i += blockDim.x) s_cen[i] = __ldg(G.cen + d.base + i);
+      for (int i = threadIdx.x; i < nw; i += blockDim.x) s_occ[i] = __ldg(G.occ + w0 + i);
+      acen = AnyCen{s_cen, d.base};
+      aocc = AnyOcc{s_occ, w0};
+    }
+    __syncthreads();
+    MatchOut mo;
+    auto obj = make_objective(G, mp, coop, aocc, acen, GlobalSlot{G.slot}, GlobalRec{G.recs}, asrc, d.ns, my_queue(smem_raw));
+    match_device(obj, mp, guess, mo);
+    double fsum = 0.0;
+    if (mp.want_fitness) fsum = fitness_pass(G, asrc, d.ns, mp, mo.p, coop);
+    if (threadIdx.x == 0) write_result(out + job, mo, d.ns, fsum, mp.want_fitness != 0, G.n_tgt);
   }
 }
 
@@ -705,9 +778,18 @@ int launch_align_pairs(Handle *h, const float4 *d_src, const double *d_guesses, 
   NDT_CUDA(h, cudaMemsetAsync(ctr + CTR_JOB, 0, sizeof(int32_t), st));
   int64_t grid = (int64_t)h->sm_count * NDT_PAIRS_KERNEL_MIN_CTAS;
   grid = std::min<int64_t>(grid, (n_pairs + 7) / 8);
-  NDT_CUDA(h, cudaFuncSetAttribute(k_align_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, QUEUE_BYTES));
-  k_align_pairs<<<(unsigned)grid, 256, QUEUE_BYTES, st>>>(G, mp, h->gb.dims.as<PairDims>(), d_src, d_guesses, d_results,
-                                                         n_pairs, ctr + CTR_JOB);
+  int64_t block_below = NDT_PAIRS_BLOCK_BELOW;          // NDT_B200_PAIRS_BLOCK_BELOW overrides (tuning / tests)
+  if (const char *e = getenv("NDT_B200_PAIRS_BLOCK_BELOW")) block_below = atoll(e);
+  if (n_pairs < block_below) {
+    grid = std::min<int64_t>((int64_t)h->sm_count * NDT_PAIRS_KERNEL_MIN_CTAS, n_pairs);
+    NDT_CUDA(h, cudaFuncSetAttribute(k_align_pairs_block, cudaFuncAttributeMaxDynamicSharedMemorySize, QUEUE_BYTES + PB_STAGE_BYTES));
+    k_align_pairs_block<<<(unsigned)grid, 256, QUEUE_BYTES + PB_STAGE_BYTES, st>>>(G, mp, h->gb.dims.as<PairDims>(), d_src, d_guesses, d_results,
+                                                                 n_pairs, ctr + CTR_JOB);
+  } else {
+    NDT_CUDA(h, cudaFuncSetAttribute(k_align_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, QUEUE_BYTES));
+    k_align_pairs<<<(unsigned)grid, 256, QUEUE_BYTES, st>>>(G, mp, h->gb.dims.as<PairDims>(), d_src, d_guesses, d_results,
+                                                           n_pairs, ctr + CTR_JOB);
+  }
   ++h->launches;
   NDT_CUDA(h, cudaGetLastError());
   return NDT_OK;

@@ -405,8 +405,17 @@ def test_match_pairs_parity_with_oracle_per_pair():
         a = g1.align(guesses[k])
         assert np.allclose(a.pose, res[k]["pose"], rtol=0, atol=1e-9) and a.score == pytest.approx(res[k]["score"], rel=1e-10)
         assert a.iters == res[k]["iters"] and a.evals == res[k]["evals"]
-    # small batches (several grid-build + match rounds inside one call) give the same bytes
+    # the warp-per-pair schedule (used for large batches) agrees with the CTA-per-pair one used above
     import os
+    os.environ["NDT_B200_PAIRS_BLOCK_BELOW"] = "0"
+    try:
+        g_w = capi.Ndt(prm)
+        res_w = g_w.match_pairs(src, so, tgt, to, guesses, n, source_leaf=common.LAUNCH["leaf"])
+    finally:
+        del os.environ["NDT_B200_PAIRS_BLOCK_BELOW"]
+    assert np.array_equal(res_w["iters"], res["iters"]) and np.array_equal(res_w["evals"], res["evals"])
+    assert np.allclose(res_w["pose"], res["pose"], rtol=0, atol=1e-9)
+    # small batches (several grid-build + match rounds inside one call) give the same bytes
     os.environ["NDT_B200_PAIRS_BATCH_POINTS"] = "9000"
     try:
         res_b = g.match_pairs(src, so, tgt, to, guesses, n, source_leaf=common.LAUNCH["leaf"])
