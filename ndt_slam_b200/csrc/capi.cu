@@ -101,7 +101,7 @@ static void all_buffers(Handle *h, std::vector<DevBuf *> &v) {
   GridBuffers &g = h->gb;
   v = {&g.tgt, &g.cell_of, &g.rank_of, &g.list, &g.sorted_idx, &g.slot, &g.leaf_id, &g.leaf_cell,
        &g.leaf_n, &g.leaf_start, &g.leaf_nr, &g.leaf_mean, &g.leaf_icov, &g.leaf_cen, &g.recs,
-       &g.counters, &g.leaf_pair, &g.big_list, &g.dims, &g.pair_off, &g.cen, &g.occ, &g.nn_cnt, &g.nn_range, &g.nn_pts,
+       &g.counters, &g.leaf_pair, &g.big_list, &g.tile_hist, &g.dims, &g.pair_off, &g.cen, &g.occ, &g.nn_cnt, &g.nn_range, &g.nn_pts,
        &g.tgt_sorted, &g.leaf_range, &h->src, &h->scratch, &h->scratch2, &h->stage, &h->io};
 }
 

@@ -260,6 +260,88 @@ __global__ void __launch_bounds__(256) k_rank(int64_t n, const int32_t *__restri
   }
 }
 
+// ---- stable counting sort by cell for small grids with dense buckets (a C2 local map: 300 k points in ~5 k cells) ----
+// Rank-by-counting (k_rank) is quadratic in the bucket size; here the points are walked in input order in tiles of
+// TILE_PTS: (1) per-tile histogram over the cells (shared-memory atomics) -> tile_hist[tile][cell], also the global
+// per-cell counts and cell_of; (2) exclusive scan over the tiles, per cell; (3) every tile places its points: position =
+// bucket start + points of the cell in earlier tiles + points of the cell earlier in this tile (rounds of 256 points, warps
+// take turns in order). The result is exactly the input-order bucket layout k_fill + k_rank produce.
+constexpr int TILE_PTS = 2048, TILE_CELLS_CAP = 12288;
+
+__global__ void __launch_bounds__(256) k_tile_hist(const float4 *__restrict__ pts, int64_t n, const PairDims *__restrict__ dims,
+                                                  float inv_leaf, int npad, int32_t *__restrict__ count,
+                                                  int32_t *__restrict__ cell_of, int32_t *__restrict__ tile_hist) {
+  extern __shared__ int32_t s_hist[];
+  for (int c = threadIdx.x; c < npad; c += blockDim.x) s_hist[c] = 0;
+  __syncthreads();
+  const PairDims d = dims[0];
+  const int64_t t0 = (int64_t)blockIdx.x * TILE_PTS;
+  for (int k = threadIdx.x; k < TILE_PTS; k += blockDim.x) {
+    const int64_t i = t0 + k;
+    if (i >= n) break;
+    const float4 p = __ldg(pts + i);
+    int pcell = -1;
+    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z) && d.div_x > 0) {
+      const int i0 = cell_coord(p.x, inv_leaf, d.min_bx), i1 = cell_coord(p.y, inv_leaf, d.min_by);
+      pcell = d.base + (i1 + 2) * d.W + i0 + 2;
+      atomicAdd(&s_hist[pcell], 1);
+    }
+    cell_of[i] = pcell;
+  }
+  __syncthreads();
+  int32_t *out = tile_hist + (size_t)blockIdx.x * npad;
+  for (int c = threadIdx.x; c < npad; c += blockDim.x) {
+    const int v = s_hist[c];
+    out[c] = v;
+    if (v) atomicAdd(count + c, v);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_tile_scan(int32_t *__restrict__ tile_hist, int n_tiles, int npad) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= npad) return;
+  int run = 0;
+  for (int t = 0; t < n_tiles; ++t) {
+    const int v = tile_hist[(size_t)t * npad + c];
+    tile_hist[(size_t)t * npad + c] = run;
+    run += v;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_tile_place(const float4 *__restrict__ pts, int64_t n, int npad,
+                                                   const int32_t *__restrict__ cell_of, const int32_t *__restrict__ leaf_id,
+                                                   const int32_t *__restrict__ leaf_start, const int32_t *__restrict__ tile_off,
+                                                   int32_t *__restrict__ sorted_idx, float2 *__restrict__ tgt_sorted) {
+  extern __shared__ int32_t s_cnt[];
+  for (int c = threadIdx.x; c < npad; c += blockDim.x) s_cnt[c] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  const int32_t *__restrict__ off = tile_off + (size_t)blockIdx.x * npad;
+  const int64_t t0 = (int64_t)blockIdx.x * TILE_PTS;
+  for (int r = 0; r < TILE_PTS; r += blockDim.x) {
+    const int64_t i = t0 + r + threadIdx.x;
+    const int cell = (i < n) ? cell_of[i] : -1;
+    const unsigned grp = __match_any_sync(0xffffffffu, cell);
+    int local = 0;
+    for (int w = 0; w < n_warps; ++w) {              // warps take turns in index order
+      if (warp == w && cell >= 0) {
+        local = s_cnt[cell] + __popc(grp & lt);
+        __syncwarp(grp);
+        if (lane == __ffs(grp) - 1) s_cnt[cell] += __popc(grp);
+      }
+      __syncthreads();
+    }
+    if (cell >= 0) {
+      const int leaf = __ldg(leaf_id + cell) - 1;
+      const int pos = __ldg(leaf_start + leaf) + __ldg(off + cell) + local;
+      sorted_idx[pos] = (int32_t)i;
+      const float4 p = __ldg(pts + i);
+      tgt_sorted[pos] = make_float2(p.x, p.y);
+    }
+  }
+}
+
 // symmetric 2x2 eigen-decomposition (a b; b d): ascending eigenvalues, orthonormal columns.
 // Expression order is fixed (IEEE ops only) so results are reproducible bit for bit.
 __device__ inline void eig2(double a, double b, double d, double *lam, double *v0, double *v1) {
@@ -651,22 +733,37 @@ int grid_build_tables(Handle *h, int64_t n, int n_grids, int64_t total_pad, int 
   NDT_CUDA(h, cudaMemsetAsync(gb.occ.p, 0, occ_words * 4, st));
   NDT_CUDA(h, cudaMemsetAsync(gb.leaf_id.p, 0, npad * 4, st));               // per-cell counts, then leaf id + 1
   NDT_CUDA(h, cudaMemsetAsync(gb.cen.p, 0xff, npad * sizeof(float2), st));   // all-ones is a NaN: "no tree cell here"
-  k_count<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(gb.tgt.as<float4>(), n, off, n_grids, dims, h->gd.inv_leaf,
-                                                        gb.leaf_id.as<int32_t>(), gb.cell_of.as<int32_t>(),
-                                                        gb.rank_of.as<int32_t>());
   // enough CTAs to fill the machine: several row chunks per grid when there are few grids
   int chunks = 1;
   if (n_grids < h->sm_count * 8) chunks = std::max(1, std::min(max_h, (h->sm_count * 8) / std::max(n_grids, 1)));
-  k_alloc<<<(unsigned)((int64_t)n_grids * chunks), 256, 0, st>>>(gb.leaf_id.as<int32_t>(), dims, chunks, gb.leaf_cell.as<int32_t>(),
-                                                                gb.leaf_pair.as<int32_t>(), gb.leaf_n.as<int32_t>(),
-                                                                gb.leaf_start.as<int32_t>(), gb.big_list.as<int32_t>(), ctr);
-  k_fill<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(n, gb.cell_of.as<int32_t>(), gb.rank_of.as<int32_t>(),
-                                                       gb.leaf_id.as<int32_t>(), gb.leaf_start.as<int32_t>(),
-                                                       gb.list.as<int32_t>());
-  k_rank<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(n, gb.cell_of.as<int32_t>(), gb.leaf_id.as<int32_t>(),
-                                                       gb.leaf_start.as<int32_t>(), gb.leaf_n.as<int32_t>(),
-                                                       gb.list.as<int32_t>(), gb.tgt.as<float4>(), gb.sorted_idx.as<int32_t>(),
-                                                       gb.tgt_sorted.as<float2>(), ctr);
+  const bool tiled = n_grids == 1 && total_pad <= TILE_CELLS_CAP && n >= 8192;     // small grid, dense buckets
+  if (tiled) {
+    const int n_tiles = (int)((n + TILE_PTS - 1) / TILE_PTS), np = (int)total_pad;
+    NDT_CUDA(h, gb.tile_hist.reserve((size_t)n_tiles * np * 4));
+    k_tile_hist<<<n_tiles, 256, np * 4, st>>>(gb.tgt.as<float4>(), n, dims, h->gd.inv_leaf, np, gb.leaf_id.as<int32_t>(),
+                                               gb.cell_of.as<int32_t>(), gb.tile_hist.as<int32_t>());
+    k_alloc<<<(unsigned)((int64_t)n_grids * chunks), 256, 0, st>>>(gb.leaf_id.as<int32_t>(), dims, chunks, gb.leaf_cell.as<int32_t>(),
+                                                                  gb.leaf_pair.as<int32_t>(), gb.leaf_n.as<int32_t>(),
+                                                                  gb.leaf_start.as<int32_t>(), gb.big_list.as<int32_t>(), ctr);
+    k_tile_scan<<<(np + 255) / 256, 256, 0, st>>>(gb.tile_hist.as<int32_t>(), n_tiles, np);
+    k_tile_place<<<n_tiles, 256, np * 4, st>>>(gb.tgt.as<float4>(), n, np, gb.cell_of.as<int32_t>(), gb.leaf_id.as<int32_t>(),
+                                                gb.leaf_start.as<int32_t>(), gb.tile_hist.as<int32_t>(), gb.sorted_idx.as<int32_t>(),
+                                                gb.tgt_sorted.as<float2>());
+  } else {
+    k_count<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(gb.tgt.as<float4>(), n, off, n_grids, dims, h->gd.inv_leaf,
+                                                          gb.leaf_id.as<int32_t>(), gb.cell_of.as<int32_t>(),
+                                                          gb.rank_of.as<int32_t>());
+    k_alloc<<<(unsigned)((int64_t)n_grids * chunks), 256, 0, st>>>(gb.leaf_id.as<int32_t>(), dims, chunks, gb.leaf_cell.as<int32_t>(),
+                                                                  gb.leaf_pair.as<int32_t>(), gb.leaf_n.as<int32_t>(),
+                                                                  gb.leaf_start.as<int32_t>(), gb.big_list.as<int32_t>(), ctr);
+    k_fill<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(n, gb.cell_of.as<int32_t>(), gb.rank_of.as<int32_t>(),
+                                                         gb.leaf_id.as<int32_t>(), gb.leaf_start.as<int32_t>(),
+                                                         gb.list.as<int32_t>());
+    k_rank<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(n, gb.cell_of.as<int32_t>(), gb.leaf_id.as<int32_t>(),
+                                                         gb.leaf_start.as<int32_t>(), gb.leaf_n.as<int32_t>(),
+                                                         gb.list.as<int32_t>(), gb.tgt.as<float4>(), gb.sorted_idx.as<int32_t>(),
+                                                         gb.tgt_sorted.as<float2>(), ctr);
+  }
   FinalizeParams fp{h->prm.min_points, h->prm.eig_mult, h->prm.quirks};
   FinalizeOut fo{gb.leaf_range.as<int2>(), gb.leaf_nr.as<int32_t>(), gb.leaf_mean.as<double2>(), gb.leaf_icov.as<double>(),
                  gb.leaf_cen.as<float2>(), gb.slot.as<int32_t>(), gb.cen.as<float2>(), gb.occ.as<uint32_t>(), gb.recs.as<CellRec>(), ctr,

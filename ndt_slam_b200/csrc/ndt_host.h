@@ -62,6 +62,7 @@ struct GridBuffers {
   DevBuf leaf_id;      // int32[padded]   per-cell point count during the build, then leaf id + 1 (0 = empty)
   DevBuf leaf_cell;    // int32[n]        per leaf: position in the shared padded tables
   DevBuf leaf_pair;    // int32[n]        per leaf: which grid it belongs to
+  DevBuf tile_hist;    // int32[tiles][padded] per-tile cell histograms / offsets (stable counting sort of small dense grids)
   DevBuf big_list;     // int32[]         leaves with more than FINALIZE_BIG_LEAF points (reduced by a warp each)
   DevBuf dims;         // PairDims[n_grids]
   DevBuf pair_off;     // int64[n_grids+1] target point ranges (batched pairs)
