@@ -297,14 +297,19 @@ __global__ void __launch_bounds__(256) k_tile_hist(const float4 *__restrict__ pt
   }
 }
 
-__global__ void __launch_bounds__(256) k_tile_scan(int32_t *__restrict__ tile_hist, int n_tiles, int npad) {
+__global__ void __launch_bounds__(64) k_tile_scan(int32_t *__restrict__ tile_hist, int n_tiles, int npad) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= npad) return;
   int run = 0;
-  for (int t = 0; t < n_tiles; ++t) {
-    const int v = tile_hist[(size_t)t * npad + c];
-    tile_hist[(size_t)t * npad + c] = run;
-    run += v;
+  for (int t0 = 0; t0 < n_tiles; t0 += 8) {          // eight independent loads in flight, then the running sum
+    int v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = (t0 + u < n_tiles) ? tile_hist[(size_t)(t0 + u) * npad + c] : 0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (t0 + u < n_tiles) tile_hist[(size_t)(t0 + u) * npad + c] = run;
+      run += v[u];
+    }
   }
 }
 
@@ -745,7 +750,7 @@ int grid_build_tables(Handle *h, int64_t n, int n_grids, int64_t total_pad, int 
     k_alloc<<<(unsigned)((int64_t)n_grids * chunks), 256, 0, st>>>(gb.leaf_id.as<int32_t>(), dims, chunks, gb.leaf_cell.as<int32_t>(),
                                                                   gb.leaf_pair.as<int32_t>(), gb.leaf_n.as<int32_t>(),
                                                                   gb.leaf_start.as<int32_t>(), gb.big_list.as<int32_t>(), ctr);
-    k_tile_scan<<<(np + 255) / 256, 256, 0, st>>>(gb.tile_hist.as<int32_t>(), n_tiles, np);
+    k_tile_scan<<<(np + 63) / 64, 64, 0, st>>>(gb.tile_hist.as<int32_t>(), n_tiles, np);
     k_tile_place<<<n_tiles, 256, np * 4, st>>>(gb.tgt.as<float4>(), n, np, gb.cell_of.as<int32_t>(), gb.leaf_id.as<int32_t>(),
                                                 gb.leaf_start.as<int32_t>(), gb.tile_hist.as<int32_t>(), gb.sorted_idx.as<int32_t>(),
                                                 gb.tgt_sorted.as<float2>());
