@@ -373,6 +373,17 @@ def main():
     g.eval_batch(d_pose.data_ptr(), n=n_h, want_hessian=False, space=capi.MEM_DEVICE, out=d_out.data_ptr())
     torch.cuda.synchronize()
     kbar = float(d_out[:, 13].sum().item()) / (n_h * ns)
+    # score-only sweep over the initial hypotheses: one objective pass (score + gradient) per hypothesis
+    sw = []
+    for _ in range(3):
+        a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+        a.record(stream)
+        g.eval_batch(d_hyp.data_ptr(), n=n_h, want_hessian=False, space=capi.MEM_DEVICE, out=d_out.data_ptr())
+        b.record(stream)
+        torch.cuda.synchronize()
+        sw.append(a.elapsed_time(b))
+    sweep = {"hypotheses": n_h, "point_evals": n_h * ns, "ms": min(sw), "point_evals_per_sec": n_h * ns / (min(sw) * 1e-3),
+             "note": "rank 0's shard; one score+gradient pass per initial hypothesis (k_eval_warp), best of 3"}
     bytes_per_eval = 160.0 + 48.0 * kbar
     kern_ms = float(np.mean(step_ms))                 # one launch per step: step time == kernel time
     achieved = pe_step * bytes_per_eval / (kern_ms * 1e-3) / 1e9
@@ -427,6 +438,7 @@ def main():
         "grid_build_ms": t_build, "grid_broadcast_ms": bcast_ms, "grid_blob_bytes": int(bcast_bytes),
         "grid_broadcast_gbs": (bcast_bytes / (bcast_ms * 1e-3) / 1e9) if bcast_ms else None,
         "reloc_best_error_m": reloc_err, "reloc_best": {"score": g_score, "hypothesis": g_index, "owner_rank": g_owner},
+        "score_sweep": sweep,
         "c5": c5_line,
         "extras": extras,
     }

@@ -402,6 +402,57 @@ __global__ void __launch_bounds__(WK_THREADS, NDT_WARP_KERNEL_MIN_CTAS) k_align_
 }
 
 // ---------------------------------------------------------------------------------------------
+// objective only, many poses (relocalisation score sweep): persistent CTAs, one warp per pose, source scan and occupancy
+// bitmap staged once per CTA -- the batch matcher's schedule without the optimiser
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256, 2) k_eval_warp(GridView G, MatchParams mp, const float4 *__restrict__ src, int ns,
+                                                      const double *__restrict__ poses, double *__restrict__ out14,
+                                                      int64_t *__restrict__ pairs_out, int64_t n_jobs,
+                                                      int32_t *__restrict__ job_counter, int occ_words) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t *s_occ = reinterpret_cast<uint32_t *>(smem_raw + QUEUE_BYTES);
+  for (int i = threadIdx.x; i < occ_words; i += blockDim.x) s_occ[i] = __ldg(G.occ + i);
+  float2 *s_src = reinterpret_cast<float2 *>(smem_raw + QUEUE_BYTES + ((occ_words * 4 + 15) & ~15));
+  for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+    const float4 v = __ldg(src + i);
+    s_src[i] = make_float2(v.x, v.y);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const bool sse = (mp.quirks & NDT_QUIRK_TRANSFORM_SSE_ORDER) != 0;
+  const HitQueue Q = my_queue(smem_raw);
+  const ProbeGeom geom = probe_geom(G);
+  for (;;) {
+    int job = 0;
+    if (lane == 0) job = atomicAdd(job_counter, 1);
+    job = __shfl_sync(0xffffffffu, job, 0);
+    if (job >= n_jobs) break;
+    const double p[3] = {poses[3 * (size_t)job], poses[3 * (size_t)job + 1], poses[3 * (size_t)job + 2]};
+    AngleCache ac;
+    angle_terms(mp, p[2], ac);
+    const PoseF pf = pose_to_float(p);
+    double acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+    int pairs = 0;
+    accumulate_points(MODE, geom, SmemOcc{s_occ}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, SmemSrc{s_src}, lane, 32, ns,
+                      pf, sse, ac.cs, ac.sn, mp.d1, mp.d2, Q, acc, pairs);
+    warp_allreduce<NACC>(acc);
+    if (lane < NACC) {
+      double v = 0.0;
+#pragma unroll
+      for (int k = 0; k < NACC; ++k) if (lane == k) v = acc[k];
+      out14[(size_t)job * (NACC + 1) + lane] = v;
+    }
+    if (lane == 0) {
+      out14[(size_t)job * (NACC + 1) + NACC] = (double)pairs;
+      if (pairs_out) pairs_out[job] = pairs;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // arg-max over batch results: highest score among converged matches, lowest index on ties
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_best_of(const ndt_result *__restrict__ res, int64_t n,
@@ -654,6 +705,29 @@ int launch_eval(Handle *h, const double *d_poses, int64_t n, int want_hessian, d
   const GridView G = grid_view(h);
   const MatchParams mp = match_params(h, false);
   const float4 *src = h->src.as<float4>();
+  {
+    // many poses: the batch matcher's schedule (one warp per pose, staged source / occupancy)
+    const int64_t npad = h->gd.n_cells > 0 ? (int64_t)(h->gd.div_x + 4) * (h->gd.div_y + 4) : 0;
+    const int occ_words = (int)((npad + 31) / 32 + 1);
+    const size_t smem = QUEUE_BYTES + (((size_t)occ_words * 4 + 15) & ~size_t(15)) + (size_t)ns * sizeof(float2);
+    if (n >= 16 * h->sm_count && h->gd.n_cells > 0 && smem <= 100 * 1024) {
+      int32_t *ctr = h->gb.counters.as<int32_t>();
+      if (h->timing) cudaEventRecord(h->ev0, st);
+      NDT_CUDA(h, cudaMemsetAsync(ctr + CTR_JOB, 0, sizeof(int32_t), st));
+      const int64_t grid = std::min<int64_t>((int64_t)h->sm_count * 2, (n + 7) / 8);
+      if (want_hessian) {
+        NDT_CUDA(h, cudaFuncSetAttribute(k_eval_warp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_eval_warp<0><<<(unsigned)grid, 256, smem, st>>>(G, mp, src, ns, d_poses, d_out14, d_pairs, n, ctr + CTR_JOB, occ_words);
+      } else {
+        NDT_CUDA(h, cudaFuncSetAttribute(k_eval_warp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_eval_warp<1><<<(unsigned)grid, 256, smem, st>>>(G, mp, src, ns, d_poses, d_out14, d_pairs, n, ctr + CTR_JOB, occ_words);
+      }
+      ++h->launches;
+      if (h->timing) cudaEventRecord(h->ev1, st);
+      NDT_CUDA(h, cudaGetLastError());
+      return NDT_OK;
+    }
+  }
   if (h->timing) cudaEventRecord(h->ev0, st);
   NDT_CUDA(h, cudaFuncSetAttribute(k_eval_partial<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, QUEUE_BYTES));
   NDT_CUDA(h, cudaFuncSetAttribute(k_eval_partial<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, QUEUE_BYTES));

@@ -153,6 +153,17 @@ def test_eval_batch_matches_single(c1):
     g.eval_batch(d_p.data_ptr(), n=300, space=capi.MEM_DEVICE, out=d_o.data_ptr())
     g.synchronize()
     assert np.array_equal(d_o.cpu().numpy(), out)      # deterministic, same kernel either way
+    # thousands of poses take the persistent warp-per-pose kernel (score sweep): same numbers up to summation order
+    many = pb["guess"] + rng.normal(0, [0.2, 0.2, 0.05], size=(3000, 3))
+    many[:300] = poses
+    big = g.eval_batch(many)
+    assert np.array_equal(big[:300, 13], out[:, 13])
+    assert np.allclose(big[:300, :13], out[:, :13], rtol=1e-11, atol=1e-12)
+    b = o.eval(many[2999])
+    assert big[2999, 0] == pytest.approx(b.score, rel=REL_EVAL) and big[2999, 13] == b.n_pairs
+    assert common.rel_err(big[2999, 4:13], b.hess) < REL_EVAL
+    nog = g.eval_batch(many, want_hessian=False)
+    assert np.allclose(nog[:, :4], big[:, :4], rtol=1e-11, atol=1e-12)
 
 
 def _assert_result_close(a, b):
