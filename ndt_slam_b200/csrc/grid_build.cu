@@ -10,17 +10,22 @@
 // of the reference stack (and as the CPU oracle used by the tests), so counts, means, centroids and inverse
 // covariances come out bit-identical rather than merely within tolerance.
 //
-// Pipeline (all on the handle's stream; the only host round trip is the 6-int bounds read-back when
-// the points are already device-resident -- host inputs get their bounds during staging):
-//   k_bounds    float min/max + finite count                      (device inputs only)
-//   k_count     cell id per point (float32, bit-exact), warp-aggregated int atomics -> count + rank
-//   k_alloc     per dense cell: leaf ids and contiguous bucket ranges (warp-aggregated allocation)
-//   k_fill      scatter point indices into their leaf bucket
-//   k_rank      one thread per bucket entry: order every bucket by point index (rank by counting) and
-//               write the points in bucket order
-//   k_finalize  one thread per leaf: walk the (contiguous) bucket in input order
-//               (fp32 centroid, fp64 sums), mean, single-pass covariance, 2x2 eigen clamp, inverse,
-//               64-byte record + cell->slot table
+// Pipeline (all on the handle's stream; host round trips: the bounds read-back when the cloud is large or already on the
+// device -- small host clouds get their bounds during staging -- and one read-back of the leaf / slot counters):
+//   k_bounds       float min/max + finite count, one set of global atomics per CTA
+//   memsets        per-cell counts = 0, probe table = NaN (all-ones), occupancy bitmap = 0; the slot table is never cleared
+//   k_count        cell id per point (float32, bit-exact), warp-aggregated int atomics -> count + arbitrary rank
+//   k_alloc        occupied cells only: leaf ids and contiguous bucket ranges (two sweeps, one pair of atomics per CTA),
+//                  count -> leaf id + 1 in place, list of dense leaves
+//   k_fill, k_rank scatter point indices into their bucket, then order every bucket by point index (rank by counting)
+//   k_tile_hist / k_tile_scan / k_tile_place   instead of count / fill / rank for small grids with dense buckets: stable
+//                  counting sort by cell over tiles of the input (linear, not quadratic in the bucket size)
+//   k_finalize     walk every bucket in input order (fp32 centroid, fp64 sums): one thread per sparse leaf, one warp per
+//                  dense leaf; mean, single-pass covariance, 2x2 eigen clamp, inverse, 64-byte record, probe / slot /
+//                  dilated-occupancy entries
+//   k_nn_*         finer lattice for the exact 1-NN of the fitness score when the NDT buckets are dense
+// Batched scan pairs: k_pair_bounds + k_pair_scan compute every pair's geometry on the device, then one pass of the
+// same kernels builds all grids in one shared padded table.
 #include "ndt_host.h"
 
 #include <cooperative_groups.h>

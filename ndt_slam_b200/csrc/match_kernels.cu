@@ -6,11 +6,13 @@
 // inside one kernel launch: no host round trip per iteration.
 //
 // Kernels
-//   k_eval_partial / k_eval_final  one objective pass for n poses (parity hook, relocalisation sweep)
+//   k_eval_partial / k_eval_final  one objective pass for a few poses (parity hook)
+//   k_eval_warp     one objective pass for thousands of poses, one warp per pose (relocalisation score sweep)
 //   k_align_block   one CTA per match, optional shared-memory tile of the whole grid (single scans)
 //   k_align_cluster one thread-block cluster per match, DSMEM reduction (single scans)
 //   k_align_grid    one match on every SM, cooperative launch + grid-wide reduction (very large source clouds)
 //   k_align_warp    persistent CTAs, one warp per match pulled from an atomic work counter (batches)
+//   k_align_pairs / k_align_pairs_block  batched scan pairs, every job with its own grid: warp per pair / CTA per pair
 //   k_best_of       arg-max of the batch results
 //   k_voxel_filter(_pairs)  ApproximateVoxelGrid, one warp per cloud (slot-parallel replay of the hash history)
 #include "ndt_host.h"
