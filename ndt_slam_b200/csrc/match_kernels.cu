@@ -360,6 +360,33 @@ __global__ void __launch_bounds__(256, 2) k_align_grid(GridView G, MatchParams m
 #endif
 constexpr int WK_THREADS = NDT_WARP_KERNEL_THREADS, WK_WARPS = WK_THREADS / 32;
 constexpr int WK_QUEUE_BYTES = WK_WARPS * QUEUE_BYTES_PER_WARP;
+#ifndef NDT_WARP_JOB_CHUNK
+#define NDT_WARP_JOB_CHUNK 8
+#endif
+// Work distribution of the persistent batch kernels: a CTA claims NDT_WARP_JOB_CHUNK consecutive jobs at a time from the
+// global counter and its warps take them one by one (shared-memory state word = chunk base << 32 | jobs handed out).
+// Consecutive relocalisation hypotheses share their position (16 headings per lattice point), so the warps of a CTA
+// probe the same neighbourhood of the map and share its centroid / record lines in L1; a single global counter would
+// scatter neighbouring hypotheses over all SMs. Returns the job for this warp (>= n_jobs: nothing left).
+__device__ __forceinline__ int next_job(unsigned long long *s_state, int32_t *job_counter, int lane) {
+  int job = 0;
+  if (lane == 0) {
+    for (;;) {
+      const unsigned long long st = atomicAdd(s_state, 1ull);
+      const int cnt = (int)(st & 0xffffffffu), base = (int)(st >> 32);
+      if (cnt < NDT_WARP_JOB_CHUNK) { job = base + cnt; break; }
+      if (cnt == NDT_WARP_JOB_CHUNK) {                       // first to find the chunk empty: fetch the next one
+        const int nb = atomicAdd(job_counter, NDT_WARP_JOB_CHUNK);
+        atomicExch(s_state, ((unsigned long long)(unsigned)nb << 32) | 1ull);
+        job = nb;
+        break;
+      }
+      while ((int)(atomicAdd(s_state, 0ull) & 0xffffffffu) > NDT_WARP_JOB_CHUNK) {}   // a neighbour is fetching
+    }
+  }
+  return __shfl_sync(0xffffffffu, job, 0);
+}
+
 template <bool SRC_SMEM>
 __global__ void __launch_bounds__(WK_THREADS, NDT_WARP_KERNEL_MIN_CTAS) k_align_warp(GridView G, MatchParams mp, const float4 *__restrict__ src,
                                                    int ns, const double *__restrict__ guesses,
@@ -377,15 +404,15 @@ __global__ void __launch_bounds__(WK_THREADS, NDT_WARP_KERNEL_MIN_CTAS) k_align_
       s_src[i] = make_float2(v.x, v.y);
     }
   }
+  __shared__ unsigned long long s_state;
+  if (threadIdx.x == 0) s_state = NDT_WARP_JOB_CHUNK;          // "chunk exhausted": the first warp fetches one
   __syncthreads();
   const int lane = threadIdx.x & 31;
   WarpCoop coop{lane};
   const GlobalSrc gsrc{src};
   const SmemSrc ssrc{s_src};
   for (;;) {
-    int job = 0;
-    if (lane == 0) job = atomicAdd(job_counter, 1);
-    job = __shfl_sync(0xffffffffu, job, 0);
+    const int job = next_job(&s_state, job_counter, lane);
     if (job >= n_jobs) break;
     const double guess[3] = {guesses[3 * (size_t)job], guesses[3 * (size_t)job + 1], guesses[3 * (size_t)job + 2]};
     MatchOut mo;
@@ -425,10 +452,11 @@ __global__ void __launch_bounds__(256, 2) k_eval_warp(GridView G, MatchParams mp
   const bool sse = (mp.quirks & NDT_QUIRK_TRANSFORM_SSE_ORDER) != 0;
   const HitQueue Q = my_queue(smem_raw);
   const ProbeGeom geom = probe_geom(G);
+  __shared__ unsigned long long s_state;
+  if (threadIdx.x == 0) s_state = NDT_WARP_JOB_CHUNK;
+  __syncthreads();
   for (;;) {
-    int job = 0;
-    if (lane == 0) job = atomicAdd(job_counter, 1);
-    job = __shfl_sync(0xffffffffu, job, 0);
+    const int job = next_job(&s_state, job_counter, lane);
     if (job >= n_jobs) break;
     const double p[3] = {poses[3 * (size_t)job], poses[3 * (size_t)job + 1], poses[3 * (size_t)job + 2]};
     AngleCache ac;
