@@ -36,8 +36,8 @@ struct GlobalSrc {
   }
 };
 struct SmemSrc {
-  const float2 *p;
-  __device__ __forceinline__ float2 operator()(int i) const { return p[i]; }
+  uint32_t a;       // shared address of float2[ns]
+  __device__ __forceinline__ float2 operator()(int i) const { return lds_float2(a + 8u * i); }
 };
 
 // One cooperative objective pass. All threads of the group call pass<MODE>() with identical
@@ -86,9 +86,8 @@ __device__ __forceinline__ Objective<Coop, OccL, CenL, SlotL, RecL, SrcL> make_o
 constexpr int QUEUE_BYTES = 8 * QUEUE_BYTES_PER_WARP;          // 8 warps per CTA: 28,672 B
 __device__ __forceinline__ HitQueue my_queue(unsigned char *smem) {
   const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  int2 *hit = reinterpret_cast<int2 *>(smem) + w * QCAP;
-  int2 *cand = reinterpret_cast<int2 *>(smem + nw * QCAP * 8) + w * CQCAP;
-  return HitQueue{hit, cand};
+  const uint32_t base = smem_addr(smem);
+  return HitQueue{base + 8u * (w * QCAP), base + 8u * (nw * QCAP + w * CQCAP)};
 }
 
 template <class Coop, class SrcL>
@@ -217,7 +216,7 @@ __global__ void __launch_bounds__(256) k_align_block(GridView G, MatchParams mp,
     for (int i = threadIdx.x; i < n_slots * 4; i += blockDim.x) sr[i] = __ldg(gr + i);
     for (int i = threadIdx.x; i < n_cells; i += blockDim.x) { s_cen[i] = __ldg(G.cen + i); s_slot[i] = __ldg(G.slot + i); }
     __syncthreads();
-    auto obj = make_objective(G, mp, coop, SmemOcc{s_occ}, SmemCen{s_cen}, SmemSlot{s_slot}, SmemRec{s_recs}, gsrc, ns, my_queue(smem_raw));
+    auto obj = make_objective(G, mp, coop, SmemOcc{smem_addr(s_occ)}, SmemCen{smem_addr(s_cen)}, SmemSlot{smem_addr(s_slot)}, SmemRec{smem_addr(s_recs)}, gsrc, ns, my_queue(smem_raw));
     match_device(obj, mp, guess, mo);
   } else {
     auto obj = make_objective(G, mp, coop, GlobalOcc{G.occ}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, my_queue(smem_raw));
@@ -396,7 +395,7 @@ __global__ void __launch_bounds__(WK_THREADS, NDT_WARP_KERNEL_MIN_CTAS) k_align_
   // dynamic shared memory: hit queues | occupancy bitmap (occ_words, 0 = left in global) | source points
   uint32_t *s_occ = reinterpret_cast<uint32_t *>(smem_raw + WK_QUEUE_BYTES);
   for (int i = threadIdx.x; i < occ_words; i += blockDim.x) s_occ[i] = __ldg(G.occ + i);
-  const uint32_t *occ_ptr = occ_words > 0 ? s_occ : G.occ;
+  const MixedOcc occ_any{smem_addr(s_occ), occ_words > 0 ? nullptr : G.occ};
   float2 *s_src = reinterpret_cast<float2 *>(smem_raw + WK_QUEUE_BYTES + ((occ_words * 4 + 15) & ~15));
   if (SRC_SMEM) {
     for (int i = threadIdx.x; i < ns; i += blockDim.x) {
@@ -410,7 +409,7 @@ __global__ void __launch_bounds__(WK_THREADS, NDT_WARP_KERNEL_MIN_CTAS) k_align_
   const int lane = threadIdx.x & 31;
   WarpCoop coop{lane};
   const GlobalSrc gsrc{src};
-  const SmemSrc ssrc{s_src};
+  const SmemSrc ssrc{smem_addr(s_src)};
   for (;;) {
     const int job = next_job(&s_state, job_counter, lane);
     if (job >= n_jobs) break;
@@ -418,11 +417,11 @@ __global__ void __launch_bounds__(WK_THREADS, NDT_WARP_KERNEL_MIN_CTAS) k_align_
     MatchOut mo;
     double fsum = 0.0;
     if (SRC_SMEM) {
-      auto obj = make_objective(G, mp, coop, SmemOcc{occ_ptr}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, ssrc, ns, my_queue(smem_raw));
+      auto obj = make_objective(G, mp, coop, occ_any, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, ssrc, ns, my_queue(smem_raw));
       match_device(obj, mp, guess, mo);
       if (mp.want_fitness) fsum = fitness_pass(G, ssrc, ns, mp, mo.p, coop);
     } else {
-      auto obj = make_objective(G, mp, coop, SmemOcc{occ_ptr}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, my_queue(smem_raw));
+      auto obj = make_objective(G, mp, coop, occ_any, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, my_queue(smem_raw));
       match_device(obj, mp, guess, mo);
       if (mp.want_fitness) fsum = fitness_pass(G, gsrc, ns, mp, mo.p, coop);
     }
@@ -466,7 +465,7 @@ __global__ void __launch_bounds__(256, 2) k_eval_warp(GridView G, MatchParams mp
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
     int pairs = 0;
-    accumulate_points(MODE, geom, SmemOcc{s_occ}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, SmemSrc{s_src}, lane, 32, ns,
+    accumulate_points(MODE, geom, SmemOcc{smem_addr(s_occ)}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, SmemSrc{smem_addr(s_src)}, lane, 32, ns,
                       pf, sse, ac.cs, ac.sn, mp.d1, mp.d2, Q, acc, pairs);
     warp_allreduce<NACC>(acc);
     if (lane < NACC) {

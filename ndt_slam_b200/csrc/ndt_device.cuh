@@ -150,9 +150,43 @@ constexpr int QUEUE_BYTES_PER_WARP = (QCAP + CQCAP) * 8;
 // Ring entries are 8 bytes: the source point index plus a table position. The float32 transform of a point is
 // eight flops, so stages B and C redo it from the (shared-memory) source point instead of carrying 16 more bytes
 // per entry -- the rings of a CTA then take 24 KB and three CTAs fit on an SM.
+// Shared memory is addressed through 32-bit shared-window addresses and explicit ld.shared / st.shared: the rings and the
+// staged tables reach the hot loop through a struct and a non-inlined call, where the compiler no longer knows that a
+// plain pointer is a shared-memory pointer and falls back to generic 64-bit loads and stores.
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ int2 lds_int2(uint32_t a) {
+  int2 v;
+  asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_int2(uint32_t a, int2 v) {
+  asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ float2 lds_float2(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t a) { return (int)lds_u32(a); }
+__device__ __forceinline__ double2 lds_double2(uint32_t a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float4 lds_float4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+
 struct HitQueue {
-  int2 *hit;      // [QCAP]  (source point index, padded-table index of the hit cell)
-  int2 *cand;     // [CQCAP] (source point index, padded-table index of the point's own cell)
+  uint32_t hit;   // shared address of int2[QCAP]:  (source point index, padded-table index of the hit cell)
+  uint32_t cand;  // shared address of int2[CQCAP]: (source point index, padded-table index of the point's own cell)
 };
 
 // NH hits per lane, evaluated side by side: the code is straight-line (the reference's guard on e turns into
@@ -288,7 +322,7 @@ __device__ __forceinline__ void accumulate_points(const int MODE, const ProbeGeo
 #pragma unroll
       for (int u = 0; u < A_STEPS; ++u) {
         const unsigned bal = __ballot_sync(0xffffffffu, b[u] >= 0);
-        if (b[u] >= 0) Q.cand[(at + __popc(bal & lt)) & (CQCAP - 1)] = make_int2(i0 + lane + u * stride, b[u]);
+        if (b[u] >= 0) sts_int2(Q.cand + 8u * ((at + __popc(bal & lt)) & (CQCAP - 1)), make_int2(i0 + lane + u * stride, b[u]));
         at += __popc(bal);
       }
       cn = at - chead;
@@ -302,7 +336,7 @@ __device__ __forceinline__ void accumulate_points(const int MODE, const ProbeGeo
       unsigned mask = 0u;
       int2 cd = make_int2(0, 0);
       if (lane < n) {
-        cd = Q.cand[(chead + lane) & (CQCAP - 1)];
+        cd = lds_int2(Q.cand + 8u * ((chead + lane) & (CQCAP - 1)));
         float2 c[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) c[k] = cen_at(cd.y + (k / 3 - 1) * g.W + (k % 3 - 1));
@@ -328,7 +362,7 @@ __device__ __forceinline__ void accumulate_points(const int MODE, const ProbeGeo
         while (mask) {
           const int k = __ffs(mask) - 1;
           mask &= mask - 1u;
-          Q.hit[pos] = make_int2(cd.x, cd.y + (k / 3 - 1) * g.W + (k % 3 - 1));
+          sts_int2(Q.hit + 8u * pos, make_int2(cd.x, cd.y + (k / 3 - 1) * g.W + (k % 3 - 1)));
           if (++pos == QCAP) pos = 0;
         }
         qn += total;
@@ -347,7 +381,7 @@ __device__ __forceinline__ void accumulate_points(const int MODE, const ProbeGeo
         valid[u] = k < n;
         int pos = qhead + (valid[u] ? k : 0);      // a lane without a hit recomputes the first one with weight zero
         if (pos >= QCAP) pos -= QCAP;
-        const int2 h = Q.hit[pos];
+        const int2 h = lds_int2(Q.hit + 8u * pos);
         const float2 xy = src(h.x);
         e[u].z = xy.x; e[u].w = xy.y;
         xform(pf, sse_order, xy.x, xy.y, e[u].x, e[u].y);
@@ -370,9 +404,14 @@ struct GlobalOcc {
   const uint32_t *__restrict__ p;
   __device__ __forceinline__ uint32_t operator()(int w) const { return __ldg(p + w); }
 };
-struct SmemOcc {
-  const uint32_t *p;
-  __device__ __forceinline__ uint32_t operator()(int w) const { return p[w]; }
+struct SmemOcc {            // bitmap staged in shared memory
+  uint32_t a;
+  __device__ __forceinline__ uint32_t operator()(int w) const { return lds_u32(a + 4u * w); }
+};
+struct MixedOcc {           // staged when it fits, else read in place (warp-uniform choice)
+  uint32_t a;
+  const uint32_t *__restrict__ g;
+  __device__ __forceinline__ uint32_t operator()(int w) const { return g ? __ldg(g + w) : lds_u32(a + 4u * w); }
 };
 struct GlobalCen {
   const float2 *__restrict__ p;
@@ -385,8 +424,8 @@ struct GlobalCen {
   }
 };
 struct SmemCen {
-  const float2 *p;
-  __device__ __forceinline__ float2 operator()(int i) const { return p[i]; }
+  uint32_t a;
+  __device__ __forceinline__ float2 operator()(int i) const { return lds_float2(a + 8u * i); }
   __device__ __forceinline__ void prefetch(int, int) const {}
 };
 struct GlobalSlot {
@@ -405,15 +444,14 @@ struct GlobalRec {
 };
 // shared-memory tile accessors (local map tile staged once per match)
 struct SmemSlot {
-  const int32_t *p;
-  __device__ __forceinline__ int operator()(int i) const { return p[i]; }
+  uint32_t a;
+  __device__ __forceinline__ int operator()(int i) const { return lds_s32(a + 4u * i); }
 };
 struct SmemRec {
-  const CellRec *p;
-  __device__ __forceinline__ float4 head(int s) const { return *reinterpret_cast<const float4 *>(p + s); }
+  uint32_t a;
+  __device__ __forceinline__ float4 head(int s) const { return lds_float4(a + 64u * s); }
   __device__ __forceinline__ void body(int s, double2 &m, double2 &r0, double2 &r1) const {
-    const double2 *q = reinterpret_cast<const double2 *>(p + s);
-    m = q[1]; r0 = q[2]; r1 = q[3];
+    m = lds_double2(a + 64u * s + 16u); r0 = lds_double2(a + 64u * s + 32u); r1 = lds_double2(a + 64u * s + 48u);
   }
 };
 
