@@ -416,7 +416,11 @@ __global__ void __launch_bounds__(WK_THREADS, NDT_WARP_KERNEL_MIN_CTAS) k_align_
     const double guess[3] = {guesses[3 * (size_t)job], guesses[3 * (size_t)job + 1], guesses[3 * (size_t)job + 2]};
     MatchOut mo;
     double fsum = 0.0;
-    if (SRC_SMEM) {
+    if (SRC_SMEM && occ_words > 0) {                 // the common batch case: bitmap and scan both staged
+      auto obj = make_objective(G, mp, coop, SmemOcc{smem_addr(s_occ)}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, ssrc, ns, my_queue(smem_raw));
+      match_device(obj, mp, guess, mo);
+      if (mp.want_fitness) fsum = fitness_pass(G, ssrc, ns, mp, mo.p, coop);
+    } else if (SRC_SMEM) {
       auto obj = make_objective(G, mp, coop, occ_any, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, ssrc, ns, my_queue(smem_raw));
       match_device(obj, mp, guess, mo);
       if (mp.want_fitness) fsum = fitness_pass(G, ssrc, ns, mp, mo.p, coop);
