@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(256) k_align_block(GridView G, MatchParams mp,
   const double guess[3] = {guesses[3 * job], guesses[3 * job + 1], guesses[3 * job + 2]};
   const GlobalSrc gsrc{src};
   MatchOut mo;
+  OptState opt;
   if (TILE) {
     // stage the local map tile (here: the whole grid) in shared memory: records first (64-B aligned), then slots
     CellRec *s_recs = reinterpret_cast<CellRec *>(smem_raw + QUEUE_BYTES);
@@ -217,10 +218,10 @@ __global__ void __launch_bounds__(256) k_align_block(GridView G, MatchParams mp,
     for (int i = threadIdx.x; i < n_cells; i += blockDim.x) { s_cen[i] = __ldg(G.cen + i); s_slot[i] = __ldg(G.slot + i); }
     __syncthreads();
     auto obj = make_objective(G, mp, coop, SmemOcc{smem_addr(s_occ)}, SmemCen{smem_addr(s_cen)}, SmemSlot{smem_addr(s_slot)}, SmemRec{smem_addr(s_recs)}, gsrc, ns, my_queue(smem_raw));
-    match_device(obj, mp, guess, mo);
+    match_device(obj, mp, guess, mo, opt);
   } else {
     auto obj = make_objective(G, mp, coop, GlobalOcc{G.occ}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, my_queue(smem_raw));
-    match_device(obj, mp, guess, mo);
+    match_device(obj, mp, guess, mo, opt);
   }
   double fsum = 0.0;
   if (mp.want_fitness) fsum = fitness_pass(G, gsrc, ns, mp, mo.p, coop);
@@ -282,8 +283,9 @@ __global__ void __launch_bounds__(256) k_align_cluster(GridView G, MatchParams m
   const double guess[3] = {guesses[3 * job], guesses[3 * job + 1], guesses[3 * job + 2]};
   const GlobalSrc gsrc{src};
   MatchOut mo;
+  OptState opt;
   auto obj = make_objective(G, mp, coop, GlobalOcc{G.occ}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, my_queue(smem_raw));
-  match_device(obj, mp, guess, mo);
+  match_device(obj, mp, guess, mo, opt);
   double fsum = 0.0;
   if (mp.want_fitness) fsum = fitness_pass(G, gsrc, ns, mp, mo.p, coop);
   if (coop.crank == 0 && threadIdx.x == 0) write_result(out + job, mo, ns, fsum, mp.want_fitness != 0, G.n_tgt);
@@ -338,8 +340,9 @@ __global__ void __launch_bounds__(256, 2) k_align_grid(GridView G, MatchParams m
   const double guess[3] = {guess3[0], guess3[1], guess3[2]};
   const GlobalSrc gsrc{src};
   MatchOut mo;
+  OptState opt;
   auto obj = make_objective(G, mp, coop, GlobalOcc{G.occ}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, my_queue(smem_raw));
-  match_device(obj, mp, guess, mo);
+  match_device(obj, mp, guess, mo, opt);
   double fsum = 0.0;
   if (mp.want_fitness) fsum = fitness_pass(G, gsrc, ns, mp, mo.p, coop);
   if (blockIdx.x == 0 && threadIdx.x == 0) write_result(out, mo, ns, fsum, mp.want_fitness != 0, G.n_tgt);
@@ -415,18 +418,19 @@ __global__ void __launch_bounds__(WK_THREADS, NDT_WARP_KERNEL_MIN_CTAS) k_align_
     if (job >= n_jobs) break;
     const double guess[3] = {guesses[3 * (size_t)job], guesses[3 * (size_t)job + 1], guesses[3 * (size_t)job + 2]};
     MatchOut mo;
+    OptState opt;
     double fsum = 0.0;
     if (SRC_SMEM && occ_words > 0) {                 // the common batch case: bitmap and scan both staged
       auto obj = make_objective(G, mp, coop, SmemOcc{smem_addr(s_occ)}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, ssrc, ns, my_queue(smem_raw));
-      match_device(obj, mp, guess, mo);
+      match_device(obj, mp, guess, mo, opt);
       if (mp.want_fitness) fsum = fitness_pass(G, ssrc, ns, mp, mo.p, coop);
     } else if (SRC_SMEM) {
       auto obj = make_objective(G, mp, coop, occ_any, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, ssrc, ns, my_queue(smem_raw));
-      match_device(obj, mp, guess, mo);
+      match_device(obj, mp, guess, mo, opt);
       if (mp.want_fitness) fsum = fitness_pass(G, ssrc, ns, mp, mo.p, coop);
     } else {
       auto obj = make_objective(G, mp, coop, occ_any, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, my_queue(smem_raw));
-      match_device(obj, mp, guess, mo);
+      match_device(obj, mp, guess, mo, opt);
       if (mp.want_fitness) fsum = fitness_pass(G, gsrc, ns, mp, mo.p, coop);
     }
     if (lane == 0) write_result(out + job, mo, ns, fsum, mp.want_fitness != 0, G.n_tgt);
@@ -640,8 +644,9 @@ __global__ void __launch_bounds__(256, NDT_PAIRS_KERNEL_MIN_CTAS) k_align_pairs(
     const double guess[3] = {guesses[3 * (size_t)job], guesses[3 * (size_t)job + 1], guesses[3 * (size_t)job + 2]};
     const GlobalSrc gsrc{src_all + d.src_off};
     MatchOut mo;
+    OptState opt;
     auto obj = make_objective(G, mp, coop, GlobalOcc{G.occ}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, d.ns, my_queue(smem_raw));
-    match_device(obj, mp, guess, mo);
+    match_device(obj, mp, guess, mo, opt);
     double fsum = 0.0;
     if (mp.want_fitness) fsum = fitness_pass(G, gsrc, d.ns, mp, mo.p, coop);
     if (lane == 0) write_result(out + job, mo, d.ns, fsum, mp.want_fitness != 0, G.n_tgt);
@@ -709,8 +714,9 @@ __global__ void __launch_bounds__(256, NDT_PAIRS_KERNEL_MIN_CTAS) k_align_pairs_
     }
     __syncthreads();
     MatchOut mo;
+    OptState opt;
     auto obj = make_objective(G, mp, coop, aocc, acen, GlobalSlot{G.slot}, GlobalRec{G.recs}, asrc, d.ns, my_queue(smem_raw));
-    match_device(obj, mp, guess, mo);
+    match_device(obj, mp, guess, mo, opt);
     double fsum = 0.0;
     if (mp.want_fitness) fsum = fitness_pass(G, asrc, d.ns, mp, mo.p, coop);
     if (threadIdx.x == 0) write_result(out + job, mo, d.ns, fsum, mp.want_fitness != 0, G.n_tgt);
