@@ -44,3 +44,20 @@ def best_over_ranks(score: float, global_index: int, pose, device="cpu"):
     order = np.lexsort((a[:, 1], -a[:, 0]))      # primary: score descending, secondary: index ascending
     w = int(order[0])
     return float(a[w, 0]), int(a[w, 1]), a[w, 2:5].copy(), w
+
+
+def gather_shards(local: np.ndarray, n_total: int, device="cpu") -> np.ndarray:
+    """Concatenate per-rank result rows (block partition by shard_range, in rank order) on every rank: the end of a
+    sharded ndt_match_pairs run (C5), where every rank holds the results of its own pairs only. `local` is a 2-D
+    float64 array with one row per unit of this rank's shard."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world == 1:
+        return np.ascontiguousarray(local)
+    width = local.shape[1]
+    sizes = [shard_range(n_total, r, world) for r in range(world)]
+    cap = max(b - a for a, b in sizes)
+    pad = torch.zeros((cap, width), dtype=torch.float64, device=device)
+    pad[: local.shape[0]] = torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64)).to(device)
+    buf = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(buf, pad)
+    return np.concatenate([buf[r][: sizes[r][1] - sizes[r][0]].cpu().numpy() for r in range(world)], axis=0)

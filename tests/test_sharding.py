@@ -73,3 +73,46 @@ def test_two_rank_shard_and_best_matches_single_process():
     bi = int(np.argmax(scores))
     assert ret[0][1] == bi and ret[0][0] == pytest.approx(scores[bi], rel=1e-15)
     assert ret[0][3] == (0 if bi < 24 else 1)
+
+
+def _pairs_worker(rank, world, port, ret):
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    sys.path.insert(0, str(root)); sys.path.insert(0, str(root / "tests"))
+    import ndt_common as cm
+    from ndt_slam_b200 import synth
+    from oracle import oracle_api as oa
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_pairs = 7                                            # odd on purpose: ragged shards
+    lo, hi = sharding.shard_range(n_pairs, rank, world)
+    o = oa.Oracle(cm.params(resolution=0.5))
+    rows = []
+    for i in range(lo, hi):                                # every rank builds its own pairs' grids: nothing is exchanged
+        d = synth.c5_pair(i)
+        o.set_target(synth.to_xyzw(cm.prep_scan(d["scan_a"])))
+        o.set_source(oa.approx_voxel_filter(synth.to_xyzw(cm.prep_scan(d["scan_b"])), cm.LAUNCH["leaf"]))
+        r = o.align([0.0, 0.0, 0.0])
+        rows.append([r.pose[0], r.pose[1], r.pose[2], r.score, float(r.converged), float(r.evals)])
+    allrows = sharding.gather_shards(np.array(rows, dtype=np.float64).reshape(-1, 6), n_pairs, device="cpu")
+    ret[rank] = allrows
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_pair_shards_gather_to_the_single_process_result():
+    """C5-style sharding: scan pairs are block-partitioned, every rank matches its own, one all_gather at the end."""
+    from ndt_slam_b200 import synth
+    from oracle import oracle_api as oa
+    world = 2
+    mgr = mp.Manager(); ret = mgr.dict()
+    mp.spawn(_pairs_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert ret[0].shape == (7, 6) and np.array_equal(ret[0], ret[1])
+    o = oa.Oracle(common.params(resolution=0.5))
+    for i in range(7):
+        d = synth.c5_pair(i)
+        o.set_target(synth.to_xyzw(common.prep_scan(d["scan_a"])))
+        o.set_source(oa.approx_voxel_filter(synth.to_xyzw(common.prep_scan(d["scan_b"])), common.LAUNCH["leaf"]))
+        r = o.align([0.0, 0.0, 0.0])
+        assert list(ret[0][i, :3]) == list(r.pose) and ret[0][i, 3] == r.score and ret[0][i, 5] == r.evals
