@@ -258,12 +258,12 @@ def main():
     if world > 1:
         nbytes_t = torch.zeros(1, dtype=torch.int64, device="cuda")
         if rank == 0:
-            nbytes_t[0] = g.grid_blob_size()
+            nbytes_t[0] = g.grid_blob_size(flags=0)          # no fitness pass in a relocalisation sweep: the points stay home
         dist.broadcast(nbytes_t, 0)
         nbytes = int(nbytes_t.item())
         blob = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
         if rank == 0:
-            g.grid_export(blob.data_ptr(), nbytes)
+            g.grid_export(blob.data_ptr(), nbytes, flags=0)
         torch.cuda.synchronize(); dist.barrier()
         e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
         e0.record(); dist.broadcast(blob, 0); e1.record(); torch.cuda.synchronize()

@@ -69,7 +69,14 @@ typedef struct {
   int32_t quirks;         /* NDT_QUIRK_* bit set                              */
   int32_t device;         /* CUDA device ordinal                              */
   void  *stream;          /* cudaStream_t to launch on, or NULL = own stream  */
+  /* Behaviour / tuning knobs of the batched entry points. 0 = library default everywhere (ndt_params_default). */
+  int32_t align_skip_fitness; /* 1: ndt_align skips the getFitnessScore pass (result.fitness = NaN)        */
+  int32_t pairs_schedule;     /* ndt_match_pairs: NDT_PAIRS_AUTO / NDT_PAIRS_WARP / NDT_PAIRS_CTA           */
+  int64_t pairs_batch_points; /* ndt_match_pairs: max target points per internal batch; 0 = 32,000,000     */
 } ndt_params;
+
+/* ndt_params.pairs_schedule: how ndt_match_pairs spreads pairs over the GPU. AUTO picks by batch size. */
+enum { NDT_PAIRS_AUTO = 0, NDT_PAIRS_WARP = 1, NDT_PAIRS_CTA = 2 };
 
 /* One evaluation of the NDT objective: pcl::NDT::computeDerivatives (reached through
  * ndt.align, PoseEstimator.cpp:28). H is row-major 3x3 over (x, y, yaw). */
@@ -146,12 +153,19 @@ int ndt_eval_batch(ndt_handle h, const double *poses, int64_t n, int want_hessia
 /* ---- matching: ndt.align(output, init_guess) + the getters ------------------------------ */
 int ndt_align(ndt_handle h, const double guess[3], ndt_result *out);
 /* n independent matches of the current source against the current grid, one per guess.
- * guesses: n x 3 doubles, results: n ndt_result, both in `memspace`. */
-int ndt_align_batch(ndt_handle h, const double *guesses, int64_t n, int memspace,
+ * guesses: n x 3 doubles, results: n ndt_result, both in `memspace`.
+ * want_fitness != 0: every result carries getFitnessScore() (one exact 1-NN pass per match); 0: result.fitness = NaN
+ * (relocalisation ranks tens of thousands of hypotheses by score and re-runs ndt_align on the winner). */
+int ndt_align_batch(ndt_handle h, const double *guesses, int64_t n, int memspace, int want_fitness,
                     ndt_result *results);
-/* Index of the best result of an ndt_align_batch (max score among converged), device-side. */
+/* Index of the best result of an ndt_align_batch (max score among converged; lowest index on ties), device-side. */
 int ndt_best_of(ndt_handle h, const ndt_result *results, int64_t n, int memspace,
                 int64_t *best_index, ndt_result *best);
+/* The same over several handles (one per GPU, each holding its shard's results in ITS device memory): every GPU
+ * reduces its own shard, the host compares the n_handles winners (ties: lowest handle, then lowest index).
+ * *best_handle = -1 when no result converged anywhere. Only n_handles x sizeof(ndt_result) bytes leave the GPUs. */
+int ndt_best_of_multi(const ndt_handle *handles, const ndt_result *const *device_results, const int64_t *counts,
+                      int n_handles, int *best_handle, int64_t *best_index, ndt_result *best);
 
 /* n independent scan-pair matches (loop-closure verification): pair i matches
  * src[src_off[i] .. src_off[i+1]) against a grid built from tgt[tgt_off[i] .. tgt_off[i+1]).
@@ -168,9 +182,21 @@ int ndt_match_pairs(ndt_handle h, const float *src_xyzw, const int64_t *src_off,
 
 /* ---- replication of a finished grid to other GPUs (one NVLink broadcast, no collectives
  *      per iteration): export to / import from a flat device blob ------------------------- */
-int ndt_grid_blob_size(ndt_handle h, int64_t *bytes);
-int ndt_grid_export(ndt_handle h, void *device_blob, int64_t bytes);
+/* flags: NDT_BLOB_POINTS also carries the target points and their 1-NN buckets (needed only for getFitnessScore on the
+ * replica: more than half of the bytes); without it a replica matches and evaluates exactly like the original but
+ * reports fitness = NaN. The per-leaf read-back tables of ndt_grid_readback are never replicated: on a replica that
+ * call returns NDT_ERR_STATE. ndt_grid_import validates the blob (magic, offsets, sizes, resolution == the handle's). */
+enum { NDT_BLOB_POINTS = 1 };
+int ndt_grid_blob_size(ndt_handle h, int flags, int64_t *bytes);
+int ndt_grid_export(ndt_handle h, int flags, void *device_blob, int64_t bytes);
 int ndt_grid_import(ndt_handle h, const void *device_blob, int64_t bytes);
+/* handles[0] holds a finished grid; copy it to handles[1 .. n_handles) (other GPUs of the box, or the same GPU):
+ * export on the source device, one peer copy per destination over NVLink (cudaMemcpyPeerAsync), import there. This is
+ * the whole multi-GPU data path of the batched workloads: the grid is replicated once, hypotheses / pairs are sharded
+ * by the caller, no collective per iteration. A C++ host needs nothing else (no NCCL, no torch). */
+int ndt_replicate_grid(const ndt_handle *handles, int n_handles, int flags);
+/* Return the device memory the handle's private pool caches beyond its live buffers to the driver. */
+int ndt_trim(ndt_handle h);
 
 /* ---- instrumentation ------------------------------------------------------------------- */
 /* Number of kernels this handle has launched since creation. */

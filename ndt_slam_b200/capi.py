@@ -14,6 +14,8 @@ import numpy as np
 from . import build as _build
 
 MEM_HOST, MEM_DEVICE = 0, 1
+PAIRS_AUTO, PAIRS_WARP, PAIRS_CTA = 0, 1, 2
+BLOB_POINTS = 1
 
 QUIRK_COV_INIT_IDENTITY = 1 << 0
 QUIRK_COV_SCALE_NM1_N = 1 << 1
@@ -27,7 +29,8 @@ class NdtParams(C.Structure):
     _fields_ = [("resolution", C.c_float), ("step_size", C.c_double), ("trans_eps", C.c_double),
                 ("max_iter", C.c_int32), ("outlier_ratio", C.c_double), ("min_points", C.c_int32),
                 ("eig_mult", C.c_double), ("quirks", C.c_int32), ("device", C.c_int32),
-                ("stream", C.c_void_p)]
+                ("stream", C.c_void_p), ("align_skip_fitness", C.c_int32), ("pairs_schedule", C.c_int32),
+                ("pairs_batch_points", C.c_int64)]
 
 
 class NdtEvalOut(C.Structure):
@@ -58,7 +61,7 @@ EXPORTS = [
     "ndt_set_target", "ndt_set_target_prefix", "ndt_get_grid_info", "ndt_grid_readback", "ndt_cell_index",
     "ndt_set_source", "ndt_approx_voxel_filter", "ndt_eval", "ndt_eval_batch",
     "ndt_align", "ndt_align_batch", "ndt_best_of", "ndt_match_pairs",
-    "ndt_grid_blob_size", "ndt_grid_export", "ndt_grid_import",
+    "ndt_grid_blob_size", "ndt_grid_export", "ndt_grid_import", "ndt_replicate_grid", "ndt_best_of_multi", "ndt_trim",
     "ndt_launch_count", "ndt_last_kernel_ms", "ndt_synchronize",
 ]
 
@@ -97,12 +100,15 @@ def load() -> C.CDLL:
     L.ndt_eval.argtypes = [vp, C.POINTER(C.c_double), i32, C.POINTER(NdtEvalOut)]
     L.ndt_eval_batch.argtypes = [vp, vp, i64, i32, i32, vp]
     L.ndt_align.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(NdtResult)]
-    L.ndt_align_batch.argtypes = [vp, vp, i64, i32, vp]
+    L.ndt_align_batch.argtypes = [vp, vp, i64, i32, i32, vp]
     L.ndt_best_of.argtypes = [vp, vp, i64, i32, C.POINTER(i64), C.POINTER(NdtResult)]
     L.ndt_match_pairs.argtypes = [vp, vp, vp, vp, vp, vp, i64, C.c_float, i32, vp]
-    L.ndt_grid_blob_size.argtypes = [vp, C.POINTER(i64)]
-    L.ndt_grid_export.argtypes = [vp, vp, i64]
+    L.ndt_grid_blob_size.argtypes = [vp, i32, C.POINTER(i64)]
+    L.ndt_grid_export.argtypes = [vp, i32, vp, i64]
     L.ndt_grid_import.argtypes = [vp, vp, i64]
+    L.ndt_replicate_grid.argtypes = [C.POINTER(vp), i32, i32]
+    L.ndt_best_of_multi.argtypes = [C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), i32, C.POINTER(i32), C.POINTER(i64), C.POINTER(NdtResult)]
+    L.ndt_trim.argtypes = [vp]
     L.ndt_launch_count.argtypes = [vp, C.POINTER(i64)]
     L.ndt_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.ndt_synchronize.argtypes = [vp]
@@ -230,12 +236,15 @@ class Ndt:
         self._ck(self.L.ndt_align(self.h, g, C.byref(r)))
         return r
 
-    def align_batch(self, guesses, n=None, space=MEM_HOST, out=None):
+    def align_batch(self, guesses, n=None, space=MEM_HOST, out=None, want_fitness=None):
+        """want_fitness=None: small batches (n < 64) carry the fitness score, large ones are ranked by score only."""
         if n is None:
             n = guesses.shape[0]
         if out is None:
             out = np.zeros(n, RESULT_DTYPE)
-        self._ck(self.L.ndt_align_batch(self.h, _ptr(guesses), n, space, _ptr(out)))
+        if want_fitness is None:
+            want_fitness = n < 64
+        self._ck(self.L.ndt_align_batch(self.h, _ptr(guesses), n, space, int(bool(want_fitness)), _ptr(out)))
         return out
 
     def best_of(self, results, n=None, space=MEM_HOST):
@@ -253,13 +262,16 @@ class Ndt:
         return out
 
     # -- replication --
-    def grid_blob_size(self) -> int:
+    def grid_blob_size(self, flags=BLOB_POINTS) -> int:
         b = C.c_int64()
-        self._ck(self.L.ndt_grid_blob_size(self.h, C.byref(b)))
+        self._ck(self.L.ndt_grid_blob_size(self.h, flags, C.byref(b)))
         return b.value
 
-    def grid_export(self, dev_ptr: int, nbytes: int):
-        self._ck(self.L.ndt_grid_export(self.h, C.c_void_p(dev_ptr), nbytes))
+    def grid_export(self, dev_ptr: int, nbytes: int, flags=BLOB_POINTS):
+        self._ck(self.L.ndt_grid_export(self.h, flags, C.c_void_p(dev_ptr), nbytes))
+
+    def trim(self):
+        self._ck(self.L.ndt_trim(self.h))
 
     def grid_import(self, dev_ptr: int, nbytes: int):
         self._ck(self.L.ndt_grid_import(self.h, C.c_void_p(dev_ptr), nbytes))
@@ -277,3 +289,27 @@ class Ndt:
 
     def synchronize(self):
         self._ck(self.L.ndt_synchronize(self.h))
+
+
+def replicate_grid(handles, flags=BLOB_POINTS):
+    """ndt_replicate_grid: copy the grid of handles[0] to the other handles (peer copies over NVLink)."""
+    L = load()
+    arr = (C.c_void_p * len(handles))(*[h.h for h in handles])
+    rc = L.ndt_replicate_grid(arr, len(handles), flags)
+    if rc != 0:
+        msg = L.ndt_last_error(handles[0].h)
+        raise NdtError(f"ndt_replicate_grid failed ({rc}): {msg.decode() if msg else ''}")
+
+
+def best_of_multi(handles, device_ptrs, counts):
+    """ndt_best_of_multi: (handle index, result index, NdtResult) of the best converged result over all shards."""
+    L = load()
+    n = len(handles)
+    hs = (C.c_void_p * n)(*[h.h for h in handles])
+    ps = (C.c_void_p * n)(*[C.c_void_p(p) for p in device_ptrs])
+    cs = (C.c_int64 * n)(*counts)
+    bh, bi, best = C.c_int32(), C.c_int64(), NdtResult()
+    rc = L.ndt_best_of_multi(hs, ps, cs, n, C.byref(bh), C.byref(bi), C.byref(best))
+    if rc != 0:
+        raise NdtError(f"ndt_best_of_multi failed ({rc})")
+    return bh.value, bi.value, best

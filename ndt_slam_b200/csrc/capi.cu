@@ -4,6 +4,7 @@
 #include "ndt_host.h"
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -27,7 +28,7 @@ int ensure_pinned(Handle *h, size_t bytes) {
   if (bytes <= h->pinned_cap) return 0;
   if (h->pinned) cudaFreeHost(h->pinned);
   h->pinned = nullptr; h->pinned_cap = 0;
-  size_t want = 2 * bytes + 4096;
+  size_t want = h->pinned_cap == 0 ? ((bytes + 4095) & ~size_t(4095)) : (bytes + bytes / 2 + 4096);
   cudaError_t e = cudaMallocHost(&h->pinned, want);
   if (e != cudaSuccess) { set_err(h, NDT_ERR_CUDA, "cudaMallocHost", e); return 1; }
   h->pinned_cap = want;
@@ -37,33 +38,50 @@ int ensure_pinned(Handle *h, size_t bytes) {
 // header of the flat grid blob used for replication
 struct BlobHeader {
   uint64_t magic;
+  int32_t flags, reserved;
   GridDims gd;
   int32_t counters[CTR_COUNT];
   int64_t off_slot, off_cen, off_occ, off_recs, off_leaf_id, off_leaf_range, off_sorted, off_tgt, off_nn_range, off_nn_pts, total;
 };
-static constexpr uint64_t kBlobMagic = 0x4e44544232303042ull;  // "NDTB200B"
+static constexpr uint64_t kBlobMagic = 0x4e44544232303043ull;  // "NDTB200C"
 
 static inline int64_t align256(int64_t v) { return (v + 255) & ~int64_t(255); }
 
-static BlobHeader blob_layout(const Handle *h) {
+// byte sizes of the blob's sections for a grid of the given geometry / counters
+struct BlobSizes { int64_t slot, cen, occ, recs, leaf_id, leaf_range, sorted, tgt, nn_range, nn_pts; };
+static BlobSizes blob_sizes(const GridDims &gd, const int32_t *counters, int flags) {
+  const int64_t nc = gd.n_cells, nl = counters[CTR_LEAVES], nsl = counters[CTR_SLOTS], nt = gd.n_tgt;
+  const int64_t npad = nc > 0 ? (int64_t)(gd.div_x + 4) * (gd.div_y + 4) : 0;
+  const bool pts = (flags & NDT_BLOB_POINTS) != 0;
+  const int64_t ncf = (pts && gd.nn_f > 0) ? (int64_t)gd.nn_div_x * gd.nn_div_y : 0;
+  BlobSizes z{};
+  z.slot = npad * 4; z.cen = npad * 8; z.occ = npad > 0 ? ((npad + 31) / 32 + 1) * 4 : 0;
+  z.recs = nsl * (int64_t)sizeof(CellRec);
+  z.leaf_id = pts ? npad * 4 : 0; z.leaf_range = pts ? nl * 8 : 0; z.sorted = pts ? nt * 8 : 0;
+  z.tgt = pts ? nt * (int64_t)sizeof(float4) : 0;
+  z.nn_range = ncf * 8; z.nn_pts = ncf > 0 ? nt * 8 : 0;
+  return z;
+}
+
+static BlobHeader blob_layout(const Handle *h, int flags) {
   BlobHeader b{};
   b.magic = kBlobMagic;
+  b.flags = flags & NDT_BLOB_POINTS;
+  if (!h->grid_has_points) b.flags = 0;                 // a replica without points cannot hand any on
   b.gd = h->gd;
   std::memcpy(b.counters, h->h_counters, sizeof(b.counters));
-  const int64_t nc = h->gd.n_cells, nl = h->h_counters[CTR_LEAVES], nsl = h->h_counters[CTR_SLOTS], nt = h->gd.n_tgt;
+  const BlobSizes z = blob_sizes(h->gd, h->h_counters, b.flags);
   int64_t o = align256(sizeof(BlobHeader));
-  const int64_t npad = nc > 0 ? (int64_t)(h->gd.div_x + 4) * (h->gd.div_y + 4) : 0;
-  b.off_slot = o; o = align256(o + npad * 4);
-  b.off_cen = o; o = align256(o + npad * 8);
-  b.off_occ = o; o = align256(o + ((npad + 31) / 32 + 1) * 4);
-  b.off_recs = o; o = align256(o + nsl * (int64_t)sizeof(CellRec));
-  b.off_leaf_id = o; o = align256(o + npad * 4);
-  b.off_leaf_range = o; o = align256(o + nl * 8);
-  b.off_sorted = o; o = align256(o + nt * 8);
-  b.off_tgt = o; o = align256(o + nt * (int64_t)sizeof(float4));
-  const int64_t ncf = h->gd.nn_f > 0 ? (int64_t)h->gd.nn_div_x * h->gd.nn_div_y : 0;
-  b.off_nn_range = o; o = align256(o + ncf * 8);
-  b.off_nn_pts = o; o = align256(o + (ncf > 0 ? nt * 8 : 0));
+  b.off_slot = o; o = align256(o + z.slot);
+  b.off_cen = o; o = align256(o + z.cen);
+  b.off_occ = o; o = align256(o + z.occ);
+  b.off_recs = o; o = align256(o + z.recs);
+  b.off_leaf_id = o; o = align256(o + z.leaf_id);
+  b.off_leaf_range = o; o = align256(o + z.leaf_range);
+  b.off_sorted = o; o = align256(o + z.sorted);
+  b.off_tgt = o; o = align256(o + z.tgt);
+  b.off_nn_range = o; o = align256(o + z.nn_range);
+  b.off_nn_pts = o; o = align256(o + z.nn_pts);
   b.total = o;
   return b;
 }
@@ -94,6 +112,9 @@ int ndt_params_default(ndt_params *p) {
   p->quirks = NDT_QUIRKS_PCL_1_10;
   p->device = 0;
   p->stream = nullptr;
+  p->align_skip_fitness = 0;
+  p->pairs_schedule = NDT_PAIRS_AUTO;
+  p->pairs_batch_points = 0;
   return NDT_OK;
 }
 
@@ -211,6 +232,7 @@ int ndt_grid_readback(ndt_handle hh, int64_t cap, int32_t *cell_idx, int32_t *nr
                       double *icov4, float *centroid2, int64_t *n_out) {
   H_OR_FAIL(hh);
   if (!h->have_grid) return set_err(h, NDT_ERR_STATE, "ndt_grid_readback: no target set");
+  if (!h->have_readback) return set_err(h, NDT_ERR_STATE, "ndt_grid_readback: this grid was imported (ndt_grid_import / ndt_replicate_grid); the per-leaf read-back tables exist only on the handle that built it");
   const int64_t nl = h->h_counters[CTR_LEAVES];
   if (n_out) *n_out = nl;
   if (nl == 0 || cap <= 0) return NDT_OK;
@@ -279,6 +301,7 @@ int ndt_approx_voxel_filter(ndt_handle hh, const float *xyzw, int64_t n, float l
     return set_err(h, NDT_ERR_ARG, "ndt_approx_voxel_filter: bad argument");
   *n_out = 0;
   if (n == 0) return NDT_OK;
+  if (n > 0x7fffffffLL) return set_err(h, NDT_ERR_CAPACITY, "ndt_approx_voxel_filter: more than 2^31-1 points");
   cudaStream_t st = h->stream;
   const size_t bytes = (size_t)n * sizeof(float4);
   NDT_CUDA(h, h->scratch.reserve(2 * bytes + 256));
@@ -303,6 +326,9 @@ int ndt_approx_voxel_filter(ndt_handle hh, const float *xyzw, int64_t n, float l
   *n_out = m;
   return NDT_OK;
 }
+
+// the persistent batch kernels hand out jobs from an int32 counter in chunks: keep counter + chunk inside int32
+static constexpr int64_t kMaxBatchJobs = (int64_t)INT32_MAX - 4096;
 
 static int need_ready(Handle *h, const char *who) {
   if (!h->have_grid) return set_err(h, NDT_ERR_STATE, (std::string(who) + ": no target set").c_str());
@@ -340,6 +366,7 @@ int ndt_eval_batch(ndt_handle hh, const double *poses, int64_t n, int want_hessi
   if (n < 0 || (n > 0 && (!poses || !out14))) return set_err(h, NDT_ERR_ARG, "ndt_eval_batch: bad argument");
   if (int rc = need_ready(h, "ndt_eval_batch")) return rc;
   if (n == 0) return NDT_OK;
+  if (n > kMaxBatchJobs) return set_err(h, NDT_ERR_CAPACITY, "ndt_eval_batch: too many poses for the 32-bit job counter");
   cudaStream_t st = h->stream;
   if (memspace == NDT_MEM_DEVICE) {
     h->ms_pending = true;
@@ -370,8 +397,7 @@ int ndt_align(ndt_handle hh, const double guess[3], ndt_result *out) {
   double *d_guess = h->stage.as<double>();
   ndt_result *d_res = (ndt_result *)(d_guess + 4);
   NDT_CUDA(h, cudaMemcpyAsync(d_guess, hp, 24, cudaMemcpyHostToDevice, st));
-  static const bool dbg_nofit = getenv("NDT_B200_DEBUG_NO_FITNESS") != nullptr;   // timing breakdowns only
-  int rc = launch_align(h, d_guess, 1, d_res, !dbg_nofit);
+  int rc = launch_align(h, d_guess, 1, d_res, !h->prm.align_skip_fitness);
   if (rc) return rc;
   NDT_CUDA(h, cudaMemcpyAsync(hres, d_res, sizeof(ndt_result), cudaMemcpyDeviceToHost, st));
   NDT_CUDA(h, cudaStreamSynchronize(st));
@@ -381,15 +407,14 @@ int ndt_align(ndt_handle hh, const double guess[3], ndt_result *out) {
   return NDT_OK;
 }
 
-int ndt_align_batch(ndt_handle hh, const double *guesses, int64_t n, int memspace, ndt_result *results) {
+int ndt_align_batch(ndt_handle hh, const double *guesses, int64_t n, int memspace, int want_fitness_arg, ndt_result *results) {
   H_OR_FAIL(hh);
   if (n < 0 || (n > 0 && (!guesses || !results))) return set_err(h, NDT_ERR_ARG, "ndt_align_batch: bad argument");
   if (int rc = need_ready(h, "ndt_align_batch")) return rc;
   if (n == 0) return NDT_OK;
+  if (n > kMaxBatchJobs) return set_err(h, NDT_ERR_CAPACITY, "ndt_align_batch: too many guesses for the 32-bit job counter");
   cudaStream_t st = h->stream;
-  // batched results carry fitness only for small batches: an exact 1-NN for tens of thousands of
-  // far-off hypotheses is not part of ranking them (rank by score, then ndt_align the winner)
-  const bool want_fitness = n < 64;
+  const bool want_fitness = want_fitness_arg != 0;
   if (memspace == NDT_MEM_DEVICE) { h->ms_pending = true; return launch_align(h, guesses, n, results, want_fitness); }
   const size_t gbytes = (size_t)n * 3 * sizeof(double), rbytes = (size_t)n * sizeof(ndt_result);
   NDT_CUDA(h, h->io.reserve(gbytes + rbytes + 256));
@@ -453,6 +478,7 @@ int ndt_match_pairs(ndt_handle hh, const float *src_xyzw, const int64_t *src_off
   GridBuffers &gb = h->gb;
   GridDims &gd = h->gd;
   h->have_grid = false; h->have_src = false;          // the handle's single grid / source are overwritten
+  h->have_readback = false; h->grid_has_points = false;
   h->tgt_on_device = 0;
   gd = GridDims();
   gd.leaf = h->prm.resolution; gd.inv_leaf = 1.0f / gd.leaf; gd.r2 = (float)((double)gd.leaf * (double)gd.leaf);
@@ -471,8 +497,7 @@ int ndt_match_pairs(ndt_handle hh, const float *src_xyzw, const int64_t *src_off
   // Pairs go through the pipeline in batches of at most `batch_points` target points: bounds the size of the shared
   // tables for very large inputs. (Measured on C5: smaller, L2-sized batches are slower -- a pair is matched by one warp
   // in ~1 ms, so every batch ends with a latency tail; see DESIGN.md.)
-  int64_t batch_points = 32000000;                     // NDT_B200_PAIRS_BATCH_POINTS overrides (tuning / tests)
-  if (const char *e = getenv("NDT_B200_PAIRS_BATCH_POINTS")) { const int64_t v = atoll(e); if (v > 0) batch_points = v; }
+  const int64_t batch_points = h->prm.pairs_batch_points > 0 ? h->prm.pairs_batch_points : 32000000;
   if (h->timing) cudaEventRecord(h->ev0, st);
   std::vector<int64_t> off_stage;
   for (int64_t p0 = 0; p0 < n_pairs;) {
@@ -514,22 +539,21 @@ int ndt_match_pairs(ndt_handle hh, const float *src_xyzw, const int64_t *src_off
   return NDT_OK;
 }
 
-int ndt_grid_blob_size(ndt_handle hh, int64_t *bytes) {
+int ndt_grid_blob_size(ndt_handle hh, int flags, int64_t *bytes) {
   H_OR_FAIL(hh);
   if (!bytes) return NDT_ERR_ARG;
   if (!h->have_grid) return set_err(h, NDT_ERR_STATE, "ndt_grid_blob_size: no target set");
-  *bytes = blob_layout(h).total;
+  *bytes = blob_layout(h, flags).total;
   return NDT_OK;
 }
 
-int ndt_grid_export(ndt_handle hh, void *device_blob, int64_t bytes) {
+int ndt_grid_export(ndt_handle hh, int flags, void *device_blob, int64_t bytes) {
   H_OR_FAIL(hh);
   if (!h->have_grid) return set_err(h, NDT_ERR_STATE, "ndt_grid_export: no target set");
-  const BlobHeader b = blob_layout(h);
+  const BlobHeader b = blob_layout(h, flags);
   if (!device_blob || bytes < b.total) return set_err(h, NDT_ERR_ARG, "ndt_grid_export: blob too small");
   cudaStream_t st = h->stream;
   char *d = (char *)device_blob;
-  const int64_t nc = h->gd.n_cells, nl = h->h_counters[CTR_LEAVES], nsl = h->h_counters[CTR_SLOTS], nt = h->gd.n_tgt;
   if (ensure_pinned(h, sizeof(BlobHeader))) return NDT_ERR_CUDA;
   std::memcpy(h->pinned, &b, sizeof(b));
   NDT_CUDA(h, cudaMemcpyAsync(d, h->pinned, sizeof(b), cudaMemcpyHostToDevice, st));
@@ -537,20 +561,47 @@ int ndt_grid_export(ndt_handle hh, void *device_blob, int64_t bytes) {
     if (nbytes <= 0) return cudaSuccess;
     return cudaMemcpyAsync(d + off, src.p, (size_t)nbytes, cudaMemcpyDeviceToDevice, st);
   };
-  const int64_t npad = nc > 0 ? (int64_t)(h->gd.div_x + 4) * (h->gd.div_y + 4) : 0;
-  NDT_CUDA(h, cp(b.off_slot, h->gb.slot, npad * 4));
-  NDT_CUDA(h, cp(b.off_cen, h->gb.cen, npad * 8));
-  NDT_CUDA(h, cp(b.off_occ, h->gb.occ, npad > 0 ? ((npad + 31) / 32 + 1) * 4 : 0));
-  NDT_CUDA(h, cp(b.off_recs, h->gb.recs, nsl * (int64_t)sizeof(CellRec)));
-  NDT_CUDA(h, cp(b.off_leaf_id, h->gb.leaf_id, npad * 4));
-  NDT_CUDA(h, cp(b.off_leaf_range, h->gb.leaf_range, nl * 8));
-  NDT_CUDA(h, cp(b.off_sorted, h->gb.tgt_sorted, nt * 8));
-  NDT_CUDA(h, cp(b.off_tgt, h->gb.tgt, nt * (int64_t)sizeof(float4)));
-  const int64_t ncf = h->gd.nn_f > 0 ? (int64_t)h->gd.nn_div_x * h->gd.nn_div_y : 0;
-  NDT_CUDA(h, cp(b.off_nn_range, h->gb.nn_range, ncf * 8));
-  NDT_CUDA(h, cp(b.off_nn_pts, h->gb.nn_pts, ncf > 0 ? nt * 8 : 0));
+  const BlobSizes z = blob_sizes(b.gd, b.counters, b.flags);
+  NDT_CUDA(h, cp(b.off_slot, h->gb.slot, z.slot));
+  NDT_CUDA(h, cp(b.off_cen, h->gb.cen, z.cen));
+  NDT_CUDA(h, cp(b.off_occ, h->gb.occ, z.occ));
+  NDT_CUDA(h, cp(b.off_recs, h->gb.recs, z.recs));
+  NDT_CUDA(h, cp(b.off_leaf_id, h->gb.leaf_id, z.leaf_id));
+  NDT_CUDA(h, cp(b.off_leaf_range, h->gb.leaf_range, z.leaf_range));
+  NDT_CUDA(h, cp(b.off_sorted, h->gb.tgt_sorted, z.sorted));
+  NDT_CUDA(h, cp(b.off_tgt, h->gb.tgt, z.tgt));
+  NDT_CUDA(h, cp(b.off_nn_range, h->gb.nn_range, z.nn_range));
+  NDT_CUDA(h, cp(b.off_nn_pts, h->gb.nn_pts, z.nn_pts));
   NDT_CUDA(h, cudaStreamSynchronize(st));
   return NDT_OK;
+}
+
+// A blob comes from another process / GPU: nothing in its header is trusted. Geometry and counters must be plausible and
+// mutually consistent, every section must lie inside [header, total] in layout order, total must fit the buffer.
+static const char *blob_check(const Handle *h, const BlobHeader &b, int64_t bytes) {
+  if (b.magic != kBlobMagic) return "not a grid blob (magic)";
+  if (b.flags & ~NDT_BLOB_POINTS) return "unknown flags";
+  const GridDims &gd = b.gd;
+  if (!(gd.leaf == h->prm.resolution)) return "the blob's cell size differs from this handle's resolution";
+  if (gd.div_x < 0 || gd.div_y < 0 || gd.n_tgt < 0 || gd.n_tgt > (int64_t)INT32_MAX) return "bad geometry";
+  if (gd.n_cells != (int64_t)gd.div_x * gd.div_y) return "bad cell count";
+  if ((int64_t)(gd.div_x + 4) * (gd.div_y + 4) > (int64_t)INT32_MAX) return "grid too large";
+  const int64_t npad = gd.n_cells > 0 ? (int64_t)(gd.div_x + 4) * (gd.div_y + 4) : 0;
+  const int64_t nl = b.counters[CTR_LEAVES], nsl = b.counters[CTR_SLOTS];
+  if (nl < 0 || nsl < 0 || nsl > nl || nl > npad || nl > gd.n_tgt) return "bad leaf / slot counters";
+  if (gd.nn_f < 0 || gd.nn_f > 64 || (gd.nn_f > 0 && (gd.nn_div_x <= 0 || gd.nn_div_y <= 0 ||
+      (int64_t)gd.nn_div_x * gd.nn_div_y > (int64_t)64 * 1024 * 1024))) return "bad 1-NN lattice";
+  const BlobSizes z = blob_sizes(gd, b.counters, b.flags);
+  const int64_t off[10] = {b.off_slot, b.off_cen, b.off_occ, b.off_recs, b.off_leaf_id, b.off_leaf_range, b.off_sorted,
+                           b.off_tgt, b.off_nn_range, b.off_nn_pts};
+  const int64_t len[10] = {z.slot, z.cen, z.occ, z.recs, z.leaf_id, z.leaf_range, z.sorted, z.tgt, z.nn_range, z.nn_pts};
+  int64_t lo = (int64_t)sizeof(BlobHeader);
+  for (int k = 0; k < 10; ++k) {
+    if (off[k] < lo || (off[k] & 255) || off[k] > b.total || len[k] > b.total - off[k]) return "section offsets out of range";
+    lo = off[k] + len[k];
+  }
+  if (b.total > bytes) return "blob truncated";
+  return nullptr;
 }
 
 int ndt_grid_import(ndt_handle hh, const void *device_blob, int64_t bytes) {
@@ -560,32 +611,97 @@ int ndt_grid_import(ndt_handle hh, const void *device_blob, int64_t bytes) {
   BlobHeader b{};
   NDT_CUDA(h, cudaMemcpyAsync(&b, device_blob, sizeof(b), cudaMemcpyDeviceToHost, st));
   NDT_CUDA(h, cudaStreamSynchronize(st));
-  if (b.magic != kBlobMagic || b.total > bytes) return set_err(h, NDT_ERR_ARG, "ndt_grid_import: not a grid blob");
-  h->have_grid = false;
+  if (const char *why = blob_check(h, b, bytes)) return set_err(h, NDT_ERR_ARG, (std::string("ndt_grid_import: ") + why).c_str());
+  h->have_grid = false; h->have_readback = false; h->grid_has_points = false;
   h->tgt_on_device = 0;
   h->gd = b.gd;
   std::memcpy(h->h_counters, b.counters, sizeof(b.counters));
-  const int64_t nc = h->gd.n_cells, nl = h->h_counters[CTR_LEAVES], nsl = h->h_counters[CTR_SLOTS], nt = h->gd.n_tgt;
   const char *d = (const char *)device_blob;
   auto take = [&](DevBuf &dst, int64_t off, int64_t nbytes) -> cudaError_t {
     cudaError_t e = dst.reserve((size_t)std::max<int64_t>(nbytes, 16));
     if (e != cudaSuccess || nbytes <= 0) return e;
     return cudaMemcpyAsync(dst.p, d + off, (size_t)nbytes, cudaMemcpyDeviceToDevice, st);
   };
-  const int64_t npad = nc > 0 ? (int64_t)(h->gd.div_x + 4) * (h->gd.div_y + 4) : 0;
-  NDT_CUDA(h, take(h->gb.slot, b.off_slot, npad * 4));
-  NDT_CUDA(h, take(h->gb.cen, b.off_cen, npad * 8));
-  NDT_CUDA(h, take(h->gb.occ, b.off_occ, npad > 0 ? ((npad + 31) / 32 + 1) * 4 : 0));
-  NDT_CUDA(h, take(h->gb.recs, b.off_recs, nsl * (int64_t)sizeof(CellRec)));
-  NDT_CUDA(h, take(h->gb.leaf_id, b.off_leaf_id, npad * 4));
-  NDT_CUDA(h, take(h->gb.leaf_range, b.off_leaf_range, nl * 8));
-  NDT_CUDA(h, take(h->gb.tgt_sorted, b.off_sorted, nt * 8));
-  NDT_CUDA(h, take(h->gb.tgt, b.off_tgt, nt * (int64_t)sizeof(float4)));
-  const int64_t ncf = h->gd.nn_f > 0 ? (int64_t)h->gd.nn_div_x * h->gd.nn_div_y : 0;
-  NDT_CUDA(h, take(h->gb.nn_range, b.off_nn_range, ncf * 8));
-  NDT_CUDA(h, take(h->gb.nn_pts, b.off_nn_pts, ncf > 0 ? nt * 8 : 0));
+  const BlobSizes z = blob_sizes(b.gd, b.counters, b.flags);
+  if (z.slot == 0) {
+    // empty grid: the 4 x 4 all-empty padded table ndt_set_target builds for an empty target
+    NDT_CUDA(h, h->gb.occ.reserve(64)); NDT_CUDA(h, h->gb.slot.reserve(64)); NDT_CUDA(h, h->gb.cen.reserve(128)); NDT_CUDA(h, h->gb.leaf_id.reserve(64));
+    NDT_CUDA(h, cudaMemsetAsync(h->gb.occ.p, 0, 64, st)); NDT_CUDA(h, cudaMemsetAsync(h->gb.slot.p, 0xff, 64, st));
+    NDT_CUDA(h, cudaMemsetAsync(h->gb.cen.p, 0xff, 128, st)); NDT_CUDA(h, cudaMemsetAsync(h->gb.leaf_id.p, 0, 64, st));
+  }
+  NDT_CUDA(h, take(h->gb.slot, b.off_slot, z.slot));
+  NDT_CUDA(h, take(h->gb.cen, b.off_cen, z.cen));
+  NDT_CUDA(h, take(h->gb.occ, b.off_occ, z.occ));
+  NDT_CUDA(h, take(h->gb.recs, b.off_recs, z.recs));
+  NDT_CUDA(h, take(h->gb.leaf_id, b.off_leaf_id, z.leaf_id));
+  NDT_CUDA(h, take(h->gb.leaf_range, b.off_leaf_range, z.leaf_range));
+  NDT_CUDA(h, take(h->gb.tgt_sorted, b.off_sorted, z.sorted));
+  NDT_CUDA(h, take(h->gb.tgt, b.off_tgt, z.tgt));
+  NDT_CUDA(h, take(h->gb.nn_range, b.off_nn_range, z.nn_range));
+  NDT_CUDA(h, take(h->gb.nn_pts, b.off_nn_pts, z.nn_pts));
   NDT_CUDA(h, cudaStreamSynchronize(st));
   h->have_grid = true;
+  h->grid_has_points = (b.flags & NDT_BLOB_POINTS) != 0;
+  return NDT_OK;
+}
+
+int ndt_replicate_grid(const ndt_handle *handles, int n_handles, int flags) {
+  if (!handles || n_handles < 1 || !handles[0]) return NDT_ERR_ARG;
+  Handle *h0 = reinterpret_cast<Handle *>(handles[0]);
+  for (int k = 1; k < n_handles; ++k) {
+    if (!handles[k] || handles[k] == handles[0]) return set_err(h0, NDT_ERR_ARG, "ndt_replicate_grid: null or repeated handle");
+    for (int j = 1; j < k; ++j) if (handles[j] == handles[k]) return set_err(h0, NDT_ERR_ARG, "ndt_replicate_grid: repeated handle");
+  }
+  if (!h0->have_grid) return set_err(h0, NDT_ERR_STATE, "ndt_replicate_grid: handles[0] has no target set");
+  if (n_handles == 1) return NDT_OK;
+  if (cudaSetDevice(h0->device) != cudaSuccess) return set_err(h0, NDT_ERR_CUDA, "cudaSetDevice");
+  const int64_t total = blob_layout(h0, flags).total;
+  // the source blob lives in its own allocation: scratch buffers are reused by other calls on the handle
+  void *src_blob = nullptr;
+  NDT_CUDA(h0, cudaMalloc(&src_blob, (size_t)total));
+  int rc = ndt_grid_export(handles[0], flags, src_blob, total);
+  for (int k = 1; k < n_handles && rc == NDT_OK; ++k) {
+    Handle *hk = reinterpret_cast<Handle *>(handles[k]);
+    if (cudaSetDevice(hk->device) != cudaSuccess) { rc = set_err(hk, NDT_ERR_CUDA, "cudaSetDevice"); break; }
+    void *dst_blob = src_blob;
+    if (hk->device != h0->device) {
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, hk->device, h0->device);
+      if (can) { cudaError_t e = cudaDeviceEnablePeerAccess(h0->device, 0); if (e != cudaSuccess) (void)cudaGetLastError(); }   // already enabled is fine
+      cudaError_t e = cudaMalloc(&dst_blob, (size_t)total);
+      if (e == cudaSuccess) e = cudaMemcpyPeerAsync(dst_blob, hk->device, src_blob, h0->device, (size_t)total, hk->stream);   // NVLink when peers, staged otherwise
+      if (e == cudaSuccess) e = cudaStreamSynchronize(hk->stream);
+      if (e != cudaSuccess) { rc = set_err(hk, NDT_ERR_CUDA, "ndt_replicate_grid: peer copy", e); if (dst_blob != src_blob) cudaFree(dst_blob); break; }
+    }
+    rc = ndt_grid_import(handles[k], dst_blob, total);
+    if (rc != NDT_OK) set_err(h0, rc, (std::string("ndt_replicate_grid: import failed: ") + hk->err).c_str());
+    if (dst_blob != src_blob) cudaFree(dst_blob);
+  }
+  cudaSetDevice(h0->device);
+  cudaFree(src_blob);
+  return rc;
+}
+
+int ndt_best_of_multi(const ndt_handle *handles, const ndt_result *const *device_results, const int64_t *counts,
+                      int n_handles, int *best_handle, int64_t *best_index, ndt_result *best) {
+  if (!handles || !device_results || !counts || n_handles < 1 || !best_handle || !best_index || !best) return NDT_ERR_ARG;
+  *best_handle = -1; *best_index = -1;
+  for (int k = 0; k < n_handles; ++k) {
+    if (!handles[k]) return NDT_ERR_ARG;
+    if (counts[k] <= 0) continue;
+    int64_t bi = -1;
+    ndt_result r;
+    const int rc = ndt_best_of(handles[k], device_results[k], counts[k], NDT_MEM_DEVICE, &bi, &r);
+    if (rc != NDT_OK) return rc;
+    if (bi >= 0 && (*best_handle < 0 || r.score > best->score)) { *best_handle = k; *best_index = bi; *best = r; }
+  }
+  return NDT_OK;
+}
+
+int ndt_trim(ndt_handle hh) {
+  H_OR_FAIL(hh);
+  NDT_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->pool) NDT_CUDA(h, cudaMemPoolTrimTo(h->pool, 0));
   return NDT_OK;
 }
 

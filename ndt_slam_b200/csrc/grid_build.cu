@@ -815,7 +815,7 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace, int64_t n_
   GridBuffers &gb = h->gb;
   GridDims &gd = h->gd;
   cudaStream_t st = h->stream;
-  h->have_grid = false;
+  h->have_grid = false; h->have_readback = false; h->grid_has_points = false;
   // n_same: the caller promises that the first n_same points equal the first n_same points of the previous target of
   // this handle (a map that only changed at its end). They are still on the device: only the rest is staged and copied.
   if (n_same < 0 || n_same > n || n_same > h->tgt_on_device || memspace != NDT_MEM_HOST) n_same = 0;
@@ -906,7 +906,7 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace, int64_t n_
     NDT_CUDA(h, gb.occ.reserve(64)); NDT_CUDA(h, gb.slot.reserve(64)); NDT_CUDA(h, gb.cen.reserve(128)); NDT_CUDA(h, gb.leaf_id.reserve(64));
     NDT_CUDA(h, cudaMemsetAsync(gb.occ.p, 0, 64, st)); NDT_CUDA(h, cudaMemsetAsync(gb.slot.p, 0xff, 64, st));
     NDT_CUDA(h, cudaMemsetAsync(gb.cen.p, 0xff, 128, st)); NDT_CUDA(h, cudaMemsetAsync(gb.leaf_id.p, 0, 64, st));
-    h->have_grid = true;
+    h->have_grid = true; h->have_readback = true; h->grid_has_points = true;
     if (h->timing) { cudaEventRecord(h->ev1, st); }
     NDT_CUDA(h, cudaStreamSynchronize(st));
     if (h->timing) cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
@@ -961,7 +961,7 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace, int64_t n_
     cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
   }
   NDT_CUDA(h, cudaGetLastError());
-  h->have_grid = true;
+  h->have_grid = true; h->have_readback = true; h->grid_has_points = true;
   h->tgt_on_device = n;
   return NDT_OK;
 }

@@ -795,7 +795,7 @@ int launch_align(Handle *h, const double *d_guesses, int64_t n, ndt_result *d_re
   const int ns = (int)h->ns;
   cudaStream_t st = h->stream;
   const GridView G = grid_view(h);
-  const MatchParams mp = match_params(h, want_fitness);
+  const MatchParams mp = match_params(h, want_fitness && h->grid_has_points);   // a replica imported without points reports fitness = NaN
   const float4 *src = h->src.as<float4>();
   int32_t *ctr = h->gb.counters.as<int32_t>();
   if (h->timing) cudaEventRecord(h->ev0, st);
@@ -891,9 +891,8 @@ int launch_align_pairs(Handle *h, const float4 *d_src, const double *d_guesses, 
   NDT_CUDA(h, cudaMemsetAsync(ctr + CTR_JOB, 0, sizeof(int32_t), st));
   int64_t grid = (int64_t)h->sm_count * NDT_PAIRS_KERNEL_MIN_CTAS;
   grid = std::min<int64_t>(grid, (n_pairs + 7) / 8);
-  int64_t block_below = NDT_PAIRS_BLOCK_BELOW;          // NDT_B200_PAIRS_BLOCK_BELOW overrides (tuning / tests)
-  if (const char *e = getenv("NDT_B200_PAIRS_BLOCK_BELOW")) block_below = atoll(e);
-  if (n_pairs < block_below) {
+  const bool cta_per_pair = h->prm.pairs_schedule == NDT_PAIRS_CTA || (h->prm.pairs_schedule == NDT_PAIRS_AUTO && n_pairs < NDT_PAIRS_BLOCK_BELOW);
+  if (cta_per_pair) {
     grid = std::min<int64_t>((int64_t)h->sm_count * NDT_PAIRS_KERNEL_MIN_CTAS, n_pairs);
     NDT_CUDA(h, cudaFuncSetAttribute(k_align_pairs_block, cudaFuncAttributeMaxDynamicSharedMemorySize, QUEUE_BYTES + PB_STAGE_BYTES));
     k_align_pairs_block<<<(unsigned)grid, 256, QUEUE_BYTES + PB_STAGE_BYTES, st>>>(G, mp, h->gb.dims.as<PairDims>(), d_src, d_guesses, d_results,

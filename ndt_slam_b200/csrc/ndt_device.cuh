@@ -212,9 +212,9 @@ __device__ __forceinline__ void hit_path(const int MODE, const RecL &rec_at, con
   }
 #pragma unroll
   for (int u = 0; u < NH; ++u) {
-    sc[u] = valid[u] ? -d1 * ex[u] : 0.0;            // the score term is added before the guard
     const double t = d2 * ex[u];
-    const bool ok = valid[u] && !(t > 1.0 || t < 0.0 || t != t);
+    const bool ok = valid[u] && !(t > 1.0 || t < 0.0 || t != t);   // updateDerivatives returns 0 for a rejected hit: no score term either
+    sc[u] = ok ? -d1 * ex[u] : 0.0;
     ex[u] = ok ? t * d1 : 0.0;
     dx[u] = ok ? dx[u] : 0.0; dy[u] = ok ? dy[u] : 0.0;      // keep a rejected term finite: its contributions are exact zeros
   }

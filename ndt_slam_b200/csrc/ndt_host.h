@@ -23,7 +23,9 @@ struct DevBuf {
   // keep > 0: the first `keep` bytes survive a reallocation (stream-ordered copy)
   cudaError_t reserve(size_t bytes, size_t keep = 0, cudaStream_t /*unused*/ = nullptr) {
     if (bytes <= cap) return cudaSuccess;
-    const size_t want = 2 * bytes + 4096;     // geometric growth
+    // first allocation: what was asked for (a handle has ~30 tables; doubling every one of them doubled the footprint of
+    // a C3-size grid for nothing); regrowth: geometric, so a map that grows scan by scan reallocates O(log n) times
+    const size_t want = cap == 0 ? ((bytes + 4095) & ~size_t(4095)) : (bytes + bytes / 2 + 4096);
     void *q = nullptr;
     cudaError_t e = pool ? cudaMallocFromPoolAsync(&q, want, pool, st) : cudaMalloc(&q, want);
     if (e != cudaSuccess) return e;
@@ -102,6 +104,8 @@ struct Handle {
   GridBuffers gb;
   GridDims gd;
   bool have_grid = false;
+  bool have_readback = false;    // the per-leaf read-back tables belong to this grid (false on an imported replica)
+  bool grid_has_points = false;  // target points + 1-NN buckets present (false on a replica imported without NDT_BLOB_POINTS)
   int64_t tgt_on_device = 0;     // leading points of gb.tgt that still hold the last ndt_set_target cloud (0: unknown)
   int32_t h_counters[CTR_COUNT] = {0};   // host copy after the last build
 

@@ -5,12 +5,18 @@
 #include <iostream>
 #include <vector>
 
-#include "ndt_slam/FrontEnd.h"
 #include "ndt_slam/PointCloudMap.h"
 #include "ndt_slam/PoseEstimator.h"
 #include "ndt_slam/PoseFuser.h"
 #include "ndt_slam/ScanMatcher.h"
 #include "ndt_slam/ScanPointResampler.h"
+// FrontEnd keeps its ScanMatcher private (include/ndt_slam/FrontEnd.h:24). The shim -- and only the shim: the
+// reference sources are compiled untouched -- opens the class so it can zero ScanMatcher::lastCov, which the
+// reference declares (ScanMatcher.h:42) and reads (ScanMatcher.cpp:61 / 64) before anything writes it. Every header
+// FrontEnd.h pulls in is already included above, so the macro touches nothing but the FrontEnd class itself.
+#define private public
+#include "ndt_slam/FrontEnd.h"
+#undef private
 
 namespace {
 struct Quiet {   // PoseFuser::fusePose prints matrices to std::cout unconditionally (PoseFuser.cpp:14-15, 27-28)
@@ -34,7 +40,13 @@ pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_of(const float *xyzw, int64_t n) {
   for (int64_t i = 0; i < n; ++i) { c->points[i].x = xyzw[4 * i]; c->points[i].y = xyzw[4 * i + 1]; c->points[i].z = xyzw[4 * i + 2]; }
   return c;
 }
-struct Slam { PointCloudMap pcmap; FrontEnd fe; PoseEstimator estim; Slam() { fe.setPoseEstimator(&estim); fe.setPointCloudMap(&pcmap); } };
+struct Slam {
+  PointCloudMap pcmap; FrontEnd fe; PoseEstimator estim;
+  Slam() {
+    fe.setPoseEstimator(&estim); fe.setPointCloudMap(&pcmap);
+    fe.smat.lastCov.setZero();      // uninitialised in the reference: a run is only reproducible with a defined value
+  }
+};
 }  // namespace
 
 extern "C" {

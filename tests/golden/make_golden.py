@@ -70,8 +70,10 @@ def host_vectors():
                         layout="last3 motion3 pred3 est3 lastCov9 Q9 fused3 cov9 odoCov9 cur3 calMotion3 (delTime 0.5, coeVel 0.1, coeOmega 0.5)")
 
 
-def sequence_vectors(n_scans=60):
-    """Short C2-style run through the reference FrontEnd (FrontEnd.cpp / ScanMatcher.cpp / PointCloudMap.cpp)."""
+def sequence_vectors(n_scans=320):
+    """C2-style run through the reference FrontEnd (FrontEnd.cpp / ScanMatcher.cpp / PointCloudMap.cpp), long enough to
+    cross a sub-map split (sepThre 10 m at 0.05 m per scan). oracle/ref_shim.cpp zeroes ScanMatcher::lastCov, which the
+    reference leaves uninitialised, so this run is reproducible (tests/test_ref_crosscheck.py checks that)."""
     ra.set_params(Resolution=0.5)
     seq = synth.c2_sequence(seed=2, n_scans=2000)
     slam = ra.RefSlam()
@@ -79,8 +81,8 @@ def sequence_vectors(n_scans=60):
     odo_deg[:, 2] = (odo_deg[:, 2] + 180.0) % 360.0 - 180.0
     for i in range(n_scans):
         slam.process(i, odo_deg[i], seq["scans"][i])
-    np.savez_compressed(OUT / "c2_first60.npz", poses=slam.poses(), odo_deg=odo_deg[:n_scans],
-                        local_map=slam.local_map(),
+    np.savez_compressed(OUT / f"c2_first{n_scans}.npz", poses=slam.poses(), odo_deg=odo_deg[:n_scans],
+                        local_map=slam.local_map()[:, :2].copy(), n_global=slam.global_map().shape[0],
                         n_submaps=slam.submaps(), truth=seq["traj"][:n_scans])
 
 

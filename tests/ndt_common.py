@@ -6,6 +6,9 @@ import numpy as np
 from ndt_slam_b200 import capi, synth
 from oracle import oracle_api as oa
 
+from pathlib import Path
+
+GOLD = Path(__file__).resolve().parent / "golden"
 LAUNCH = dict(space=0.05, space_thre=0.25, leaf=0.05, trans_eps=0.01, step_size=0.1, max_iter=35)
 
 
@@ -47,3 +50,60 @@ def rel_err(a, b):
     a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
     scale = max(np.max(np.abs(b)), 1e-300)
     return float(np.max(np.abs(a - b)) / scale)
+
+
+def oracle_align_many(prm, tgt, src, guesses, want_fitness=False, threads=None):
+    """Full oracle matches of every guess on host threads (one oracle per thread; ctypes drops the GIL)."""
+    import os
+    import threading
+    from concurrent.futures import ThreadPoolExecutor
+
+    guesses = np.asarray(guesses, dtype=np.float64)
+    threads = threads or min(os.cpu_count() or 1, 32)
+    out = [None] * guesses.shape[0]
+    todo = list(range(guesses.shape[0]))
+    lock = threading.Lock()
+
+    def work(_):
+        o = oa.Oracle(prm)
+        o.set_target(tgt); o.set_source(src); o.want_fitness(want_fitness)
+        while True:
+            with lock:
+                if not todo:
+                    return
+                ids = [todo.pop() for _ in range(min(8, len(todo)))]
+            for i in ids:
+                out[i] = o.align(guesses[i])
+
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(work, range(threads)))
+    return out
+
+
+def oracle_eval_many(prm, tgt, src, poses, want_hessian=True, threads=None):
+    """Oracle objective at every pose -> (n, 14) like ndt_eval_batch: score, g[3], H[9], n_pairs."""
+    import os
+    import threading
+    from concurrent.futures import ThreadPoolExecutor
+
+    poses = np.asarray(poses, dtype=np.float64)
+    threads = threads or min(os.cpu_count() or 1, 32)
+    out = np.zeros((poses.shape[0], 14))
+    todo = list(range(poses.shape[0]))
+    lock = threading.Lock()
+
+    def work(_):
+        o = oa.Oracle(prm)
+        o.set_target(tgt); o.set_source(src)
+        while True:
+            with lock:
+                if not todo:
+                    return
+                ids = [todo.pop() for _ in range(min(16, len(todo)))]
+            for i in ids:
+                e = o.eval(poses[i], want_hessian)
+                out[i, 0] = e.score; out[i, 1:4] = e.grad; out[i, 4:13] = e.hess; out[i, 13] = e.n_pairs
+
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(work, range(threads)))
+    return out

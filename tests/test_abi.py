@@ -40,12 +40,34 @@ def test_struct_layouts_match_header():
     assert C.sizeof(capi.NdtGridInfo) == 40
 
 
+def test_pod_layouts_match_what_a_c_compiler_sees(tmp_path):
+    """gcc compiles include/ndt_b200.h as plain C and prints sizeof / offsetof of every POD: the ctypes views must agree."""
+    import subprocess
+    fields = {"ndt_params": capi.NdtParams, "ndt_result": capi.NdtResult, "ndt_eval_out": capi.NdtEvalOut, "ndt_grid_info": capi.NdtGridInfo}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "ndt_b200.h"', 'int main(void) {']
+    for cname, cls in fields.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for f, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{f} %zu\\n", offsetof({cname}, {f}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in fields.items():
+        assert int(out[cname]) == C.sizeof(cls), cname
+        for f, _ in cls._fields_:
+            assert int(out[f"{cname}.{f}"]) == getattr(cls, f).offset, (cname, f)
+
+
 def test_default_params_are_the_reference_defaults():
     """PoseEstimator.h:63-64 C++ defaults + PCL internals."""
     p = capi.default_params()
     assert (p.resolution, p.step_size, p.trans_eps, p.max_iter) == (1.0, 0.1, 0.01, 35)
     assert (p.outlier_ratio, p.min_points, p.eig_mult) == (0.55, 6, 0.01)
     assert p.quirks == capi.QUIRKS_PCL_1_10
+    assert (p.align_skip_fitness, p.pairs_schedule, p.pairs_batch_points) == (0, capi.PAIRS_AUTO, 0)
 
 
 def test_sass_is_sm100a_only():

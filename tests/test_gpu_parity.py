@@ -297,6 +297,71 @@ def test_grid_export_import_roundtrip(c1):
     g2.set_source(pb["src"])
     a, b = g2.align(pb["guess"]), g.align(pb["guess"])
     assert bytes(a) == bytes(b)        # bit-identical result from the replicated grid
+    # the per-leaf read-back tables are not replicated: a defined error, not a read of stale buffers
+    with pytest.raises(capi.NdtError, match="imported"):
+        g2.grid_readback()
+    # a replica without the target points: same match, no fitness; less than half the bytes
+    nb2 = g.grid_blob_size(flags=0)
+    assert nb2 < 0.6 * nbytes
+    g.grid_export(blob.data_ptr(), nb2, flags=0)
+    g3 = capi.Ndt(common.params(resolution=0.5))
+    g3.grid_import(blob.data_ptr(), nb2)
+    g3.set_source(pb["src"])
+    c = g3.align(pb["guess"])
+    assert list(c.pose) == list(b.pose) and c.score == b.score and c.evals == b.evals and np.isnan(c.fitness)
+    # ndt_replicate_grid (peer copy between handles; same device here) + ndt_best_of_multi
+    g4, g5 = capi.Ndt(common.params(resolution=0.5)), capi.Ndt(common.params(resolution=0.5))
+    capi.replicate_grid([g, g4, g5])
+    rng = synth.rng_for(61)
+    guesses = pb["guess"] + rng.normal(0, [0.1, 0.1, 0.02], size=(192, 3))
+    outs, ptrs = [], []
+    for k, gg in enumerate((g, g4, g5)):
+        gg.set_source(pb["src"])
+        d_g = torch.from_numpy(np.ascontiguousarray(guesses[64 * k:64 * k + 64])).cuda()
+        d_r = torch.zeros(64 * capi.RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+        gg.align_batch(d_g.data_ptr(), n=64, space=capi.MEM_DEVICE, out=d_r.data_ptr())
+        gg.synchronize()
+        outs.append(d_r); ptrs.append(d_r.data_ptr())
+    allr = np.concatenate([np.frombuffer(t.cpu().numpy().tobytes(), dtype=capi.RESULT_DTYPE) for t in outs])
+    ref = g.align_batch(np.ascontiguousarray(guesses))
+    assert np.array_equal(allr["pose"], ref["pose"]) and np.array_equal(allr["score"], ref["score"])
+    bh, bi, best = capi.best_of_multi([g, g4, g5], ptrs, [64, 64, 64])
+    conv = allr["converged"] == 1
+    k = int(np.argmax(np.where(conv, allr["score"], -np.inf)))
+    assert (bh, bi) == (k // 64, k % 64) and best.score == allr["score"][k]
+
+
+def test_grid_import_rejects_bad_blobs(c1):
+    """Nothing in a blob header is trusted: wrong magic, truncated, offsets out of range, another resolution."""
+    pb, g, o = c1
+    nbytes = g.grid_blob_size()
+    blob = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    g.grid_export(blob.data_ptr(), nbytes)
+    g2 = capi.Ndt(common.params(resolution=0.5))
+    with pytest.raises(capi.NdtError, match="truncated"):
+        g2.grid_import(blob.data_ptr(), nbytes - 4096)
+    bad = blob.clone(); bad[0] ^= 0xFF
+    with pytest.raises(capi.NdtError, match="magic"):
+        g2.grid_import(bad.data_ptr(), nbytes)
+    hdr = blob[:512].cpu().numpy().copy()
+    # find the off_recs field: corrupt every int64 of the offset table in turn, each must be rejected or harmless
+    rejected = 0
+    words = hdr.view(np.int64)
+    for w in range(words.shape[0]):
+        if 256 <= words[w] <= nbytes and words[w] % 256 == 0:        # looks like a section offset / the total
+            bad = blob.clone()
+            h2 = hdr.copy(); h2.view(np.int64)[w] = nbytes + 256 * (w + 1)
+            bad[:512] = torch.from_numpy(h2).cuda()
+            try:
+                g2.grid_import(bad.data_ptr(), nbytes)
+            except capi.NdtError:
+                rejected += 1
+    assert rejected >= 8
+    g3 = capi.Ndt(common.params(resolution=1.0))
+    with pytest.raises(capi.NdtError, match="resolution"):
+        g3.grid_import(blob.data_ptr(), nbytes)
+    with pytest.raises(capi.NdtError):
+        capi.Ndt(common.params(resolution=0.5)).grid_blob_size()          # no target set
 
 
 def test_run_to_run_determinism(c1):
@@ -417,21 +482,13 @@ def test_match_pairs_parity_with_oracle_per_pair():
         assert np.allclose(a.pose, res[k]["pose"], rtol=0, atol=1e-9) and a.score == pytest.approx(res[k]["score"], rel=1e-10)
         assert a.iters == res[k]["iters"] and a.evals == res[k]["evals"]
     # the warp-per-pair schedule (used for large batches) agrees with the CTA-per-pair one used above
-    import os
-    os.environ["NDT_B200_PAIRS_BLOCK_BELOW"] = "0"
-    try:
-        g_w = capi.Ndt(prm)
-        res_w = g_w.match_pairs(src, so, tgt, to, guesses, n, source_leaf=common.LAUNCH["leaf"])
-    finally:
-        del os.environ["NDT_B200_PAIRS_BLOCK_BELOW"]
+    g_w = capi.Ndt(common.params(resolution=0.5, pairs_schedule=capi.PAIRS_WARP))
+    res_w = g_w.match_pairs(src, so, tgt, to, guesses, n, source_leaf=common.LAUNCH["leaf"])
     assert np.array_equal(res_w["iters"], res["iters"]) and np.array_equal(res_w["evals"], res["evals"])
     assert np.allclose(res_w["pose"], res["pose"], rtol=0, atol=1e-9)
     # small batches (several grid-build + match rounds inside one call) give the same bytes
-    os.environ["NDT_B200_PAIRS_BATCH_POINTS"] = "9000"
-    try:
-        res_b = g.match_pairs(src, so, tgt, to, guesses, n, source_leaf=common.LAUNCH["leaf"])
-    finally:
-        del os.environ["NDT_B200_PAIRS_BATCH_POINTS"]
+    g_b = capi.Ndt(common.params(resolution=0.5, pairs_batch_points=9000))
+    res_b = g_b.match_pairs(src, so, tgt, to, guesses, n, source_leaf=common.LAUNCH["leaf"])
     assert np.array_equal(res_b["pose"], res["pose"]) and np.array_equal(res_b["fitness"], res["fitness"])
     # device-resident inputs / outputs give the same bytes
     d_src, d_tgt = torch.from_numpy(src).cuda(), torch.from_numpy(tgt).cuda()

@@ -36,30 +36,37 @@ def _odo_deg(seq, n):
 
 
 def test_frontend_sequence_matches_reference_frontend():
-    """60 scans through FrontEnd::process: poses vs the reference FrontEnd (compiled from its own sources)."""
-    z = np.load(GOLD / "c2_first60.npz")
+    """320 scans through FrontEnd::process (crossing the sub-map split at sepThre = 10 m): poses vs the reference
+    FrontEnd compiled from its own sources. The reference run is reproducible (oracle/ref_shim.cpp zeroes
+    ScanMatcher::lastCov; tests/test_ref_crosscheck.py), so the fixture is not one draw of many."""
+    z = np.load(GOLD / "c2_first320.npz")
+    n = z["poses"].shape[0]
+    assert n == 320
     ha.set_params(Resolution=0.5)
     seq = synth.c2_sequence(seed=2, n_scans=2000)
-    odo = _odo_deg(seq, 60)
+    odo = _odo_deg(seq, n)
     assert np.array_equal(odo, z["odo_deg"])
     slam = ha.Slam()
-    for i in range(60):
+    for i in range(n):
         slam.process(i, odo[i], seq["scans"][i])
     poses = slam.poses()
     ref = z["poses"]
     assert poses.shape == ref.shape
-    assert np.max(np.hypot(poses[:, 0] - ref[:, 0], poses[:, 1] - ref[:, 1])) < 2e-3
-    assert np.max(np.abs(np.deg2rad(poses[:, 2] - ref[:, 2]))) < 5e-4
-    assert slam.submaps() == int(z["n_submaps"])
-    # mm-level pose differences move a few points across 5 cm voxel faces of the map filter: compare the
-    # clouds as point sets (size within 1 %, every point has a reference point within one map-filter voxel)
+    dpos = np.hypot(poses[:, 0] - ref[:, 0], poses[:, 1] - ref[:, 1])
+    dyaw = np.abs(np.deg2rad(poses[:, 2] - ref[:, 2]))
+    # per-match bar is 1e-4 m / 1e-5 rad; over a sequence the map feeds back into the next match (a 1e-8 pose
+    # difference can move a map point across a 5 cm voxel face of the map filter), so the bar on the whole trajectory
+    # is looser: 2 mm / 5e-4 rad
+    assert np.max(dpos[:60]) < 1e-4 and np.max(dyaw[:60]) < 1e-5, (np.max(dpos[:60]), np.max(dyaw[:60]))
+    assert np.max(dpos) < 2e-3 and np.max(dyaw) < 5e-4, (np.max(dpos), np.max(dyaw))
+    assert slam.submaps() == int(z["n_submaps"]) == 2
     from scipy.spatial import cKDTree
     lm, ref_lm = slam.local_map(), z["local_map"]
     assert abs(lm.shape[0] - ref_lm.shape[0]) < 0.01 * ref_lm.shape[0]
     dist, _ = cKDTree(ref_lm[:, :2]).query(lm[:, :2])
     assert np.max(dist) < 0.05 and np.mean(dist) < 0.002
     st = slam.stats()
-    assert st["matches"] == 59 and st["point_evals"] > 0
+    assert st["matches"] == n - 1 and st["point_evals"] > 0
 
 
 def test_launcher_reads_text_log_and_writes_outputs(tmp_path):
