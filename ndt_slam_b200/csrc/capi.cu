@@ -43,7 +43,7 @@ struct BlobHeader {
   int32_t counters[CTR_COUNT];
   int64_t off_slot, off_cen, off_occ, off_recs, off_leaf_id, off_leaf_range, off_sorted, off_tgt, off_nn_range, off_nn_pts, total;
 };
-static constexpr uint64_t kBlobMagic = 0x4e44544232303043ull;  // "NDTB200C"
+static constexpr uint64_t kBlobMagic = 0x4e44544232303045ull;  // "NDTB200E"
 
 static inline int64_t align256(int64_t v) { return (v + 255) & ~int64_t(255); }
 
@@ -122,7 +122,7 @@ static void all_buffers(Handle *h, std::vector<DevBuf *> &v) {
   GridBuffers &g = h->gb;
   v = {&g.tgt, &g.cell_of, &g.rank_of, &g.list, &g.sorted_idx, &g.slot, &g.leaf_id, &g.leaf_cell,
        &g.leaf_n, &g.leaf_start, &g.leaf_nr, &g.leaf_mean, &g.leaf_icov, &g.leaf_cen, &g.recs,
-       &g.counters, &g.leaf_pair, &g.big_list, &g.tile_hist, &g.dims, &g.pair_off, &g.cen, &g.occ, &g.nn_cnt, &g.nn_range, &g.nn_pts,
+       &g.counters, &g.leaf_pair, &g.big_list, &g.tile_hist, &g.dims, &g.pair_off, &g.cen, &g.occ, &g.nbr, &g.nn_cnt, &g.nn_range, &g.nn_pts,
        &g.tgt_sorted, &g.leaf_range, &h->src, &h->scratch, &h->scratch2, &h->stage, &h->io};
 }
 
@@ -639,6 +639,18 @@ int ndt_grid_import(ndt_handle hh, const void *device_blob, int64_t bytes) {
   NDT_CUDA(h, take(h->gb.tgt, b.off_tgt, z.tgt));
   NDT_CUDA(h, take(h->gb.nn_range, b.off_nn_range, z.nn_range));
   NDT_CUDA(h, take(h->gb.nn_pts, b.off_nn_pts, z.nn_pts));
+  // one grid at base 0 (the geometry the batch kernels' neighbour masks are derived from, on demand)
+  {
+    PairDims pd{};
+    pd.min_bx = b.gd.min_bx; pd.min_by = b.gd.min_by; pd.div_x = b.gd.div_x; pd.div_y = b.gd.div_y;
+    pd.W = b.gd.div_x + 4; pd.H = b.gd.div_y + 4; pd.base = 0; pd.nt = b.gd.n_tgt;
+    NDT_CUDA(h, h->gb.dims.reserve(sizeof(PairDims)));
+    if (ensure_pinned(h, sizeof(PairDims))) return NDT_ERR_CUDA;
+    std::memcpy(h->pinned, &pd, sizeof(pd));
+    NDT_CUDA(h, cudaMemcpyAsync(h->gb.dims.p, h->pinned, sizeof(pd), cudaMemcpyHostToDevice, st));
+    h->have_nbr = false; h->nbr_grids = 1;
+    h->nbr_cells = z.slot > 0 ? (int64_t)pd.W * pd.H : 0;
+  }
   NDT_CUDA(h, cudaStreamSynchronize(st));
   h->have_grid = true;
   h->grid_has_points = (b.flags & NDT_BLOB_POINTS) != 0;

@@ -378,6 +378,35 @@ __device__ inline void eig2(double a, double b, double d, double *lam, double *v
 
 struct FinalizeParams { int32_t min_points; double eig_mult; int32_t quirks; };
 
+// Neighbour masks for the batch kernels, derived from the probe table: entry t gets bit (dj + 1) * 4 + (di + 1) for every
+// tree cell (non-NaN centroid) at offset (di, dj). The tables carry two empty cells of padding on every side of every
+// grid, so the eight neighbours of any *interior or first-ring* entry exist; entries on the outermost ring are never
+// addressed by a point (a candidate's own cell is at most one cell outside the grid) and get 0.
+__global__ void __launch_bounds__(256) k_nbr_from_cen(const float2 *__restrict__ cen, const PairDims *__restrict__ dims, int n_grids,
+                                                      int64_t n_entries, uint16_t *__restrict__ nbr) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_entries; t += (int64_t)gridDim.x * blockDim.x) {
+    int lo = 0, hi = n_grids;                 // which grid owns entry t: dims[lo].base <= t < dims[hi].base
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if ((int64_t)__ldg(&dims[mid].base) <= t) lo = mid; else hi = mid;
+    }
+    const int W = __ldg(&dims[lo].W), H = __ldg(&dims[lo].H);
+    const int r = (int)(t - __ldg(&dims[lo].base));
+    const int row = r / W, col = r - row * W;
+    unsigned m = 0u;
+    if (row >= 1 && row < H - 1 && col >= 1 && col < W - 1) {
+#pragma unroll
+      for (int dj = -1; dj <= 1; ++dj)
+#pragma unroll
+        for (int di = -1; di <= 1; ++di) {
+          const float2 c = __ldg(cen + t + dj * W + di);
+          if (c.x == c.x) m |= 1u << ((dj + 1) * 4 + (di + 1));
+        }
+    }
+    nbr[t] = (uint16_t)m;
+  }
+}
+
 // pass 2. The bucket of a leaf is contiguous and already in input order (k_rank); its sums must be taken in that
 // order (fp32 centroid and fp64 sums accumulate exactly like the reference's pass 1: bit-identical results), so a
 // leaf is one sequential chain of adds. Sparse leaves (C3: ~7 points) take one thread each. A dense leaf (C2 local
@@ -741,6 +770,7 @@ int grid_build_tables(Handle *h, int64_t n, int n_grids, int64_t total_pad, int 
   const PairDims *dims = gb.dims.as<PairDims>();
   const int64_t *off = gb.pair_off.as<int64_t>();
   NDT_CUDA(h, cudaMemsetAsync(gb.occ.p, 0, occ_words * 4, st));
+  h->have_nbr = false; h->nbr_cells = (int64_t)npad; h->nbr_grids = n_grids;
   NDT_CUDA(h, cudaMemsetAsync(gb.leaf_id.p, 0, npad * 4, st));               // per-cell counts, then leaf id + 1
   NDT_CUDA(h, cudaMemsetAsync(gb.cen.p, 0xff, npad * sizeof(float2), st));   // all-ones is a NaN: "no tree cell here"
   // enough CTAs to fill the machine: several row chunks per grid when there are few grids
@@ -899,11 +929,18 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace, int64_t n_
     gd.n_cells = (int64_t)gd.div_x * gd.div_y;
     if ((int64_t)(gd.div_x + 4) * (gd.div_y + 4) > (int64_t)INT_MAX)
       return set_err(h, NDT_ERR_CAPACITY, "ndt_set_target: grid exceeds 2^31-1 cells");
+    // the matcher takes floor(x / leaf) with one float -> int conversion, exact while cell indices stay below 2^22 in
+    // magnitude (at 0.1 m cells: +-419 km); beyond that PCL's own float index arithmetic starts to round as well
+    if (std::abs((int64_t)min_bx) >= NDT_MAX_CELL_INDEX || std::abs((int64_t)min_by) >= NDT_MAX_CELL_INDEX ||
+        std::abs((int64_t)max_bx) >= NDT_MAX_CELL_INDEX || std::abs((int64_t)max_by) >= NDT_MAX_CELL_INDEX)
+      return set_err(h, NDT_ERR_CAPACITY, "ndt_set_target: cell indices beyond +-4,194,304 are not supported");
   }
   if (empty) {
     gd.div_x = gd.div_y = 0; gd.n_cells = 0;
     // a 4 x 4 all-empty padded table (clear occupancy bits): a match against an empty target probes nothing
     NDT_CUDA(h, gb.occ.reserve(64)); NDT_CUDA(h, gb.slot.reserve(64)); NDT_CUDA(h, gb.cen.reserve(128)); NDT_CUDA(h, gb.leaf_id.reserve(64));
+    NDT_CUDA(h, gb.nbr.reserve(64)); NDT_CUDA(h, cudaMemsetAsync(gb.nbr.p, 0, 64, st));
+    h->have_nbr = true; h->nbr_cells = 0; h->nbr_grids = 0;
     NDT_CUDA(h, cudaMemsetAsync(gb.occ.p, 0, 64, st)); NDT_CUDA(h, cudaMemsetAsync(gb.slot.p, 0xff, 64, st));
     NDT_CUDA(h, cudaMemsetAsync(gb.cen.p, 0xff, 128, st)); NDT_CUDA(h, cudaMemsetAsync(gb.leaf_id.p, 0, 64, st));
     h->have_grid = true; h->have_readback = true; h->grid_has_points = true;
@@ -986,6 +1023,23 @@ int grid_cell_index(Handle *h, const float *xyzw, int64_t n, int memspace, int32
   return NDT_OK;
 }
 
+int ensure_nbr(Handle *h) {
+  if (h->have_nbr) return NDT_OK;
+  GridBuffers &gb = h->gb;
+  if (h->nbr_cells > 0) {
+    NDT_CUDA(h, gb.nbr.reserve((size_t)h->nbr_cells * sizeof(uint16_t)));
+    k_nbr_from_cen<<<grid_for(h->nbr_cells, 256, h->sm_count), 256, 0, h->stream>>>(gb.cen.as<float2>(), gb.dims.as<PairDims>(), h->nbr_grids,
+                                                                                    h->nbr_cells, gb.nbr.as<uint16_t>());
+    ++h->launches;
+    NDT_CUDA(h, cudaGetLastError());
+  } else {
+    NDT_CUDA(h, gb.nbr.reserve(64));
+    NDT_CUDA(h, cudaMemsetAsync(gb.nbr.p, 0, 64, h->stream));
+  }
+  h->have_nbr = true;
+  return NDT_OK;
+}
+
 GridView grid_view(const Handle *h) {
   GridView G{};
   const GridBuffers &gb = h->gb;
@@ -994,6 +1048,7 @@ GridView grid_view(const Handle *h) {
   G.table_base = 0;
   G.cen = gb.cen.as<float2>();
   G.occ = gb.occ.as<uint32_t>();
+  G.nbr = gb.nbr.as<uint16_t>();
   G.recs = gb.recs.as<CellRec>();
   G.min_bx = h->gd.min_bx; G.min_by = h->gd.min_by; G.div_x = h->gd.div_x; G.div_y = h->gd.div_y;
   G.inv_leaf = h->gd.inv_leaf; G.r2 = h->gd.r2; G.leaf = h->gd.leaf;

@@ -19,6 +19,7 @@
 
 #include <cooperative_groups.h>
 #include <algorithm>
+#include <type_traits>
 #include <cstdlib>
 #include <cstring>
 
@@ -43,10 +44,11 @@ struct SmemSrc {
 // One cooperative objective pass. All threads of the group call pass<MODE>() with identical
 // arguments and leave with identical totals. Everything the hot loop touches is copied into
 // locals first (the object itself lives in local memory behind `this`).
-template <class Coop, class OccL, class CenL, class SlotL, class RecL, class SrcL>
+template <class Coop, class OccL, class NbrL, class CenL, class SlotL, class RecL, class SrcL>
 struct Objective {
   ProbeGeom geom;
   OccL occ;
+  NbrL nbr;
   CenL cen;
   SlotL slot;
   RecL rec;
@@ -62,23 +64,24 @@ struct Objective {
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
     const PoseF pf = pose_to_float(p);
+    const double cs = ac.cs, sn = ac.sn;
     const Coop co = coop;
     int pairs = 0;
-    accumulate_points(mode, geom, occ, cen, slot, rec, src, co.rank(), co.size(), ns, pf, sse != 0, ac.cs, ac.sn, d1, d2,
+    accumulate_points(mode, geom, occ, nbr, cen, slot, rec, src, co.rank(), co.size(), ns, pf, sse != 0, cs, sn, d1, d2,
                       Q, acc, pairs);
     if (mode == 0) co.template allreduce<13>(acc);
     else if (mode == 1) co.template allreduce<4>(acc);
     else co.template allreduce<9>(acc + 4);
 #pragma unroll
-    for (int k = 0; k < NACC; ++k) out[k] = acc[k];
+    for (int k = 0; k < NACC; ++k) out[k] = acc[k];     // identical in every cooperating thread (fixed-order reduction)
   }
 };
 
-template <class Coop, class OccL, class CenL, class SlotL, class RecL, class SrcL>
-__device__ __forceinline__ Objective<Coop, OccL, CenL, SlotL, RecL, SrcL> make_objective(
-    const GridView &G, const MatchParams &mp, const Coop &coop, OccL occ, CenL cen, SlotL slot, RecL rec, SrcL src, int ns,
+template <class Coop, class OccL, class NbrL, class CenL, class SlotL, class RecL, class SrcL>
+__device__ __forceinline__ Objective<Coop, OccL, NbrL, CenL, SlotL, RecL, SrcL> make_objective(
+    const GridView &G, const MatchParams &mp, const Coop &coop, OccL occ, NbrL nbr, CenL cen, SlotL slot, RecL rec, SrcL src, int ns,
     HitQueue Q) {
-  return Objective<Coop, OccL, CenL, SlotL, RecL, SrcL>{probe_geom(G), occ, cen, slot, rec, src, ns, mp.d1, mp.d2,
+  return Objective<Coop, OccL, NbrL, CenL, SlotL, RecL, SrcL>{probe_geom(G), occ, nbr, cen, slot, rec, src, ns, mp.d1, mp.d2,
                                                   (mp.quirks & NDT_QUIRK_TRANSFORM_SSE_ORDER) ? 1 : 0, coop, Q};
 }
 
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(256) k_eval_partial(GridView G, MatchParams mp
   // slice s owns points [s * chunk, (s + 1) * chunk)
   const int chunk = (ns + slices - 1) / slices;
   const int lo = slice * chunk, hi = min(ns, lo + chunk);
-  accumulate_points(MODE, probe_geom(G), GlobalOcc{G.occ}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, GlobalSrc{src},
+  accumulate_points(MODE, probe_geom(G), GlobalOcc{G.occ}, NoNbr{}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, GlobalSrc{src},
                           lo + (int)threadIdx.x, (int)blockDim.x, hi, pf, sse, ac.cs, ac.sn, mp.d1, mp.d2, my_queue(smem_raw),
                           acc, pairs);
   BlockCoop coop{scratch};
@@ -217,10 +220,10 @@ __global__ void __launch_bounds__(256) k_align_block(GridView G, MatchParams mp,
     for (int i = threadIdx.x; i < n_slots * 4; i += blockDim.x) sr[i] = __ldg(gr + i);
     for (int i = threadIdx.x; i < n_cells; i += blockDim.x) { s_cen[i] = __ldg(G.cen + i); s_slot[i] = __ldg(G.slot + i); }
     __syncthreads();
-    auto obj = make_objective(G, mp, coop, SmemOcc{smem_addr(s_occ)}, SmemCen{smem_addr(s_cen)}, SmemSlot{smem_addr(s_slot)}, SmemRec{smem_addr(s_recs)}, gsrc, ns, my_queue(smem_raw));
+    auto obj = make_objective(G, mp, coop, SmemOcc{smem_addr(s_occ)}, NoNbr{}, SmemCen{smem_addr(s_cen)}, SmemSlot{smem_addr(s_slot)}, SmemRec{smem_addr(s_recs)}, gsrc, ns, my_queue(smem_raw));
     match_device(obj, mp, guess, mo, opt);
   } else {
-    auto obj = make_objective(G, mp, coop, GlobalOcc{G.occ}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, my_queue(smem_raw));
+    auto obj = make_objective(G, mp, coop, GlobalOcc{G.occ}, NoNbr{}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, my_queue(smem_raw));
     match_device(obj, mp, guess, mo, opt);
   }
   double fsum = 0.0;
@@ -284,7 +287,7 @@ __global__ void __launch_bounds__(256) k_align_cluster(GridView G, MatchParams m
   const GlobalSrc gsrc{src};
   MatchOut mo;
   OptState opt;
-  auto obj = make_objective(G, mp, coop, GlobalOcc{G.occ}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, my_queue(smem_raw));
+  auto obj = make_objective(G, mp, coop, GlobalOcc{G.occ}, NoNbr{}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, my_queue(smem_raw));
   match_device(obj, mp, guess, mo, opt);
   double fsum = 0.0;
   if (mp.want_fitness) fsum = fitness_pass(G, gsrc, ns, mp, mo.p, coop);
@@ -341,7 +344,7 @@ __global__ void __launch_bounds__(256, 2) k_align_grid(GridView G, MatchParams m
   const GlobalSrc gsrc{src};
   MatchOut mo;
   OptState opt;
-  auto obj = make_objective(G, mp, coop, GlobalOcc{G.occ}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, my_queue(smem_raw));
+  auto obj = make_objective(G, mp, coop, GlobalOcc{G.occ}, NoNbr{}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, my_queue(smem_raw));
   match_device(obj, mp, guess, mo, opt);
   double fsum = 0.0;
   if (mp.want_fitness) fsum = fitness_pass(G, gsrc, ns, mp, mo.p, coop);
@@ -362,6 +365,7 @@ __global__ void __launch_bounds__(256, 2) k_align_grid(GridView G, MatchParams m
 #endif
 constexpr int WK_THREADS = NDT_WARP_KERNEL_THREADS, WK_WARPS = WK_THREADS / 32;
 constexpr int WK_QUEUE_BYTES = WK_WARPS * QUEUE_BYTES_PER_WARP;
+struct __align__(16) WarpState { MatchOut mo; };
 #ifndef NDT_WARP_JOB_CHUNK
 #define NDT_WARP_JOB_CHUNK 8
 #endif
@@ -389,51 +393,48 @@ __device__ __forceinline__ int next_job(unsigned long long *s_state, int32_t *jo
   return __shfl_sync(0xffffffffu, job, 0);
 }
 
-template <bool SRC_SMEM>
+// One instantiation per staging combination, chosen at launch: each holds exactly one copy of the optimiser + objective.
+template <bool SRC_SMEM, bool OCC_SMEM>
 __global__ void __launch_bounds__(WK_THREADS, NDT_WARP_KERNEL_MIN_CTAS) k_align_warp(GridView G, MatchParams mp, const float4 *__restrict__ src,
                                                    int ns, const double *__restrict__ guesses,
                                                    ndt_result *__restrict__ out, int64_t n_jobs,
                                                    int32_t *__restrict__ job_counter, int occ_words) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // dynamic shared memory: hit queues | occupancy bitmap (occ_words, 0 = left in global) | source points
+  // dynamic shared memory: hit queues | occupancy bitmap (OCC_SMEM) | source points (SRC_SMEM) | per-warp results
   uint32_t *s_occ = reinterpret_cast<uint32_t *>(smem_raw + WK_QUEUE_BYTES);
-  for (int i = threadIdx.x; i < occ_words; i += blockDim.x) s_occ[i] = __ldg(G.occ + i);
-  const MixedOcc occ_any{smem_addr(s_occ), occ_words > 0 ? nullptr : G.occ};
-  float2 *s_src = reinterpret_cast<float2 *>(smem_raw + WK_QUEUE_BYTES + ((occ_words * 4 + 15) & ~15));
+  const int occ_bytes = OCC_SMEM ? ((occ_words * 4 + 15) & ~15) : 0;
+  if (OCC_SMEM) for (int i = threadIdx.x; i < occ_words; i += blockDim.x) s_occ[i] = __ldg(G.occ + i);
+  float2 *s_src = reinterpret_cast<float2 *>(smem_raw + WK_QUEUE_BYTES + occ_bytes);
   if (SRC_SMEM) {
     for (int i = threadIdx.x; i < ns; i += blockDim.x) {
       const float4 v = __ldg(src + i);
       s_src[i] = make_float2(v.x, v.y);
     }
   }
+  // the result of a match: one copy per warp in shared memory (written once per match, read by lane 0)
+  WarpState *ws = reinterpret_cast<WarpState *>(smem_raw + WK_QUEUE_BYTES + occ_bytes + (SRC_SMEM ? ((ns * 8 + 15) & ~15) : 0)) + (threadIdx.x >> 5);
   __shared__ unsigned long long s_state;
   if (threadIdx.x == 0) s_state = NDT_WARP_JOB_CHUNK;          // "chunk exhausted": the first warp fetches one
   __syncthreads();
   const int lane = threadIdx.x & 31;
   WarpCoop coop{lane};
-  const GlobalSrc gsrc{src};
-  const SmemSrc ssrc{smem_addr(s_src)};
+  using OccL = typename std::conditional<OCC_SMEM, SmemOcc, GlobalOcc>::type;
+  using SrcL = typename std::conditional<SRC_SMEM, SmemSrc, GlobalSrc>::type;
+  OccL occ_acc; SrcL src_acc;
+  if constexpr (OCC_SMEM) occ_acc = SmemOcc{smem_addr(s_occ)}; else occ_acc = GlobalOcc{G.occ};
+  if constexpr (SRC_SMEM) src_acc = SmemSrc{smem_addr(s_src)}; else src_acc = GlobalSrc{src};
   for (;;) {
     const int job = next_job(&s_state, job_counter, lane);
     if (job >= n_jobs) break;
     const double guess[3] = {guesses[3 * (size_t)job], guesses[3 * (size_t)job + 1], guesses[3 * (size_t)job + 2]};
-    MatchOut mo;
+    MatchOut &mo = ws->mo;
     OptState opt;
+    auto obj = make_objective(G, mp, coop, occ_acc, GlobalNbr{G.nbr}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, src_acc, ns, my_queue(smem_raw));
+    match_device(obj, mp, guess, mo, opt);
     double fsum = 0.0;
-    if (SRC_SMEM && occ_words > 0) {                 // the common batch case: bitmap and scan both staged
-      auto obj = make_objective(G, mp, coop, SmemOcc{smem_addr(s_occ)}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, ssrc, ns, my_queue(smem_raw));
-      match_device(obj, mp, guess, mo, opt);
-      if (mp.want_fitness) fsum = fitness_pass(G, ssrc, ns, mp, mo.p, coop);
-    } else if (SRC_SMEM) {
-      auto obj = make_objective(G, mp, coop, occ_any, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, ssrc, ns, my_queue(smem_raw));
-      match_device(obj, mp, guess, mo, opt);
-      if (mp.want_fitness) fsum = fitness_pass(G, ssrc, ns, mp, mo.p, coop);
-    } else {
-      auto obj = make_objective(G, mp, coop, occ_any, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, my_queue(smem_raw));
-      match_device(obj, mp, guess, mo, opt);
-      if (mp.want_fitness) fsum = fitness_pass(G, gsrc, ns, mp, mo.p, coop);
-    }
+    if (mp.want_fitness) fsum = fitness_pass(G, src_acc, ns, mp, mo.p, coop);
     if (lane == 0) write_result(out + job, mo, ns, fsum, mp.want_fitness != 0, G.n_tgt);
+    __syncwarp();
   }
 }
 
@@ -473,7 +474,7 @@ __global__ void __launch_bounds__(256, 2) k_eval_warp(GridView G, MatchParams mp
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
     int pairs = 0;
-    accumulate_points(MODE, geom, SmemOcc{smem_addr(s_occ)}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, SmemSrc{smem_addr(s_src)}, lane, 32, ns,
+    accumulate_points(MODE, geom, SmemOcc{smem_addr(s_occ)}, GlobalNbr{G.nbr}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, SmemSrc{smem_addr(s_src)}, lane, 32, ns,
                       pf, sse, ac.cs, ac.sn, mp.d1, mp.d2, Q, acc, pairs);
     warp_allreduce<NACC>(acc);
     if (lane < NACC) {
@@ -631,6 +632,7 @@ __global__ void __launch_bounds__(256, NDT_PAIRS_KERNEL_MIN_CTAS) k_align_pairs(
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   WarpCoop coop{lane};
+  WarpState *ws = reinterpret_cast<WarpState *>(smem_raw + QUEUE_BYTES) + (threadIdx.x >> 5);
   for (;;) {
     int job = 0;
     if (lane == 0) job = atomicAdd(job_counter, 1);
@@ -643,9 +645,9 @@ __global__ void __launch_bounds__(256, NDT_PAIRS_KERNEL_MIN_CTAS) k_align_pairs(
     G.tgt = G0.tgt + d.tgt_off; G.n_tgt = d.nt; G.nn_f = 0;
     const double guess[3] = {guesses[3 * (size_t)job], guesses[3 * (size_t)job + 1], guesses[3 * (size_t)job + 2]};
     const GlobalSrc gsrc{src_all + d.src_off};
-    MatchOut mo;
+    MatchOut &mo = ws->mo;
     OptState opt;
-    auto obj = make_objective(G, mp, coop, GlobalOcc{G.occ}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, d.ns, my_queue(smem_raw));
+    auto obj = make_objective(G, mp, coop, GlobalOcc{G.occ}, NoNbr{}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, d.ns, my_queue(smem_raw));   // cold per-pair tables: a mask table would be one more stream
     match_device(obj, mp, guess, mo, opt);
     double fsum = 0.0;
     if (mp.want_fitness) fsum = fitness_pass(G, gsrc, d.ns, mp, mo.p, coop);
@@ -668,8 +670,8 @@ struct AnyOcc {
 struct AnyCen {
   const float2 *p; int i0;
   __device__ __forceinline__ float2 operator()(int i) const { return p[i - i0]; }
-  __device__ __forceinline__ void prefetch(int, int) const {}
 };
+
 struct AnySrc {
   const float *p; int stride;      // floats between consecutive points (2: staged float2, 4: the caller's float4)
   __device__ __forceinline__ float2 operator()(int i) const { return *reinterpret_cast<const float2 *>(p + (size_t)i * stride); }
@@ -715,7 +717,7 @@ __global__ void __launch_bounds__(256, NDT_PAIRS_KERNEL_MIN_CTAS) k_align_pairs_
     __syncthreads();
     MatchOut mo;
     OptState opt;
-    auto obj = make_objective(G, mp, coop, aocc, acen, GlobalSlot{G.slot}, GlobalRec{G.recs}, asrc, d.ns, my_queue(smem_raw));
+    auto obj = make_objective(G, mp, coop, aocc, NoNbr{}, acen, GlobalSlot{G.slot}, GlobalRec{G.recs}, asrc, d.ns, my_queue(smem_raw));
     match_device(obj, mp, guess, mo, opt);
     double fsum = 0.0;
     if (mp.want_fitness) fsum = fitness_pass(G, asrc, d.ns, mp, mo.p, coop);
@@ -750,6 +752,8 @@ int launch_eval(Handle *h, const double *d_poses, int64_t n, int want_hessian, d
     const int occ_words = (int)((npad + 31) / 32 + 1);
     const size_t smem = QUEUE_BYTES + (((size_t)occ_words * 4 + 15) & ~size_t(15)) + (size_t)ns * sizeof(float2);
     if (n >= 16 * h->sm_count && h->gd.n_cells > 0 && smem <= 100 * 1024) {
+      if (int rc = ensure_nbr(h)) return rc;
+      const GridView G = grid_view(h);                 // with the neighbour masks
       int32_t *ctr = h->gb.counters.as<int32_t>();
       if (h->timing) cudaEventRecord(h->ev0, st);
       NDT_CUDA(h, cudaMemsetAsync(ctr + CTR_JOB, 0, sizeof(int32_t), st));
@@ -801,22 +805,27 @@ int launch_align(Handle *h, const double *d_guesses, int64_t n, ndt_result *d_re
   if (h->timing) cudaEventRecord(h->ev0, st);
   if (n >= 64) {
     // batch: persistent CTAs, one warp per match
+    if (int rc = ensure_nbr(h)) return rc;
+    const GridView G = grid_view(h);                   // with the neighbour masks
     NDT_CUDA(h, cudaMemsetAsync(ctr + CTR_JOB, 0, sizeof(int32_t), st));
     const bool src_smem = (size_t)ns * sizeof(float2) <= 64 * 1024;
     const int64_t npad = h->gd.n_cells > 0 ? (int64_t)(h->gd.div_x + 4) * (h->gd.div_y + 4) : 0;
     int occ_words = (int)((npad + 31) / 32 + 1);
-    if ((size_t)occ_words * 4 > NDT_WARP_OCC_SMEM_MAX) occ_words = 0;          // large grids: bitmap stays in global memory / L1
-    const size_t smem = WK_QUEUE_BYTES + (((size_t)occ_words * 4 + 15) & ~size_t(15)) + (src_smem ? (size_t)ns * sizeof(float2) : 0);
+    const bool occ_smem = src_smem && (size_t)occ_words * 4 <= NDT_WARP_OCC_SMEM_MAX;          // large grids: bitmap stays in global memory / L1
+    const size_t smem = WK_QUEUE_BYTES + (occ_smem ? (((size_t)occ_words * 4 + 15) & ~size_t(15)) : 0) +
+                        (src_smem ? (((size_t)ns * sizeof(float2) + 15) & ~size_t(15)) : 0) + WK_WARPS * sizeof(WarpState);
     const int ctas_per_sm = NDT_WARP_KERNEL_MIN_CTAS;
     int64_t grid = (int64_t)h->sm_count * ctas_per_sm;
     grid = std::min<int64_t>(grid, (n + WK_WARPS - 1) / WK_WARPS);
-    if (src_smem) {
-      NDT_CUDA(h, cudaFuncSetAttribute(k_align_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_align_warp<true><<<(unsigned)grid, WK_THREADS, smem, st>>>(G, mp, src, ns, d_guesses, d_results, n, ctr + CTR_JOB, occ_words);
-    } else {
-      NDT_CUDA(h, cudaFuncSetAttribute(k_align_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_align_warp<false><<<(unsigned)grid, WK_THREADS, smem, st>>>(G, mp, src, ns, d_guesses, d_results, n, ctr + CTR_JOB, occ_words);
-    }
+    auto go = [&](auto kern) -> cudaError_t {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      kern<<<(unsigned)grid, WK_THREADS, smem, st>>>(G, mp, src, ns, d_guesses, d_results, n, ctr + CTR_JOB, occ_words);
+      return cudaSuccess;
+    };
+    if (occ_smem) NDT_CUDA(h, go(k_align_warp<true, true>));
+    else if (src_smem) NDT_CUDA(h, go(k_align_warp<true, false>));
+    else NDT_CUDA(h, go(k_align_warp<false, false>));
   } else if (ns > NDT_GRID_MIN_NS && h->coop_launch) {
     // very large source cloud: one match at a time on every SM (cooperative launch, grid-wide reduction)
     int per_sm = 0;
@@ -898,8 +907,8 @@ int launch_align_pairs(Handle *h, const float4 *d_src, const double *d_guesses, 
     k_align_pairs_block<<<(unsigned)grid, 256, QUEUE_BYTES + PB_STAGE_BYTES, st>>>(G, mp, h->gb.dims.as<PairDims>(), d_src, d_guesses, d_results,
                                                                  n_pairs, ctr + CTR_JOB);
   } else {
-    NDT_CUDA(h, cudaFuncSetAttribute(k_align_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, QUEUE_BYTES));
-    k_align_pairs<<<(unsigned)grid, 256, QUEUE_BYTES, st>>>(G, mp, h->gb.dims.as<PairDims>(), d_src, d_guesses, d_results,
+    NDT_CUDA(h, cudaFuncSetAttribute(k_align_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, QUEUE_BYTES + 8 * (int)sizeof(WarpState)));
+    k_align_pairs<<<(unsigned)grid, 256, QUEUE_BYTES + 8 * sizeof(WarpState), st>>>(G, mp, h->gb.dims.as<PairDims>(), d_src, d_guesses, d_results,
                                                            n_pairs, ctr + CTR_JOB);
   }
   ++h->launches;

@@ -43,6 +43,9 @@ struct GridView {
                                         // (dilated occupancy: a clear bit means the point cannot hit anything)
   const float2 *__restrict__ cen;       // same padded indexing: float32 centroid of tree cells, NaN elsewhere
                                         // (the probe is one load + a float compare: NaN < r2 is false)
+  const uint16_t *__restrict__ nbr;     // same padded indexing: which cells of the 3x3 block around a cell are tree cells,
+                                        // bit (dj + 1) * 4 + (di + 1) for the neighbour at (di, dj); nbr != 0 <=> occ bit.
+                                        // Derived from cen on demand, for the batch kernels only (ensure_nbr)
   const CellRec *__restrict__ recs;     // compact records of cells with n >= min_points
   int32_t min_bx, min_by, div_x, div_y;
   float inv_leaf;                       // 1.0f / leaf
@@ -108,19 +111,38 @@ __device__ __forceinline__ PoseF pose_to_float(const double p[3]) {
   return f;
 }
 
+// Two float32 additions in one instruction (sm_100 FADD2): (rx, ry) = (ax + bx, ay + by), each rounded to nearest like
+// __fadd_rn. Only ADDITIONS are packed: ptxas contracts a packed multiply that feeds a packed add into FFMA2 even when both
+// carry .rn (measured: profiles/microbench.cu, 29,204 of 65,531 transform chains differ from the scalar result), which
+// would break the bit-exact transform; scalar __fmul_rn products feeding a packed add stay unfused (0 mismatches).
+#ifndef NDT_PACKED_ADD
+#define NDT_PACKED_ADD 1
+#endif
+__device__ __forceinline__ void add2_rn(float &rx, float &ry, float ax, float ay, float bx, float by) {
+#if NDT_PACKED_ADD
+  asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
+      : "=f"(rx), "=f"(ry) : "f"(ax), "f"(ay), "f"(bx), "f"(by));
+#else
+  rx = __fadd_rn(ax, bx); ry = __fadd_rn(ay, by);
+#endif
+}
+
 __device__ __forceinline__ void xform(const PoseF &f, bool sse_order, float x, float y, float &ox, float &oy) {
   const float ns = -f.s;
-  if (sse_order) {
-    ox = __fadd_rn(__fmul_rn(f.c, x), __fadd_rn(__fmul_rn(ns, y), f.tx));
-    oy = __fadd_rn(__fmul_rn(f.s, x), __fadd_rn(__fmul_rn(f.c, y), f.ty));
-  } else {
-    ox = __fadd_rn(__fadd_rn(__fmul_rn(f.c, x), __fmul_rn(ns, y)), f.tx);
-    oy = __fadd_rn(__fadd_rn(__fmul_rn(f.s, x), __fmul_rn(f.c, y)), f.ty);
+  const float cx = __fmul_rn(f.c, x), sx = __fmul_rn(f.s, x), nsy = __fmul_rn(ns, y), cy = __fmul_rn(f.c, y);
+  float ux, uy;
+  if (sse_order) {               // x' = c x + ((-s) y + tx)
+    add2_rn(ux, uy, nsy, cy, f.tx, f.ty);
+    add2_rn(ox, oy, cx, sx, ux, uy);
+  } else {                       // x' = (c x + (-s) y) + tx
+    add2_rn(ux, uy, cx, sx, nsy, cy);
+    add2_rn(ox, oy, ux, uy, f.tx, f.ty);
   }
 }
 
 __device__ __forceinline__ float dist2f(float ax, float ay, float bx, float by) {
-  const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by);
+  float dx, dy;
+  add2_rn(dx, dy, ax, ay, -bx, -by);          // a - b == a + (-b) exactly
   return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
 }
 
@@ -135,6 +157,7 @@ __device__ __forceinline__ float dist2f(float ax, float ay, float bx, float by) 
 // two per-warp rings in shared memory.
 // ------------------------------------------------------------------------------------------------
 constexpr int NACC = 13;
+constexpr int NDT_MAX_CELL_INDEX = 1 << 22;    // |floor(x / leaf)| of every target point stays below this (host-checked)
 #ifndef NDT_HITS_PER_LANE
 #define NDT_HITS_PER_LANE 2
 #endif
@@ -250,12 +273,20 @@ __device__ __forceinline__ void hit_path(const int MODE, const RecL &rec_at, con
 
 // the scalars of the grid the probe loop needs, held in registers (not re-read through a struct pointer)
 struct ProbeGeom {
-  int W, div_x, div_y, min_bx, min_by, base;
+  int W, base;
+  int lo_x, lo_y;         // min_b - 1: the floor index of the first column / row whose 3x3 block touches the grid
+  unsigned span_x, span_y;// div + 1: floor indices lo .. lo + span (inclusive) can hit something
+  int cell0;              // padded-table index of floor index (0, 0): a point with floor indices (fi, fj) lives at cell0 + fj * W + fi
   float inv_leaf, r2;
 };
 __device__ __forceinline__ ProbeGeom probe_geom(const GridView &G) {
-  return ProbeGeom{G.slot_w, G.div_x, G.div_y, G.min_bx, G.min_by, G.table_base, G.inv_leaf, G.r2};
+  return ProbeGeom{G.slot_w, G.table_base, G.min_bx - 1, G.min_by - 1, (unsigned)(G.div_x + 1), (unsigned)(G.div_y + 1),
+                   G.table_base + (2 - G.min_by) * G.slot_w + 2 - G.min_bx, G.inv_leaf, G.r2};
 }
+// floor(v * inv) as an integer in one conversion (cvt.rmi). Equal to the reference's float expression
+// (int)(floorf(v * inv) - (float)min_b) + min_b whenever every quantity stays below 2^23 in magnitude, which the host
+// guarantees for the grid (NDT_MAX_CELL_INDEX) -- a point farther out lands outside the grid either way.
+__device__ __forceinline__ int floor_index(float v, float inv) { return __float2int_rd(__fmul_rn(v, inv)); }
 
 // Accumulate the objective over points i = first + k * stride (k = 0, 1, ...), i < hi, where `first`
 // is lane-contiguous inside a warp (first = warp_first + lane): every lane of a warp iterates the same
@@ -275,30 +306,23 @@ __device__ __forceinline__ ProbeGeom probe_geom(const GridView &G) {
 // Without the rings the probe would run for every point (all 32 lanes pay when one is a candidate) and the
 // hit path once per neighbour position with a handful of active lanes.
 // stage A for one point: padded-table index of its own cell if the point can hit anything, else -1
-#ifndef NDT_PREFETCH_CEN
-#define NDT_PREFETCH_CEN 0      // measured: an L1 prefetch of the centroid rows at candidate time is slower (C4 13.2 -> 14.4 ms)
-#endif
-template <class OccL, class CenL, class SrcL>
-__device__ __forceinline__ int candidate_cell(const ProbeGeom &g, const OccL &occ_at, const CenL &cen_at, const SrcL &src, const int i,
+template <class OccL, class SrcL>
+__device__ __forceinline__ int candidate_cell(const ProbeGeom &g, const OccL &occ_at, const SrcL &src, const int i,
                                               const bool valid, const PoseF &pf, const bool sse_order) {
   const float2 xy = src(i);
   float xt, yt;
   xform(pf, sse_order, xy.x, xy.y, xt, yt);
-  const int ci = cell_coord(xt, g.inv_leaf, g.min_bx);
-  const int cj = cell_coord(yt, g.inv_leaf, g.min_by);
-  // -1 <= ci <= div_x and -1 <= cj <= div_y: the cells whose 3x3 block can touch the grid
-  const bool in = valid && (unsigned)(ci + 1) <= (unsigned)(g.div_x + 1) && (unsigned)(cj + 1) <= (unsigned)(g.div_y + 1);
-  const int base = in ? (g.base + (cj + 2) * g.W + ci + 2) : g.base;      // out of range: any valid entry of this grid (unused)
+  const int fi = floor_index(xt, g.inv_leaf), fj = floor_index(yt, g.inv_leaf);
+  // cell -1 .. div in both directions: the cells whose 3x3 block can touch the grid
+  const bool in = valid && (unsigned)(fi - g.lo_x) <= g.span_x && (unsigned)(fj - g.lo_y) <= g.span_y;
+  const int base = in ? (g.cell0 + fj * g.W + fi) : g.base;      // out of range: any valid entry of this grid (unused)
   const unsigned word = occ_at(base >> 5);
   const bool cand = in && ((word >> (base & 31)) & 1u);
-#if NDT_PREFETCH_CEN
-  if (cand) cen_at.prefetch(base, g.W);        // stage B reads these nine centroids a few hundred cycles from now
-#endif
   return cand ? base : -1;
 }
 
-template <class OccL, class CenL, class SlotL, class RecL, class SrcL>
-__device__ __forceinline__ void accumulate_points(const int MODE, const ProbeGeom g, const OccL occ_at, const CenL cen_at, const SlotL slot_at,
+template <class OccL, class NbrL, class CenL, class SlotL, class RecL, class SrcL>
+__device__ __forceinline__ void accumulate_points(const int MODE, const ProbeGeom g, const OccL occ_at, const NbrL nbr_at, const CenL cen_at, const SlotL slot_at,
                                                   const RecL rec_at, const SrcL src, const int first,
                                                   const int stride, const int hi, const PoseF pf,
                                                   const bool sse_order, const double cs, const double sn,
@@ -316,7 +340,7 @@ __device__ __forceinline__ void accumulate_points(const int MODE, const ProbeGeo
 #pragma unroll
       for (int u = 0; u < A_STEPS; ++u) {
         const int i = i0 + lane + u * stride;
-        b[u] = candidate_cell(g, occ_at, cen_at, src, min(i, hi - 1), i < hi, pf, sse_order);
+        b[u] = candidate_cell(g, occ_at, src, min(i, hi - 1), i < hi, pf, sse_order);
       }
       int at = chead + cn;
 #pragma unroll
@@ -337,14 +361,36 @@ __device__ __forceinline__ void accumulate_points(const int MODE, const ProbeGeo
       int2 cd = make_int2(0, 0);
       if (lane < n) {
         cd = lds_int2(Q.cand + 8u * ((chead + lane) & (CQCAP - 1)));
-        float2 c[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) c[k] = cen_at(cd.y + (k / 3 - 1) * g.W + (k % 3 - 1));
         const float2 xy = src(cd.x);
         float xt, yt;
         xform(pf, sse_order, xy.x, xy.y, xt, yt);
+        const int org = cd.y - (g.W + 1);
+        if constexpr (NbrL::enabled) {
+          // throughput-bound batch kernels: the neighbour mask names the tree cells of the 3x3 block (a wall crosses ~3 of
+          // the 9); only those are loaded and tested, four at a time so the loads overlap (half the L1 wavefronts of
+          // nine blind loads). bit b of the mask <-> cell offset (b >> 2) * W + (b & 3) - (W + 1)
+          unsigned todo = nbr_at(cd.y);
+          while (todo) {
+            int bit[4];
+            float2 c[4];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) mask |= (dist2f(xt, yt, c[k].x, c[k].y) < g.r2) ? (1u << k) : 0u;
+            for (int u = 0; u < 4; ++u) {
+              bit[u] = __ffs(todo) - 1;                 // -1 once the mask is exhausted
+              todo &= todo - 1u;
+              c[u] = bit[u] >= 0 ? cen_at(org + (bit[u] >> 2) * g.W + (bit[u] & 3)) : make_float2(NAN, NAN);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) mask |= (dist2f(xt, yt, c[u].x, c[u].y) < g.r2) ? (1u << (bit[u] & 31)) : 0u;
+          }
+        } else {
+          // latency-bound single matches: nine independent centroid loads issued back to back (no dependent mask load in
+          // front of them; NaN centroids of non-tree cells fail the compare)
+          float2 c[9];
+#pragma unroll
+          for (int k = 0; k < 9; ++k) c[k] = cen_at(org + (k / 3) * g.W + (k % 3));
+#pragma unroll
+          for (int k = 0; k < 9; ++k) mask |= (dist2f(xt, yt, c[k].x, c[k].y) < g.r2) ? (1u << ((k / 3) * 4 + (k % 3))) : 0u;
+        }
       }
       chead = (chead + n) & (CQCAP - 1);
       cn -= n;
@@ -359,10 +405,11 @@ __device__ __forceinline__ void accumulate_points(const int MODE, const ProbeGeo
         const int total = __shfl_sync(0xffffffffu, incl, 31);
         int pos = qhead + qn + incl - cnt;
         if (pos >= QCAP) pos -= QCAP;
+        const int org = cd.y - (g.W + 1);
         while (mask) {
           const int k = __ffs(mask) - 1;
           mask &= mask - 1u;
-          sts_int2(Q.hit + 8u * pos, make_int2(cd.x, cd.y + (k / 3 - 1) * g.W + (k % 3 - 1)));
+          sts_int2(Q.hit + 8u * pos, make_int2(cd.x, org + (k >> 2) * g.W + (k & 3)));
           if (++pos == QCAP) pos = 0;
         }
         qn += total;
@@ -413,20 +460,22 @@ struct MixedOcc {           // staged when it fits, else read in place (warp-uni
   const uint32_t *__restrict__ g;
   __device__ __forceinline__ uint32_t operator()(int w) const { return g ? __ldg(g + w) : lds_u32(a + 4u * w); }
 };
+struct GlobalNbr {
+  static constexpr bool enabled = true;
+  const uint16_t *__restrict__ p;
+  __device__ __forceinline__ unsigned operator()(int i) const { return (unsigned)__ldg(p + i); }
+};
+struct NoNbr {                // probe all nine cells (single-match kernels)
+  static constexpr bool enabled = false;
+  __device__ __forceinline__ unsigned operator()(int) const { return 0u; }
+};
 struct GlobalCen {
   const float2 *__restrict__ p;
   __device__ __forceinline__ float2 operator()(int i) const { return __ldg(p + i); }
-  // L1 prefetch of the three rows of the 3x3 block around entry i (each row: 24 contiguous bytes)
-  __device__ __forceinline__ void prefetch(int i, int W) const {
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p + i - W - 1));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p + i - 1));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p + i + W - 1));
-  }
 };
 struct SmemCen {
   uint32_t a;
   __device__ __forceinline__ float2 operator()(int i) const { return lds_float2(a + 8u * i); }
-  __device__ __forceinline__ void prefetch(int, int) const {}
 };
 struct GlobalSlot {
   const int32_t *__restrict__ p;
@@ -654,8 +703,12 @@ struct MatchOut {
 // Optimiser state of one match, kept together in one struct that the Newton loop and the line search share (a per-thread
 // local: registers where they fit, local memory around the non-inlined objective passes). Passing the pieces around as
 // separate by-reference scalars made the compiler spill 880 bytes per thread around every pass; as one object it is 250
-// (C4 12.6 -> 11.8 ms on the same GPU). A per-warp copy in shared memory was tried too: faster still for the pair kernels,
-// but it crashed k_align_warp for reasons not understood, so it is not used anywhere.
+// (C4 12.6 -> 11.8 ms on the same GPU).
+// Round 2 experiments, all measured on the GPU and all rejected (profiles/r2_summary.md): (a) a per-warp copy in shared
+// memory runs in k_align_pairs but raises "illegal instruction" in k_align_warp (bisected with profiles/smoke_variants.py:
+// MatchOut in shared memory is fine, OptState is not; compute-sanitizer is closed on this pool, root cause open);
+// (b) the optimiser as a state machine around one inlined objective call site keeps the state in registers but makes the
+// compiler spill inside the hot loop (C4 11.8 -> 14.4 ms); (c) the same with the call not inlined grows the frame to 760 B.
 struct OptState {
   double p[3], dp[3], g[3], H[9], x_t[3], acc[NACC];
   double score, a_l, f_l, g_l, a_u, f_u, g_u, a_t, phi_0, d_phi_0;

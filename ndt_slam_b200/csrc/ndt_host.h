@@ -61,6 +61,7 @@ struct GridBuffers {
   DevBuf slot;         // int32[padded]   cell -> record slot (written for tree cells only; never initialised elsewhere)
   DevBuf cen;          // float2[padded]  probe table: float32 centroid of tree cells, NaN elsewhere
   DevBuf occ;          // uint32[padded/32] dilated occupancy bitmap (3x3 block contains a tree cell)
+  DevBuf nbr;          // uint16[padded]   which cells of the 3x3 block around a cell are tree cells (bit (dj+1)*4 + di+1); on demand
   DevBuf leaf_id;      // int32[padded]   per-cell point count during the build, then leaf id + 1 (0 = empty)
   DevBuf leaf_cell;    // int32[n]        per leaf: position in the shared padded tables
   DevBuf leaf_pair;    // int32[n]        per leaf: which grid it belongs to
@@ -104,6 +105,9 @@ struct Handle {
   GridBuffers gb;
   GridDims gd;
   bool have_grid = false;
+  bool have_nbr = false;         // gb.nbr matches the current tables (derived from gb.cen on demand: ensure_nbr)
+  int64_t nbr_cells = 0;         // padded entries of all grids in the shared tables (what ensure_nbr covers)
+  int nbr_grids = 0;             // entries of gb.dims
   bool have_readback = false;    // the per-leaf read-back tables belong to this grid (false on an imported replica)
   bool grid_has_points = false;  // target points + 1-NN buckets present (false on a replica imported without NDT_BLOB_POINTS)
   int64_t tgt_on_device = 0;     // leading points of gb.tgt that still hold the last ndt_set_target cloud (0: unknown)
@@ -132,6 +136,8 @@ int grid_build_tables(Handle *h, int64_t n, int n_grids, int64_t total_pad, int 
 int pairs_prepare(Handle *h, int64_t n_pairs, int64_t *total_pad, int *max_h);
 int grid_cell_index(Handle *h, const float *xyzw, int64_t n, int memspace, int32_t *idx_out);
 GridView grid_view(const Handle *h);
+// neighbour masks for the batch kernels (k_align_warp, k_eval_warp, k_align_pairs), derived from the probe table once per grid
+int ensure_nbr(Handle *h);
 MatchParams match_params(const Handle *h, bool want_fitness);
 
 // match_kernels.cu

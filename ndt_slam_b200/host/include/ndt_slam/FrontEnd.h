@@ -30,6 +30,7 @@ class FrontEnd {
   geometry_msgs::PoseArray get_poseArray() { return smat.get_poseArray(); }
   std::vector<Pose2D> get_poses() { return smat.poses; }
   const ScanMatcher &matcher() const { return smat; }      // instrumentation access (not in the reference)
+  ScanMatcher &matcher() { return smat; }
 
   void saveMap() {
     pcmap->makeGlobalMap();

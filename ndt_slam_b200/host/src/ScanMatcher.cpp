@@ -85,11 +85,11 @@ bool ScanMatcher::matchScan(Scan2D &curScan) {
     pfu.calOdometryCovariance(odoMotion, lastPose, lastCov, cov);
     fusedPose = predPose;
   }
-  lastCov = cov;
+  lastCov = forceCov ? *forceCov : cov;
   msFuse = now_ms() - t;
 
   t = now_ms();
-  growMap(curScan, fusedPose);
+  growMap(curScan, forcePose ? *forcePose : fusedPose);
   msGrowMap = now_ms() - t;
   prevScan = curScan;
 

@@ -129,6 +129,25 @@ int host_slam_process(void *h, int sid, const double odo[3], const double *xy, i
     return -1;
   }
 }
+// Teacher forcing (tests): process one scan, then let the map / the next fusion continue from the given pose (deg) and
+// covariance -- the reference's own outputs for this scan -- instead of this scan's result (see ScanMatcher.h).
+int host_slam_process_forced(void *h, int sid, const double odo[3], const double *xy, int64_t n, const double pose3[3], const double cov9[9]) {
+  Slam *s = (Slam *)h;
+  Pose2D fp(pose3[0], pose3[1], pose3[2]);
+  Eigen::Matrix3d fc;
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) fc(i, j) = cov9[3 * i + j];
+  ScanMatcher &sm = s->fe.matcher();
+  sm.forcePose = &fp; sm.forceCov = &fc;
+  const int rc = host_slam_process(h, sid, odo, xy, n);
+  sm.forcePose = nullptr; sm.forceCov = nullptr;
+  return rc;
+}
+int64_t host_slam_covs(void *h, double *out9, int64_t cap) {
+  const ScanMatcher &sm = ((Slam *)h)->fe.matcher();
+  const int64_t m = std::min<int64_t>(cap, (int64_t)sm.Covs.size());
+  for (int64_t k = 0; k < m; ++k) for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) out9[9 * k + 3 * i + j] = sm.Covs[k](i, j);
+  return (int64_t)sm.Covs.size();
+}
 int64_t host_slam_poses(void *h, double *out3, int64_t cap) {
   Slam *s = (Slam *)h;
   std::vector<Pose2D> p = s->fe.get_poses();

@@ -43,6 +43,8 @@ def load():
     L.host_slam_create.restype = vp
     L.host_slam_destroy.argtypes = [vp]
     L.host_slam_process.argtypes = [vp, C.c_int, dp, vp, i64]; L.host_slam_process.restype = C.c_int
+    L.host_slam_process_forced.argtypes = [vp, C.c_int, dp, vp, i64, dp, dp]; L.host_slam_process_forced.restype = C.c_int
+    L.host_slam_covs.argtypes = [vp, vp, i64]; L.host_slam_covs.restype = i64
     L.host_slam_poses.argtypes = [vp, vp, i64]; L.host_slam_poses.restype = i64
     L.host_slam_local_map.argtypes = [vp, vp, i64]; L.host_slam_local_map.restype = i64
     L.host_slam_global_map.argtypes = [vp, vp, i64]; L.host_slam_global_map.restype = i64
@@ -154,6 +156,18 @@ class Slam:
         xy = np.ascontiguousarray(xy, np.float64)
         if self.L.host_slam_process(self.h, sid, _d(list(odo_deg)), _p(xy), xy.shape[0]) != 0:
             raise RuntimeError(self.L.host_last_error().decode())
+
+    def process_forced(self, sid, odo_deg, xy, pose_deg, cov):
+        """Teacher forcing: match this scan, then continue from the given pose / covariance (the reference's)."""
+        xy = np.ascontiguousarray(xy, np.float64)
+        if self.L.host_slam_process_forced(self.h, sid, _d(list(odo_deg)), _p(xy), xy.shape[0], _d(list(pose_deg)),
+                                           _d(list(np.asarray(cov, dtype=np.float64).ravel()))) != 0:
+            raise RuntimeError(self.L.host_last_error().decode())
+
+    def covs(self):
+        n = self.L.host_slam_covs(self.h, None, 0)
+        out = np.zeros((n, 3, 3)); self.L.host_slam_covs(self.h, _p(out), n)
+        return out
 
     def poses(self):
         n = self.L.host_slam_poses(self.h, None, 0)

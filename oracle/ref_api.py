@@ -171,9 +171,13 @@ class RefNdt:
         o = np.array(out)
         return dict(score=o[0], grad=o[1:4], hess=o[4:13], off_block=off)
 
-    def align(self, guess):
+    def align(self, guess, want_fitness=True):
         out = (C.c_double * 17)()
-        self.L.ref_ndt_align(self.h, _d(list(guess)), out)
+        if want_fitness:
+            self.L.ref_ndt_align(self.h, _d(list(guess)), out)
+        else:
+            self.L.ref_ndt_align_nofit.argtypes = self.L.ref_ndt_align.argtypes
+            self.L.ref_ndt_align_nofit(self.h, _d(list(guess)), out)
         o = np.array(out)
         return dict(pose=o[0:3], score=o[3], iters=int(o[4]), converged=int(o[5]), evals=int(o[6]), fitness=o[7], hess=o[8:17])
 
@@ -199,6 +203,14 @@ class RefSlam:
         n = self.L.ref_slam_poses(self.h, None, 0)
         out = np.zeros((n, 3))
         self.L.ref_slam_poses(self.h, _p(out), n)
+        return out
+
+    def covs(self):
+        self.L.ref_slam_covs.restype = C.c_int64
+        self.L.ref_slam_covs.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        n = self.L.ref_slam_covs(self.h, None, 0)
+        out = np.zeros((n, 3, 3))
+        self.L.ref_slam_covs(self.h, _p(out), n)
         return out
 
     def local_map(self):

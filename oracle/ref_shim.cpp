@@ -151,7 +151,11 @@ double ref_ndt_eval(void *h, const double pose[3], int want_hessian, double out1
   return off;
 }
 // align from guess (x, y, yaw rad): out = final p (x, y, yaw), score, iterations, converged, passes, fitness, H3x3
-void ref_ndt_align(void *h, const double guess[3], double out[17]) {
+static void ndt_align_impl(void *h, const double guess[3], double out[17], bool want_fitness);
+void ref_ndt_align(void *h, const double guess[3], double out[17]) { ndt_align_impl(h, guess, out, true); }
+// the same without Registration::getFitnessScore (the batched device call ranks relocalisation hypotheses by score only)
+void ref_ndt_align_nofit(void *h, const double guess[3], double out[17]) { ndt_align_impl(h, guess, out, false); }
+static void ndt_align_impl(void *h, const double guess[3], double out[17], bool want_fitness) {
   NdtBox *b = (NdtBox *)h;
   const float yaw = (float)guess[2];
   Eigen::Matrix4f G = Eigen::Matrix4f::Identity();
@@ -161,7 +165,7 @@ void ref_ndt_align(void *h, const double guess[3], double out[17]) {
   b->ndt.align(outc, G);
   out[0] = b->ndt.final_p_(0); out[1] = b->ndt.final_p_(1); out[2] = b->ndt.final_p_(5);
   out[3] = b->ndt.final_score_; out[4] = b->ndt.getFinalNumIteration(); out[5] = b->ndt.hasConverged() ? 1 : 0;
-  out[6] = b->ndt.objectivePasses(); out[7] = b->ndt.getFitnessScore();
+  out[6] = b->ndt.objectivePasses(); out[7] = want_fitness ? b->ndt.getFitnessScore() : std::nan("");
   const int id[3] = {0, 1, 5};
   for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) out[8 + 3 * i + j] = b->ndt.final_hessian_(id[i], id[j]);
 }
@@ -189,6 +193,14 @@ int64_t ref_slam_poses(void *h, double *out3, int64_t cap) {
   const int64_t m = std::min<int64_t>(cap, (int64_t)p.size());
   for (int64_t i = 0; i < m; ++i) { out3[3 * i] = p[i].tx; out3[3 * i + 1] = p[i].ty; out3[3 * i + 2] = p[i].th; }
   return (int64_t)p.size();
+}
+// per-scan pose covariances (ScanMatcher::Covs, public member; reached through the opened FrontEnd)
+int64_t ref_slam_covs(void *h, double *out9, int64_t cap) {
+  Slam *s = (Slam *)h;
+  const std::vector<Eigen::Matrix3d> &c = s->fe.smat.Covs;
+  const int64_t m = std::min<int64_t>(cap, (int64_t)c.size());
+  for (int64_t k = 0; k < m; ++k) for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) out9[9 * k + 3 * i + j] = c[k](i, j);
+  return (int64_t)c.size();
 }
 int64_t ref_slam_local_map(void *h, float *xyzw, int64_t cap) {
   Slam *s = (Slam *)h;

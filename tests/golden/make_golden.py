@@ -82,7 +82,7 @@ def sequence_vectors(n_scans=320):
     for i in range(n_scans):
         slam.process(i, odo_deg[i], seq["scans"][i])
     np.savez_compressed(OUT / f"c2_first{n_scans}.npz", poses=slam.poses(), odo_deg=odo_deg[:n_scans],
-                        local_map=slam.local_map()[:, :2].copy(), n_global=slam.global_map().shape[0],
+                        covs=slam.covs(), local_map=slam.local_map()[:, :2].copy(), n_global=slam.global_map().shape[0],
                         n_submaps=slam.submaps(), truth=seq["traj"][:n_scans])
 
 
@@ -108,11 +108,16 @@ def map_vectors():
 if __name__ == "__main__":
     if not ra.available():
         raise SystemExit("oracle/_ref is not built (needs /root/reference): run `make -C oracle`")
-    c1_vectors(1, 0.5)
-    c1_vectors(2, 0.5)
-    c1_vectors(3, 1.0)
-    host_vectors()
-    sequence_vectors()
-    map_vectors()
+    only = set(sys.argv[1:])              # e.g. `make_golden.py seq` regenerates one family
+    if not only or "c1" in only:
+        c1_vectors(1, 0.5)
+        c1_vectors(2, 0.5)
+        c1_vectors(3, 1.0)
+    if not only or "host" in only:
+        host_vectors()
+    if not only or "seq" in only:
+        sequence_vectors()
+    if not only or "map" in only:
+        map_vectors()
     for p in sorted(OUT.glob("*.npz")):
         print(p.name, p.stat().st_size)

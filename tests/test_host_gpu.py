@@ -35,38 +35,64 @@ def _odo_deg(seq, n):
     return o
 
 
-def test_frontend_sequence_matches_reference_frontend():
-    """320 scans through FrontEnd::process (crossing the sub-map split at sepThre = 10 m): poses vs the reference
-    FrontEnd compiled from its own sources. The reference run is reproducible (oracle/ref_shim.cpp zeroes
-    ScanMatcher::lastCov; tests/test_ref_crosscheck.py), so the fixture is not one draw of many."""
+def test_frontend_sequence_matches_reference_frontend_scan_by_scan():
+    """320 scans through FrontEnd::process (crossing the sub-map split at sepThre = 10 m) against the reference FrontEnd
+    compiled from its own sources (reproducible: oracle/ref_shim.cpp zeroes ScanMatcher::lastCov).
+
+    Teacher-forced: after every scan the map and the fusion state continue from the REFERENCE's pose / covariance for that
+    scan, so every one of the 319 matches sees exactly the inputs the reference's match saw (the local maps are then
+    bit-identical) and the per-match bar applies to each: 1e-4 m, 1e-5 rad."""
     z = np.load(GOLD / "c2_first320.npz")
-    n = z["poses"].shape[0]
-    assert n == 320
+    ref, ref_cov = z["poses"], z["covs"]
+    n = ref.shape[0]
+    assert n == 320 and ref_cov.shape == (n, 3, 3)
     ha.set_params(Resolution=0.5)
     seq = synth.c2_sequence(seed=2, n_scans=2000)
     odo = _odo_deg(seq, n)
     assert np.array_equal(odo, z["odo_deg"])
     slam = ha.Slam()
     for i in range(n):
-        slam.process(i, odo[i], seq["scans"][i])
-    poses = slam.poses()
-    ref = z["poses"]
-    assert poses.shape == ref.shape
+        slam.process_forced(i, odo[i], seq["scans"][i], ref[i], ref_cov[i])
+    poses, covs = slam.poses(), slam.covs()
     dpos = np.hypot(poses[:, 0] - ref[:, 0], poses[:, 1] - ref[:, 1])
     dyaw = np.abs(np.deg2rad(poses[:, 2] - ref[:, 2]))
-    # per-match bar is 1e-4 m / 1e-5 rad; over a sequence the map feeds back into the next match (a 1e-8 pose
-    # difference can move a map point across a 5 cm voxel face of the map filter), so the bar on the whole trajectory
-    # is looser: 2 mm / 5e-4 rad
-    assert np.max(dpos[:60]) < 1e-4 and np.max(dyaw[:60]) < 1e-5, (np.max(dpos[:60]), np.max(dyaw[:60]))
-    assert np.max(dpos) < 2e-3 and np.max(dyaw) < 5e-4, (np.max(dpos), np.max(dyaw))
+    assert np.max(dpos) < 1e-4 and np.max(dyaw) < 1e-5, (np.max(dpos), np.max(dyaw), int(np.argmax(dpos)))
+    scale = np.max(np.abs(ref_cov[1:]), axis=(1, 2))
+    # the covariance is (-H)^-1 at the final pose: a final pose that differs inside the pose bar moves H a little
+    assert np.max(np.max(np.abs(covs[1:] - ref_cov[1:]), axis=(1, 2)) / scale) < 1e-3
+    assert np.median(np.max(np.abs(covs[1:] - ref_cov[1:]), axis=(1, 2)) / scale) < 1e-6
     assert slam.submaps() == int(z["n_submaps"]) == 2
+    lm = slam.local_map()
+    assert np.array_equal(lm[:, :2], z["local_map"])          # same poses in -> the reference's local map, bit for bit
+    st = slam.stats()
+    assert st["matches"] == n - 1 and st["point_evals"] > 0
+
+
+def test_frontend_sequence_free_running_stays_on_the_reference_trajectory():
+    """The same 320 scans without forcing. A match only converges to within TransformationEpsilon (0.01), so its result
+    moves by up to ~1e-3 m when an upstream 1e-9 difference flips one discrete decision (a point across a 5 cm voxel face
+    of the map filter, one More-Thuente trial more); the free-running trajectories therefore agree to millimetres, not to
+    the per-match bar -- that one is checked scan by scan above."""
+    z = np.load(GOLD / "c2_first320.npz")
+    ref = z["poses"]
+    n = ref.shape[0]
+    ha.set_params(Resolution=0.5)
+    seq = synth.c2_sequence(seed=2, n_scans=2000)
+    odo = _odo_deg(seq, n)
+    slam = ha.Slam()
+    for i in range(n):
+        slam.process(i, odo[i], seq["scans"][i])
+    poses = slam.poses()
+    dpos = np.hypot(poses[:, 0] - ref[:, 0], poses[:, 1] - ref[:, 1])
+    dyaw = np.abs(np.deg2rad(poses[:, 2] - ref[:, 2]))
+    assert np.max(dpos[:8]) < 1e-6                       # identical until the first discrete flip
+    assert np.max(dpos) < 5e-3 and np.max(dyaw) < 1e-3, (np.max(dpos), np.max(dyaw))
+    assert slam.submaps() == int(z["n_submaps"])
     from scipy.spatial import cKDTree
     lm, ref_lm = slam.local_map(), z["local_map"]
     assert abs(lm.shape[0] - ref_lm.shape[0]) < 0.01 * ref_lm.shape[0]
-    dist, _ = cKDTree(ref_lm[:, :2]).query(lm[:, :2])
+    dist, _ = cKDTree(ref_lm).query(lm[:, :2])
     assert np.max(dist) < 0.05 and np.mean(dist) < 0.002
-    st = slam.stats()
-    assert st["matches"] == n - 1 and st["point_evals"] > 0
 
 
 def test_launcher_reads_text_log_and_writes_outputs(tmp_path):
