@@ -61,6 +61,15 @@ def bytes_of(h, u, r, key):
     return float(r[i]) * UNIT.get(u[i], 1.0)
 
 
+def point_evals_per_launch():
+    """Point-evals of the captured launch = point_evals_per_step of the plain bench line of the same command."""
+    p = G / f"{rnd}_bench_plain.json"
+    try:
+        return float(json.loads(p.read_text().strip().splitlines()[-1])["point_evals_per_step"])
+    except Exception:
+        return None
+
+
 def tool(script, *args):
     return subprocess.run([sys.executable, str(P / script), *map(str, args)], capture_output=True, text=True).stdout
 
@@ -83,7 +92,11 @@ if fw.exists():
     r = rows[0]
     traffic = {"k_align_warp_C4_bytes_per_launch": bytes_of(h, u, r, "dram__bytes_read.sum") + bytes_of(h, u, r, "dram__bytes_write.sum"),
                "dram_read_bytes": bytes_of(h, u, r, "dram__bytes_read.sum"), "dram_write_bytes": bytes_of(h, u, r, "dram__bytes_write.sum"),
-               "l2_bytes": bytes_of(h, u, r, "lts__t_bytes.sum") if "lts__t_bytes.sum" in h else None,
+               "l2_bytes": (bytes_of(h, u, r, "lts__t_bytes.sum") if "lts__t_bytes.sum" in h else
+                            (float(r[h.index("lts__t_sectors.sum")]) * 32.0 if "lts__t_sectors.sum" in h else None)),
+               "l1_to_l2_write_bytes": bytes_of(h, u, r, "l1tex__m_l1tex2xbar_write_bytes.sum") if "l1tex__m_l1tex2xbar_write_bytes.sum" in h else None,
+               "l2_to_l1_read_bytes": bytes_of(h, u, r, "l1tex__m_xbar2l1tex_read_bytes.sum") if "l1tex__m_xbar2l1tex_read_bytes.sum" in h else None,
+               "point_evals_per_launch": point_evals_per_launch(),
                "issue_slots_busy_pct": float(r[h.index("smsp__issue_active.avg.pct_of_peak_sustained_active")]),
                "fp64_pipe_pct": float(r[h.index("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active")]),
                "l1_hit_pct": float(r[h.index("l1tex__t_sector_hit_rate.pct")]), "l2_hit_pct": float(r[h.index("lts__t_sector_hit_rate.pct")]),
