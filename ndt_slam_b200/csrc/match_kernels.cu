@@ -19,6 +19,7 @@
 
 #include <cooperative_groups.h>
 #include <algorithm>
+#include <cstdio>
 #include <type_traits>
 #include <cstdlib>
 #include <cstring>
@@ -59,21 +60,48 @@ struct Objective {
   Coop coop;
   HitQueue Q;          // this warp's hit queue (shared memory)
 
+#ifndef NDT_PHASE_CLOCK
+#define NDT_PHASE_CLOCK 0           // 1: per-phase clock64() totals of block 0 / thread 0 printed at kernel end (diagnostic builds only)
+#endif
+#if NDT_PHASE_CLOCK
+  long long t_enter = 0, t_leave = 0, c_pose = 0, c_acc = 0, c_red = 0, c_between = 0, n_pass = 0;
+#endif
   __device__ __noinline__ void pass(const int mode, const double *p, const AngleCache &ac, double *out) {
+#if NDT_PHASE_CLOCK
+    t_enter = clock64();
+    if (t_leave) c_between += t_enter - t_leave;
+    ++n_pass;
+#endif
     double acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
     const PoseF pf = pose_to_float(p);
+#if NDT_PHASE_CLOCK
+    const long long t1 = clock64(); c_pose += t1 - t_enter;
+#endif
     const double cs = ac.cs, sn = ac.sn;
     const Coop co = coop;
     int pairs = 0;
     accumulate_points(mode, geom, occ, nbr, cen, slot, rec, src, co.rank(), co.size(), ns, pf, sse != 0, cs, sn, d1, d2,
                       Q, acc, pairs);
+#if NDT_PHASE_CLOCK
+    const long long t2 = clock64(); c_acc += t2 - t1;
+#endif
     if (mode == 0) co.template allreduce<13>(acc);
     else if (mode == 1) co.template allreduce<4>(acc);
     else co.template allreduce<9>(acc + 4);
 #pragma unroll
     for (int k = 0; k < NACC; ++k) out[k] = acc[k];     // identical in every cooperating thread (fixed-order reduction)
+#if NDT_PHASE_CLOCK
+    t_leave = clock64(); c_red += t_leave - t2;
+#endif
+  }
+  __device__ void report(const char *who, long long t_fit) const {
+#if NDT_PHASE_CLOCK
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+      printf("PHASE %s passes %lld: pose_to_float %lld  accumulate %lld  allreduce %lld  optimiser(between passes) %lld  fitness %lld  [cycles per pass: %lld %lld %lld %lld]\n",
+             who, n_pass, c_pose, c_acc, c_red, c_between, t_fit, c_pose / n_pass, c_acc / n_pass, c_red / n_pass, c_between / (n_pass > 1 ? n_pass - 1 : 1));
+#endif
   }
 };
 
@@ -222,9 +250,11 @@ __global__ void __launch_bounds__(256) k_align_block(GridView G, MatchParams mp,
     __syncthreads();
     auto obj = make_objective(G, mp, coop, SmemOcc{smem_addr(s_occ)}, NoNbr{}, SmemCen{smem_addr(s_cen)}, SmemSlot{smem_addr(s_slot)}, SmemRec{smem_addr(s_recs)}, gsrc, ns, my_queue(smem_raw));
     match_device(obj, mp, guess, mo, opt);
+    obj.report("block<tile>", 0);
   } else {
     auto obj = make_objective(G, mp, coop, GlobalOcc{G.occ}, NoNbr{}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, my_queue(smem_raw));
     match_device(obj, mp, guess, mo, opt);
+    obj.report("block", 0);
   }
   double fsum = 0.0;
   if (mp.want_fitness) fsum = fitness_pass(G, gsrc, ns, mp, mo.p, coop);
@@ -234,6 +264,9 @@ __global__ void __launch_bounds__(256) k_align_block(GridView G, MatchParams mp,
 // ---------------------------------------------------------------------------------------------
 // one thread-block cluster per match: block reduction, then a DSMEM exchange of the 13 partials
 // ---------------------------------------------------------------------------------------------
+#ifndef NDT_CLUSTER_SIZE
+#define NDT_CLUSTER_SIZE 8
+#endif
 struct ClusterCoop {
   double *scratch;       // [9 * NACC] block scratch (one row per warp + the block totals)
   double *xchg;          // [2][16] this CTA's partial (double-buffered), read by every CTA of the cluster through DSMEM
@@ -263,8 +296,13 @@ struct ClusterCoop {
     }
     cluster.sync();
     if (threadIdx.x < N) {
+      // all remote partials are fetched before the first add: one DSMEM round trip instead of csize dependent ones
+      double part[NDT_CLUSTER_SIZE];
+#pragma unroll
+      for (int r = 0; r < NDT_CLUSTER_SIZE; ++r) part[r] = r < csize ? cluster.map_shared_rank(xb, r)[threadIdx.x] : 0.0;
       double t = 0.0;
-      for (int r = 0; r < csize; ++r) t += cluster.map_shared_rank(xb, r)[threadIdx.x];
+#pragma unroll
+      for (int r = 0; r < NDT_CLUSTER_SIZE; ++r) if (r < csize) t += part[r];      // rank order, like before: bit-identical totals
       total[threadIdx.x] = t;
     }
     __syncthreads();
@@ -290,7 +328,13 @@ __global__ void __launch_bounds__(256) k_align_cluster(GridView G, MatchParams m
   auto obj = make_objective(G, mp, coop, GlobalOcc{G.occ}, NoNbr{}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, gsrc, ns, my_queue(smem_raw));
   match_device(obj, mp, guess, mo, opt);
   double fsum = 0.0;
+#if NDT_PHASE_CLOCK
+  const long long tf0 = clock64();
+#endif
   if (mp.want_fitness) fsum = fitness_pass(G, gsrc, ns, mp, mo.p, coop);
+#if NDT_PHASE_CLOCK
+  obj.report("cluster", clock64() - tf0);
+#endif
   if (coop.crank == 0 && threadIdx.x == 0) write_result(out + job, mo, ns, fsum, mp.want_fitness != 0, G.n_tgt);
   cluster.sync();        // no CTA may retire while a neighbour can still read its exchange buffer through DSMEM
 }
@@ -661,8 +705,8 @@ __global__ void __launch_bounds__(256, NDT_PAIRS_KERNEL_MIN_CTAS) k_align_pairs(
 // The CTA first stages what stages A and B read -- the pair's source cloud (as float2), its slice of the occupancy bitmap
 // and of the centroid table -- in shared memory with coalesced loads; a pair too large for the staging area is read in
 // place. The accessors take generic pointers, so both cases run the same code.
-constexpr int PB_SRC_CAP = 1280, PB_CEN_CAP = 2560, PB_OCC_CAP = PB_CEN_CAP / 32 + 2;
-constexpr int PB_STAGE_BYTES = PB_SRC_CAP * 8 + PB_CEN_CAP * 8 + PB_OCC_CAP * 4;
+constexpr int PB_SRC_CAP = 1280, PB_CEN_CAP = 2560, PB_OCC_CAP = PB_CEN_CAP / 32 + 2, PB_REC_CAP = 320;
+constexpr int PB_STAGE_BYTES = PB_SRC_CAP * 8 + PB_CEN_CAP * 8 + ((PB_OCC_CAP * 4 + 15) & ~15) + PB_CEN_CAP * 4 + PB_REC_CAP * 64;
 struct AnyOcc {
   const uint32_t *p; int w0;
   __device__ __forceinline__ uint32_t operator()(int w) const { return p[w - w0]; }
@@ -672,6 +716,17 @@ struct AnyCen {
   __device__ __forceinline__ float2 operator()(int i) const { return p[i - i0]; }
 };
 
+struct AnySlot {
+  const int32_t *p; int i0;
+  __device__ __forceinline__ int operator()(int i) const { return p[i - i0]; }
+};
+struct AnyRec {
+  const CellRec *p;
+  __device__ __forceinline__ void body(int s, double2 &m, double2 &r0, double2 &r1) const {
+    const double2 *q = reinterpret_cast<const double2 *>(p + s);
+    m = q[1]; r0 = q[2]; r1 = q[3];
+  }
+};
 struct AnySrc {
   const float *p; int stride;      // floats between consecutive points (2: staged float2, 4: the caller's float4)
   __device__ __forceinline__ float2 operator()(int i) const { return *reinterpret_cast<const float2 *>(p + (size_t)i * stride); }
@@ -687,6 +742,9 @@ __global__ void __launch_bounds__(256, NDT_PAIRS_KERNEL_MIN_CTAS) k_align_pairs_
   float2 *s_src = reinterpret_cast<float2 *>(smem_raw + QUEUE_BYTES);
   float2 *s_cen = s_src + PB_SRC_CAP;
   uint32_t *s_occ = reinterpret_cast<uint32_t *>(s_cen + PB_CEN_CAP);
+  int32_t *s_slot = reinterpret_cast<int32_t *>(reinterpret_cast<unsigned char *>(s_occ) + ((PB_OCC_CAP * 4 + 15) & ~15));
+  CellRec *s_recs = reinterpret_cast<CellRec *>(s_slot + PB_CEN_CAP);
+  __shared__ int s_wcnt[8];
   BlockCoop coop{scratch};
   for (;;) {
     if (threadIdx.x == 0) s_job = atomicAdd(job_counter, 1);
@@ -715,12 +773,49 @@ __global__ void __launch_bounds__(256, NDT_PAIRS_KERNEL_MIN_CTAS) k_align_pairs_
       aocc = AnyOcc{s_occ, w0};
     }
     __syncthreads();
+    // the records of the pair's tree cells, compacted into shared memory (they sit scattered in the global array: slots are
+    // handed out in completion order across all pairs) with a local cell -> record table: after this the whole match
+    // -- probes, hits, records -- runs out of shared memory
+    AnySlot aslot{G.slot, 0};
+    AnyRec arec{G.recs};
+    if (ncell <= PB_CEN_CAP) {
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      int n_tree = 0;
+      for (int c0 = 0; c0 < ncell; c0 += blockDim.x) {
+        const int c = c0 + threadIdx.x;
+        const bool tree = c < ncell && (s_cen[c].x == s_cen[c].x);
+        const unsigned bal = __ballot_sync(0xffffffffu, tree);
+        if (lane == 0) s_wcnt[warp] = __popc(bal);
+        __syncthreads();
+        int off = n_tree, tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { const int v = s_wcnt[w]; tot += v; if (w < warp) off += v; }
+        const int j = off + __popc(bal & ((1u << lane) - 1u));
+        if (c < ncell) s_slot[c] = tree ? j : -1;
+        if (tree && j < PB_REC_CAP) {
+          const int4 *gr = reinterpret_cast<const int4 *>(G.recs + __ldg(G.slot + d.base + c));
+          int4 *sr = reinterpret_cast<int4 *>(s_recs + j);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) sr[q] = __ldg(gr + q);
+        }
+        n_tree += tot;
+        __syncthreads();
+      }
+      if (n_tree <= PB_REC_CAP) { aslot = AnySlot{s_slot, d.base}; arec = AnyRec{s_recs}; }      // block-uniform
+    }
+    __syncthreads();
     MatchOut mo;
     OptState opt;
-    auto obj = make_objective(G, mp, coop, aocc, NoNbr{}, acen, GlobalSlot{G.slot}, GlobalRec{G.recs}, asrc, d.ns, my_queue(smem_raw));
+    auto obj = make_objective(G, mp, coop, aocc, NoNbr{}, acen, aslot, arec, asrc, d.ns, my_queue(smem_raw));
     match_device(obj, mp, guess, mo, opt);
     double fsum = 0.0;
+#if NDT_PHASE_CLOCK
+    const long long tf0 = clock64();
+#endif
     if (mp.want_fitness) fsum = fitness_pass(G, asrc, d.ns, mp, mo.p, coop);
+#if NDT_PHASE_CLOCK
+    if (job < 3) obj.report("pairs_block", clock64() - tf0);
+#endif
     if (threadIdx.x == 0) write_result(out + job, mo, d.ns, fsum, mp.want_fitness != 0, G.n_tgt);
   }
 }
@@ -787,9 +882,6 @@ int launch_eval(Handle *h, const double *d_poses, int64_t n, int want_hessian, d
 
 #ifndef NDT_GRID_MIN_NS
 #define NDT_GRID_MIN_NS 16384     // above this one match takes the whole GPU (cooperative launch)
-#endif
-#ifndef NDT_CLUSTER_SIZE
-#define NDT_CLUSTER_SIZE 8
 #endif
 #ifndef NDT_CLUSTER_MIN_NS
 #define NDT_CLUSTER_MIN_NS 600      // measured on C1 (855 points): 8-CTA cluster 0.090 ms vs one CTA 0.113 ms

@@ -872,10 +872,17 @@ __device__ __forceinline__ void nn_ring(const GridView &G, int ci, int cj, int r
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float2 *__restrict__ q = pts + rg[k].x;
-      for (int j = 0; j < rg[k].y; ++j) {
-        const float2 t = __ldg(q + j);
-        const float dd = dist2f(xt, yt, t.x, t.y);
-        if (dd < best) best = dd;
+      // four points per trip, loads issued together (a bucket along a wall holds ~10 points; one dependent L2 round trip
+      // per point made this loop half of a warp-per-pair match); a NaN stand-in fails the compare
+      for (int j = 0; j < rg[k].y; j += 4) {
+        float2 t[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) t[u] = (j + u < rg[k].y) ? __ldg(q + j + u) : make_float2(NAN, NAN);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float dd = dist2f(xt, yt, t[u].x, t[u].y);
+          if (dd < best) best = dd;
+        }
       }
     }
   }
@@ -965,10 +972,15 @@ __device__ inline float nn_stage2_warp(const GridView &G, float xt, float yt, fl
           if (ring > 0) ring_cell(ring, t, di, dj);
           const int2 rg = nn_bucket<false>(G, ci + di, cj + dj);
           const float2 *__restrict__ q = G.tgt_sorted + rg.x;
-          for (int j = 0; j < rg.y; ++j) {
-            const float2 p = __ldg(q + j);
-            const float dd = dist2f(xt, yt, p.x, p.y);
-            if (dd < best) best = dd;
+          for (int j = 0; j < rg.y; j += 4) {
+            float2 p[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) p[u] = (j + u < rg.y) ? __ldg(q + j + u) : make_float2(NAN, NAN);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float dd = dist2f(xt, yt, p[u].x, p[u].y);
+              if (dd < best) best = dd;
+            }
           }
         }
       }

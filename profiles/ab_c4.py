@@ -22,7 +22,7 @@ def child(args):
     from ndt_slam_b200 import capi
 
     out = {"lib": os.environ.get("NDT_B200_LIB", "default")}
-    wl = bench.build_c4(1, 65536)
+    wl = bench.build_c4(65536)
     stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
     prm = capi.default_params(resolution=0.5, stream=stream.cuda_stream)
     g = capi.Ndt(prm)
@@ -51,9 +51,11 @@ def child(args):
         torch.cuda.synchronize(); sw.append(a.elapsed_time(b))
     out["sweep_ms"] = float(min(sw))
     if "--pairs" in args:
-        for npairs in (8192, 1024):
+        for npairs, sched in ((8192, capi.PAIRS_WARP), (8192, capi.PAIRS_CTA), (2048, capi.PAIRS_CTA), (1024, capi.PAIRS_CTA)):
             c5 = bench.build_c5(0, npairs)
-            g5 = capi.Ndt(prm)
+            prm5 = capi.default_params(resolution=0.5, stream=stream.cuda_stream, pairs_schedule=sched)
+            g5 = capi.Ndt(prm5)
+            tag = f"{npairs}" + {capi.PAIRS_WARP: "warp", capi.PAIRS_CTA: "cta", capi.PAIRS_AUTO: ""}[sched]
             d_s, d_t = torch.from_numpy(c5["src"]).cuda(), torch.from_numpy(c5["tgt"]).cuda()
             d_g = torch.zeros((npairs, 3), dtype=torch.float64, device="cuda")
             d_r5 = torch.zeros(npairs * capi.RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
@@ -68,9 +70,9 @@ def child(args):
                     t5.append(a.elapsed_time(b))
             r5 = np.frombuffer(d_r5.cpu().numpy().tobytes(), dtype=capi.RESULT_DTYPE)
             if os.environ.get("NDT_AB_DUMP"):
-                np.save(ROOT / "gpurun_out" / "r2" / f"c5_{npairs}_{Path(out['lib']).stem}.npy", r5)
-            out[f"c5_{npairs}_ms"] = float(np.median(t5))
-            out[f"c5_{npairs}_digest"] = hashlib.sha256(r5["pose"].tobytes() + r5["fitness"].tobytes() + r5["evals"].tobytes()).hexdigest()[:12]
+                np.save(ROOT / "gpurun_out" / "r2" / f"c5_{tag}_{Path(out['lib']).stem}.npy", r5)
+            out[f"c5_{tag}_ms"] = float(np.median(t5))
+            out[f"c5_{tag}_digest"] = hashlib.sha256(r5["pose"].tobytes() + r5["fitness"].tobytes() + r5["evals"].tobytes()).hexdigest()[:12]
     if "--c1" in args:
         sys.path.insert(0, str(ROOT / "tests"))
         import ndt_common as common

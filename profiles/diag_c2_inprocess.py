@@ -4,7 +4,7 @@ import torch, numpy as np
 import bench
 from ndt_slam_b200 import capi
 # mimic the bench process before the extras: C4 batch on a torch stream + flush buffer + pinned buffers
-wl = bench.build_c4(1, 65536)
+wl = bench.build_c4(65536)
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 prm = capi.default_params(resolution=0.5, device=0, stream=stream.cuda_stream)
 g = capi.Ndt(prm); g.set_target(wl["tgt"]); g.set_source(wl["src"])

@@ -13,7 +13,7 @@ from ndt_slam_b200 import capi, synth  # noqa: E402
 from oracle import oracle_api as oa  # noqa: E402  (data preparation only)
 
 n_hyp = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
-wl = bench.build_c4(1, 65536)
+wl = bench.build_c4(65536)
 prm = capi.default_params(resolution=0.5)
 g = capi.Ndt(prm)
 g.set_target(wl["tgt"]); g.set_source(wl["src"])

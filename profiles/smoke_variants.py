@@ -7,7 +7,7 @@ if os.environ.get("NDT_SMOKE_CHILD"):
     import numpy as np
     import bench
     from ndt_slam_b200 import capi
-    wl = bench.build_c4(1, 65536)
+    wl = bench.build_c4(65536)
     g = capi.Ndt(capi.default_params(resolution=0.5))
     g.set_target(wl["tgt"]); g.set_source(wl["src"])
     try:
