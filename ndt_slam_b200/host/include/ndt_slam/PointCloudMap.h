@@ -45,17 +45,24 @@ class Submap {
   // grows while p_cloud grows at its end), `tail` = the end-of-cloud flush (<= 512 points, changes every scan).
   // filterPoints() == prefix + tail. Lets makeLocalMap update localMap_cloud in O(new points).
   const std::vector<pcl::PointXYZ> &thinnedPrefix();
-  void thinnedTail(std::vector<pcl::PointXYZ> &tail) const { thin.append_live(tail); }
+  void thinnedTail(std::vector<pcl::PointXYZ> &tail) const {
+    thin.append_with_tail(p_cloud->points.data() + thin.consumed, p_cloud->points.size() - thin.consumed, tail);
+  }
 
  private:
   // Incremental state (not in the reference, which rebuilds p_cloud and re-filters it from scratch every scan --
-  // quadratic over a sub-map's life). Without moving-object removal a sub-map only ever appends whole scans, so both
-  // the concatenation and the order-dependent voxel filter can continue from where they stopped; the clouds produced
-  // are bit-identical to the from-scratch ones.
+  // quadratic over a sub-map's life, and with moving-object removal every rebuild re-runs the octree difference and the
+  // brute-force neighbour removal of every scan triple). A sub-map only ever appends whole scans, and with removeMoving the
+  // filtered version of scan i+1 depends on scans i, i+1, i+2 only, so: p_cloud = [stable part that never changes again]
+  // + [the newest scan, raw, replaced one scan later by its filtered version]. Both the concatenation and the
+  // order-dependent voxel filter continue from the end of the stable part; the clouds produced are bit-identical to the
+  // from-scratch ones.
   size_t appended_scans = 0;                 // scans[first .. appended_scans) are already in p_cloud
   const void *appended_into = nullptr;       // the p_cloud object they were appended to
   size_t appended_points = 0;
-  ndt_host::IncrementalVoxelGrid thin;
+  size_t rm_triples = 0;                     // removeMoving: triples (i, i+1, i+2), i < rm_triples, are folded into p_cloud
+  size_t stable_points = 0;                  // p_cloud[0 .. stable_points) is final
+  ndt_host::IncrementalVoxelGrid thin;       // has consumed a prefix of the stable part
   const void *thin_of = nullptr;             // the p_cloud object `thin` has consumed a prefix of
   void syncThin();
 

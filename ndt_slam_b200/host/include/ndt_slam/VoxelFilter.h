@@ -31,27 +31,25 @@ class IncrementalVoxelGrid {
   }
   // consume points[consumed .. n) of a cloud that only ever grows at its end
   void feed(const pcl::PointXYZ *points, size_t n) {
-    for (size_t i = consumed; i < n; ++i) {
-      const pcl::PointXYZ &p = points[i];
-      const int ix = static_cast<int>(std::floor(p.x * inv));
-      const int iy = static_cast<int>(std::floor(p.y * inv));
-      const int iz = static_cast<int>(std::floor(p.z * inv));
-      const unsigned h = (static_cast<unsigned>(ix) * 7171u + static_cast<unsigned>(iy) * 3079u + static_cast<unsigned>(iz) * 4231u) & (kSlots - 1);
-      Slot &s = table[h];
-      if (s.n != 0 && (s.ix != ix || s.iy != iy || s.iz != iz)) {   // a different voxel claims the slot
-        emitted.push_back(centroid(s));
-        s.n = 0; s.sx = s.sy = s.sz = 0.f;
-      }
-      s.ix = ix; s.iy = iy; s.iz = iz;
-      ++s.n;
-      s.sx += p.x; s.sy += p.y; s.sz += p.z;
-    }
+    for (size_t i = consumed; i < n; ++i) step(table, points[i], emitted);
     if (n > consumed) consumed = n;
   }
   // centroids of the slots that are still live, in slot order (what the end-of-cloud flush would emit)
   template <class Vec>
   void append_live(Vec &out) const {
     for (const Slot &s : table) if (s.n != 0) out.push_back(centroid(s));
+  }
+  // What the filter would still emit if `tail[0 .. n)` followed the points consumed so far: the centroids flushed while
+  // the tail is consumed, then the end-of-cloud flush -- computed on a copy of the 512 slots, so the state stays where it
+  // is. Used when the end of the cloud is provisional (moving-object removal replaces the newest scan's raw points by a
+  // filtered version one scan later).
+  template <class Vec>
+  void append_with_tail(const pcl::PointXYZ *tail, size_t n, Vec &out) const {
+    if (n == 0) { append_live(out); return; }
+    Slot scratch[kSlots];
+    for (unsigned k = 0; k < kSlots; ++k) scratch[k] = table[k];
+    for (size_t i = 0; i < n; ++i) step(scratch, tail[i], out);
+    for (const Slot &s : scratch) if (s.n != 0) out.push_back(centroid(s));
   }
   float leaf = 0.f;
   size_t consumed = 0;
@@ -61,6 +59,22 @@ class IncrementalVoxelGrid {
   static pcl::PointXYZ centroid(const Slot &s) {
     const float cnt = static_cast<float>(s.n);
     return pcl::PointXYZ(s.sx / cnt, s.sy / cnt, s.sz / cnt);
+  }
+  // one point of the hash history
+  template <class Vec>
+  void step(Slot *slots, const pcl::PointXYZ &p, Vec &flushed) const {
+    const int ix = static_cast<int>(std::floor(p.x * inv));
+    const int iy = static_cast<int>(std::floor(p.y * inv));
+    const int iz = static_cast<int>(std::floor(p.z * inv));
+    const unsigned h = (static_cast<unsigned>(ix) * 7171u + static_cast<unsigned>(iy) * 3079u + static_cast<unsigned>(iz) * 4231u) & (kSlots - 1);
+    Slot &s = slots[h];
+    if (s.n != 0 && (s.ix != ix || s.iy != iy || s.iz != iz)) {   // a different voxel claims the slot
+      flushed.push_back(centroid(s));
+      s.n = 0; s.sx = s.sy = s.sz = 0.f;
+    }
+    s.ix = ix; s.iy = iy; s.iz = iz;
+    ++s.n;
+    s.sx += p.x; s.sy += p.y; s.sz += p.z;
   }
   float inv = 0.f;
   Slot table[kSlots];

@@ -11,15 +11,16 @@
 
 typedef pcl::PointCloud<pcl::PointXYZ> Cloud;
 
-// Bring the incremental filter up to date with p_cloud. Anything other than "the same cloud object grew at its end"
-// (a new cloud object, a shorter cloud, a different leaf size, moving-object removal rebuilding the cloud) restarts it.
+// Bring the incremental filter up to date with the stable part of p_cloud. Anything other than "the same cloud object
+// grew at the end of its stable part" (a new cloud object, a shorter cloud, a different leaf size) restarts it.
 void Submap::syncThin() {
   const float leaf = static_cast<float>(LeafSize);
-  if (thin_of != p_cloud.get() || p_cloud->points.size() < thin.consumed || thin.leaf != leaf || removeMoving) {
+  const size_t stable = std::min(stable_points, p_cloud->points.size());
+  if (thin_of != p_cloud.get() || stable < thin.consumed || thin.leaf != leaf) {
     thin.reset(leaf);
     thin_of = p_cloud.get();
   }
-  thin.feed(p_cloud->points.data(), p_cloud->points.size());
+  thin.feed(p_cloud->points.data(), stable);
 }
 
 const std::vector<pcl::PointXYZ> &Submap::thinnedPrefix() {
@@ -31,44 +32,52 @@ Cloud::Ptr Submap::filterPoints() {
   Cloud::Ptr thinned = std::make_shared<Cloud>();
   syncThin();
   thinned->points.assign(thin.emitted.begin(), thin.emitted.end());
-  thin.append_live(thinned->points);
+  thinnedTail(thinned->points);
   thinned->width = static_cast<uint32_t>(thinned->points.size());
   thinned->height = 1;
   thinned->is_dense = false;
   return thinned;
 }
 
-// Rebuild p_cloud from the stored scans.
+// Bring p_cloud up to date with the stored scans [REF src/PointCloudMap.cpp:15-39].
 //  removeMoving: for every consecutive triple (i, i+1, i+2) keep scan i+1 minus the points that lie near
 //                voxels seen only by i+1 and not by {i, i+2}; the first sub-map also keeps its first scan
-//                and the newest sub-map its latest scan unfiltered.
+//                and the newest sub-map its latest scan unfiltered (so a single scan appears twice, like the reference).
 //  otherwise:    plain concatenation; sub-maps after the first skip the two scans carried over from their
-//                predecessor. Only the scans added since the last call are appended (same cloud as clearing
-//                and re-concatenating everything).
+//                predecessor.
+// Only what the scans added since the last call change is recomputed (same cloud as clearing and rebuilding everything).
 void Submap::makeMap() {
-  const int n = static_cast<int>(scans.size());
+  const size_t n = scans.size();
+  const size_t first = removeMoving ? 0 : (cntS == 0 ? 0 : 2);
+  if (appended_into != p_cloud.get() || p_cloud->points.size() != appended_points || stable_points > appended_points ||
+      (removeMoving ? rm_triples + 2 > std::max<size_t>(n, 2) : (appended_scans < first || appended_scans > n))) {
+    p_cloud->clear();                              // someone else touched the cloud: start over
+    appended_into = p_cloud.get();
+    appended_scans = first;
+    rm_triples = 0;
+    if (removeMoving && cntS == 0 && n > 0) *p_cloud += *scans[0];
+    stable_points = p_cloud->points.size();
+  }
   if (removeMoving) {
-    p_cloud->clear();
-    if (cntS == 0) *p_cloud += *scans[0];
-    for (int i = 0; i + 2 < n; ++i) {
+    p_cloud->points.resize(stable_points);         // the previous newest scan was there raw: its filtered version follows
+    for (size_t i = rm_triples; i + 2 < n; ++i) {
       Cloud::Ptr outer = std::make_shared<Cloud>();
       *outer += *scans[i];
       *outer += *scans[i + 2];
       Cloud::Ptr transient = pcf.difference_extraction(outer, scans[i + 1]);
-      *p_cloud += *pcf.remove_neighborPoint(scans[i + 1], transient);
+      Cloud::Ptr kept = pcf.remove_neighborPoint(scans[i + 1], transient);
+      p_cloud->points.insert(p_cloud->points.end(), kept->points.begin(), kept->points.end());
     }
-    if (newest) *p_cloud += *scans[n - 1];
-    return;
+    rm_triples = n >= 2 ? n - 2 : 0;
+    stable_points = p_cloud->points.size();
+    if (newest && n > 0) p_cloud->points.insert(p_cloud->points.end(), scans[n - 1]->points.begin(), scans[n - 1]->points.end());
+  } else {
+    for (size_t i = appended_scans; i < n; ++i) p_cloud->points.insert(p_cloud->points.end(), scans[i]->points.begin(), scans[i]->points.end());
+    appended_scans = std::max(appended_scans, n);
+    stable_points = p_cloud->points.size();
   }
-  const size_t first = (cntS == 0 ? 0 : 2);
-  if (appended_into != p_cloud.get() || appended_points != p_cloud->points.size() || appended_scans < first ||
-      appended_scans > static_cast<size_t>(n)) {
-    p_cloud->clear();                              // someone else touched the cloud: start over
-    appended_scans = first;
-    appended_into = p_cloud.get();
-  }
-  for (size_t i = appended_scans; i < static_cast<size_t>(n); ++i) *p_cloud += *scans[i];
-  appended_scans = std::max(appended_scans, static_cast<size_t>(n));
+  p_cloud->width = static_cast<uint32_t>(p_cloud->points.size());
+  p_cloud->height = 1;
   appended_points = p_cloud->points.size();
 }
 

@@ -196,6 +196,16 @@ int64_t host_map_replay(const double *poses3, const double *xy, const int64_t *o
   return (int64_t)pcmap.submaps.size();
 }
 
+// PCFilter on its own: diff = difference_extraction(base, test), kept = remove_neighborPoint(test, diff)
+void host_pcfilter(const float *base_xyzw, int64_t n_base, const float *test_xyzw, int64_t n_test, float *diff_out, int64_t *n_diff,
+                   float *kept_out, int64_t *n_kept) {
+  PCFilter f;
+  auto diff = f.difference_extraction(cloud_of(base_xyzw, n_base), cloud_of(test_xyzw, n_test));
+  auto kept = f.remove_neighborPoint(cloud_of(test_xyzw, n_test), diff);
+  *n_diff = cloud_out(*diff, diff_out, n_test);
+  *n_kept = cloud_out(*kept, kept_out, n_test);
+}
+
 // SlamLauncher: run a text scan log end to end (parameters filename_in / poses_name / map_name ... must be set)
 int host_launcher_run() {
   try {

@@ -90,6 +90,18 @@ def voxel_filter(xyzw, leaf):
     return np.ascontiguousarray(out[:m])
 
 
+def pcfilter(base_xyzw, test_xyzw):
+    """PCFilter::difference_extraction(base, test) and remove_neighborPoint(test, diff) -> (diff xyzw, kept xyzw)."""
+    L = load()
+    base = np.ascontiguousarray(base_xyzw, np.float32); test = np.ascontiguousarray(test_xyzw, np.float32)
+    d, k = np.zeros_like(test), np.zeros_like(test)
+    nd, nk = C.c_int64(), C.c_int64()
+    L.host_pcfilter.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.POINTER(C.c_int64)]
+    L.host_pcfilter.restype = None
+    L.host_pcfilter(_p(base), base.shape[0], _p(test), test.shape[0], _p(d), C.byref(nd), _p(k), C.byref(nk))
+    return np.ascontiguousarray(d[: nd.value]), np.ascontiguousarray(k[: nk.value])
+
+
 def map_replay(poses_deg, scans_map_xy, check_every=0):
     """PointCloudMap alone: (addPose, addPoints, makeLocalMap) per scan, makeGlobalMap at the end.
     Returns (n_submaps, local_map xyzw, global_map xyzw). Raises if the incremental local map ever differs from a

@@ -94,6 +94,18 @@ def voxel_filter(xyzw, leaf):
     return np.ascontiguousarray(out[:m])
 
 
+def pcfilter(base_xyzw, test_xyzw):
+    """The reference's PCFilter: (difference_extraction(base, test), remove_neighborPoint(test, diff))."""
+    L = load()
+    base = np.ascontiguousarray(base_xyzw, np.float32); test = np.ascontiguousarray(test_xyzw, np.float32)
+    d, k = np.zeros_like(test), np.zeros_like(test)
+    nd, nk = C.c_int64(), C.c_int64()
+    L.ref_pcfilter.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.POINTER(C.c_int64)]
+    L.ref_pcfilter.restype = None
+    L.ref_pcfilter(_p(base), base.shape[0], _p(test), test.shape[0], _p(d), C.byref(nd), _p(k), C.byref(nk))
+    return np.ascontiguousarray(d[: nd.value]), np.ascontiguousarray(k[: nk.value])
+
+
 def map_replay(poses_deg, scans_map_xy):
     """The reference's PointCloudMap alone (same driver as ndt_slam_b200.host_api.map_replay)."""
     L = load()

@@ -218,6 +218,22 @@ int64_t ref_slam_global_map(void *h, float *xyzw, int64_t cap) {
 }
 int ref_slam_submaps(void *h) { return (int)((Slam *)h)->pcmap.submaps.size(); }
 
+// The reference's own PCFilter (include/ndt_slam/PCFilter.h, unmodified) on the restated change-detector octree:
+// diff = difference_extraction(base, test), kept = remove_neighborPoint(test, diff)
+void ref_pcfilter(const float *base_xyzw, int64_t n_base, const float *test_xyzw, int64_t n_test, float *diff_out, int64_t *n_diff,
+                  float *kept_out, int64_t *n_kept) {
+  PCFilter f;
+  pcl::PointCloud<pcl::PointXYZ>::Ptr base = cloud_of(base_xyzw, n_base), test = cloud_of(test_xyzw, n_test);
+  pcl::PointCloud<pcl::PointXYZ>::Ptr diff = f.difference_extraction(base, test);
+  pcl::PointCloud<pcl::PointXYZ>::Ptr kept = f.remove_neighborPoint(test, diff);
+  auto dump = [](const pcl::PointCloud<pcl::PointXYZ> &c, float *o) {
+    for (size_t i = 0; i < c.points.size(); ++i) { o[4 * i] = c.points[i].x; o[4 * i + 1] = c.points[i].y; o[4 * i + 2] = c.points[i].z; o[4 * i + 3] = 0.f; }
+    return (int64_t)c.points.size();
+  };
+  *n_diff = dump(*diff, diff_out);
+  *n_kept = dump(*kept, kept_out);
+}
+
 // The reference's own PointCloudMap on its own: same driver as host_map_replay in the product's harness.
 int64_t ref_map_replay(const double *poses3, const double *xy, const int64_t *off, int n_scans,
                        float *local_out, int64_t lcap, int64_t *n_local, float *global_out, int64_t gcap, int64_t *n_global) {

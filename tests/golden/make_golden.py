@@ -86,6 +86,43 @@ def sequence_vectors(n_scans=320):
                         n_submaps=slam.submaps(), truth=seq["traj"][:n_scans])
 
 
+def moving_object(scans, first=8, last=70):
+    """A small box crossing the corridor: 14 points on a 0.35 m face, 0.12 m further along every scan (map frame)."""
+    out = []
+    for i, sc in enumerate(scans):
+        if first <= i < last:
+            c = sc.mean(axis=0) + np.array([-1.5 + 0.12 * (i - first), 0.4])
+            box = c + np.stack([np.linspace(-0.175, 0.175, 14), 0.02 * np.sin(np.arange(14))], axis=1)
+            sc = np.concatenate([sc, box], axis=0)
+        out.append(sc)
+    return out
+
+
+def moving_vectors():
+    """Moving-object removal (removeMoving = true, the launch default): the reference's PCFilter.h / PointCloudMap.cpp on
+    the restated change-detector octree, a map replay with a moving box, and a FrontEnd run with sub-map splits."""
+    poses, scans = map_replay_inputs(90)
+    scans = moving_object(scans)
+    prm = dict(removeMoving="true", sepThre=2.0, LeafSize=0.05, resol=0.05, thre_neighbor=0.2)
+    ra.set_params(**prm)
+    n_sub, local, glob = ra.map_replay(poses, scans)
+    base = synth.to_xyzw(np.concatenate([scans[20], scans[22]])); test = synth.to_xyzw(scans[21])
+    diff, kept = ra.pcfilter(base, test)
+    # FrontEnd with removeMoving over 150 scans, sub-map split every 3 m
+    ra.set_params(Resolution=0.5, removeMoving="true", sepThre=3.0, thre_neighbor=0.2)
+    seq = synth.c2_sequence(seed=2, n_scans=2000)
+    odo_deg = np.column_stack([seq["odo"][:, 0], seq["odo"][:, 1], np.rad2deg(seq["odo"][:, 2])])
+    odo_deg[:, 2] = (odo_deg[:, 2] + 180.0) % 360.0 - 180.0
+    slam = ra.RefSlam()
+    n = 150
+    for i in range(n):
+        slam.process(i, odo_deg[i], seq["scans"][i])
+    ra.set_params()
+    np.savez_compressed(OUT / "moving_removal.npz", n_submaps=n_sub, local_map=local[:, :2].copy(), global_map=glob[:, :2].copy(),
+                        pcf_base=base, pcf_test=test, pcf_diff=diff, pcf_kept=kept,
+                        fe_poses=slam.poses(), fe_covs=slam.covs(), fe_local_map=slam.local_map()[:, :2].copy(), fe_submaps=slam.submaps())
+
+
 def map_replay_inputs(n_scans=150):
     """Map-frame scans along the C2 ground-truth trajectory (the inputs of PointCloudMap::addPose / addPoints)."""
     seq = synth.c2_sequence(seed=2, n_scans=2000)
@@ -119,5 +156,7 @@ if __name__ == "__main__":
         sequence_vectors()
     if not only or "map" in only:
         map_vectors()
+    if not only or "moving" in only:
+        moving_vectors()
     for p in sorted(OUT.glob("*.npz")):
         print(p.name, p.stat().st_size)

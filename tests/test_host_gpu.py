@@ -95,6 +95,29 @@ def test_frontend_sequence_free_running_stays_on_the_reference_trajectory():
     assert np.max(dist) < 0.05 and np.mean(dist) < 0.002
 
 
+def test_frontend_with_moving_object_removal_matches_reference_scan_by_scan():
+    """removeMoving = true (the launch default, ndt_mapping.launch:20), 150 scans, sub-map split every 3 m: the reference's
+    FrontEnd with its own PCFilter / PointCloudMap against the product (teacher-forced like the test above): every match
+    within the per-match bar, the filtered local map bit-identical."""
+    z = np.load(GOLD / "moving_removal.npz")
+    ref, ref_cov = z["fe_poses"], z["fe_covs"]
+    n = ref.shape[0]
+    assert n == 150
+    ha.set_params(Resolution=0.5, removeMoving="true", sepThre=3.0, thre_neighbor=0.2)
+    seq = synth.c2_sequence(seed=2, n_scans=2000)
+    odo = _odo_deg(seq, n)
+    slam = ha.Slam()
+    for i in range(n):
+        slam.process_forced(i, odo[i], seq["scans"][i], ref[i], ref_cov[i])
+    poses = slam.poses()
+    dpos = np.hypot(poses[:, 0] - ref[:, 0], poses[:, 1] - ref[:, 1])
+    dyaw = np.abs(np.deg2rad(poses[:, 2] - ref[:, 2]))
+    assert np.max(dpos) < 1e-4 and np.max(dyaw) < 1e-5, (np.max(dpos), np.max(dyaw), int(np.argmax(dpos)))
+    assert slam.submaps() == int(z["fe_submaps"]) >= 3
+    assert np.array_equal(slam.local_map()[:, :2], z["fe_local_map"])
+    ha.set_params()
+
+
 def test_launcher_reads_text_log_and_writes_outputs(tmp_path):
     seq = synth.c2_sequence(seed=2, n_scans=2000)
     n = 25
