@@ -206,6 +206,35 @@ void host_pcfilter(const float *base_xyzw, int64_t n_base, const float *test_xyz
   *n_kept = cloud_out(*kept, kept_out, n_test);
 }
 
+// SlamLauncher's reader and writers on their own (no device needed): same drivers as the ref_launcher_* / ref_save_maps
+// entry points of oracle/ref_shim.cpp over the reference's own SlamLauncher.cpp
+int64_t host_launcher_parse(double *meta5, int64_t meta_cap, double *xy, int64_t xy_cap, int64_t *n_points) {
+  SlamLauncher sl;
+  if (!sl.ok) return -1;
+  sl.readFormat();
+  int64_t n = 0, np = 0;
+  while (!sl.input_file_line()) {
+    if (n < meta_cap) { meta5[5 * n] = sl.scan.sid; meta5[5 * n + 1] = sl.scan.pose.tx; meta5[5 * n + 2] = sl.scan.pose.ty; meta5[5 * n + 3] = sl.scan.pose.th; meta5[5 * n + 4] = (double)sl.scan.lps.size(); }
+    for (const LPoint2D &lp : sl.scan.lps) { if (np < xy_cap) { xy[2 * np] = lp.x; xy[2 * np + 1] = lp.y; } ++np; }
+    ++n;
+  }
+  *n_points = np;
+  return n;
+}
+void host_launcher_write_poses(const double *poses3, int64_t n) {
+  std::vector<Pose2D> poses;
+  for (int64_t i = 0; i < n; ++i) poses.push_back(Pose2D(poses3[3 * i], poses3[3 * i + 1], poses3[3 * i + 2]));
+  SlamLauncher sl;
+  sl.output_file_poses(poses);
+  sl.outputfile.close();
+}
+void host_save_maps(const float *global_xyzw, int64_t n_global, const float *sub_xyzw, const int64_t *sub_off, int n_sub) {
+  PointCloudMap pcmap;
+  pcmap.globalMap_cloud = cloud_of(global_xyzw, n_global);
+  for (int k = 0; k < n_sub; ++k) pcmap.maps.push_back(cloud_of(sub_xyzw + 4 * sub_off[k], sub_off[k + 1] - sub_off[k]));
+  pcmap.saveGlobalMap();
+}
+
 // SlamLauncher: run a text scan log end to end (parameters filename_in / poses_name / map_name ... must be set)
 int host_launcher_run() {
   try {

@@ -215,15 +215,55 @@ def launcher_run() -> int:
     return n
 
 
-def write_scan_log(path, odo_deg, scans, header_lines=("# synthetic", "# ndt_slam text log", "#", "#")):
+def write_scan_log(path, odo_deg, scans, header_lines=("# synthetic", "# ndt_slam text log", "#", "#"), left=None, right=None):
     """The reference's text scan log (SlamLauncher.cpp:37-105): 4 header lines, then per
     scan 'stamp x y theta_deg image' and three point groups 'count x y x y ...' (front, left, right)."""
+    def group(xy):
+        return f"{xy.shape[0]} " + " ".join(f"{float(x)!r} {float(y)!r}" for x, y in xy) + (" " if xy.shape[0] else "")
+    empty = np.zeros((0, 2))
     with open(path, "w") as f:
         for h in header_lines:
             f.write(h + "\n")
         for i, (o, xy) in enumerate(zip(odo_deg, scans)):
             f.write(f"{i} {float(o[0])!r} {float(o[1])!r} {float(o[2])!r} img{i}.png\n")
-            f.write(f"{xy.shape[0]} " + " ".join(f"{float(x)!r} {float(y)!r}" for x, y in xy) + " \n")
-            # left / right lidar groups (empty). The file must end right after the last token: the reader
-            # detects the end of data by hitting EOF inside the last getline (SlamLauncher.cpp:96-99).
-            f.write("0 \n0 \n" if i + 1 < len(scans) else "0 \n0")
+            f.write(group(xy) + "\n")
+            lg = group(left[i] if left is not None else empty)
+            rg = group(right[i] if right is not None else empty)
+            # The file must end right after the last token: the reader detects the end of data by hitting EOF inside
+            # the last getline (SlamLauncher.cpp:96-99), so the record that reaches EOF is parsed but not processed.
+            f.write(lg + "\n" + (rg + "\n" if i + 1 < len(scans) else rg.rstrip(" ")))
+
+
+def launcher_parse(path, sidelidar=True, cap_scans=4096, cap_points=4_000_000):
+    """host's SlamLauncher::readFormat + input_file_line over a text log -> (meta (n, 5): sid x y th n_points, points (m, 2))."""
+    L = load()
+    set_params(filename_in=str(path), poses_name=str(path) + ".poses.tmp", sidelidar="true" if sidelidar else "false")
+    meta = np.zeros((cap_scans, 5)); xy = np.zeros((cap_points, 2)); npts = C.c_int64()
+    f = L.host_launcher_parse
+    f.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]; f.restype = C.c_int64
+    n = f(_p(meta), cap_scans, _p(xy), cap_points, C.byref(npts))
+    return meta[:n].copy(), xy[: npts.value].copy()
+
+
+def launcher_write_poses(path, poses_deg):
+    """host's SlamLauncher::output_file_poses into `path`."""
+    L = load()
+    import tempfile
+    dummy = tempfile.NamedTemporaryFile(suffix=".log", delete=False); dummy.write(b"#\n#\n#\n#\n"); dummy.close()
+    set_params(filename_in=dummy.name, poses_name=str(path))
+    poses = np.ascontiguousarray(poses_deg, np.float64)
+    f = L.host_launcher_write_poses
+    f.argtypes = [C.c_void_p, C.c_int64]; f.restype = None
+    f(_p(poses), poses.shape[0])
+
+
+def save_maps(map_name, separated_name, global_xyzw, submaps_xyzw):
+    """host's PointCloudMap::saveGlobalMap: global PCD + one PCD per sub-map."""
+    L = load()
+    set_params(map_name=str(map_name), separated_map_name=str(separated_name))
+    g = np.ascontiguousarray(global_xyzw, np.float32)
+    off = np.zeros(len(submaps_xyzw) + 1, np.int64); off[1:] = np.cumsum([s.shape[0] for s in submaps_xyzw])
+    sub = np.ascontiguousarray(np.concatenate(submaps_xyzw, axis=0), np.float32) if len(submaps_xyzw) else np.zeros((0, 4), np.float32)
+    f = L.host_save_maps
+    f.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]; f.restype = None
+    f(_p(g), g.shape[0], _p(sub), _p(off), len(submaps_xyzw))

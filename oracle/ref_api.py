@@ -239,3 +239,38 @@ class RefSlam:
 
     def submaps(self):
         return self.L.ref_slam_submaps(self.h)
+
+
+def launcher_parse(path, sidelidar=True, cap_scans=4096, cap_points=4_000_000):
+    """the reference's SlamLauncher::readFormat + input_file_line over a text log -> (meta (n, 5): sid x y th n_points, points (m, 2))."""
+    L = load()
+    set_params(filename_in=str(path), poses_name=str(path) + ".poses.tmp", sidelidar="true" if sidelidar else "false")
+    meta = np.zeros((cap_scans, 5)); xy = np.zeros((cap_points, 2)); npts = C.c_int64()
+    f = L.ref_launcher_parse
+    f.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]; f.restype = C.c_int64
+    n = f(_p(meta), cap_scans, _p(xy), cap_points, C.byref(npts))
+    return meta[:n].copy(), xy[: npts.value].copy()
+
+
+def launcher_write_poses(path, poses_deg):
+    """the reference's SlamLauncher::output_file_poses into `path`."""
+    L = load()
+    import tempfile
+    dummy = tempfile.NamedTemporaryFile(suffix=".log", delete=False); dummy.write(b"#\n#\n#\n#\n"); dummy.close()
+    set_params(filename_in=dummy.name, poses_name=str(path))
+    poses = np.ascontiguousarray(poses_deg, np.float64)
+    f = L.ref_launcher_write_poses
+    f.argtypes = [C.c_void_p, C.c_int64]; f.restype = None
+    f(_p(poses), poses.shape[0])
+
+
+def save_maps(map_name, separated_name, global_xyzw, submaps_xyzw):
+    """the reference's PointCloudMap::saveGlobalMap: global PCD + one PCD per sub-map."""
+    L = load()
+    set_params(map_name=str(map_name), separated_map_name=str(separated_name))
+    g = np.ascontiguousarray(global_xyzw, np.float32)
+    off = np.zeros(len(submaps_xyzw) + 1, np.int64); off[1:] = np.cumsum([s.shape[0] for s in submaps_xyzw])
+    sub = np.ascontiguousarray(np.concatenate(submaps_xyzw, axis=0), np.float32) if len(submaps_xyzw) else np.zeros((0, 4), np.float32)
+    f = L.ref_save_maps
+    f.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]; f.restype = None
+    f(_p(g), g.shape[0], _p(sub), _p(off), len(submaps_xyzw))

@@ -17,6 +17,7 @@
 #define private public
 #include "ndt_slam/FrontEnd.h"
 #undef private
+#include "ndt_slam/SlamLauncher.h"
 
 namespace {
 struct Quiet {   // PoseFuser::fusePose prints matrices to std::cout unconditionally (PoseFuser.cpp:14-15, 27-28)
@@ -217,6 +218,40 @@ int64_t ref_slam_global_map(void *h, float *xyzw, int64_t cap) {
   return (int64_t)c.points.size();
 }
 int ref_slam_submaps(void *h) { return (int)((Slam *)h)->pcmap.submaps.size(); }
+
+// ---- SlamLauncher (src/SlamLauncher.cpp, unmodified): the text scan-log reader and the poses writer -------------------
+// Parses the log named by the filename_in parameter exactly like loop_wait does (readFormat, then input_file_line until it
+// reports the end); returns the records: per scan (sid, pose x y th_deg, n points) in meta5 and all points in xy.
+int64_t ref_launcher_parse(double *meta5, int64_t meta_cap, double *xy, int64_t xy_cap, int64_t *n_points) {
+  Quiet q;
+  SlamLauncher sl;
+  sl.readFormat();
+  int64_t n = 0, np = 0;
+  while (!sl.input_file_line()) {
+    if (n < meta_cap) { meta5[5 * n] = sl.scan.sid; meta5[5 * n + 1] = sl.scan.pose.tx; meta5[5 * n + 2] = sl.scan.pose.ty; meta5[5 * n + 3] = sl.scan.pose.th; meta5[5 * n + 4] = (double)sl.scan.lps.size(); }
+    for (const LPoint2D &lp : sl.scan.lps) { if (np < xy_cap) { xy[2 * np] = lp.x; xy[2 * np + 1] = lp.y; } ++np; }
+    ++n;
+  }
+  *n_points = np;
+  return n;
+}
+// output_file_poses on the given trajectory, into the file named by the poses_name parameter
+void ref_launcher_write_poses(const double *poses3, int64_t n) {
+  Quiet q;
+  std::vector<Pose2D> poses;
+  for (int64_t i = 0; i < n; ++i) poses.push_back(Pose2D(poses3[3 * i], poses3[3 * i + 1], poses3[3 * i + 2]));
+  SlamLauncher sl;
+  sl.output_file_poses(poses);
+  sl.outputfile.close();
+}
+// PointCloudMap::saveGlobalMap (PointCloudMap.h:124-136) with the given clouds as global map / sub-maps
+void ref_save_maps(const float *global_xyzw, int64_t n_global, const float *sub_xyzw, const int64_t *sub_off, int n_sub) {
+  Quiet q;
+  PointCloudMap pcmap;
+  pcmap.globalMap_cloud = cloud_of(global_xyzw, n_global);
+  for (int k = 0; k < n_sub; ++k) pcmap.maps.push_back(cloud_of(sub_xyzw + 4 * sub_off[k], sub_off[k + 1] - sub_off[k]));
+  pcmap.saveGlobalMap();
+}
 
 // The reference's own PCFilter (include/ndt_slam/PCFilter.h, unmodified) on the restated change-detector octree:
 // diff = difference_extraction(base, test), kept = remove_neighborPoint(test, diff)

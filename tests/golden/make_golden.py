@@ -123,6 +123,41 @@ def moving_vectors():
                         fe_poses=slam.poses(), fe_covs=slam.covs(), fe_local_map=slam.local_map()[:, :2].copy(), fe_submaps=slam.submaps())
 
 
+def launcher_io_inputs():
+    """A short text scan log with all three lidar groups populated, a trajectory and clouds for the writers."""
+    seq = synth.c2_sequence(seed=2, n_scans=40)
+    odo = np.column_stack([seq["odo"][:, 0], seq["odo"][:, 1], np.rad2deg(seq["odo"][:, 2])])[:9]
+    rng = synth.rng_for(5150)
+    front = [seq["scans"][i][::7] for i in range(9)]
+    left = [rng.normal(size=(i % 4, 2)) * 3.0 for i in range(9)]
+    right = [rng.normal(size=((i + 2) % 3, 2)) * 3.0 for i in range(9)]
+    poses = rng.normal(size=(37, 3)) * [10.0, 10.0, 90.0]
+    g = synth.to_xyzw(rng.normal(size=(300, 2)) * 20.0)
+    g[5, 0] = 1e-7; g[6, 1] = -123456.789          # formatting corner cases (setprecision(8), exponent notation)
+    return odo, front, left, right, poses, g, [g[:100], g[100:180], g[180:]]
+
+
+def launcher_io_vectors():
+    """The reference's own SlamLauncher.cpp (reader, poses writer) and PointCloudMap::saveGlobalMap (PCD writer)."""
+    import tempfile
+    from ndt_slam_b200 import host_api as ha      # only its log WRITER (test tooling), nothing of the product's reader
+    odo, front, left, right, poses, g, subs = launcher_io_inputs()
+    d = Path(tempfile.mkdtemp())
+    ha.write_scan_log(d / "scan.txt", odo, front, left=left, right=right)
+    out = {"log": np.frombuffer((d / "scan.txt").read_bytes(), np.uint8)}
+    for side in (True, False):
+        meta, xy = ra.launcher_parse(d / "scan.txt", side)
+        out[f"meta_{int(side)}"], out[f"xy_{int(side)}"] = meta, xy
+    ra.launcher_write_poses(d / "poses.txt", poses)
+    out["poses_bytes"] = np.frombuffer((d / "poses.txt").read_bytes(), np.uint8)
+    ra.save_maps(d / "map.pcd", d / "sub", g, subs)
+    out["map_bytes"] = np.frombuffer((d / "map.pcd").read_bytes(), np.uint8)
+    for k in range(3):
+        out[f"sub{k}_bytes"] = np.frombuffer((d / f"sub{k}.pcd").read_bytes(), np.uint8)
+    ra.set_params()
+    np.savez_compressed(OUT / "launcher_io.npz", **out)
+
+
 def map_replay_inputs(n_scans=150):
     """Map-frame scans along the C2 ground-truth trajectory (the inputs of PointCloudMap::addPose / addPoints)."""
     seq = synth.c2_sequence(seed=2, n_scans=2000)
@@ -158,5 +193,7 @@ if __name__ == "__main__":
         map_vectors()
     if not only or "moving" in only:
         moving_vectors()
+    if not only or "io" in only:
+        launcher_io_vectors()
     for p in sorted(OUT.glob("*.npz")):
         print(p.name, p.stat().st_size)

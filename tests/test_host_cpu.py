@@ -122,3 +122,38 @@ def test_moving_object_removal_matches_the_reference_point_cloud_map():
             assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
         rf.set_params()
     ha.set_params()
+
+
+def test_launcher_reader_and_writers_match_the_reference_bytes(tmp_path):
+    """f2 (I/O formats): the text scan-log reader (all three lidar groups, sidelidar on / off, the parsed-but-unprocessed
+    last record), the poses writer and the PCD writers against the reference's own SlamLauncher.cpp / PointCloudMap.h
+    compiled unmodified into oracle/_ref [REF src/SlamLauncher.cpp:30-35, 37-105; include/ndt_slam/PointCloudMap.h:124-136]:
+    parsed records equal, output files byte-identical. Golden fixture for machines without oracle/_ref, live otherwise."""
+    import sys
+    sys.path.insert(0, str(GOLD))
+    import make_golden as mg
+    z = np.load(GOLD / "launcher_io.npz")
+    odo, front, left, right, poses, g, subs = mg.launcher_io_inputs()
+    log = tmp_path / "scan.txt"
+    ha.write_scan_log(log, odo, front, left=left, right=right)
+    assert log.read_bytes() == z["log"].tobytes()
+    for side in (True, False):
+        meta, xy = ha.launcher_parse(log, side)
+        assert np.array_equal(meta, z[f"meta_{int(side)}"]) and np.array_equal(xy, z[f"xy_{int(side)}"])
+        assert meta.shape[0] == len(front) - 1            # the record that reaches EOF is not handed on
+    assert z["meta_1"][:, 4].sum() > z["meta_0"][:, 4].sum()   # the side lidars were in the log
+    ha.launcher_write_poses(tmp_path / "poses.txt", poses)
+    assert (tmp_path / "poses.txt").read_bytes() == z["poses_bytes"].tobytes()
+    ha.save_maps(tmp_path / "map.pcd", tmp_path / "sub", g, subs)
+    assert (tmp_path / "map.pcd").read_bytes() == z["map_bytes"].tobytes()
+    for k in range(3):
+        assert (tmp_path / f"sub{k}.pcd").read_bytes() == z[f"sub{k}_bytes"].tobytes()
+    from oracle import ref_api as rf
+    if rf.available():
+        for side in (True, False):
+            a, b = ha.launcher_parse(log, side), rf.launcher_parse(log, side)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        rf.launcher_write_poses(tmp_path / "poses_ref.txt", poses)
+        assert (tmp_path / "poses_ref.txt").read_bytes() == (tmp_path / "poses.txt").read_bytes()
+        rf.set_params()
+    ha.set_params()
