@@ -198,6 +198,14 @@ int ndt_replicate_grid(const ndt_handle *handles, int n_handles, int flags);
 /* Return the device memory the handle's private pool caches beyond its live buffers to the driver. */
 int ndt_trim(ndt_handle h);
 
+/* ---- device memory for callers without a CUDA runtime of their own (a plain C / C++ host driving the
+ *      NDT_MEM_DEVICE forms of the batched calls): buffers live on the handle's device, copies are ordered on
+ *      its stream; upload / download return when the copy is done --------------------------------------- */
+int ndt_alloc(ndt_handle h, int64_t bytes, void **device_ptr);
+int ndt_free(ndt_handle h, void *device_ptr);
+int ndt_upload(ndt_handle h, void *device_dst, const void *host_src, int64_t bytes);
+int ndt_download(ndt_handle h, void *host_dst, const void *device_src, int64_t bytes);
+
 /* ---- instrumentation ------------------------------------------------------------------- */
 /* Number of kernels this handle has launched since creation. */
 int ndt_launch_count(ndt_handle h, int64_t *n);

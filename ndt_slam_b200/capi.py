@@ -62,6 +62,7 @@ EXPORTS = [
     "ndt_set_source", "ndt_approx_voxel_filter", "ndt_eval", "ndt_eval_batch",
     "ndt_align", "ndt_align_batch", "ndt_best_of", "ndt_match_pairs",
     "ndt_grid_blob_size", "ndt_grid_export", "ndt_grid_import", "ndt_replicate_grid", "ndt_best_of_multi", "ndt_trim",
+    "ndt_alloc", "ndt_free", "ndt_upload", "ndt_download",
     "ndt_launch_count", "ndt_last_kernel_ms", "ndt_synchronize",
 ]
 
@@ -109,6 +110,10 @@ def load() -> C.CDLL:
     L.ndt_replicate_grid.argtypes = [C.POINTER(vp), i32, i32]
     L.ndt_best_of_multi.argtypes = [C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), i32, C.POINTER(i32), C.POINTER(i64), C.POINTER(NdtResult)]
     L.ndt_trim.argtypes = [vp]
+    L.ndt_alloc.argtypes = [vp, i64, C.POINTER(vp)]
+    L.ndt_free.argtypes = [vp, vp]
+    L.ndt_upload.argtypes = [vp, vp, vp, i64]
+    L.ndt_download.argtypes = [vp, vp, vp, i64]
     L.ndt_launch_count.argtypes = [vp, C.POINTER(i64)]
     L.ndt_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.ndt_synchronize.argtypes = [vp]

@@ -717,6 +717,38 @@ int ndt_trim(ndt_handle hh) {
   return NDT_OK;
 }
 
+int ndt_alloc(ndt_handle hh, int64_t bytes, void **device_ptr) {
+  H_OR_FAIL(hh);
+  if (!device_ptr || bytes < 0) return set_err(h, NDT_ERR_ARG, "ndt_alloc: bad argument");
+  *device_ptr = nullptr;
+  NDT_CUDA(h, cudaMalloc(device_ptr, (size_t)std::max<int64_t>(bytes, 16)));
+  return NDT_OK;
+}
+
+int ndt_free(ndt_handle hh, void *device_ptr) {
+  H_OR_FAIL(hh);
+  if (device_ptr) { NDT_CUDA(h, cudaStreamSynchronize(h->stream)); NDT_CUDA(h, cudaFree(device_ptr)); }
+  return NDT_OK;
+}
+
+int ndt_upload(ndt_handle hh, void *device_dst, const void *host_src, int64_t bytes) {
+  H_OR_FAIL(hh);
+  if (bytes < 0 || (bytes > 0 && (!device_dst || !host_src))) return set_err(h, NDT_ERR_ARG, "ndt_upload: bad argument");
+  if (bytes == 0) return NDT_OK;
+  NDT_CUDA(h, cudaMemcpyAsync(device_dst, host_src, (size_t)bytes, cudaMemcpyHostToDevice, h->stream));
+  NDT_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NDT_OK;
+}
+
+int ndt_download(ndt_handle hh, void *host_dst, const void *device_src, int64_t bytes) {
+  H_OR_FAIL(hh);
+  if (bytes < 0 || (bytes > 0 && (!host_dst || !device_src))) return set_err(h, NDT_ERR_ARG, "ndt_download: bad argument");
+  if (bytes == 0) return NDT_OK;
+  NDT_CUDA(h, cudaMemcpyAsync(host_dst, device_src, (size_t)bytes, cudaMemcpyDeviceToHost, h->stream));
+  NDT_CUDA(h, cudaStreamSynchronize(h->stream));
+  return NDT_OK;
+}
+
 int ndt_launch_count(ndt_handle hh, int64_t *n) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h || !n) return NDT_ERR_ARG;

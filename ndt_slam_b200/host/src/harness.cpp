@@ -10,6 +10,7 @@
 #include "ndt_slam/PointCloudMap.h"
 #include "ndt_slam/PoseEstimator.h"
 #include "ndt_slam/PoseFuser.h"
+#include "ndt_slam/Relocalizer.h"
 #include "ndt_slam/ScanMatcher.h"
 #include "ndt_slam/ScanPointResampler.h"
 #include "ndt_slam/SlamLauncher.h"
@@ -204,6 +205,69 @@ void host_pcfilter(const float *base_xyzw, int64_t n_base, const float *test_xyz
   auto kept = f.remove_neighborPoint(cloud_of(test_xyzw, n_test), diff);
   *n_diff = cloud_out(*diff, diff_out, n_test);
   *n_kept = cloud_out(*kept, kept_out, n_test);
+}
+
+// Relocalizer (C++ host, C ABI only): n_handles handles on devices dev[0..n_handles), grid replicated, hypotheses sharded
+int64_t host_relocalize(const int *dev, int n_handles, const float *map_xyzw, int64_t n_map, const float *scan_xyzw, int64_t n_scan,
+                        const double *hyp, int64_t n_hyp, double resolution, ndt_result *best, ndt_result *results, double *device_ms) {
+  try {
+    Relocalizer rl(std::vector<int>(dev, dev + n_handles), resolution);
+    rl.setMap(*cloud_of(map_xyzw, n_map));
+    rl.setScan(*cloud_of(scan_xyzw, n_scan));
+    const int64_t bi = rl.relocalize(hyp, n_hyp, best, results);
+    if (device_ms) *device_ms = rl.lastDeviceMs;
+    return bi;
+  } catch (const std::exception &e) {
+    std::strncpy(g_err, e.what(), sizeof(g_err) - 1);
+    return -2;
+  }
+}
+
+// loop closure: what the last processed scan's LoopDetector call did (cur node, ref node, relPose x y th_deg, cost, accepted,
+// iters, evals, converged) x candidates; totals in counts3 = {pose-graph nodes, arcs, loop arcs}
+int64_t host_slam_loops(void *h, double *rows10, int64_t cap, int64_t counts3[3]) {
+  Slam *s = (Slam *)h;
+  const std::vector<LoopMatch> &lm = s->fe.lpd.lastMatches;
+  const int64_t m = std::min<int64_t>(cap, (int64_t)lm.size());
+  for (int64_t k = 0; k < m; ++k) {
+    double *r = rows10 + 10 * k;
+    r[0] = lm[k].curId; r[1] = lm[k].refId; r[2] = lm[k].relPose.tx; r[3] = lm[k].relPose.ty; r[4] = lm[k].relPose.th; r[5] = lm[k].cost;
+    r[6] = lm[k].accepted; r[7] = lm[k].result.iters; r[8] = lm[k].result.evals; r[9] = lm[k].result.converged;
+  }
+  int64_t loops = 0;
+  for (const PoseArc *a : s->fe.pg.arcs) loops += a->loop ? 1 : 0;
+  counts3[0] = (int64_t)s->fe.pg.nodes.size(); counts3[1] = (int64_t)s->fe.pg.arcs.size(); counts3[2] = loops;
+  return (int64_t)lm.size();
+}
+// every loop arc of the pose graph: src node, dst node, relPose (x, y, th_deg), cost
+int64_t host_slam_loop_arcs(void *h, double *rows6, int64_t cap) {
+  Slam *s = (Slam *)h;
+  int64_t n = 0;
+  for (const PoseArc *a : s->fe.pg.arcs) {
+    if (!a->loop) continue;
+    if (n < cap) { double *r = rows6 + 6 * n; r[0] = a->src->nid; r[1] = a->dst->nid; r[2] = a->relPose.tx; r[3] = a->relPose.ty; r[4] = a->relPose.th; r[5] = a->cost; }
+    ++n;
+  }
+  return n;
+}
+// key-frame poses (pose-graph nodes)
+int64_t host_slam_nodes(void *h, double *rows3, int64_t cap) {
+  Slam *s = (Slam *)h;
+  const int64_t m = std::min<int64_t>(cap, (int64_t)s->fe.pg.nodes.size());
+  for (int64_t k = 0; k < m; ++k) { rows3[3 * k] = s->fe.pg.nodes[k]->pose.tx; rows3[3 * k + 1] = s->fe.pg.nodes[k]->pose.ty; rows3[3 * k + 2] = s->fe.pg.nodes[k]->pose.th; }
+  return (int64_t)s->fe.pg.nodes.size();
+}
+// LoopDetector::findCandidates on its own (host only): key frames at poses3 / atd, query at index n - 1
+int64_t host_loop_candidates(const double *poses3, const double *atd, int64_t n, int *out, int64_t cap) {
+  LoopDetector ld;
+  Scan2D empty;
+  const int keep = ld.maxCandidates;
+  ld.maxCandidates = 0;                            // store the key frames only: nothing to verify, no device needed
+  for (int64_t k = 0; k + 1 < n; ++k) ld.detectLoop(&empty, Pose2D(poses3[3 * k], poses3[3 * k + 1], poses3[3 * k + 2]), -1, atd[k]);
+  ld.maxCandidates = keep;
+  const std::vector<int> c = ld.findCandidates(Pose2D(poses3[3 * (n - 1)], poses3[3 * (n - 1) + 1], poses3[3 * (n - 1) + 2]), atd[n - 1]);
+  for (size_t k = 0; k < c.size() && (int64_t)k < cap; ++k) out[k] = c[k];
+  return (int64_t)c.size();
 }
 
 // SlamLauncher's reader and writers on their own (no device needed): same drivers as the ref_launcher_* / ref_save_maps

@@ -181,6 +181,29 @@ class Slam:
         out = np.zeros((n, 3, 3)); self.L.host_slam_covs(self.h, _p(out), n)
         return out
 
+    def loops(self):
+        """What the LoopDetector did for the last processed scan and the pose-graph totals:
+        (rows: cur node, ref node, rel x, rel y, rel th_deg, cost, accepted, iters, evals, converged), {nodes, arcs, loop_arcs}"""
+        f = self.L.host_slam_loops
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]; f.restype = C.c_int64
+        rows = np.zeros((64, 10)); cnt = np.zeros(3, np.int64)
+        n = f(self.h, _p(rows), 64, _p(cnt))
+        return rows[:n].copy(), dict(nodes=int(cnt[0]), arcs=int(cnt[1]), loop_arcs=int(cnt[2]))
+
+    def loop_arcs(self):
+        f = self.L.host_slam_loop_arcs
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]; f.restype = C.c_int64
+        n = f(self.h, None, 0)
+        rows = np.zeros((max(n, 1), 6)); f(self.h, _p(rows), n)
+        return rows[:n]
+
+    def nodes(self):
+        f = self.L.host_slam_nodes
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]; f.restype = C.c_int64
+        n = f(self.h, None, 0)
+        rows = np.zeros((max(n, 1), 3)); f(self.h, _p(rows), n)
+        return rows[:n]
+
     def poses(self):
         n = self.L.host_slam_poses(self.h, None, 0)
         out = np.zeros((n, 3)); self.L.host_slam_poses(self.h, _p(out), n)
@@ -267,3 +290,34 @@ def save_maps(map_name, separated_name, global_xyzw, submaps_xyzw):
     f = L.host_save_maps
     f.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]; f.restype = None
     f(_p(g), g.shape[0], _p(sub), _p(off), len(submaps_xyzw))
+
+
+def loop_candidates(poses_deg, atd):
+    """LoopDetector::findCandidates for the last pose against all earlier key frames (host only)."""
+    L = load()
+    f = L.host_loop_candidates
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]; f.restype = C.c_int64
+    poses = np.ascontiguousarray(poses_deg, np.float64); a = np.ascontiguousarray(atd, np.float64)
+    out = np.zeros(256, np.int32)
+    n = f(_p(poses), _p(a), poses.shape[0], _p(out), 256)
+    return out[:n].copy()
+
+
+def relocalize(devices, map_xyzw, scan_xyzw, hypotheses, resolution=0.5, want_all=False):
+    """Relocalizer (C++ host over the C ABI): returns (best index, best NdtResult, all results or None, slowest shard ms)."""
+    from .capi import NdtResult, RESULT_DTYPE
+    L = load()
+    f = L.host_relocalize
+    f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_double,
+                  C.POINTER(NdtResult), C.c_void_p, C.POINTER(C.c_double)]
+    f.restype = C.c_int64
+    dev = np.ascontiguousarray(devices, np.int32)
+    m = np.ascontiguousarray(map_xyzw, np.float32); sc = np.ascontiguousarray(scan_xyzw, np.float32)
+    hyp = np.ascontiguousarray(hypotheses, np.float64)
+    best = NdtResult(); ms = C.c_double()
+    res = np.zeros(hyp.shape[0], RESULT_DTYPE) if want_all else None
+    bi = f(_p(dev), dev.shape[0], _p(m), m.shape[0], _p(sc), sc.shape[0], _p(hyp), hyp.shape[0], resolution, C.byref(best),
+           _p(res) if want_all else None, C.byref(ms))
+    if bi == -2:
+        raise RuntimeError(L.host_last_error().decode())
+    return int(bi), best, res, ms.value

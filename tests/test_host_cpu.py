@@ -157,3 +157,21 @@ def test_launcher_reader_and_writers_match_the_reference_bytes(tmp_path):
         assert (tmp_path / "poses_ref.txt").read_bytes() == (tmp_path / "poses.txt").read_bytes()
         rf.set_params()
     ha.set_params()
+
+
+def test_loop_candidates_are_revisits_not_the_stretch_just_driven():
+    """LoopDetector::findCandidates (host logic of f3): key frames within loop_radius whose travel distance lies at least
+    loop_min_travel back, nearest first, capped."""
+    n = 200
+    ang = np.linspace(0.0, 2.0 * np.pi, n)          # one lap of a 10 m circle, a key frame every ~0.31 m
+    poses = np.column_stack([10.0 * np.cos(ang), 10.0 * np.sin(ang), np.rad2deg(ang + np.pi / 2)])
+    atd = 10.0 * ang
+    ha.set_params(loop_radius=2.0, loop_min_travel=15.0, loop_max_candidates=5)
+    assert ha.loop_candidates(poses[:100], atd[:100]).size == 0          # half a lap: nothing nearby is old enough
+    c = ha.loop_candidates(poses, atd)                                    # back at the start
+    assert c.size == 5 and set(c) <= set(range(0, 8))                     # the first key frames of the lap, nearest first
+    d = np.hypot(poses[c, 0] - poses[-1, 0], poses[c, 1] - poses[-1, 1])
+    assert np.all(np.diff(d) >= 0) and d[-1] <= 2.0
+    ha.set_params(loop_radius=2.0, loop_min_travel=70.0, loop_max_candidates=5)
+    assert ha.loop_candidates(poses, atd).size == 0                       # a lap is only 62.8 m long
+    ha.set_params()

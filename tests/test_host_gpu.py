@@ -141,3 +141,85 @@ def test_launcher_reads_text_log_and_writes_outputs(tmp_path):
     p0 = slam.poses()[0]
     got = np.array(lines[1].split(), dtype=float)
     assert np.allclose(got, p0, atol=1e-4)
+
+
+def test_loop_closure_pipeline_verifies_revisits_in_one_batched_call():
+    """f3: key frames -> pose-graph nodes + odometry arcs; revisit candidates verified by ONE ndt_match_pairs call per key
+    frame; accepted matches become loop arcs. A short closed lap (the robot returns to its start): loop arcs must appear at
+    the end, link the last key frames to the first ones, agree with the ground-truth relative pose, and every verification
+    must be the oracle's per-pair match (iterations / evaluations identical, pose within the per-match bar)."""
+    import ndt_common as common
+    from oracle import oracle_api as oa
+    n = 240
+    segs = synth.office(7, 16.0, 12.0, 6)
+    t = np.linspace(0.0, 2.0 * np.pi, n, endpoint=False)
+    traj = np.column_stack([8.0 + 3.5 * np.cos(t), 6.0 + 2.5 * np.sin(t), t + np.pi / 2])       # an elliptic lap back to the start
+    traj = np.concatenate([traj, traj[:12]])                                                    # ... and a little beyond
+    rng = synth.rng_for(707)
+    scans = [synth.raycast(segs, tuple(p), rng) for p in traj]
+    c0, s0 = np.cos(traj[0, 2]), np.sin(traj[0, 2])
+    rel = np.stack([c0 * (traj[:, 0] - traj[0, 0]) + s0 * (traj[:, 1] - traj[0, 1]), -s0 * (traj[:, 0] - traj[0, 0]) + c0 * (traj[:, 1] - traj[0, 1])], axis=1)
+    odo = np.column_stack([rel[:, 0], rel[:, 1], np.rad2deg(traj[:, 2] - traj[0, 2])])
+    odo[:, 2] = (odo[:, 2] + 180.0) % 360.0 - 180.0
+    ha.set_params(Resolution=0.5, loop_closure="true", keyframe_skip=6, loop_radius=1.5, loop_min_travel=10.0, loop_max_candidates=4,
+                  loop_score_thre=0.05)
+    slam = ha.Slam()
+    verified = []
+    for i in range(traj.shape[0]):
+        slam.process(i, odo[i], scans[i])
+        rows, counts = slam.loops()
+        if i % 6 == 0 and rows.shape[0]:
+            verified.append((i, rows))
+    rows, counts = slam.loops()
+    arcs, nodes = slam.loop_arcs(), slam.nodes()
+    assert counts["nodes"] == (traj.shape[0] + 5) // 6 and counts["arcs"] == counts["nodes"] - 1 + counts["loop_arcs"]
+    assert counts["loop_arcs"] >= 3 and len(verified) >= 2
+    assert all(i >= 200 for i, _ in verified)                    # nothing is a "revisit" before the lap closes
+    # loop arcs: late key frames linked to early ones, relative pose = ground truth within a few centimetres
+    for src, dst, rx, ry, rth, cost in arcs:
+        a, b = traj[int(src) * 6], traj[int(dst) * 6]
+        ca, sa = np.cos(a[2]), np.sin(a[2])
+        gt = (ca * (b[0] - a[0]) + sa * (b[1] - a[1]), -sa * (b[0] - a[0]) + ca * (b[1] - a[1]))
+        assert int(src) <= 3 and int(dst) >= 34 and np.hypot(rx - gt[0], ry - gt[1]) < 0.05 and cost <= 0.05
+    # every verification of the last key frame against the oracle, pair by pair (same inputs: resampled scans, relative guess)
+    i_last, rows = verified[-1]
+    prm = common.params(resolution=0.5)
+    o = oa.Oracle(prm)
+    cur = synth.to_xyzw(oa.resample(scans[i_last], 0.05, 0.25))
+    for r in rows:
+        ref_scan = synth.to_xyzw(oa.resample(scans[int(r[1]) * 6], 0.05, 0.25))
+        o.set_target(ref_scan); o.set_source(oa.approx_voxel_filter(cur, 0.05))
+        # the guess the detector used: current key-frame pose seen from the candidate's (estimated poses, degrees)
+        pc, pr = nodes[int(r[0])], nodes[int(r[1])]
+        cr, sr = np.cos(np.deg2rad(pr[2])), np.sin(np.deg2rad(pr[2]))
+        g = [cr * (pc[0] - pr[0]) + sr * (pc[1] - pr[1]), -sr * (pc[0] - pr[0]) + cr * (pc[1] - pr[1]), np.deg2rad((pc[2] - pr[2] + 180.0) % 360.0 - 180.0)]
+        b = o.align(g)
+        assert int(r[7]) == b.iters and int(r[8]) == b.evals and int(r[9]) == b.converged
+        assert np.hypot(r[2] - float(np.float32(b.pose[0])), r[3] - float(np.float32(b.pose[1]))) < 1e-4
+    ha.set_params()
+
+
+def test_relocalizer_cpp_host_shards_hypotheses_over_replicated_grids():
+    """The C++ Relocalizer (C ABI only: ndt_replicate_grid, device-space ndt_align_batch per handle, ndt_best_of_multi) gives
+    the same matches and the same winner as one handle matching every hypothesis; as many GPUs as the box has (two handles
+    on one GPU otherwise)."""
+    import torch
+    import ndt_common as common
+    from ndt_slam_b200 import capi
+    from oracle import oracle_api as oa
+    d = synth.c4_reloc(seed=4)
+    src = oa.approx_voxel_filter(synth.to_xyzw(common.prep_scan(d["scan"])), 0.05)
+    tgt = synth.to_xyzw(d["map_pts"])
+    rng = synth.rng_for(99)
+    hyp = np.ascontiguousarray(d["hypotheses"][np.sort(rng.choice(65536, 1023, replace=False))])
+    hyp = np.concatenate([hyp, [np.array(d["true_pose"]) + [0.2, -0.1, 0.02]]])
+    ndev = torch.cuda.device_count()
+    devices = list(range(ndev)) if ndev > 1 else [0, 0, 0]
+    bi, best, res, ms = ha.relocalize(devices, tgt, src, hyp, want_all=True)
+    g = capi.Ndt(common.params(resolution=0.5))
+    g.set_target(tgt); g.set_source(src)
+    ref = g.align_batch(hyp, want_fitness=False)
+    assert np.array_equal(res["pose"], ref["pose"]) and np.array_equal(res["score"], ref["score"]) and np.array_equal(res["evals"], ref["evals"])
+    bi_ref, best_ref = g.best_of(ref)
+    assert bi == bi_ref == 1023 and best.score == best_ref.score
+    assert np.hypot(best.pose[0] - d["true_pose"][0], best.pose[1] - d["true_pose"][1]) < 0.05 and ms > 0
