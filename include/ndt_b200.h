@@ -109,7 +109,7 @@ typedef struct {
   int32_t n_leaves;       /* occupied cells (any count)                    */
   int32_t n_slots;        /* cells with n >= min_points (kd-tree members)  */
   int32_t n_valid;        /* of those, cells that passed the eigen checks  */
-  int32_t reserved;
+  int32_t reserved;       /* 1 if the last target call was an incremental update   */
 } ndt_grid_info;
 
 /* ---- lifetime ------------------------------------------------------------------------- */
@@ -126,6 +126,16 @@ int ndt_set_target(ndt_handle h, const float *xyzw, int64_t n, int memspace);
  * first n_same points are identical to the previous call's, so only points [n_same, n) are staged and copied to the
  * device; the grid itself is rebuilt in full and is identical to ndt_set_target's. n_same = 0 is ndt_set_target. */
 int ndt_set_target_prefix(ndt_handle h, const float *xyzw, int64_t n, int64_t n_same, int memspace);
+/* The same for a map with a settled part (PointCloudMap's local map = previous sub-map + the current sub-map's thinned
+ * prefix + a provisional tail that is replaced every scan): n_same as above; n_stable <= n: the caller promises that the
+ * first n_stable points stay a prefix of every later target handed to this handle. The library then keeps per-cell running
+ * sums of the settled prefix ON THE DEVICE, folds the points that became settled since the last call into them, adds the
+ * tail on top and re-derives only the cells any of this touched (plus the cells of the previous tail) -- in the reference's
+ * input order, so every cell is bit-identical to what ndt_set_target builds from the whole cloud. Falls back to a full
+ * rebuild (which also (re)initialises the running sums) whenever that is not possible: first call, grid bounds moved, the
+ * settled prefix shrank, device input. After an incremental update ndt_grid_readback returns NDT_ERR_STATE (the per-leaf
+ * read-back tables are not maintained); the matcher, the fitness score and ndt_get_grid_info see the same grid. */
+int ndt_set_target_incremental(ndt_handle h, const float *xyzw, int64_t n, int64_t n_same, int64_t n_stable, int memspace);
 int ndt_get_grid_info(ndt_handle h, ndt_grid_info *info);
 /* Leaves in ascending cell-index order (the std::map order of PCL's leaves_), for parity
  * checks: cell index, nr_points (-1 = failed eigen check), mean[2], icov[4] (xx,xy,yx,yy),

@@ -67,7 +67,8 @@ static BlobHeader blob_layout(const Handle *h, int flags) {
   BlobHeader b{};
   b.magic = kBlobMagic;
   b.flags = flags & NDT_BLOB_POINTS;
-  if (!h->grid_has_points) b.flags = 0;                 // a replica without points cannot hand any on
+  if (!h->grid_has_points || h->inc_active) b.flags = 0;   // a replica without points cannot hand any on; after an incremental
+                                                          // update the ordered 1-NN buckets are stale (only the lattice is kept)
   b.gd = h->gd;
   std::memcpy(b.counters, h->h_counters, sizeof(b.counters));
   const BlobSizes z = blob_sizes(h->gd, h->h_counters, b.flags);
@@ -122,7 +123,7 @@ static void all_buffers(Handle *h, std::vector<DevBuf *> &v) {
   GridBuffers &g = h->gb;
   v = {&g.tgt, &g.cell_of, &g.rank_of, &g.list, &g.sorted_idx, &g.slot, &g.leaf_id, &g.leaf_cell,
        &g.leaf_n, &g.leaf_start, &g.leaf_nr, &g.leaf_mean, &g.leaf_icov, &g.leaf_cen, &g.recs,
-       &g.counters, &g.leaf_pair, &g.big_list, &g.tile_hist, &g.dims, &g.pair_off, &g.cen, &g.occ, &g.nbr, &g.nn_cnt, &g.nn_range, &g.nn_pts,
+       &g.counters, &g.leaf_pair, &g.big_list, &g.tile_hist, &g.dims, &g.pair_off, &g.cen, &g.occ, &g.nbr, &g.inc_acc, &g.inc_status, &g.inc_mark, &g.inc_lists, &g.inc_cellof, &g.inc_lid, &g.inc_cnt, &g.nn_cnt, &g.nn_range, &g.nn_pts,
        &g.tgt_sorted, &g.leaf_range, &h->src, &h->scratch, &h->scratch2, &h->stage, &h->io};
 }
 
@@ -214,6 +215,11 @@ int ndt_set_target_prefix(ndt_handle hh, const float *xyzw, int64_t n, int64_t n
   return grid_build(h, xyzw, n, memspace, n_same);
 }
 
+int ndt_set_target_incremental(ndt_handle hh, const float *xyzw, int64_t n, int64_t n_same, int64_t n_stable, int memspace) {
+  H_OR_FAIL(hh);
+  return grid_build_incremental(h, xyzw, n, n_same, n_stable, memspace);
+}
+
 int ndt_get_grid_info(ndt_handle hh, ndt_grid_info *info) {
   H_OR_FAIL(hh);
   if (!info) return NDT_ERR_ARG;
@@ -225,6 +231,7 @@ int ndt_get_grid_info(ndt_handle hh, ndt_grid_info *info) {
   info->n_leaves = h->h_counters[CTR_LEAVES];
   info->n_slots = h->h_counters[CTR_SLOTS];
   info->n_valid = h->h_counters[CTR_VALID];
+  info->reserved = h->inc_active ? 1 : 0;          // 1: the last target call was an incremental update
   return NDT_OK;
 }
 
@@ -479,6 +486,7 @@ int ndt_match_pairs(ndt_handle hh, const float *src_xyzw, const int64_t *src_off
   GridDims &gd = h->gd;
   h->have_grid = false; h->have_src = false;          // the handle's single grid / source are overwritten
   h->have_readback = false; h->grid_has_points = false;
+  h->inc_ok = false; h->inc_active = false;
   h->tgt_on_device = 0;
   gd = GridDims();
   gd.leaf = h->prm.resolution; gd.inv_leaf = 1.0f / gd.leaf; gd.r2 = (float)((double)gd.leaf * (double)gd.leaf);
@@ -613,6 +621,7 @@ int ndt_grid_import(ndt_handle hh, const void *device_blob, int64_t bytes) {
   NDT_CUDA(h, cudaStreamSynchronize(st));
   if (const char *why = blob_check(h, b, bytes)) return set_err(h, NDT_ERR_ARG, (std::string("ndt_grid_import: ") + why).c_str());
   h->have_grid = false; h->have_readback = false; h->grid_has_points = false;
+  h->inc_ok = false; h->inc_active = false;
   h->tgt_on_device = 0;
   h->gd = b.gd;
   std::memcpy(h->h_counters, b.counters, sizeof(b.counters));

@@ -421,13 +421,12 @@ struct FinalizeOut {
   const int32_t *__restrict__ leaf_cell; const int32_t *__restrict__ leaf_pair; const PairDims *__restrict__ dims;
 };
 
-__device__ __forceinline__ void finish_leaf(const int leaf, const int n, const int st, const LeafSums sums, const FinalizeParams fp,
-                                            const FinalizeOut &o) {
-    int2 *leaf_range = o.leaf_range; int32_t *leaf_nr = o.leaf_nr; double2 *leaf_mean = o.leaf_mean; double *leaf_icov = o.leaf_icov;
-    float2 *leaf_cen = o.leaf_cen; int32_t *slot = o.slot; float2 *cen_tab = o.cen_tab; uint32_t *occ = o.occ; CellRec *recs = o.recs;
-    int32_t *ctr = o.ctr; const int32_t *leaf_cell = o.leaf_cell; const int32_t *leaf_pair = o.leaf_pair; const PairDims *dims = o.dims;
-    leaf_range[leaf] = make_int2(st, n);
-    double sx = sums.sx, sy = sums.sy;
+// Mean, single-pass covariance, eigenvalue clamp and inverse of one cell from its in-order sums (VoxelGridCovariance pass 2,
+// SURVEY App. A.2). Shared by the full build (finish_leaf) and the incremental update (k_inc_finalize): same IEEE operations
+// in the same order, so a cell comes out bit-identical whichever path touched it last.
+struct LeafStats { int nr; bool in_tree; float cx, cy; double m0, m1, ic0, ic1, ic2, ic3; };
+__device__ __forceinline__ LeafStats leaf_stats(const int n, const LeafSums sums, const FinalizeParams fp) {
+  double sx = sums.sx, sy = sums.sy;
     const double sxx = sums.sxx, syx = sums.syx, syy = sums.syy;
     float cx = sums.cx, cy = sums.cy;
     const double nn = (double)n;
@@ -492,6 +491,22 @@ __device__ __forceinline__ void finish_leaf(const int leaf, const int n, const i
         if (mxc == (double)INFINITY || mnc == -(double)INFINITY) nr = -1;
       }
     }
+    LeafStats z;
+    z.nr = nr; z.in_tree = in_tree; z.cx = cx; z.cy = cy; z.m0 = m0; z.m1 = m1; z.ic0 = ic0; z.ic1 = ic1; z.ic2 = ic2; z.ic3 = ic3;
+    return z;
+}
+
+__device__ __forceinline__ void finish_leaf(const int leaf, const int n, const int st, const LeafSums sums, const FinalizeParams fp,
+                                            const FinalizeOut &o) {
+    int2 *leaf_range = o.leaf_range; int32_t *leaf_nr = o.leaf_nr; double2 *leaf_mean = o.leaf_mean; double *leaf_icov = o.leaf_icov;
+    float2 *leaf_cen = o.leaf_cen; int32_t *slot = o.slot; float2 *cen_tab = o.cen_tab; uint32_t *occ = o.occ; CellRec *recs = o.recs;
+    int32_t *ctr = o.ctr; const int32_t *leaf_cell = o.leaf_cell; const int32_t *leaf_pair = o.leaf_pair; const PairDims *dims = o.dims;
+    leaf_range[leaf] = make_int2(st, n);
+    const LeafStats z = leaf_stats(n, sums, fp);
+    const float cx = z.cx, cy = z.cy;
+    const double m0 = z.m0, m1 = z.m1, ic0 = z.ic0, ic1 = z.ic1, ic2 = z.ic2, ic3 = z.ic3;
+    const int nr = z.nr;
+    const bool in_tree = z.in_tree;
     leaf_nr[leaf] = nr;
     leaf_mean[leaf] = make_double2(m0, m1);
     leaf_icov[4 * (size_t)leaf + 0] = ic0; leaf_icov[4 * (size_t)leaf + 1] = ic1;
@@ -727,6 +742,247 @@ __global__ void __launch_bounds__(1024) k_pair_scan(PairDims *__restrict__ dims,
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Incremental target (ndt_set_target_incremental): a map whose settled part only grows. Per padded cell the running sums
+// of the settled prefix stay on the device (CellAcc); a call folds the newly settled points into them, adds the provisional
+// tail on top and re-derives the cells touched by either (and by the previous call's tail). Sums are taken in input order --
+// all settled points precede the tail in the cloud, and the settled prefix only grows at its end -- so every cell comes out
+// bit-identical to a full build over the whole cloud (tests/test_gpu_incremental.py compares every table).
+// ------------------------------------------------------------------------------------------------------------------
+struct __align__(16) CellAcc { double sx, sy, sxx, syx, syy; float cx, cy; int32_t n; int32_t pad; };
+static_assert(sizeof(CellAcc) == 64, "CellAcc must be 64 bytes");
+enum { ST_OCC = 1, ST_TREE = 2, ST_VALID = 4, ST_SLOT = 8, ST_CHANGED = 128 };
+enum { INC_A = 0, INC_B = 1, INC_P = 2, INC_U = 3 };     // inc_cnt entries: fold cells, tail cells, previous tail cells, union
+
+// The batch of a call = the points that became settled since the last call followed by the provisional tail: cloud[lo .. hi),
+// at most INC_BATCH_CAP points. Three small kernels order it by cell (stable):
+//   k_inc_rank     cell of every batch point; its rank among the batch points of the same cell (all-pairs compare over a
+//                  shared-memory copy of the batch's cells: B^2 / threads steps, B ~ 1,000); the first point of a cell
+//                  registers the cell (list, local id, point count)
+//   k_inc_starts   exclusive scan of the per-cell counts (one CTA)
+//   k_inc_scatter  order[start(cell) + rank] = batch index
+constexpr int INC_BATCH_CAP = 4096;
+
+__global__ void __launch_bounds__(256) k_inc_rank(const float4 *__restrict__ pts, int64_t lo, int B, const PairDims *__restrict__ dims, float inv_leaf,
+                                                 int32_t *__restrict__ cell_of, int32_t *__restrict__ rank_of, int2 *__restrict__ lid_tab,
+                                                 int32_t epoch, int32_t *__restrict__ list, int32_t *__restrict__ list_n,
+                                                 int32_t *__restrict__ cell_cnt) {
+  __shared__ __align__(16) int s_cell[INC_BATCH_CAP];
+  const PairDims d = dims[0];
+  const int B4 = (B + 3) & ~3;
+  for (int k = threadIdx.x; k < B4; k += blockDim.x) {
+    int c = -2;                                    // padding up to a multiple of four: matches nothing
+    if (k < B) {
+      const float4 p = __ldg(pts + lo + k);
+      c = -1;
+      if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z))
+        c = d.base + (cell_coord(p.y, inv_leaf, d.min_by) + 2) * d.W + cell_coord(p.x, inv_leaf, d.min_bx) + 2;
+    }
+    s_cell[k] = c;
+  }
+  __syncthreads();
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= B) return;
+  const int c = s_cell[k];
+  int before = 0, total = 0;
+  if (c >= 0) {
+    // four cells per 16-byte shared load; every thread of the CTA reads the same words (broadcast). Matches in the group
+    // that contains k itself are split by position, groups before k count fully towards the rank.
+    const int4 *s4 = reinterpret_cast<const int4 *>(s_cell);
+    const int kg = k >> 2;
+#pragma unroll 4
+    for (int g = 0; g < B4 / 4; ++g) {
+      const int4 v = s4[g];
+      const int m = (v.x == c) + (v.y == c) + (v.z == c) + (v.w == c);
+      total += m;
+      before += g < kg ? m : 0;
+    }
+    const int4 v = s4[kg];
+    const int r = k & 3;
+    before += (r > 0 && v.x == c) + (r > 1 && v.y == c) + (r > 2 && v.z == c);
+  }
+  cell_of[k] = c;
+  rank_of[k] = before;
+  if (c >= 0 && before == 0) {
+    const int lid = atomicAdd(list_n, 1);
+    list[lid] = c;
+    lid_tab[c] = make_int2(epoch, lid);
+    cell_cnt[lid] = total;
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_inc_starts(const int32_t *__restrict__ cell_cnt, const int32_t *__restrict__ list_n, int32_t *__restrict__ cell_start) {
+  __shared__ int s_warp[32];
+  const int n = *list_n, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int carry = 0;
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < n ? cell_cnt[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int dlt = 1; dlt < 32; dlt <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, dlt); if (lane >= dlt) incl += t; }
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    int before = carry;
+    for (int q = 0; q < w; ++q) before += s_warp[q];
+    if (i < n) cell_start[i] = before + incl - v;
+    int tot = 0;
+    for (int q = 0; q < 32; ++q) tot += s_warp[q];
+    carry += tot;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) k_inc_scatter(int B, const int32_t *__restrict__ cell_of, const int32_t *__restrict__ rank_of,
+                                                    const int2 *__restrict__ lid_tab, const int32_t *__restrict__ cell_start, int32_t *__restrict__ order) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= B) return;
+  const int c = cell_of[k];
+  if (c < 0) return;
+  order[cell_start[lid_tab[c].y] + rank_of[k]] = k;
+}
+
+// U = batch cells + previous call's cells, without duplicates
+__global__ void __launch_bounds__(256) k_inc_union(const int32_t *__restrict__ lb, const int32_t *__restrict__ lp,
+                                                  int32_t *__restrict__ cnt, int32_t *__restrict__ mark, int32_t epoch, int32_t *__restrict__ lu) {
+  const int nb = cnt[INC_B], np = cnt[INC_P];
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nb + np; t += gridDim.x * blockDim.x) {
+    const int c = t < nb ? lb[t] : lp[t - nb];
+    if (atomicExch(mark + c, epoch) != epoch) lu[atomicAdd(cnt + INC_U, 1)] = c;
+  }
+}
+
+struct IncTables {
+  uint8_t *__restrict__ status; int32_t *__restrict__ slot; float2 *__restrict__ cen;
+  CellRec *__restrict__ recs; int32_t *__restrict__ ctr;
+};
+
+// Every cell of U: add its batch points in input order to the settled sums -- the settled ones (cloud index < n_stable) for
+// good (stored back), the tail ones on top for this call only -- then statistics -> probe tables, record, counters
+__global__ void __launch_bounds__(128) k_inc_finalize(const float4 *__restrict__ pts, int64_t lo, int64_t n_stable, const int32_t *__restrict__ order,
+                                                     const int2 *__restrict__ lid_tab, int32_t epoch, const int32_t *__restrict__ cell_start,
+                                                     const int32_t *__restrict__ cell_cnt, const int32_t *__restrict__ lu, const int32_t *__restrict__ cnt,
+                                                     CellAcc *__restrict__ acc, FinalizeParams fp, IncTables T) {
+  const int m = cnt[INC_U];
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < m; t += gridDim.x * blockDim.x) {
+    const int c = lu[t];
+    CellAcc v = acc[c];
+    LeafSums a{v.sx, v.sy, v.sxx, v.syx, v.syy, v.cx, v.cy};
+    int n = v.n;
+    const int2 e = lid_tab[c];
+    if (e.x == epoch) {                              // the cell has points in this call's batch
+      const int st = cell_start[e.y], num = cell_cnt[e.y];
+      bool settled_part = true, grew = false;
+      for (int q = 0; q < num; ++q) {
+        const int64_t i = lo + order[st + q];
+        if (settled_part && i >= n_stable) {         // everything from here on is tail: park the settled sums first
+          if (grew) { v.sx = a.sx; v.sy = a.sy; v.sxx = a.sxx; v.syx = a.syx; v.syy = a.syy; v.cx = a.cx; v.cy = a.cy; v.n = n; acc[c] = v; }
+          settled_part = false;
+        }
+        const float4 p = __ldg(pts + i);
+        const double xd = (double)p.x, yd = (double)p.y;
+        a.sx += xd; a.sy += yd;
+        a.sxx += xd * xd; a.syx += yd * xd; a.syy += yd * yd;
+        a.cx = __fadd_rn(a.cx, p.x); a.cy = __fadd_rn(a.cy, p.y);
+        ++n;
+        grew = true;
+      }
+      if (settled_part && grew) { v.sx = a.sx; v.sy = a.sy; v.sxx = a.sxx; v.syx = a.syx; v.syy = a.syy; v.cx = a.cx; v.cy = a.cy; v.n = n; acc[c] = v; }
+    }
+    const int old = T.status[c];
+    int now = old & ST_SLOT;
+    if (n > 0) {
+      const LeafStats z = leaf_stats(n, a, fp);
+      now |= ST_OCC;
+      if (z.in_tree) {
+        int sl;
+        if (old & ST_SLOT) sl = T.slot[c]; else { sl = atomicAdd(T.ctr + CTR_SLOTS, 1); now |= ST_SLOT; }
+        CellRec r;
+        r.cx = z.cx; r.cy = z.cy; r.nr_points = z.nr; r.cell = c;
+        r.mx = z.m0; r.my = z.m1; r.c00 = z.ic0; r.c01 = z.ic1; r.c10 = z.ic2; r.c11 = z.ic3;
+        T.recs[sl] = r;
+        T.slot[c] = sl;
+        T.cen[c] = make_float2(z.cx, z.cy);
+        now |= ST_TREE | (z.nr > 0 ? ST_VALID : 0);
+      }
+    }
+    if (!(now & ST_TREE)) T.cen[c] = make_float2(__int_as_float(-1), __int_as_float(-1));      // all-ones NaN, like the memset of a full build
+    if ((now ^ old) & ST_TREE) now |= ST_CHANGED;
+    const int d_occ = ((now & ST_OCC) ? 1 : 0) - ((old & ST_OCC) ? 1 : 0), d_val = ((now & ST_VALID) ? 1 : 0) - ((old & ST_VALID) ? 1 : 0);
+    if (d_occ) atomicAdd(T.ctr + CTR_LEAVES, d_occ);
+    if (d_val) atomicAdd(T.ctr + CTR_VALID, d_val);
+    T.status[c] = (uint8_t)now;
+  }
+}
+
+// dilated occupancy around every cell whose tree status changed: each of its nine neighbours gets the OR over ITS 3x3 block
+__global__ void __launch_bounds__(128) k_inc_occ(const int32_t *__restrict__ lu, const int32_t *__restrict__ cnt, uint8_t *__restrict__ status,
+                                                int W, uint32_t *__restrict__ occ) {
+  const int m = cnt[INC_U];
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < m; t += gridDim.x * blockDim.x) {
+    const int c = lu[t];
+    if (!(status[c] & ST_CHANGED)) continue;
+    for (int dj = -1; dj <= 1; ++dj)
+      for (int di = -1; di <= 1; ++di) {
+        const int q = c + dj * W + di;
+        bool any = false;
+        for (int ej = -1; ej <= 1; ++ej)
+          for (int ei = -1; ei <= 1; ++ei) any = any || (status[q + ej * W + ei] & ST_TREE);
+        if (any) atomicOr(occ + (q >> 5), 1u << (q & 31)); else atomicAnd(occ + (q >> 5), ~(1u << (q & 31)));
+      }
+  }
+}
+__global__ void __launch_bounds__(128) k_inc_clear_changed(const int32_t *__restrict__ lu, const int32_t *__restrict__ cnt, uint8_t *__restrict__ status) {
+  const int m = cnt[INC_U];
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < m; t += gridDim.x * blockDim.x) status[lu[t]] &= (uint8_t)~ST_CHANGED;
+}
+
+// After a full build: the settled sums of every leaf (its bucket is in input order; sorted_idx carries the original indices, the
+// first one >= n_stable ends the settled part), the state byte of its cell, and the list of cells the tail touches.
+// One warp per leaf: 32 bucket entries per load, every lane replays the adds from shuffles.
+__global__ void __launch_bounds__(128) k_inc_init(const float2 *__restrict__ tgt_sorted, const int32_t *__restrict__ sorted_idx,
+                                                 const int32_t *__restrict__ leaf_n, const int32_t *__restrict__ leaf_start,
+                                                 const int32_t *__restrict__ leaf_cell, const int32_t *__restrict__ leaf_nr, int32_t n_stable,
+                                                 int32_t min_points, const int32_t *__restrict__ ctr, CellAcc *__restrict__ acc,
+                                                 uint8_t *__restrict__ status, int32_t *__restrict__ tail_list, int32_t *__restrict__ tail_n) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  const int n_leaves = ctr[CTR_LEAVES];
+  for (int leaf = warp; leaf < n_leaves; leaf += n_warps) {
+    const int n = leaf_n[leaf], st = leaf_start[leaf], c = leaf_cell[leaf];
+    LeafSums a{0, 0, 0, 0, 0, 0.f, 0.f};
+    int settled = 0;
+    bool more = true;
+    for (int k0 = 0; k0 < n && more; k0 += 32) {
+      const int k = k0 + lane;
+      float2 p = make_float2(0.f, 0.f);
+      int idx = INT_MAX;
+      if (k < n) { p = __ldg(tgt_sorted + st + k); idx = __ldg(sorted_idx + st + k); }
+      const int m = min(32, n - k0);
+      for (int j = 0; j < m; ++j) {
+        const int ij = __shfl_sync(0xffffffffu, idx, j);
+        if (ij >= n_stable) { more = false; break; }          // ascending indices: everything after is tail
+        const float px = __shfl_sync(0xffffffffu, p.x, j), py = __shfl_sync(0xffffffffu, p.y, j);
+        const double xd = (double)px, yd = (double)py;
+        a.sx += xd; a.sy += yd;
+        a.sxx += xd * xd; a.syx += yd * xd; a.syy += yd * yd;
+        a.cx = __fadd_rn(a.cx, px); a.cy = __fadd_rn(a.cy, py);
+        ++settled;
+      }
+    }
+    if (lane == 0) {
+      CellAcc v;
+      v.sx = a.sx; v.sy = a.sy; v.sxx = a.sxx; v.syx = a.syx; v.syy = a.syy; v.cx = a.cx; v.cy = a.cy; v.n = settled; v.pad = 0;
+      acc[c] = v;
+      const int nr = leaf_nr[leaf];
+      const bool tree = n >= min_points;
+      status[c] = (uint8_t)(ST_OCC | (tree ? (ST_TREE | ST_SLOT) : 0) | ((tree && nr > 0) ? ST_VALID : 0));
+      if (settled < n) tail_list[atomicAdd(tail_n, 1)] = c;
+    }
+  }
+}
+
 inline int grid_for(int64_t work, int threads, int sm_count, int per_sm = 8) {
   int64_t b = (work + threads - 1) / threads;
   const int64_t cap = (int64_t)sm_count * per_sm;
@@ -841,11 +1097,114 @@ int pairs_prepare(Handle *h, int64_t n_pairs, int64_t *total_pad, int *max_h) {
   return NDT_OK;
 }
 
-int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace, int64_t n_same) {
+
+// Finer lattice for the exact 1-NN of the fitness score: built when the NDT buckets are dense (walls: hundreds of points per
+// 0.5 m cell), or always (force: factor >= 1) for incrementally maintained targets, whose ordered buckets go stale.
+static int build_nn_lattice(Handle *h, int64_t n, const float mn[2], const float mx[2], int64_t nfin, bool force) {
+  GridBuffers &gb = h->gb;
+  GridDims &gd = h->gd;
+  cudaStream_t st = h->stream;
+  int32_t *ctr = gb.counters.as<int32_t>();
+  const size_t npts = (size_t)(n > 0 ? n : 1);
+  gd.nn_f = 0;
+  const int64_t n_leaves = h->h_counters[CTR_LEAVES];
+  int f = 0;
+  if (n_leaves > 0 && nfin / n_leaves > 24) {
+    f = 2;
+    while (f < 64 && nfin / (n_leaves * f) > 12) f *= 2;                   // walls: points per fine cell fall like 1 / f
+  } else if (force && n_leaves > 0) {
+    f = 1;
+  }
+  while (f > 1 && (int64_t)gd.div_x * f * ((int64_t)gd.div_y * f) > (int64_t)8 * 1024 * 1024) f /= 2;   // lattice <= 64 MB
+  if (f > 1 || (force && f == 1)) {
+    gd.nn_f = f;
+    gd.nn_leaf = gd.leaf / (float)f;
+    gd.nn_inv_leaf = 1.0f / gd.nn_leaf;
+    gd.nn_min_bx = (int)std::floor(mn[0] * gd.nn_inv_leaf); gd.nn_min_by = (int)std::floor(mn[1] * gd.nn_inv_leaf);
+    gd.nn_div_x = (int)std::floor(mx[0] * gd.nn_inv_leaf) - gd.nn_min_bx + 1;
+    gd.nn_div_y = (int)std::floor(mx[1] * gd.nn_inv_leaf) - gd.nn_min_by + 1;
+    const int64_t ncf = (int64_t)gd.nn_div_x * gd.nn_div_y;
+    NDT_CUDA(h, gb.cell_of.reserve(npts * 4));
+    NDT_CUDA(h, gb.rank_of.reserve(npts * 4));
+    NDT_CUDA(h, gb.nn_cnt.reserve((size_t)ncf * 4));
+    NDT_CUDA(h, gb.nn_range.reserve((size_t)ncf * sizeof(int2)));
+    NDT_CUDA(h, gb.nn_pts.reserve(npts * sizeof(float2)));
+    NDT_CUDA(h, cudaMemsetAsync(gb.nn_cnt.p, 0, (size_t)ncf * 4, st));
+    NDT_CUDA(h, cudaMemsetAsync(ctr + CTR_JOB, 0, 4, st));
+    Dims df{gd.nn_min_bx, gd.nn_min_by, gd.nn_div_x, gd.nn_div_y, gd.nn_inv_leaf};
+    k_nn_count<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(gb.tgt.as<float4>(), n, df, gb.nn_cnt.as<int32_t>(),
+                                                             gb.cell_of.as<int32_t>(), gb.rank_of.as<int32_t>());
+    k_nn_alloc<<<grid_for(ncf, 256, h->sm_count), 256, 0, st>>>(gb.nn_cnt.as<int32_t>(), ncf, gb.nn_range.as<int2>(), ctr);
+    k_nn_fill<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(gb.tgt.as<float4>(), n, gb.cell_of.as<int32_t>(),
+                                                            gb.rank_of.as<int32_t>(), gb.nn_range.as<int2>(),
+                                                            gb.nn_pts.as<float2>());
+    h->launches += 3;
+    NDT_CUDA(h, cudaGetLastError());
+  }
+  return NDT_OK;
+}
+
+constexpr int64_t INC_MAX_CELLS = 1 << 20;
+
+// exact bounds / count of the finite points among xyzw[lo .. hi)
+static void host_bounds(const float *xyzw, int64_t lo, int64_t hi, float mn[2], float mx[2], int64_t &nfin) {
+  for (int64_t i = lo; i < hi; ++i) {
+    const float x = xyzw[4 * i], y = xyzw[4 * i + 1], z = xyzw[4 * i + 2];
+    if (std::isfinite(x) && std::isfinite(y) && std::isfinite(z)) {
+      mn[0] = std::min(mn[0], x); mn[1] = std::min(mn[1], y);
+      mx[0] = std::max(mx[0], x); mx[1] = std::max(mx[1], y);
+      ++nfin;
+    }
+  }
+}
+
+// After a full build of one grid from a host cloud: set up the state incremental updates continue from.
+static int inc_init(Handle *h, const float *xyzw, int64_t n, int64_t n_stable, int64_t nfin_all) {
+  GridBuffers &gb = h->gb;
+  const GridDims &gd = h->gd;
+  cudaStream_t st = h->stream;
+  h->inc_ok = false; h->inc_active = false;
+  const int64_t npad = gd.n_cells > 0 ? (int64_t)(gd.div_x + 4) * (gd.div_y + 4) : 0;
+  if (npad == 0 || npad > INC_MAX_CELLS || nfin_all == 0) return NDT_OK;            // not worth it / not possible: stay with full builds
+  NDT_CUDA(h, gb.inc_acc.reserve((size_t)npad * sizeof(CellAcc)));
+  NDT_CUDA(h, gb.inc_status.reserve((size_t)npad));
+  NDT_CUDA(h, gb.inc_mark.reserve((size_t)npad * 4));
+  NDT_CUDA(h, gb.inc_lists.reserve((size_t)4 * npad * 4));
+  NDT_CUDA(h, gb.inc_lid.reserve((size_t)npad * sizeof(int2)));
+  NDT_CUDA(h, gb.inc_cellof.reserve((size_t)5 * INC_BATCH_CAP * 4));          // cell_of | rank_of | order | cell_cnt | cell_start
+  NDT_CUDA(h, gb.inc_cnt.reserve(8 * 4));
+  NDT_CUDA(h, gb.recs.reserve((size_t)npad * sizeof(CellRec), (size_t)h->h_counters[CTR_SLOTS] * sizeof(CellRec)));   // room for every cell's record
+  NDT_CUDA(h, cudaMemsetAsync(gb.inc_acc.p, 0, (size_t)npad * sizeof(CellAcc), st));
+  NDT_CUDA(h, cudaMemsetAsync(gb.inc_status.p, 0, (size_t)npad, st));
+  NDT_CUDA(h, cudaMemsetAsync(gb.inc_mark.p, 0, (size_t)npad * 4, st));
+  NDT_CUDA(h, cudaMemsetAsync(gb.inc_lid.p, 0, (size_t)npad * sizeof(int2), st));
+  NDT_CUDA(h, cudaMemsetAsync(gb.inc_cnt.p, 0, 8 * 4, st));
+  int32_t *lists = gb.inc_lists.as<int32_t>();
+  const int64_t n_leaves = h->h_counters[CTR_LEAVES];
+  k_inc_init<<<grid_for(n_leaves * 32, 128, h->sm_count, 16), 128, 0, st>>>(
+      gb.tgt_sorted.as<float2>(), gb.sorted_idx.as<int32_t>(), gb.leaf_n.as<int32_t>(), gb.leaf_start.as<int32_t>(), gb.leaf_cell.as<int32_t>(),
+      gb.leaf_nr.as<int32_t>(), (int32_t)n_stable, h->prm.min_points, gb.counters.as<int32_t>(), gb.inc_acc.as<CellAcc>(),
+      gb.inc_status.as<uint8_t>(), lists + (size_t)INC_P * npad, gb.inc_cnt.as<int32_t>() + INC_P);
+  ++h->launches;
+  NDT_CUDA(h, cudaGetLastError());
+  h->inc_mn[0] = h->inc_mn[1] = std::numeric_limits<float>::max();
+  h->inc_mx[0] = h->inc_mx[1] = -std::numeric_limits<float>::max();
+  h->inc_nfin = 0;
+  host_bounds(xyzw, 0, n_stable, h->inc_mn, h->inc_mx, h->inc_nfin);
+  h->inc_m = n_stable;
+  h->inc_epoch = 0;
+  h->inc_list_prev = INC_P;
+  h->inc_ok = true;
+  return NDT_OK;
+}
+
+int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace, int64_t n_same, int64_t n_stable) {
   GridBuffers &gb = h->gb;
   GridDims &gd = h->gd;
   cudaStream_t st = h->stream;
   h->have_grid = false; h->have_readback = false; h->grid_has_points = false;
+  h->inc_ok = false; h->inc_active = false;
+  if (memspace != NDT_MEM_HOST) n_stable = -1;      // the settled prefix is tracked with host-side bounds: host clouds only
   // n_same: the caller promises that the first n_same points equal the first n_same points of the previous target of
   // this handle (a map that only changed at its end). They are still on the device: only the rest is staged and copied.
   if (n_same < 0 || n_same > n || n_same > h->tgt_on_device || memspace != NDT_MEM_HOST) n_same = 0;
@@ -962,36 +1321,8 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace, int64_t n_
   NDT_CUDA(h, cudaGetLastError());
   h->h_counters[CTR_NFIN] = (int32_t)nfin;
 
-  // Dense NDT buckets make the exact 1-NN of the fitness score expensive: add a finer lattice for it.
-  gd.nn_f = 0;
-  const int64_t n_leaves = h->h_counters[CTR_LEAVES];
-  if (n_leaves > 0 && nfin / n_leaves > 24) {
-    int f = 2;
-    while (f < 64 && nfin / (n_leaves * f) > 12) f *= 2;                   // walls: points per fine cell fall like 1 / f
-    while (f > 1 && (int64_t)gd.div_x * f * ((int64_t)gd.div_y * f) > (int64_t)8 * 1024 * 1024) f /= 2;   // lattice <= 64 MB
-    if (f > 1) {
-      gd.nn_f = f;
-      gd.nn_leaf = gd.leaf / (float)f;
-      gd.nn_inv_leaf = 1.0f / gd.nn_leaf;
-      gd.nn_min_bx = (int)std::floor(mn[0] * gd.nn_inv_leaf); gd.nn_min_by = (int)std::floor(mn[1] * gd.nn_inv_leaf);
-      gd.nn_div_x = (int)std::floor(mx[0] * gd.nn_inv_leaf) - gd.nn_min_bx + 1;
-      gd.nn_div_y = (int)std::floor(mx[1] * gd.nn_inv_leaf) - gd.nn_min_by + 1;
-      const int64_t ncf = (int64_t)gd.nn_div_x * gd.nn_div_y;
-      NDT_CUDA(h, gb.nn_cnt.reserve((size_t)ncf * 4));
-      NDT_CUDA(h, gb.nn_range.reserve((size_t)ncf * sizeof(int2)));
-      NDT_CUDA(h, gb.nn_pts.reserve(npts * sizeof(float2)));
-      NDT_CUDA(h, cudaMemsetAsync(gb.nn_cnt.p, 0, (size_t)ncf * 4, st));
-      NDT_CUDA(h, cudaMemsetAsync(ctr + CTR_JOB, 0, 4, st));
-      Dims df{gd.nn_min_bx, gd.nn_min_by, gd.nn_div_x, gd.nn_div_y, gd.nn_inv_leaf};
-      k_nn_count<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(gb.tgt.as<float4>(), n, df, gb.nn_cnt.as<int32_t>(),
-                                                               gb.cell_of.as<int32_t>(), gb.rank_of.as<int32_t>());
-      k_nn_alloc<<<grid_for(ncf, 256, h->sm_count), 256, 0, st>>>(gb.nn_cnt.as<int32_t>(), ncf, gb.nn_range.as<int2>(), ctr);
-      k_nn_fill<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(gb.tgt.as<float4>(), n, gb.cell_of.as<int32_t>(),
-                                                              gb.rank_of.as<int32_t>(), gb.nn_range.as<int2>(),
-                                                              gb.nn_pts.as<float2>());
-      h->launches += 3;
-    }
-  }
+  if (int rc = build_nn_lattice(h, n, mn, mx, nfin, /*force=*/n_stable >= 0)) return rc;
+  if (n_stable >= 0) { if (int rc = inc_init(h, xyzw, n, std::min(n_stable, n), nfin)) return rc; }
   if (h->timing) {
     cudaEventRecord(h->ev1, st);
     NDT_CUDA(h, cudaEventSynchronize(h->ev1));
@@ -999,6 +1330,107 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace, int64_t n_
   }
   NDT_CUDA(h, cudaGetLastError());
   h->have_grid = true; h->have_readback = true; h->grid_has_points = true;
+  h->tgt_on_device = n;
+  return NDT_OK;
+}
+
+
+int grid_build_incremental(Handle *h, const float *xyzw, int64_t n, int64_t n_same, int64_t n_stable, int memspace) {
+  if (n < 0 || (n > 0 && !xyzw)) return set_err(h, NDT_ERR_ARG, "ndt_set_target_incremental: bad points");
+  if (n_stable < 0) n_stable = 0;
+  if (n_stable > n) n_stable = n;
+  if (n_same < 0 || n_same > n || n_same > h->tgt_on_device) n_same = 0;
+  const int64_t m = h->inc_m;
+  // anything the running sums cannot continue from is a full build (which re-initialises them)
+  const bool can = memspace == NDT_MEM_HOST && h->inc_ok && h->have_grid && n_same >= m && n_stable >= m && n <= (int64_t)INT_MAX &&
+                   n - m <= INC_BATCH_CAP && n > 0;
+  if (!can) return grid_build(h, xyzw, n, memspace, n_same, n_stable);
+  GridBuffers &gb = h->gb;
+  GridDims &gd = h->gd;
+  cudaStream_t st = h->stream;
+  // bounds of the whole cloud = settled prefix (cached) + newly settled points + tail, exact floats like getMinMax3D
+  float mnA[2] = {h->inc_mn[0], h->inc_mn[1]}, mxA[2] = {h->inc_mx[0], h->inc_mx[1]};
+  int64_t nfinA = h->inc_nfin;
+  host_bounds(xyzw, m, n_stable, mnA, mxA, nfinA);
+  float mn[2] = {mnA[0], mnA[1]}, mx[2] = {mxA[0], mxA[1]};
+  int64_t nfin = nfinA;
+  host_bounds(xyzw, n_stable, n, mn, mx, nfin);
+  bool same_geom = nfin > 0;
+  if (same_geom) {
+    const int64_t dx = (int64_t)((mx[0] - mn[0]) * gd.inv_leaf) + 1, dy = (int64_t)((mx[1] - mn[1]) * gd.inv_leaf) + 1;
+    if (dx * dy > (int64_t)std::numeric_limits<int32_t>::max()) same_geom = false;
+  }
+  if (same_geom) {
+    const int min_bx = (int)std::floor(mn[0] * gd.inv_leaf), min_by = (int)std::floor(mn[1] * gd.inv_leaf);
+    const int max_bx = (int)std::floor(mx[0] * gd.inv_leaf), max_by = (int)std::floor(mx[1] * gd.inv_leaf);
+    same_geom = min_bx == gd.min_bx && min_by == gd.min_by && max_bx - min_bx + 1 == gd.div_x && max_by - min_by + 1 == gd.div_y;
+  }
+  if (!same_geom) return grid_build(h, xyzw, n, memspace, n_same, n_stable);      // the map grew past the grid: every index shifts
+
+  h->have_grid = false; h->have_readback = false; h->have_nbr = false;
+  const int64_t npad = (int64_t)(gd.div_x + 4) * (gd.div_y + 4);
+  const size_t npts = (size_t)n;
+  NDT_CUDA(h, gb.tgt.reserve(npts * sizeof(float4), (size_t)n_same * sizeof(float4), st));
+  const int B = (int)(n - m);                        // this call's batch: newly settled points, then the tail
+  if (n > n_same) {
+    if (ensure_pinned(h, (size_t)(n - n_same) * sizeof(float4) + 256)) return NDT_ERR_CUDA;
+    std::memcpy(h->pinned, xyzw + 4 * n_same, (size_t)(n - n_same) * sizeof(float4));
+  }
+  if (h->timing) cudaEventRecord(h->ev0, st);
+  if (n > n_same)
+    NDT_CUDA(h, cudaMemcpyAsync(gb.tgt.as<float4>() + n_same, h->pinned, (size_t)(n - n_same) * sizeof(float4), cudaMemcpyHostToDevice, st));
+  const int32_t epoch = ++h->inc_epoch;
+  int32_t *lists = gb.inc_lists.as<int32_t>(), *cnt = gb.inc_cnt.as<int32_t>(), *mark = gb.inc_mark.as<int32_t>();
+  int32_t *ctr = gb.counters.as<int32_t>();
+  // list buffers: the previous call's cells sit in buffer inc_list_prev; this call's batch cells and the union take two others
+  int buf[3], k = 0;
+  for (int b = 0; b < 4; ++b) if (b != h->inc_list_prev) buf[k++] = b;
+  int32_t *LB = lists + (size_t)buf[0] * npad, *LU = lists + (size_t)buf[1] * npad, *LP = lists + (size_t)h->inc_list_prev * npad;
+  NDT_CUDA(h, cudaMemsetAsync(cnt + INC_B, 0, sizeof(int32_t), st));
+  NDT_CUDA(h, cudaMemsetAsync(cnt + INC_U, 0, sizeof(int32_t), st));
+  const PairDims *dims = gb.dims.as<PairDims>();
+  const float4 *pts = gb.tgt.as<float4>();
+  int32_t *cell_of = gb.inc_cellof.as<int32_t>(), *rank_of = cell_of + INC_BATCH_CAP, *order = rank_of + INC_BATCH_CAP,
+          *cell_cnt = order + INC_BATCH_CAP, *cell_start = cell_cnt + INC_BATCH_CAP;
+  int2 *lid_tab = gb.inc_lid.as<int2>();
+  if (B > 0) {
+    const int blocks = (B + 255) / 256;
+    k_inc_rank<<<blocks, 256, 0, st>>>(pts, m, B, dims, gd.inv_leaf, cell_of, rank_of, lid_tab, epoch, LB, cnt + INC_B, cell_cnt);
+    k_inc_starts<<<1, 1024, 0, st>>>(cell_cnt, cnt + INC_B, cell_start);
+    k_inc_scatter<<<blocks, 256, 0, st>>>(B, cell_of, rank_of, lid_tab, cell_start, order);
+    h->launches += 3;
+  }
+  const int64_t work = B + npad / 16 + 1024;          // the previous call's list length lives on the device: enough threads either way
+  k_inc_union<<<grid_for(work, 256, h->sm_count), 256, 0, st>>>(LB, LP, cnt, mark, epoch, LU);
+  FinalizeParams fp{h->prm.min_points, h->prm.eig_mult, h->prm.quirks};
+  IncTables T{gb.inc_status.as<uint8_t>(), gb.slot.as<int32_t>(), gb.cen.as<float2>(), gb.recs.as<CellRec>(), ctr};
+  k_inc_finalize<<<grid_for(work, 128, h->sm_count), 128, 0, st>>>(pts, m, n_stable, order, lid_tab, epoch, cell_start, cell_cnt, LU, cnt,
+                                                                  gb.inc_acc.as<CellAcc>(), fp, T);
+  k_inc_occ<<<grid_for(work, 128, h->sm_count), 128, 0, st>>>(LU, cnt, gb.inc_status.as<uint8_t>(), gd.div_x + 4, gb.occ.as<uint32_t>());
+  k_inc_clear_changed<<<grid_for(work, 128, h->sm_count), 128, 0, st>>>(LU, cnt, gb.inc_status.as<uint8_t>());
+  h->launches += 4;
+  NDT_CUDA(h, cudaMemcpyAsync(cnt + INC_P, cnt + INC_B, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));   // this call's tail cells are the next call's "previous tail"
+  h->inc_list_prev = buf[0];
+  NDT_CUDA(h, cudaGetLastError());
+  // counters -> host (also the stream fence that lets the pinned stage be reused)
+  NDT_CUDA(h, cudaMemcpyAsync(h->pinned_ctr, ctr, sizeof(h->h_counters), cudaMemcpyDeviceToHost, st));
+  NDT_CUDA(h, cudaStreamSynchronize(st));
+  std::memcpy(h->h_counters, h->pinned_ctr, sizeof(h->h_counters));
+  h->h_counters[CTR_NFIN] = (int32_t)nfin;
+  h->h_counters[CTR_PTS] = (int32_t)nfin;
+  gd.n_tgt = n;
+  if (int rc = build_nn_lattice(h, n, mn, mx, nfin, /*force=*/true)) return rc;
+  if (h->timing) {
+    cudaEventRecord(h->ev1, st);
+    NDT_CUDA(h, cudaEventSynchronize(h->ev1));
+    cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
+  }
+  h->inc_mn[0] = mnA[0]; h->inc_mn[1] = mnA[1]; h->inc_mx[0] = mxA[0]; h->inc_mx[1] = mxA[1];
+  h->inc_nfin = nfinA;
+  h->inc_m = n_stable;
+  h->inc_active = true;
+  h->nbr_cells = npad; h->nbr_grids = 1;
+  h->have_grid = true; h->grid_has_points = true;
   h->tgt_on_device = n;
   return NDT_OK;
 }
@@ -1052,9 +1484,10 @@ GridView grid_view(const Handle *h) {
   G.recs = gb.recs.as<CellRec>();
   G.min_bx = h->gd.min_bx; G.min_by = h->gd.min_by; G.div_x = h->gd.div_x; G.div_y = h->gd.div_y;
   G.inv_leaf = h->gd.inv_leaf; G.r2 = h->gd.r2; G.leaf = h->gd.leaf;
-  G.leaf_id = gb.leaf_id.as<int32_t>();
-  G.leaf_range = gb.leaf_range.as<int2>();
-  G.tgt_sorted = gb.tgt_sorted.as<float2>();
+  // after an incremental update only the lattice is current: no ordered buckets (the 1-NN then stays on the lattice)
+  G.leaf_id = h->inc_active ? nullptr : gb.leaf_id.as<int32_t>();
+  G.leaf_range = h->inc_active ? nullptr : gb.leaf_range.as<int2>();
+  G.tgt_sorted = h->inc_active ? nullptr : gb.tgt_sorted.as<float2>();
   G.tgt = gb.tgt.as<float4>();
   G.n_tgt = h->gd.n_tgt;
   G.nn_f = h->gd.nn_f;

@@ -939,7 +939,28 @@ __device__ __forceinline__ bool nn_stage1(const GridView &G, float xt, float yt,
 // stage 2: the whole warp finishes one query (all lanes pass the same xt, yt, best); returns the exact answer
 __device__ inline float nn_stage2_warp(const GridView &G, float xt, float yt, float best) {
   const int lane = threadIdx.x & 31;
-  if (G.div_x > 0) {
+  if (G.div_x > 0 && G.leaf_id == nullptr && G.nn_f > 0) {
+    // incrementally maintained target: only the lattice is current. Lanes take the cells of a lattice ring, 32 at a time, and
+    // every lane walks its own bucket; rings until the certificate holds.
+    const int ci = cell_coord(xt, G.nn_inv_leaf, G.nn_min_bx), cj = cell_coord(yt, G.nn_inv_leaf, G.nn_min_by);
+    const int r0 = first_ring(ci, cj, G.nn_div_x, G.nn_div_y);
+    for (int ring = r0; ring <= r0 + NN_MAX_RINGS * max(G.nn_f, 1); ++ring) {
+      const int ncell = ring == 0 ? 1 : 8 * ring;
+      for (int t = lane; t < ncell; t += 32) {
+        int di = 0, dj = 0;
+        if (ring > 0) ring_cell(ring, t, di, dj);
+        const int2 rg = nn_bucket<true>(G, ci + di, cj + dj);
+        const float2 *__restrict__ q = G.nn_pts + rg.x;
+        for (int j = 0; j < rg.y; ++j) {
+          const float2 p = __ldg(q + j);
+          const float dd = dist2f(xt, yt, p.x, p.y);
+          if (dd < best) best = dd;
+        }
+      }
+      best = __int_as_float(__reduce_min_sync(0xffffffffu, __float_as_int(best)));
+      if (ring_certifies(ring, (double)G.nn_leaf, best)) return best;
+    }
+  } else if (G.div_x > 0) {
     const int ci = cell_coord(xt, G.inv_leaf, G.min_bx), cj = cell_coord(yt, G.inv_leaf, G.min_by);
     const int r0 = first_ring(ci, cj, G.div_x, G.div_y);
     const bool dense = G.nn_f > 0;          // dense NDT buckets (hundreds of points): lanes share a bucket instead of a ring

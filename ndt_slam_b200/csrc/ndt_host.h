@@ -77,6 +77,15 @@ struct GridBuffers {
   DevBuf leaf_cen;     // float2[n]
   DevBuf recs;         // CellRec[n]      compact records (n >= min_points)
   DevBuf counters;     // int32[CTR_COUNT] + bounds int32[4]
+  // incremental target (ndt_set_target_incremental): per-cell running sums of the settled prefix of the cloud, the state
+  // of every cell after the last call, work lists
+  DevBuf inc_acc;      // CellAcc[padded]  in-order sums over the settled prefix
+  DevBuf inc_status;   // uint8[padded]    bit0 occupied, bit1 tree cell, bit2 valid, bit3 has a record slot, bit7 tree status changed
+  DevBuf inc_mark;     // int32[padded]    epoch marks (distinct-cell lists without clearing)
+  DevBuf inc_lists;    // int32[4][padded] this call's batch cells | the previous call's | union (rotating)
+  DevBuf inc_cellof;   // int32[5][cap]    per batch point: cell, rank in its cell, order; per batch cell: count, start
+  DevBuf inc_lid;      // int2[padded]     (epoch, local id) of the cells of the current batch
+  DevBuf inc_cnt;      // int32[8]         list lengths
 };
 
 struct GridDims {
@@ -105,6 +114,14 @@ struct Handle {
   GridBuffers gb;
   GridDims gd;
   bool have_grid = false;
+  // incremental target state (valid while inc_ok)
+  bool inc_ok = false;           // the tables were produced by / are ready for incremental updates
+  bool inc_active = false;       // ... and the last call WAS an incremental update (ordered buckets are stale)
+  int64_t inc_m = 0;             // points [0, inc_m) are folded into inc_acc
+  int32_t inc_epoch = 0;
+  float inc_mn[2] = {0.f, 0.f}, inc_mx[2] = {0.f, 0.f};   // exact bounds of the finite points among [0, inc_m)
+  int64_t inc_nfin = 0;          // finite points among [0, inc_m)
+  int inc_list_prev = 2;         // which of the list buffers holds the previous call's tail cells
   bool have_nbr = false;         // gb.nbr matches the current tables (derived from gb.cen on demand: ensure_nbr)
   int64_t nbr_cells = 0;         // padded entries of all grids in the shared tables (what ensure_nbr covers)
   int nbr_grids = 0;             // entries of gb.dims
@@ -129,7 +146,10 @@ struct Handle {
 };
 
 // grid_build.cu
-int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace, int64_t n_same = 0);
+// n_stable >= 0: the caller promises that the first n_stable points stay a prefix of future targets; the build then also
+// prepares the state ndt_set_target_incremental continues from
+int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace, int64_t n_same = 0, int64_t n_stable = -1);
+int grid_build_incremental(Handle *h, const float *xyzw, int64_t n, int64_t n_same, int64_t n_stable, int memspace);
 // shared by ndt_set_target (one grid) and ndt_match_pairs (one grid per pair): target points are in gb.tgt,
 // geometry in gb.dims (device), point ranges in gb.pair_off (device, n_grids + 1 entries; unused for one grid)
 int grid_build_tables(Handle *h, int64_t n, int n_grids, int64_t total_pad, int max_h);

@@ -96,6 +96,9 @@ class PointCloudMap {
   // localMap_cloud exactly as call localMapEpoch - 1 had them (lets the matcher upload only the changed tail)
   uint64_t localMapEpoch = 0;
   size_t localMapStablePrefix = 0;
+  // ... and its first `localMapSettled` points (previous sub-map + what the current sub-map's voxel filter has emitted for
+  // good) stay a prefix of every later local map until the layout changes (a new sub-map), when localMapStablePrefix drops to 0
+  size_t localMapSettled = 0;
 
   PointCloudMap() : startFrame(0), sepThre(30), atd(0) {
     ros::param::get("start_frame", startFrame);
@@ -124,6 +127,9 @@ class PointCloudMap {
   // what changed since the last call (same content as rebuilding it from scratch)
   const void *lm_prev = nullptr, *lm_cur = nullptr;
   size_t lm_prev_points = 0, lm_prefix_points = 0, lm_fixed = 0;
+  // makeGlobalMap keeps the frozen sub-maps' part of globalMap_cloud / maps
+  const void *gm_cloud = nullptr;
+  size_t gm_frozen = 0, gm_frozen_points = 0;
 };
 
 // PCD v0.7 ASCII writer for x y z float clouds (what pcl::io::savePCDFileASCII emits)

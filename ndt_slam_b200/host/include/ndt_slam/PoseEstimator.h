@@ -37,9 +37,10 @@ class PoseEstimator {
   double LeafSize;
 
   uint64_t hintEpoch = 0, uploadedEpoch = 0;     // see hintTargetPrefix
-  size_t hintPrefix = 0;
+  size_t hintPrefix = 0, hintSettled = 0;
   const void *uploadedCloud = nullptr;
 
+  bool incrementalTarget;   // parameter incremental_target (default true): use ndt_set_target_incremental when the map hints a settled prefix
   ndt_handle ndt;       // stands where the reference has  pcl::NDT<pcl::PointXYZ, pcl::PointXYZ> ndt;
   Timer timer;
 
@@ -63,7 +64,12 @@ class PoseEstimator {
   // Optional hint (not in the reference): the reference cloud handed to the next estimatePose is version `epoch` of a
   // cloud whose first `stablePoints` points did not change since version epoch - 1. When the previous estimatePose
   // uploaded exactly that previous version, only the changed tail is copied to the device (ndt_set_target_prefix).
-  void hintTargetPrefix(uint64_t epoch, size_t stablePoints) { hintEpoch = epoch; hintPrefix = stablePoints; }
+  // `settledPoints`: the first settledPoints points of this version stay a prefix of every later version (until a version
+  // arrives whose stablePoints is smaller): the device then keeps running per-cell sums of that part and re-derives only the
+  // cells a scan touches (ndt_set_target_incremental).
+  void hintTargetPrefix(uint64_t epoch, size_t stablePoints, size_t settledPoints = 0) {
+    hintEpoch = epoch; hintPrefix = stablePoints; hintSettled = settledPoints;
+  }
 
   void setScanPair(const Scan2D *curScan, pcl::PointCloud<pcl::PointXYZ>::Ptr refScan);
   void setScanPair(const Scan2D *curScan, const Scan2D *refScan);

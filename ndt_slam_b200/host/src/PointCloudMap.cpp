@@ -128,16 +128,29 @@ void PointCloudMap::addPoints(const std::vector<LPoint2D> &lps) {
   submaps.emplace_back(next);
 }
 
+// [REF src/PointCloudMap.cpp:96-116] global map = every frozen sub-map's thinned cloud + the current sub-map thinned now.
+// Frozen sub-maps never change, so their part of the cloud (and of `maps`) is kept from call to call and only the current
+// sub-map's part is rebuilt: the same cloud the reference produces by clearing and re-concatenating everything every key frame.
 void PointCloudMap::makeGlobalMap() {
-  globalMap_cloud->clear();
-  maps.clear();
-  for (size_t i = 0; i + 1 < submaps.size(); ++i) {            // frozen sub-maps are already thinned
-    *globalMap_cloud += *submaps[i].p_cloud;
+  const size_t frozen = submaps.size() - 1;
+  std::vector<pcl::PointXYZ> &gm = globalMap_cloud->points;
+  bool keep = gm_cloud == globalMap_cloud.get() && gm_frozen <= frozen && gm.size() >= gm_frozen_points && maps.size() >= gm_frozen;
+  for (size_t i = 0; keep && i < gm_frozen; ++i) keep = maps[i].get() == submaps[i].p_cloud.get();
+  if (!keep) { gm.clear(); maps.clear(); gm_frozen = 0; gm_frozen_points = 0; gm_cloud = globalMap_cloud.get(); }
+  gm.resize(gm_frozen_points);
+  maps.resize(gm_frozen);
+  for (size_t i = gm_frozen; i < frozen; ++i) {
+    gm.insert(gm.end(), submaps[i].p_cloud->points.begin(), submaps[i].p_cloud->points.end());
     maps.emplace_back(submaps[i].p_cloud);
   }
+  gm_frozen = frozen;
+  gm_frozen_points = gm.size();
   Cloud::Ptr current = submaps.back().filterPoints();
-  *globalMap_cloud += *current;
+  gm.insert(gm.end(), current->points.begin(), current->points.end());
   maps.emplace_back(current);
+  globalMap_cloud->width = static_cast<uint32_t>(gm.size());
+  globalMap_cloud->height = 1;
+  globalMap_cloud->is_dense = false;
 }
 
 void PointCloudMap::makeLocalMap() {
@@ -160,6 +173,7 @@ void PointCloudMap::makeLocalMap() {
   lm.insert(lm.end(), prefix.begin() + lm_prefix_points, prefix.end());
   lm_prefix_points = prefix.size();
   lm_fixed = lm.size();
+  localMapSettled = lm_fixed;
   cur.thinnedTail(lm);
   localMap_cloud->width = static_cast<uint32_t>(lm.size());
   localMap_cloud->height = 1;

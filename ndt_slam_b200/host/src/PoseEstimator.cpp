@@ -22,7 +22,7 @@ inline double now_ms() {
 
 PoseEstimator::PoseEstimator()
     : curScan(nullptr), refScan(nullptr), coeNDTCov(1.0), TransformationEpsilon(0.01), StepSize(0.1), Resolution(1.0),
-      MaximumIterations(35), LeafSize(0.1), ndt(nullptr), totalError(0.0), lastGridMs(0), lastMatchMs(0), lastFilterMs(0),
+      MaximumIterations(35), LeafSize(0.1), incrementalTarget(true), ndt(nullptr), totalError(0.0), lastGridMs(0), lastMatchMs(0), lastFilterMs(0),
       lastSetSourceWallMs(0), lastSetTargetWallMs(0), lastAlignWallMs(0),
       lastSourcePoints(0), lastTargetPoints(0) {
   ros::param::get("coeNDTCov", coeNDTCov);
@@ -31,6 +31,7 @@ PoseEstimator::PoseEstimator()
   ros::param::get("Resolution", Resolution);
   ros::param::get("MaximumIterations", MaximumIterations);
   ros::param::get("LeafSize", LeafSize);
+  ros::param::get("incremental_target", incrementalTarget);
   source_cloud = std::make_shared<pcl::PointCloud<pcl::PointXYZ>>();
   target_cloud = std::make_shared<pcl::PointCloud<pcl::PointXYZ>>();
   std::memset(&lastResult, 0, sizeof(lastResult));
@@ -107,11 +108,16 @@ double PoseEstimator::estimatePose(Pose2D &initPose, Pose2D &estPose, Eigen::Mat
   int64_t n_same = 0;
   if (hintEpoch != 0 && uploadedEpoch != 0 && hintEpoch == uploadedEpoch + 1 && uploadedCloud == target_cloud.get())
     n_same = (int64_t)std::min(hintPrefix, target_cloud->points.size());
-  if (ndt_set_target_prefix(ndt, reinterpret_cast<const float *>(target_cloud->points.data()), (int64_t)target_cloud->points.size(), n_same,
-                            NDT_MEM_HOST) != NDT_OK)
-    fail(ndt, "ndt_set_target");
+  const int64_t n_target = (int64_t)target_cloud->points.size();
+  const float *target_pts = reinterpret_cast<const float *>(target_cloud->points.data());
+  int rc;
+  if (hintEpoch != 0 && incrementalTarget)
+    rc = ndt_set_target_incremental(ndt, target_pts, n_target, n_same, (int64_t)std::min(hintSettled, target_cloud->points.size()), NDT_MEM_HOST);
+  else
+    rc = ndt_set_target_prefix(ndt, target_pts, n_target, n_same, NDT_MEM_HOST);
+  if (rc != NDT_OK) fail(ndt, "ndt_set_target");
   uploadedEpoch = hintEpoch; uploadedCloud = target_cloud.get();
-  hintEpoch = 0; hintPrefix = 0;
+  hintEpoch = 0; hintPrefix = 0; hintSettled = 0;
   lastSetTargetWallMs = now_ms() - t0;
   float ms = 0.f;
   ndt_last_kernel_ms(ndt, &ms);

@@ -69,7 +69,7 @@ bool ScanMatcher::matchScan(Scan2D &curScan) {
   // NDT against the local map, starting from the prediction
   t = now_ms();
   estim->setScanPair(&curScan, pcmap->localMap_cloud);
-  estim->hintTargetPrefix(pcmap->localMapEpoch, pcmap->localMapStablePrefix);   // optional: upload only what makeLocalMap changed
+  estim->hintTargetPrefix(pcmap->localMapEpoch, pcmap->localMapStablePrefix, pcmap->localMapSettled);   // optional: upload only what makeLocalMap changed
   Pose2D estPose;
   Eigen::Matrix3d Qmat;
   const double cost = estim->estimatePose(predPose, estPose, Qmat);

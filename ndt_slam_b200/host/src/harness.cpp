@@ -179,6 +179,7 @@ int64_t host_map_replay(const double *poses3, const double *xy, const int64_t *o
     for (int64_t i = off[s]; i < off[s + 1]; ++i) lps[i - off[s]].setData(s, xy[2 * i], xy[2 * i + 1]);
     pcmap.addPoints(lps);
     pcmap.makeLocalMap();
+    if (s % 5 == 0) pcmap.makeGlobalMap();        // like FrontEnd at key frames: the kept frozen part must not change the final cloud
     if (check_every > 0 && (s + 1) % check_every == 0) {
       pcl::PointCloud<pcl::PointXYZ> expect, thinned;
       if (pcmap.submaps.size() >= 2) expect += *pcmap.submaps[pcmap.submaps.size() - 2].p_cloud;
