@@ -97,9 +97,10 @@ typedef struct {
   double hess[9];         /* getHessian() rows/cols {x, y, yaw}, row-major                */
   int32_t converged;      /* hasConverged()                                               */
   int32_t iters;          /* nr_iterations_ (outer Newton iterations)                     */
-  int32_t evals;          /* full objective passes (computeDerivatives + computeHessian)  */
-  int32_t reserved;
-  int64_t point_evals;    /* source points x objective passes, counted on the device      */
+  int32_t evals;          /* objective passes the reference makes (computeDerivatives + computeHessian) */
+  int32_t passes_run;     /* the ones run on the device: a line-search trial at the very pose of the
+                             previous trial returns the same numbers and is served from them */
+  int64_t point_evals;    /* source points x evals, counted on the device                 */
 } ndt_result;
 
 typedef struct {

@@ -42,7 +42,7 @@ class NdtResult(C.Structure):
     _fields_ = [("pose", C.c_double * 3), ("T", C.c_float * 16), ("score", C.c_double),
                 ("trans_prob", C.c_double), ("fitness", C.c_double), ("hess", C.c_double * 9),
                 ("converged", C.c_int32), ("iters", C.c_int32), ("evals", C.c_int32),
-                ("reserved", C.c_int32), ("point_evals", C.c_int64)]
+                ("passes_run", C.c_int32), ("point_evals", C.c_int64)]
 
 
 class NdtGridInfo(C.Structure):
@@ -54,7 +54,7 @@ class NdtGridInfo(C.Structure):
 # numpy view of ndt_result for batched calls (must match the C layout; checked in tests)
 RESULT_DTYPE = np.dtype([("pose", "<f8", 3), ("T", "<f4", 16), ("score", "<f8"), ("trans_prob", "<f8"),
                          ("fitness", "<f8"), ("hess", "<f8", 9), ("converged", "<i4"), ("iters", "<i4"),
-                         ("evals", "<i4"), ("reserved", "<i4"), ("point_evals", "<i8")], align=True)
+                         ("evals", "<i4"), ("passes_run", "<i4"), ("point_evals", "<i8")], align=True)
 
 EXPORTS = [
     "ndt_params_default", "ndt_create", "ndt_destroy", "ndt_last_error", "ndt_version",

@@ -66,7 +66,10 @@ struct Objective {
 #if NDT_PHASE_CLOCK
   long long t_enter = 0, t_leave = 0, c_pose = 0, c_acc = 0, c_red = 0, c_between = 0, n_pass = 0;
 #endif
-  __device__ __noinline__ void pass(const int mode, const double *p, const AngleCache &ac, double *out) {
+  __device__ __noinline__ void pass(const int mode_asked, const double *p, const AngleCache &ac, double *out) {
+    // the optimiser only ever asks for mode 0 when its trial passes carry the Hessian (NDT_TRIAL_MODE 0, ndt_device.cuh):
+    // the mode is then a compile-time constant and the Hessian-only / gradient-only predication drops out of the hot loop
+    const int mode = NDT_TRIAL_MODE == 0 ? 0 : mode_asked;
 #if NDT_PHASE_CLOCK
     t_enter = clock64();
     if (t_leave) c_between += t_enter - t_leave;
@@ -165,7 +168,7 @@ __device__ inline void write_result(ndt_result *out, const MatchOut &mo, int ns,
   else r.fitness = nan("");
 #pragma unroll
   for (int k = 0; k < 9; ++k) r.hess[k] = mo.H[k];
-  r.converged = mo.converged; r.iters = mo.iters; r.evals = mo.evals; r.reserved = 0;
+  r.converged = mo.converged; r.iters = mo.iters; r.evals = mo.evals; r.passes_run = mo.passes;
   r.point_evals = (int64_t)mo.evals * (int64_t)ns;
   *out = r;
 }

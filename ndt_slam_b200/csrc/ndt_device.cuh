@@ -697,7 +697,7 @@ struct MatchOut {
   double p[3];
   double score;
   double H[9];
-  int converged, iters, evals;
+  int converged, iters, evals, passes;   // evals: passes the reference makes; passes: the ones run here (see step_length_mt)
 };
 
 // Optimiser state of one match, kept together in one struct that the Newton loop and the line search share (a per-thread
@@ -715,8 +715,11 @@ struct OptState {
   AngleCache ac;
 };
 
+#ifndef NDT_TRIAL_MODE
+#define NDT_TRIAL_MODE 0     // mode of a line-search trial pass: 0 = with Hessian (no computeHessian pass afterwards), 1 = PCL's split
+#endif
 template <class Obj>
-__device__ inline double step_length_mt(Obj &obj, const MatchParams &mp, OptState &S, double step_init, int &evals) {
+__device__ inline double step_length_mt(Obj &obj, const MatchParams &mp, OptState &S, double step_init, int &evals, int &repeats) {
   const double *x = S.p;
   double *dir = S.dp, *g = S.g, *H = S.H, *x_t = S.x_t, *acc = S.acc;
   double &score = S.score;
@@ -754,16 +757,28 @@ __device__ inline double step_length_mt(Obj &obj, const MatchParams &mp, OptStat
   double d_phi_t = -(g[0] * dir[0] + g[1] * dir[1] + g[2] * dir[2]);
   double psi_t = phi_t - phi_0 - mu * d_phi_0 * a_t;
   double d_psi_t = d_phi_t - mu * d_phi_0;
+  // A search whose interval has collapsed onto a clamp (typically a_t == step_min) asks for the same trial step again and
+  // again until the iteration cap ends it: on C4 31 % of all passes are such repeats. x_t = x + dir * a_t is then the same
+  // three doubles, so the pass would transform the same points with the same matrix and return the same score and
+  // gradient bit for bit; it is not run, its result (still in score / g) is reused. `evals` keeps counting what the
+  // reference executes, `repeats` what was skipped.
+  double a_run = -1.0;                               // step of the last trial pass that ran (a_t >= step_min > 0)
   while (!interval_converged && step_iterations < max_step_iterations &&
          !(psi_t <= 0 && d_phi_t <= -nu * d_phi_0)) {
     a_t = mt_trial_value(a_l, f_l, g_l, a_u, f_u, g_u, a_t, open_interval ? psi_t : phi_t, open_interval ? d_psi_t : d_phi_t);
     a_t = std_min(a_t, step_max);
     a_t = std_max(a_t, step_min);
+    ++evals;
+    if (a_t == a_run) {
+      ++repeats;
+    } else {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) x_t[k] = x[k] + dir[k] * a_t;
-    angle_terms(mp, x_t[2], ac);
-    obj.pass(1, x_t, ac, acc); ++evals;
-    score = acc[0]; g[0] = acc[1]; g[1] = acc[2]; g[2] = acc[3];
+      for (int k = 0; k < 3; ++k) x_t[k] = x[k] + dir[k] * a_t;
+      angle_terms(mp, x_t[2], ac);
+      obj.pass(NDT_TRIAL_MODE, x_t, ac, acc);
+      score = acc[0]; g[0] = acc[1]; g[1] = acc[2]; g[2] = acc[3];
+      a_run = a_t;
+    }
     phi_t = -score;
     d_phi_t = -(g[0] * dir[0] + g[1] * dir[1] + g[2] * dir[2]);
     psi_t = phi_t - phi_0 - mu * d_phi_0 * a_t;
@@ -778,8 +793,15 @@ __device__ inline double step_length_mt(Obj &obj, const MatchParams &mp, OptStat
     step_iterations++;
   }
   if (step_iterations) {
-    // computeHessian: Hessian only, angle terms as cached by the last computeDerivatives (same x_t)
-    obj.pass(2, x_t, ac, acc); ++evals;
+    // computeHessian at the last trial's x_t. The trial passes already accumulated the Hessian next to score and gradient
+    // (same instruction stream as a Hessian-only pass, so the same bits): 92 % of the searches that try at all run one
+    // distinct trial, and a second pass over the same transformed points would cost more than the nine extra sums did.
+    ++evals;
+#if NDT_TRIAL_MODE == 0
+    ++repeats;
+#else
+    obj.pass(2, x_t, ac, acc);
+#endif
 #pragma unroll
     for (int k = 0; k < 9; ++k) H[k] = acc[4 + k];
   }
@@ -793,7 +815,7 @@ __device__ inline void match_device(Obj &obj, const MatchParams &mp, const doubl
   double &score = S.score;
   __syncwarp();
   p[0] = (double)(float)guess[0]; p[1] = (double)(float)guess[1]; p[2] = (double)(float)guess[2];
-  int evals = 0, nr_iterations = 0;
+  int evals = 0, repeats = 0, nr_iterations = 0;
   bool converged = false;
   angle_terms(mp, p[2], S.ac);
   obj.pass(0, p, S.ac, acc); ++evals;
@@ -808,7 +830,7 @@ __device__ inline void match_device(Obj &obj, const MatchParams &mp, const doubl
     const double nrm = sqrt(sol[0] * sol[0] + sol[1] * sol[1] + sol[2] * sol[2]);
     if (nrm == 0.0 || nrm != nrm) { converged = (nrm == nrm); break; }
     dp[0] = sol[0] / nrm; dp[1] = sol[1] / nrm; dp[2] = sol[2] / nrm;
-    const double a = step_length_mt(obj, mp, S, nrm, evals);
+    const double a = step_length_mt(obj, mp, S, nrm, evals, repeats);
 #pragma unroll
     for (int k = 0; k < 3; ++k) { const double d = dp[k] * a; p[k] = p[k] + d; }
     if (nr_iterations > mp.max_iter || (nr_iterations && fabs(a) < mp.trans_eps)) converged = true;
@@ -821,6 +843,7 @@ __device__ inline void match_device(Obj &obj, const MatchParams &mp, const doubl
   mo.converged = converged ? 1 : 0;
   mo.iters = nr_iterations;
   mo.evals = evals;
+  mo.passes = evals - repeats;
   __syncwarp();
 }
 

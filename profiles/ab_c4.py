@@ -41,6 +41,10 @@ def child(args):
             ms.append(a.elapsed_time(b))
     res = np.frombuffer(d_r.cpu().numpy().tobytes(), dtype=capi.RESULT_DTYPE)
     pe = int(res["point_evals"].sum())
+    if os.environ.get("NDT_AB_DUMP"):
+        (ROOT / "gpurun_out" / "r2").mkdir(parents=True, exist_ok=True)
+        np.save(ROOT / "gpurun_out" / "r2" / f"c4_{Path(out['lib']).stem}.npy", res)
+    out["c4_passes_run_frac"] = float(res["passes_run"].sum() / max(res["evals"].sum(), 1))
     out["c4_ms"] = float(np.median(ms)); out["c4_gpe"] = pe / (np.median(ms) * 1e-3) / 1e9
     out["c4_digest"] = hashlib.sha256(res["pose"].tobytes() + res["score"].tobytes() + res["iters"].tobytes() + res["evals"].tobytes()).hexdigest()[:12]
     d_o = torch.zeros((n, 14), dtype=torch.float64, device="cuda")
