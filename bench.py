@@ -60,15 +60,23 @@ def measured_peaks():
 # ---------------------------------------------------------------------------------------------
 # workload
 # ---------------------------------------------------------------------------------------------
+def _host_prep():
+    """Workload preparation runs the product's own host code (ScanPointResampler and the approximate voxel filter of
+    libndt_slam_host.so, launch-file parameters), never the oracle."""
+    from ndt_slam_b200 import host_api as ha
+    ha.set_params(space=LAUNCH["space"], space_thre=LAUNCH["space_thre"])
+    return ha
+
+
 def build_c4(n_total: int):
     """Map cloud, filtered source scan and the global hypothesis set (n_total poses; the generator's 65,536 lattice
     hypotheses, jittered copies of them beyond that)."""
     from ndt_slam_b200 import synth
-    from oracle import oracle_api as oa   # data preparation only (resampler / voxel filter restatement)
+    ha = _host_prep()
 
     d = synth.c4_reloc(seed=4)
-    scan = oa.resample(d["scan"], LAUNCH["space"], LAUNCH["space_thre"])          # ScanMatcher.cpp:6
-    src = oa.approx_voxel_filter(synth.to_xyzw(scan), LAUNCH["leaf"])              # PoseEstimator.cpp:6-10
+    scan = ha.resample(d["scan"])                                                  # ScanMatcher.cpp:6
+    src = ha.voxel_filter(synth.to_xyzw(scan), LAUNCH["leaf"])                      # PoseEstimator.cpp:6-10
     tgt = synth.to_xyzw(d["map_pts"])
     hyp = d["hypotheses"]
     if n_total != hyp.shape[0]:
@@ -343,7 +351,8 @@ def main():
             step_device()
         torch.cuda.synchronize()
         res = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype=capi.RESULT_DTYPE).copy()
-        pe_step = int(res["point_evals"].sum())
+        pe_step = int(res["point_evals"].sum())              # passes the reference makes x points (what its CPU arm counts too)
+        pe_run = int(res["passes_run"].astype(np.int64).sum()) * ns   # passes that ran on the device (repeated trials are reused)
         sampler = ClockSampler(local_rank) if rank == 0 else None
         launches0 = g.launch_count()
         if world > 1:
@@ -384,12 +393,13 @@ def main():
             e2e_s += time.perf_counter() - te0
         assert int(h_res_np["point_evals"].sum()) == pe_step
         t = torch.tensor([float(sum(step_ms)), e2e_s], dtype=torch.float64, device="cuda")
-        c = torch.tensor([float(pe_step), float(n_h)], dtype=torch.float64, device="cuda")
+        c = torch.tensor([float(pe_step), float(n_h), float(pe_run)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dist.all_reduce(c, op=dist.ReduceOp.SUM)
         ms_per_step = float(t[0].item()) / K
-        return dict(res=res, d_res=d_res, n_h=n_h, pe_step=pe_step, pe_all=float(c[0].item()), nh_all=float(c[1].item()),
+        return dict(res=res, d_res=d_res, n_h=n_h, pe_step=pe_step, pe_run=pe_run, pe_all=float(c[0].item()), nh_all=float(c[1].item()),
+                    pe_run_all=float(c[2].item()), value_run=float(c[2].item()) / (ms_per_step * 1e-3),
                     ms_per_step=ms_per_step, e2e_s=float(t[1].item()), step_ms=step_ms, launches=launches, clocks=clocks,
                     value=float(c[0].item()) / (ms_per_step * 1e-3), matches_per_s=float(c[1].item()) / (ms_per_step * 1e-3),
                     e2e_value=float(c[0].item()) * K / float(t[1].item()), e2e_matches_per_s=float(c[1].item()) * K / float(t[1].item()))
@@ -460,7 +470,7 @@ def main():
             tj = json.loads(tp.read_text())
         except Exception:
             tj = {}
-    scale = m["pe_step"] / tj["point_evals_per_launch"] if tj.get("point_evals_per_launch") else None   # this launch vs the captured one
+    scale = m["pe_run"] / tj["point_evals_run_per_launch"] if tj.get("point_evals_run_per_launch") else None   # this launch vs the captured one (executed work)
     inst = tj["warp_instructions"] * scale if scale and tj.get("warp_instructions") else None
     dram = tj["k_align_warp_C4_bytes_per_launch"] * scale if scale and tj.get("k_align_warp_C4_bytes_per_launch") else None
     l2b = tj["l2_bytes"] * scale if scale and tj.get("l2_bytes") else None
@@ -477,8 +487,8 @@ def main():
                 "note": "measured DRAM bytes per launch (ncu dram__bytes_read + write): the kernel does not live on this roof"},
         "l2": {"bytes_per_launch": l2b, "achieved_gbs": (l2b / (kern_ms * 1e-3) / 1e9) if l2b else None, "peak_gbs": px.get("l2_read_gbs_32mb"),
                "frac": (l2b / (kern_ms * 1e-3) / 1e9 / px["l2_read_gbs_32mb"]) if l2b and px.get("l2_read_gbs_32mb") else None},
-        "algorithmic": {"bytes_per_point_eval": bytes_per_eval, "kbar": kbar, "bytes_per_launch": m["pe_step"] * bytes_per_eval,
-                        "hbm_equivalent_gbs": m["pe_step"] * bytes_per_eval / (kern_ms * 1e-3) / 1e9,
+        "algorithmic": {"bytes_per_point_eval": bytes_per_eval, "kbar": kbar, "bytes_per_launch": m["pe_run"] * bytes_per_eval,
+                        "hbm_equivalent_gbs": m["pe_run"] * bytes_per_eval / (kern_ms * 1e-3) / 1e9,
                         "note": "SURVEY 8d: 160 + 48 k bytes per point-eval if every probe went to HBM; they are served by shared memory / L1 / L2, "
                                 "so this is NOT a fraction of anything physical (kept for comparison with round 1)"},
         "ncu": {k: tj.get(k) for k in ("issue_slots_busy_pct", "fp64_pipe_pct", "l1_hit_pct", "l2_hit_pct", "dram_read_bytes", "dram_write_bytes", "source")}}
@@ -490,10 +500,10 @@ def main():
         cpu_baseline = {"value": None, "unit": UNIT, "cores": cores, "kind": "skipped", "sample": "--no-cpu-baseline"}
     else:
         rng = np.random.Generator(np.random.PCG64(2024))
-        ids = np.sort(rng.choice(n_h, size=min(n_h, 16 * cores), replace=False))
-        sub = cpu_matches(wl, prm, hyp[ids], max_seconds=15.0, threads=cores, kind="auto")
+        ids = np.sort(rng.choice(n_h, size=min(n_h, 512 * cores), replace=False))      # ~10 s of the box's host cores
+        sub = cpu_matches(wl, prm, hyp[ids], max_seconds=12.0, threads=cores, kind="auto")
         parity = parity_block({int(ids[i]): v for i, v in sub["results"].items()}, res)
-        port = cpu_matches(wl, prm, hyp[ids[: 8 * cores]], max_seconds=8.0, threads=cores, kind="port")
+        port = cpu_matches(wl, prm, hyp[ids[: 256 * cores]], max_seconds=6.0, threads=cores, kind="port")
         parity_port = parity_block({int(ids[i]): v for i, v in port["results"].items()}, res)
         cpu_baseline = {"value": sub["point_evals"] / sub["seconds"], "unit": UNIT, "cores": cores, "kind": sub["kind"],
                         "sample": f"{sub['matches']} random hypotheses of this rank's {n_h}, full matches, {cores} threads, {sub['seconds']:.1f} s",
@@ -514,6 +524,12 @@ def main():
                    "resolution_m": RESOLUTION, "parallelism": f"hypothesis-shard x{n_gpus}, grid replicated once",
                    "l2": "flushed between timed iterations (256 MiB write), device-timed and end-to-end loops alike"},
         "matches_per_sec": m["matches_per_s"], "evals_per_match": evals_mean, "point_evals_per_step": m["pe_all"],
+        "executed": {"point_evals_per_step": m["pe_run_all"], "value": m["value_run"], "unit": UNIT,
+                     "passes_run_fraction": m["pe_run_all"] / max(m["pe_all"], 1.0),
+                     "note": "`value` counts the objective passes the reference makes for these matches (its CPU arm counts the same way: "
+                             "same matches, same per-match work). The device does not re-run a line-search trial whose step equals the "
+                             "previous trial's (same pose, same numbers) nor the Hessian-only pass after a search (the trial passes carry "
+                             "the Hessian): this block is the rate of the passes that actually ran; the roofline uses these"},
         "e2e": {"value": m["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": int(n_h * 24),
                 "d2h_bytes_per_step": int(n_h * capi.RESULT_DTYPE.itemsize), "matches_per_sec": m["e2e_matches_per_s"]},
         "gpu_launches": int(m["launches"]),
@@ -537,13 +553,13 @@ def main():
 def build_c5(lo: int, hi: int):
     """Scan pairs [lo, hi) of C5 (seeds 1000 + i): resampled target / source clouds packed back to back."""
     from ndt_slam_b200 import synth
-    from oracle import oracle_api as oa   # data preparation only (resampler restatement)
+    ha = _host_prep()
 
     srcs, tgts, offs = [], [], []
     for i in range(lo, hi):
         d = synth.c5_pair(i)
-        tgts.append(synth.to_xyzw(oa.resample(d["scan_a"], LAUNCH["space"], LAUNCH["space_thre"])))
-        srcs.append(synth.to_xyzw(oa.resample(d["scan_b"], LAUNCH["space"], LAUNCH["space_thre"])))
+        tgts.append(synth.to_xyzw(ha.resample(d["scan_a"])))
+        srcs.append(synth.to_xyzw(ha.resample(d["scan_b"])))
         offs.append(d["offset"])
 
     def pack(cl):
@@ -580,6 +596,7 @@ def run_c5(prm, capi, torch, dist, stream, rank, world, n_total, K, W, cpu_basel
     torch.cuda.synchronize()
     res = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype=capi.RESULT_DTYPE)
     pe = int(res["point_evals"].sum())
+    run_frac = float(res["passes_run"].sum()) / max(float(res["evals"].sum()), 1.0)
     l0 = g.launch_count()
     if world > 1:
         dist.barrier()
@@ -622,7 +639,7 @@ def run_c5(prm, capi, torch, dist, stream, rank, world, n_total, K, W, cpu_basel
                        "match + fitness per pair), sharded x%d" % (int(n_all), world),
            "scaling": "strong", "pairs_total": int(n_all), "matches_per_sec": n_all / (ms_max / K * 1e-3),
            "ms_per_step": ms_max / K, "point_evals_per_sec": pe_all / (ms_max / K * 1e-3),
-           "evals_per_match": float(res["evals"].mean()), "gpu_launches_per_step": launches / K,
+           "evals_per_match": float(res["evals"].mean()), "passes_run_fraction_rank0": run_frac, "gpu_launches_per_step": launches / K,
            "e2e": {"matches_per_sec": n_all * K / e2e_max, "h2d_bytes_per_step": int(c5["src"].nbytes + c5["tgt"].nbytes + n * 24),
                    "d2h_bytes_per_step": int(n * capi.RESULT_DTYPE.itemsize)},
            "roofline": c5_roofline(c5, res, n, ms_max / K, world),
@@ -639,7 +656,7 @@ def c5_roofline(c5, res, n, ms_per_step, world):
     (k measured ~1.9 for scan-to-scan pairs), 208 B per result."""
     peaks, src = measured_peaks()
     nsrc, ntgt = c5["src"].shape[0], c5["tgt"].shape[0]
-    pe = float(res["point_evals"].sum())
+    pe = float(res["point_evals"].sum()) * float(res["passes_run"].sum()) / max(float(res["evals"].sum()), 1.0)   # passes that ran
     stream_bytes = 16.0 * (nsrc + ntgt) + 208.0 * n
     probe_bytes = pe * (160.0 + 48.0 * 1.9)
     ach = stream_bytes / (ms_per_step * 1e-3) / 1e9
@@ -681,15 +698,16 @@ def cpu_pairs(prm, c5, n_sample, threads):
 def run_extras(g, prm, capi, torch, c2_scans=300, c3=True):
     """Secondary figures on 1 GPU: C1 single-match latency, C2 FrontEnd sequence, C3 dense single match."""
     from ndt_slam_b200 import synth
-    from oracle import oracle_api as oa
+    from oracle import oracle_api as oa   # CPU baseline legs only (the oracle timed / compared on the same problem)
 
     out = {}
     # ---- C1: single scan vs grid of the previous scan -------------------------------------------------
     d = synth.c1_pair(1)
-    ra_ = oa.resample(d["scan_a"], LAUNCH["space"], LAUNCH["space_thre"])
-    rb = oa.resample(d["scan_b"], LAUNCH["space"], LAUNCH["space_thre"])
+    hp = _host_prep()
+    ra_ = hp.resample(d["scan_a"])
+    rb = hp.resample(d["scan_b"])
     tgt = synth.to_xyzw(synth.transform(ra_, d["pose_a"]))
-    src = oa.approx_voxel_filter(synth.to_xyzw(rb), LAUNCH["leaf"])
+    src = hp.voxel_filter(synth.to_xyzw(rb), LAUNCH["leaf"])
     g1 = capi.Ndt(prm)
     guess = np.array(d["pose_a"])
     ks, bs, ws = [], [], []
@@ -706,7 +724,7 @@ def run_extras(g, prm, capi, torch, c2_scans=300, c3=True):
     cpu_ms = (time.perf_counter() - t0) * 1e3 / 25
     out["C1"] = {"match_kernel_ms": float(np.median(ks[5:])), "grid_build_kernels_ms": float(np.median(bs[5:])),
                  "e2e_host_call_ms": float(np.median(ws[5:])), "cpu_oracle_ms_1thread": cpu_ms,
-                 "evals": int(r.evals), "n_source": int(src.shape[0]), "n_target": int(tgt.shape[0]),
+                 "evals": int(r.evals), "passes_run": int(r.passes_run), "n_source": int(src.shape[0]), "n_target": int(tgt.shape[0]),
                  "pose_matches_oracle": bool(np.hypot(r.pose[0] - ro.pose[0], r.pose[1] - ro.pose[1]) < 1e-4)}
 
     # ---- C2: synthetic office sequence through the full FrontEnd (host classes on the CUDA path) ------
@@ -811,7 +829,7 @@ def run_extras(g, prm, capi, torch, c2_scans=300, c3=True):
             kbar3 = e3.n_pairs / src3.shape[0]
             peaks, _ = measured_peaks()
             grid_bytes = 16.0 * tgt3.shape[0] + 64.0 * gi3.n_leaves
-            match_bytes = r3.point_evals * (160.0 + 48.0 * kbar3)
+            match_bytes = float(r3.passes_run) * src3.shape[0] * (160.0 + 48.0 * kbar3)     # passes that ran on the device
             tp = d3["true_pose"]
             out["C3"] = {"target_points": int(tgt3.shape[0]), "source_points": int(src3.shape[0]),
                          "grid_cells": [int(gi3.div_b[0]), int(gi3.div_b[1])], "occupied_cells": int(gi3.n_leaves),
@@ -825,7 +843,7 @@ def run_extras(g, prm, capi, torch, c2_scans=300, c3=True):
                                             "unit": "GB/s", "frac": match_bytes / (np.median(kms[1:]) * 1e-3) / 1e9 / peaks["hbm_gbs"],
                                             "note": "random 8 / 64-byte gathers over 250 MB of tables (> L2) by 65,536 points per pass, 6-7 dependent passes: "
                                                     "latency of a grid-wide pass (one grid.sync each), not bandwidth"},
-                         "match_latency_ms": float(np.median(kms[1:])), "evals": int(r3.evals), "iters": int(r3.iters),
+                         "match_latency_ms": float(np.median(kms[1:])), "evals": int(r3.evals), "passes_run": int(r3.passes_run), "iters": int(r3.iters),
                          "kbar": kbar3, "point_evals_per_sec": r3.point_evals / (np.median(kms[1:]) * 1e-3),
                          "match_hbm_equiv_frac": match_bytes / (np.median(kms[1:]) * 1e-3) / 1e9 / peaks["hbm_gbs"],
                          "pose_error_m": float(np.hypot(r3.pose[0] - tp[0], r3.pose[1] - tp[1])),
@@ -859,7 +877,7 @@ def reference_arm(args, rank, n_gpus, K, W):
     hyp = wl["hyp"]
     ns = wl["src"].shape[0]
     cores = os.cpu_count() or 1
-    per_step = max(64, min(hyp.shape[0], 16 * cores))     # bounded sample per step
+    per_step = max(64, min(hyp.shape[0], 64 * cores))     # bounded sample per step (~1.5 s of the host cores)
     rng = np.random.Generator(np.random.PCG64(99))
     tot_pe = tot_nm = 0
     tot_s = 0.0

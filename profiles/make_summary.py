@@ -61,11 +61,13 @@ def bytes_of(h, u, r, key):
     return float(r[i]) * UNIT.get(u[i], 1.0)
 
 
-def point_evals_per_launch():
-    """Point-evals of the captured launch = point_evals_per_step of the plain bench line of the same command."""
+def point_evals_per_launch(executed=False):
+    """Point-evals of the captured launch = point_evals_per_step of the plain bench line of the same command
+    (executed=True: the passes that ran on the device, the line's `executed` block)."""
     p = G / f"{rnd}_bench_plain.json"
     try:
-        return float(json.loads(p.read_text().strip().splitlines()[-1])["point_evals_per_step"])
+        line = json.loads(p.read_text().strip().splitlines()[-1])
+        return float(line["executed"]["point_evals_per_step"] if executed else line["point_evals_per_step"])
     except Exception:
         return None
 
@@ -97,6 +99,7 @@ if fw.exists():
                "l1_to_l2_write_bytes": bytes_of(h, u, r, "l1tex__m_l1tex2xbar_write_bytes.sum") if "l1tex__m_l1tex2xbar_write_bytes.sum" in h else None,
                "l2_to_l1_read_bytes": bytes_of(h, u, r, "l1tex__m_xbar2l1tex_read_bytes.sum") if "l1tex__m_xbar2l1tex_read_bytes.sum" in h else None,
                "point_evals_per_launch": point_evals_per_launch(),
+               "point_evals_run_per_launch": point_evals_per_launch(executed=True),
                "issue_slots_busy_pct": float(r[h.index("smsp__issue_active.avg.pct_of_peak_sustained_active")]),
                "fp64_pipe_pct": float(r[h.index("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active")]),
                "l1_hit_pct": float(r[h.index("l1tex__t_sector_hit_rate.pct")]), "l2_hit_pct": float(r[h.index("lts__t_sector_hit_rate.pct")]),

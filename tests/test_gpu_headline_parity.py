@@ -101,6 +101,35 @@ def test_c4_align_batch_matches_oracle_on_2048_hypotheses(c4):
     assert few[3]["fitness"] == pytest.approx(o1.fitness(list(few[3]["pose"])), rel=1e-9)
 
 
+def test_c4_passes_run_are_the_oracle_passes_minus_exact_repeats(c4):
+    """ndt_result.passes_run: the device skips exactly (a) line-search trials whose step equals the step of the trial before
+    (same pose: the oracle's trace shows the same score again) and (b) the Hessian-only pass after a search (its trial passes
+    carry the Hessian). Everything else the oracle evaluates is evaluated on the device: counted from the oracle's trace."""
+    d, prm, g, tgt, src = c4
+    guesses, _ = c4_hypothesis_sample(d)
+    pick = np.r_[0:160, 1984:2048]
+    res = g.align_batch(np.ascontiguousarray(guesses[pick]))     # n >= 64: k_align_warp
+    o = oa.Oracle(prm); o.set_target(tgt); o.set_source(src); o.want_fitness(False)
+    skipped_total = 0
+    for k, i in enumerate(pick):
+        b, tr = o.align_trace(list(guesses[i]))
+        expect, last_step = 0, None
+        for row in tr:                                 # x, y, yaw, score, a_t, kind
+            kind = int(row[5])
+            if kind == 0:
+                expect += 1; last_step = None
+            elif kind == 1:
+                if last_step is None or row[4] != last_step:
+                    expect += 1
+                else:
+                    assert row[3] == prev_score        # the oracle itself got the same number again
+                last_step = row[4]; prev_score = row[3]
+        assert res[k]["evals"] == b.evals == len(tr), (i, res[k]["evals"], b.evals)
+        assert res[k]["passes_run"] == expect, (i, res[k]["passes_run"], expect)
+        skipped_total += b.evals - expect
+    assert skipped_total > 0
+
+
 def test_c4_eval_batch_matches_oracle_score_sweep(c4):
     """k_eval_warp (the relocalisation score sweep) on 4,096 lattice hypotheses + the off-map ones."""
     d, prm, g, tgt, src = c4
