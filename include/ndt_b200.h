@@ -73,6 +73,10 @@ typedef struct {
   int32_t align_skip_fitness; /* 1: ndt_align skips the getFitnessScore pass (result.fitness = NaN)        */
   int32_t pairs_schedule;     /* ndt_match_pairs: NDT_PAIRS_AUTO / NDT_PAIRS_WARP / NDT_PAIRS_CTA           */
   int64_t pairs_batch_points; /* ndt_match_pairs: max target points per internal batch; 0 = 32,000,000     */
+  int32_t align_team;         /* ndt_align_batch (n >= 64): warps that share one match, 1 / 2 / 4 / 8;
+                                 0 = chosen from the batch size (few matches per resident warp: larger teams,
+                                 shorter latency; many: one warp per match, best throughput)                */
+  int32_t reserved0;
 } ndt_params;
 
 /* ndt_params.pairs_schedule: how ndt_match_pairs spreads pairs over the GPU. AUTO picks by batch size. */
@@ -190,6 +194,13 @@ int ndt_best_of_multi(const ndt_handle *handles, const ndt_result *const *device
 int ndt_match_pairs(ndt_handle h, const float *src_xyzw, const int64_t *src_off,
                     const float *tgt_xyzw, const int64_t *tgt_off, const double *guesses,
                     int64_t n_pairs, float source_leaf, int memspace, ndt_result *results);
+
+/* The same call for planar clouds given as (x, y) float pairs, 8 bytes per point instead of 16 (z = 0 like every
+ * LPoint2D the reference turns into a pcl::PointXYZ, PointCloudMap.cpp:72-86): halves the host-to-device upload
+ * that bounds ndt_match_pairs on host inputs. src_xy / tgt_xy: 2 floats per point; offsets count points. */
+int ndt_match_pairs_xy(ndt_handle h, const float *src_xy, const int64_t *src_off,
+                       const float *tgt_xy, const int64_t *tgt_off, const double *guesses,
+                       int64_t n_pairs, float source_leaf, int memspace, ndt_result *results);
 
 /* ---- replication of a finished grid to other GPUs (one NVLink broadcast, no collectives
  *      per iteration): export to / import from a flat device blob ------------------------- */

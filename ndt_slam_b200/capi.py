@@ -30,7 +30,7 @@ class NdtParams(C.Structure):
                 ("max_iter", C.c_int32), ("outlier_ratio", C.c_double), ("min_points", C.c_int32),
                 ("eig_mult", C.c_double), ("quirks", C.c_int32), ("device", C.c_int32),
                 ("stream", C.c_void_p), ("align_skip_fitness", C.c_int32), ("pairs_schedule", C.c_int32),
-                ("pairs_batch_points", C.c_int64)]
+                ("pairs_batch_points", C.c_int64), ("align_team", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class NdtEvalOut(C.Structure):
@@ -60,7 +60,7 @@ EXPORTS = [
     "ndt_params_default", "ndt_create", "ndt_destroy", "ndt_last_error", "ndt_version",
     "ndt_set_target", "ndt_set_target_prefix", "ndt_set_target_incremental", "ndt_get_grid_info", "ndt_grid_readback", "ndt_cell_index",
     "ndt_set_source", "ndt_approx_voxel_filter", "ndt_eval", "ndt_eval_batch",
-    "ndt_align", "ndt_align_batch", "ndt_best_of", "ndt_match_pairs",
+    "ndt_align", "ndt_align_batch", "ndt_best_of", "ndt_match_pairs", "ndt_match_pairs_xy",
     "ndt_grid_blob_size", "ndt_grid_export", "ndt_grid_import", "ndt_replicate_grid", "ndt_best_of_multi", "ndt_trim",
     "ndt_alloc", "ndt_free", "ndt_upload", "ndt_download",
     "ndt_launch_count", "ndt_last_kernel_ms", "ndt_synchronize",
@@ -105,6 +105,7 @@ def load() -> C.CDLL:
     L.ndt_align_batch.argtypes = [vp, vp, i64, i32, i32, vp]
     L.ndt_best_of.argtypes = [vp, vp, i64, i32, C.POINTER(i64), C.POINTER(NdtResult)]
     L.ndt_match_pairs.argtypes = [vp, vp, vp, vp, vp, vp, i64, C.c_float, i32, vp]
+    L.ndt_match_pairs_xy.argtypes = [vp, vp, vp, vp, vp, vp, i64, C.c_float, i32, vp]
     L.ndt_grid_blob_size.argtypes = [vp, i32, C.POINTER(i64)]
     L.ndt_grid_export.argtypes = [vp, i32, vp, i64]
     L.ndt_grid_import.argtypes = [vp, vp, i64]
@@ -263,11 +264,12 @@ class Ndt:
         self._ck(self.L.ndt_best_of(self.h, _ptr(results), n, space, C.byref(bi), C.byref(best)))
         return bi.value, best
 
-    def match_pairs(self, src, src_off, tgt, tgt_off, guesses, n_pairs, source_leaf=0.0, space=MEM_HOST, out=None):
+    def match_pairs(self, src, src_off, tgt, tgt_off, guesses, n_pairs, source_leaf=0.0, space=MEM_HOST, out=None, xy=False):
+        """xy=True: src / tgt hold (x, y) float pairs, 8 bytes per point (ndt_match_pairs_xy)."""
         if out is None:
             out = np.zeros(n_pairs, RESULT_DTYPE)
-        self._ck(self.L.ndt_match_pairs(self.h, _ptr(src), _ptr(src_off), _ptr(tgt), _ptr(tgt_off), _ptr(guesses),
-                                        n_pairs, source_leaf, space, _ptr(out)))
+        fn = self.L.ndt_match_pairs_xy if xy else self.L.ndt_match_pairs
+        self._ck(fn(self.h, _ptr(src), _ptr(src_off), _ptr(tgt), _ptr(tgt_off), _ptr(guesses), n_pairs, source_leaf, space, _ptr(out)))
         return out
 
     # -- replication --

@@ -116,6 +116,8 @@ int ndt_params_default(ndt_params *p) {
   p->align_skip_fitness = 0;
   p->pairs_schedule = NDT_PAIRS_AUTO;
   p->pairs_batch_points = 0;
+  p->align_team = 0;
+  p->reserved0 = 0;
   return NDT_OK;
 }
 
@@ -124,7 +126,7 @@ static void all_buffers(Handle *h, std::vector<DevBuf *> &v) {
   v = {&g.tgt, &g.cell_of, &g.rank_of, &g.list, &g.sorted_idx, &g.slot, &g.leaf_id, &g.leaf_cell,
        &g.leaf_n, &g.leaf_start, &g.leaf_nr, &g.leaf_mean, &g.leaf_icov, &g.leaf_cen, &g.recs,
        &g.counters, &g.leaf_pair, &g.big_list, &g.tile_hist, &g.dims, &g.pair_off, &g.cen, &g.occ, &g.nbr, &g.inc_acc, &g.inc_status, &g.inc_mark, &g.inc_lists, &g.inc_cellof, &g.inc_lid, &g.inc_cnt, &g.nn_cnt, &g.nn_range, &g.nn_pts,
-       &g.tgt_sorted, &g.leaf_range, &h->src, &h->scratch, &h->scratch2, &h->stage, &h->io};
+       &g.tgt_sorted, &g.leaf_range, &h->src, &h->scratch, &h->scratch2, &h->pair_tgt_next, &h->pair_raw_next, &h->stage, &h->io};
 }
 
 int ndt_create(const ndt_params *p, ndt_handle *out) {
@@ -195,6 +197,11 @@ int ndt_destroy(ndt_handle hh) {
   if (h->pinned_ctr) cudaFreeHost(h->pinned_ctr);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  for (int k = 0; k < 2; ++k) {
+    if (h->ev_up[k]) cudaEventDestroy(h->ev_up[k]);
+    if (h->ev_done[k]) cudaEventDestroy(h->ev_done[k]);
+  }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return NDT_OK;
@@ -464,9 +471,17 @@ int ndt_best_of(ndt_handle hh, const ndt_result *results, int64_t n, int memspac
   return NDT_OK;
 }
 
-int ndt_match_pairs(ndt_handle hh, const float *src_xyzw, const int64_t *src_off, const float *tgt_xyzw,
-                    const int64_t *tgt_off, const double *guesses, int64_t n_pairs, float source_leaf,
-                    int memspace, ndt_result *results) {
+// z = 0 planes of 2-D SLAM carry 8 useful bytes per point: the compact entry uploads (x, y) pairs and widens them on the device
+__global__ void k_expand_xy(const float2 *__restrict__ in, float4 *__restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float2 p = __ldg(in + i);
+    out[i] = make_float4(p.x, p.y, 0.f, 0.f);
+  }
+}
+
+static int match_pairs_impl(ndt_handle hh, const float *src_xyzw, const int64_t *src_off, const float *tgt_xyzw,
+                            const int64_t *tgt_off, const double *guesses, int64_t n_pairs, float source_leaf,
+                            int memspace, ndt_result *results, const bool xy) {
   H_OR_FAIL(hh);
   if (n_pairs < 0 || (n_pairs > 0 && (!src_off || !tgt_off || !guesses || !results)))
     return set_err(h, NDT_ERR_ARG, "ndt_match_pairs: bad argument");
@@ -503,40 +518,117 @@ int ndt_match_pairs(ndt_handle hh, const float *src_xyzw, const int64_t *src_off
     NDT_CUDA(h, cudaMemcpyAsync(h->io.p, guesses, gbytes, cudaMemcpyHostToDevice, st));
   }
   // Pairs go through the pipeline in batches of at most `batch_points` target points: bounds the size of the shared
-  // tables for very large inputs. (Measured on C5: smaller, L2-sized batches are slower -- a pair is matched by one warp
-  // in ~1 ms, so every batch ends with a latency tail; see DESIGN.md.)
-  const int64_t batch_points = h->prm.pairs_batch_points > 0 ? h->prm.pairs_batch_points : 32000000;
-  if (h->timing) cudaEventRecord(h->ev0, st);
-  std::vector<int64_t> off_stage;
+  // tables for very large inputs. Device inputs: one batch is best (measured on C5: a pair is matched by one warp in
+  // ~1 ms, so every batch ends with a latency tail). Host inputs: the upload of the clouds (16 B per point over PCIe)
+  // takes as long as matching them, so the call is cut into a few batches and batch k+1 is uploaded on a second stream
+  // into a second pair of buffers while batch k is filtered, gridded and matched.
+  int64_t batch_points = h->prm.pairs_batch_points > 0 ? h->prm.pairs_batch_points : 32000000;
+  if (host && !xy && h->prm.pairs_batch_points <= 0)
+    batch_points = std::min<int64_t>(batch_points, std::max<int64_t>(nt_total / 4 + 1, (int64_t)1 << 20));
+  std::vector<int64_t> cuts{0};
+  int64_t max_nt = 1, max_ns = 1, max_nb = 1;
   for (int64_t p0 = 0; p0 < n_pairs;) {
     int64_t p1 = p0 + 1;
     while (p1 < n_pairs && tgt_off[p1 + 1] - tgt_off[p0] <= batch_points && src_off[p1 + 1] - src_off[p0] <= 2 * batch_points) ++p1;
+    max_nt = std::max(max_nt, tgt_off[p1] - tgt_off[p0]);
+    max_ns = std::max(max_ns, src_off[p1] - src_off[p0]);
+    max_nb = std::max(max_nb, p1 - p0);
+    cuts.push_back(p1);
+    p0 = p1;
+  }
+  const int n_batches = (int)cuts.size() - 1;
+  const bool pipelined = host && !xy && n_batches > 1;   // compact clouds halve the upload instead: one batch, best schedule
+  // every buffer a batch needs is sized for the largest batch before the first upload: nothing is reallocated under a copy
+  NDT_CUDA(h, gb.tgt.reserve((size_t)max_nt * sizeof(float4)));
+  NDT_CUDA(h, h->src.reserve((size_t)max_ns * sizeof(float4)));
+  NDT_CUDA(h, gb.pair_off.reserve(2 * ((size_t)max_nb + 1) * sizeof(int64_t)));
+  if (host || xy) NDT_CUDA(h, h->scratch.reserve((size_t)max_ns * sizeof(float4)));
+  if (xy && host) {                                        // staging of the (x, y) uploads
+    NDT_CUDA(h, h->pair_tgt_next.reserve((size_t)max_nt * sizeof(float2)));
+    NDT_CUDA(h, h->pair_raw_next.reserve((size_t)max_ns * sizeof(float2)));
+  }
+  cudaStream_t cs = nullptr;
+  if (pipelined) {
+    NDT_CUDA(h, h->pair_tgt_next.reserve((size_t)max_nt * sizeof(float4)));
+    NDT_CUDA(h, h->pair_raw_next.reserve((size_t)max_ns * sizeof(float4)));
+    if (!h->copy_stream) {
+      NDT_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+      for (int k = 0; k < 2; ++k) {
+        NDT_CUDA(h, cudaEventCreateWithFlags(&h->ev_up[k], cudaEventDisableTiming));
+        NDT_CUDA(h, cudaEventCreateWithFlags(&h->ev_done[k], cudaEventDisableTiming));
+      }
+    }
+    cs = h->copy_stream;
+  }
+  if (h->timing) cudaEventRecord(h->ev0, st);
+  const int pf = xy ? 2 : 4;                               // floats per input point
+  auto expand_blocks = [&](int64_t n) { return (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 8)); };
+  auto upload = [&](int k, DevBuf &tgt_buf, DevBuf &raw_buf, cudaStream_t s) -> cudaError_t {
+    const int64_t q0 = cuts[k], q1 = cuts[k + 1];
+    const int64_t nt = tgt_off[q1] - tgt_off[q0], ns = src_off[q1] - src_off[q0];
+    cudaError_t e = cudaSuccess;
+    if (xy) {
+      const float2 *t2 = reinterpret_cast<const float2 *>(tgt_xyzw) + tgt_off[q0], *s2 = reinterpret_cast<const float2 *>(src_xyzw) + src_off[q0];
+      if (host) {
+        if (nt > 0) e = cudaMemcpyAsync(h->pair_tgt_next.p, t2, (size_t)nt * sizeof(float2), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess && ns > 0) e = cudaMemcpyAsync(h->pair_raw_next.p, s2, (size_t)ns * sizeof(float2), cudaMemcpyHostToDevice, s);
+        t2 = h->pair_tgt_next.as<float2>(); s2 = h->pair_raw_next.as<float2>();
+      }
+      if (e != cudaSuccess) return e;
+      if (nt > 0) { k_expand_xy<<<expand_blocks(nt), 256, 0, s>>>(t2, tgt_buf.as<float4>(), nt); ++h->launches; }
+      if (ns > 0) { k_expand_xy<<<expand_blocks(ns), 256, 0, s>>>(s2, raw_buf.as<float4>(), ns); ++h->launches; }
+      return cudaGetLastError();
+    }
+    if (nt > 0) e = cudaMemcpyAsync(tgt_buf.p, tgt_xyzw + pf * tgt_off[q0], (size_t)nt * sizeof(float4), in_kind, s);
+    if (e == cudaSuccess && host && ns > 0)
+      e = cudaMemcpyAsync(raw_buf.p, src_xyzw + pf * src_off[q0], (size_t)ns * sizeof(float4), cudaMemcpyHostToDevice, s);
+    return e;
+  };
+  auto fail = [&](int rc) { if (cs) cudaStreamSynchronize(cs); return rc; };     // no upload may outlive the call
+  if (pipelined) {
+    // the buffers were (re)allocated in order of `st`: the upload stream starts behind that point
+    NDT_CUDA(h, cudaEventRecord(h->ev_done[1], st));
+    NDT_CUDA(h, cudaStreamWaitEvent(cs, h->ev_done[1], 0));
+    if (upload(0, h->pair_tgt_next, h->pair_raw_next, cs) != cudaSuccess || cudaEventRecord(h->ev_up[0], cs) != cudaSuccess)
+      return fail(set_err(h, NDT_ERR_CUDA, "ndt_match_pairs: upload", cudaGetLastError()));
+  }
+  std::vector<int64_t> off_stage;
+  for (int k = 0; k < n_batches; ++k) {
+    const int64_t p0 = cuts[k], p1 = cuts[k + 1];
     const int64_t nb = p1 - p0, nt = tgt_off[p1] - tgt_off[p0], ns = src_off[p1] - src_off[p0];
-    NDT_CUDA(h, gb.tgt.reserve((size_t)std::max<int64_t>(nt, 1) * sizeof(float4)));
-    NDT_CUDA(h, h->src.reserve((size_t)std::max<int64_t>(ns, 1) * sizeof(float4)));
-    NDT_CUDA(h, gb.pair_off.reserve(2 * ((size_t)nb + 1) * sizeof(int64_t)));
+    if (pipelined) {
+      std::swap(gb.tgt, h->pair_tgt_next);           // batch k's clouds were uploaded into the `next` pair of buffers
+      std::swap(h->scratch, h->pair_raw_next);
+      cudaError_t e = cudaStreamWaitEvent(st, h->ev_up[k & 1], 0);
+      if (e == cudaSuccess && k + 1 < n_batches) {
+        // the `next` buffers now are the ones batch k-1 computed on: its kernels must be done before they are overwritten
+        if (k >= 1) e = cudaStreamWaitEvent(cs, h->ev_done[(k - 1) & 1], 0);
+        if (e == cudaSuccess) e = upload(k + 1, h->pair_tgt_next, h->pair_raw_next, cs);
+        if (e == cudaSuccess) e = cudaEventRecord(h->ev_up[(k + 1) & 1], cs);
+      }
+      if (e != cudaSuccess) return fail(set_err(h, NDT_ERR_CUDA, "ndt_match_pairs: upload", e));
+    } else if (upload(k, gb.tgt, h->scratch, st) != cudaSuccess) {
+      return set_err(h, NDT_ERR_CUDA, "ndt_match_pairs: upload", cudaGetLastError());
+    }
     off_stage.resize(2 * ((size_t)nb + 1));
     for (int64_t i = 0; i <= nb; ++i) {
       off_stage[i] = tgt_off[p0 + i] - tgt_off[p0];
       off_stage[nb + 1 + i] = src_off[p0 + i] - src_off[p0];
     }
-    NDT_CUDA(h, cudaMemcpyAsync(gb.pair_off.p, off_stage.data(), off_stage.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    if (nt > 0) NDT_CUDA(h, cudaMemcpyAsync(gb.tgt.p, tgt_xyzw + 4 * tgt_off[p0], (size_t)nt * sizeof(float4), in_kind, st));
+    if (cudaMemcpyAsync(gb.pair_off.p, off_stage.data(), off_stage.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st) != cudaSuccess)
+      return fail(set_err(h, NDT_ERR_CUDA, "ndt_match_pairs: offsets", cudaGetLastError()));
     // raw source clouds: device inputs are filtered straight from the caller's buffer
-    const float4 *d_raw = reinterpret_cast<const float4 *>(src_xyzw) + src_off[p0];
-    if (host) {
-      NDT_CUDA(h, h->scratch.reserve((size_t)std::max<int64_t>(ns, 1) * sizeof(float4)));
-      if (ns > 0) NDT_CUDA(h, cudaMemcpyAsync(h->scratch.p, src_xyzw + 4 * src_off[p0], (size_t)ns * sizeof(float4), cudaMemcpyHostToDevice, st));
-      d_raw = h->scratch.as<float4>();
-    }
+    const float4 *d_raw = (host || xy) ? h->scratch.as<float4>() : reinterpret_cast<const float4 *>(src_xyzw) + src_off[p0];
     int64_t total_pad = 0;
     int max_h = 0;
-    if (int rc = pairs_prepare(h, nb, &total_pad, &max_h)) return rc;          // one 16-byte read-back (also fences off_stage)
-    if (int rc = launch_pairs_filter(h, d_raw, h->src.as<float4>(), nb, source_leaf)) return rc;
+    if (int rc = pairs_prepare(h, nb, &total_pad, &max_h)) return fail(rc);    // one 16-byte read-back (also fences off_stage)
+    if (int rc = launch_pairs_filter(h, d_raw, h->src.as<float4>(), nb, source_leaf)) return fail(rc);
     gd.n_tgt = nt;
-    if (int rc = grid_build_tables(h, nt, (int)nb, total_pad, max_h)) return rc;
-    if (int rc = launch_align_pairs(h, h->src.as<float4>(), d_g + 3 * p0, nb, d_r + p0, /*want_fitness=*/true)) return rc;
-    p0 = p1;
+    if (int rc = grid_build_tables(h, nt, (int)nb, total_pad, max_h)) return fail(rc);
+    if (int rc = launch_align_pairs(h, h->src.as<float4>(), d_g + 3 * p0, nb, d_r + p0, /*want_fitness=*/true)) return fail(rc);
+    if (pipelined && cudaEventRecord(h->ev_done[k & 1], st) != cudaSuccess)
+      return fail(set_err(h, NDT_ERR_CUDA, "ndt_match_pairs: event", cudaGetLastError()));
+    (void)ns;
   }
   if (h->timing) cudaEventRecord(h->ev1, st);
   if (!host) { h->ms_pending = true; return NDT_OK; }
@@ -545,6 +637,18 @@ int ndt_match_pairs(ndt_handle hh, const float *src_xyzw, const int64_t *src_off
   if (h->timing) cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
   h->ms_pending = false;
   return NDT_OK;
+}
+
+int ndt_match_pairs(ndt_handle hh, const float *src_xyzw, const int64_t *src_off, const float *tgt_xyzw,
+                    const int64_t *tgt_off, const double *guesses, int64_t n_pairs, float source_leaf,
+                    int memspace, ndt_result *results) {
+  return match_pairs_impl(hh, src_xyzw, src_off, tgt_xyzw, tgt_off, guesses, n_pairs, source_leaf, memspace, results, false);
+}
+
+int ndt_match_pairs_xy(ndt_handle hh, const float *src_xy, const int64_t *src_off, const float *tgt_xy,
+                       const int64_t *tgt_off, const double *guesses, int64_t n_pairs, float source_leaf,
+                       int memspace, ndt_result *results) {
+  return match_pairs_impl(hh, src_xy, src_off, tgt_xy, tgt_off, guesses, n_pairs, source_leaf, memspace, results, true);
 }
 
 int ndt_grid_blob_size(ndt_handle hh, int flags, int64_t *bytes) {

@@ -413,6 +413,18 @@ __global__ void __launch_bounds__(256, 2) k_align_grid(GridView G, MatchParams m
 #ifndef NDT_WARP_KERNEL_MIN_CTAS
 #define NDT_WARP_KERNEL_MIN_CTAS 2
 #endif
+// ndt_align_batch picks the warps per match from the matches per resident warp (2,368 warps on a B200)
+// (measured on C4, ms per call for 1 / 2 / 4 / 8 warps per match: 65,536 matches 7.85 / 9.74 / 14.3 / 25.3; 8,192: 1.60 / 1.56 /
+// 1.99 / 3.34; 4,096: 1.28 / 1.04 / 1.16 / 1.82; 2,048: 0.82 / 0.64 / 0.61 / 0.90; 512: 0.62 / 0.44 / 0.36 / 0.46)
+#ifndef NDT_TEAM1_FROM
+#define NDT_TEAM1_FROM 4
+#endif
+#ifndef NDT_TEAM2_FROM
+#define NDT_TEAM2_FROM 1
+#endif
+#ifndef NDT_TEAM4_FROM
+#define NDT_TEAM4_FROM 0
+#endif
 #ifndef NDT_WARP_OCC_SMEM_MAX
 #define NDT_WARP_OCC_SMEM_MAX (64 * 1024)
 #endif
@@ -430,20 +442,21 @@ struct __align__(16) WarpState { MatchOut mo; };
 // Consecutive relocalisation hypotheses share their position (16 headings per lattice point), so the warps of a CTA
 // probe the same neighbourhood of the map and share its centroid / record lines in L1; a single global counter would
 // scatter neighbouring hypotheses over all SMs. Returns the job for this warp (>= n_jobs: nothing left).
+template <int CHUNK = NDT_WARP_JOB_CHUNK>
 __device__ __forceinline__ int next_job(unsigned long long *s_state, int32_t *job_counter, int lane) {
   int job = 0;
   if (lane == 0) {
     for (;;) {
       const unsigned long long st = atomicAdd(s_state, 1ull);
       const int cnt = (int)(st & 0xffffffffu), base = (int)(st >> 32);
-      if (cnt < NDT_WARP_JOB_CHUNK) { job = base + cnt; break; }
-      if (cnt == NDT_WARP_JOB_CHUNK) {                       // first to find the chunk empty: fetch the next one
-        const int nb = atomicAdd(job_counter, NDT_WARP_JOB_CHUNK);
+      if (cnt < CHUNK) { job = base + cnt; break; }
+      if (cnt == CHUNK) {                                    // first to find the chunk empty: fetch the next one
+        const int nb = atomicAdd(job_counter, CHUNK);
         atomicExch(s_state, ((unsigned long long)(unsigned)nb << 32) | 1ull);
         job = nb;
         break;
       }
-      while ((int)(atomicAdd(s_state, 0ull) & 0xffffffffu) > NDT_WARP_JOB_CHUNK) {}   // a neighbour is fetching
+      while ((int)(atomicAdd(s_state, 0ull) & 0xffffffffu) > CHUNK) {}   // a neighbour is fetching
     }
   }
   return __shfl_sync(0xffffffffu, job, 0);
@@ -490,6 +503,90 @@ __global__ void __launch_bounds__(WK_THREADS, NDT_WARP_KERNEL_MIN_CTAS) k_align_
     double fsum = 0.0;
     if (mp.want_fitness) fsum = fitness_pass_cold(G, src_acc, ns, mp, mo.p, coop);
     if (lane == 0) write_result(out + job, mo, ns, fsum, mp.want_fitness != 0, G.n_tgt);
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same persistent schedule with a TEAM of WPM warps per match (WPM = 2, 4, 8). A match is a serial chain of passes:
+// when a call brings only a few matches per resident warp (a shard of a relocalisation on 8 GPUs, a small multi-start),
+// the call lasts as long as its longest match, however many warps sit idle. A team splits every pass of a match over its
+// warps (points rank, rank + 32 WPM, ...), each warp with its own rings, and adds the WPM warp totals in warp order after
+// one named barrier -- a fixed order, so every thread of the team holds bit-identical totals and runs the optimiser in
+// lock step, and results are run-to-run deterministic (they differ from the one-warp kernel's in the last bits: another
+// summation tree). Throughput per SM is a little lower than with one warp per match (barrier + redundant optimiser).
+// ---------------------------------------------------------------------------------------------
+template <int WPM>
+struct TeamCoop {
+  double *rows;          // [2][WPM][NACC] doubles of this team in shared memory (double-buffered by pass parity)
+  int *epoch;            // per-thread pass counter (kernel local)
+  int warp_in_team, lane, bar_id;
+  __device__ __forceinline__ int rank() const { return warp_in_team * 32 + lane; }
+  __device__ __forceinline__ int size() const { return 32 * WPM; }
+  __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(32 * WPM) : "memory"); }
+  template <int N> __device__ __forceinline__ void allreduce(double *v) const {
+    warp_allreduce<N>(v);
+    double *buf = rows + ((*epoch) & 1) * (WPM * NACC);
+    ++(*epoch);
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) buf[warp_in_team * NACC + k] = v[k];
+    }
+    sync();                 // one barrier per reduction: the other buffer is rewritten only after everyone passed this one again
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      double t = buf[k];
+#pragma unroll
+      for (int i = 1; i < WPM; ++i) t += buf[i * NACC + k];
+      v[k] = t;
+    }
+  }
+};
+
+template <int WPM>
+__global__ void __launch_bounds__(WK_THREADS, NDT_WARP_KERNEL_MIN_CTAS) k_align_team(GridView G, MatchParams mp, const float4 *__restrict__ src,
+                                                   int ns, const double *__restrict__ guesses,
+                                                   ndt_result *__restrict__ out, int64_t n_jobs,
+                                                   int32_t *__restrict__ job_counter, int occ_words) {
+  static_assert(WK_WARPS % WPM == 0, "teams tile the CTA");
+  constexpr int TEAMS = WK_WARPS / WPM;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // dynamic shared memory: hit queues | occupancy bitmap | source points | per-warp results (one per team used)
+  uint32_t *s_occ = reinterpret_cast<uint32_t *>(smem_raw + WK_QUEUE_BYTES);
+  const int occ_bytes = (occ_words * 4 + 15) & ~15;
+  for (int i = threadIdx.x; i < occ_words; i += blockDim.x) s_occ[i] = __ldg(G.occ + i);
+  float2 *s_src = reinterpret_cast<float2 *>(smem_raw + WK_QUEUE_BYTES + occ_bytes);
+  for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+    const float4 v = __ldg(src + i);
+    s_src[i] = make_float2(v.x, v.y);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, team = warp / WPM, wit = warp % WPM;
+  WarpState *ws = reinterpret_cast<WarpState *>(smem_raw + WK_QUEUE_BYTES + occ_bytes + ((ns * 8 + 15) & ~15)) + team * WPM;
+  __shared__ unsigned long long s_state;
+  __shared__ double s_rows[TEAMS][2][WPM][NACC];
+  __shared__ int s_job[TEAMS];
+  if (threadIdx.x == 0) s_state = TEAMS;                       // "chunk exhausted": the first team fetches one (a chunk = one job per team)
+  __syncthreads();
+  int epoch = 0;
+  TeamCoop<WPM> coop{&s_rows[team][0][0][0], &epoch, wit, lane, 1 + team};
+  const SmemOcc occ_acc{smem_addr(s_occ)};
+  const SmemSrc src_acc{smem_addr(s_src)};
+  for (;;) {
+    if (wit == 0) {
+      const int j = next_job<TEAMS>(&s_state, job_counter, lane);
+      if (lane == 0) s_job[team] = j;
+    }
+    coop.sync();            // the next write of s_job lies behind at least one reduction barrier of the match below
+    const int job = s_job[team];
+    if (job >= n_jobs) break;
+    const double guess[3] = {guesses[3 * (size_t)job], guesses[3 * (size_t)job + 1], guesses[3 * (size_t)job + 2]};
+    MatchOut &mo = ws->mo;  // every warp of the team writes the same bits
+    OptState opt;
+    auto obj = make_objective(G, mp, coop, occ_acc, GlobalNbr{G.nbr}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, src_acc, ns, my_queue(smem_raw));
+    match_device(obj, mp, guess, mo, opt);
+    double fsum = 0.0;
+    if (mp.want_fitness) fsum = fitness_pass_cold(G, src_acc, ns, mp, mo.p, coop);
+    if (wit == 0 && lane == 0) write_result(out + job, mo, ns, fsum, mp.want_fitness != 0, G.n_tgt);
     __syncwarp();
   }
 }
@@ -927,7 +1024,21 @@ int launch_align(Handle *h, const double *d_guesses, int64_t n, ndt_result *d_re
       kern<<<(unsigned)grid, WK_THREADS, smem, st>>>(G, mp, src, ns, d_guesses, d_results, n, ctr + CTR_JOB, occ_words);
       return cudaSuccess;
     };
-    if (occ_smem) NDT_CUDA(h, go(k_align_warp<true, true>));
+    // warps per match: one when every resident warp has a queue of matches to hide the tail behind; teams otherwise
+    // (measured on C4, profiles/ab_c4.py --team: see DESIGN.md 4.3). Teams need the staged source + bitmap.
+    int wpm = h->prm.align_team;
+    if (wpm != 1 && wpm != 2 && wpm != 4 && wpm != 8) {
+      const int64_t per_warp = n / std::max<int64_t>(1, (int64_t)h->sm_count * ctas_per_sm * WK_WARPS);   // matches per resident warp
+      wpm = per_warp >= NDT_TEAM1_FROM ? 1 : per_warp >= NDT_TEAM2_FROM ? 2 : per_warp >= NDT_TEAM4_FROM ? 4 : 8;
+    }
+    if (!occ_smem) wpm = 1;
+    if (wpm > 1) {
+      grid = std::min<int64_t>((int64_t)h->sm_count * ctas_per_sm, (n * wpm + WK_WARPS - 1) / WK_WARPS);
+      if (wpm == 2) NDT_CUDA(h, go(k_align_team<2>));
+      else if (wpm == 4) NDT_CUDA(h, go(k_align_team<4>));
+      else NDT_CUDA(h, go(k_align_team<8>));
+    }
+    else if (occ_smem) NDT_CUDA(h, go(k_align_warp<true, true>));
     else if (src_smem) NDT_CUDA(h, go(k_align_warp<true, false>));
     else NDT_CUDA(h, go(k_align_warp<false, false>));
   } else if (ns > NDT_GRID_MIN_NS && h->coop_launch) {

@@ -136,6 +136,9 @@ struct Handle {
 
   DevBuf scratch;      // misc device scratch (eval partials, guesses, results staging)
   DevBuf scratch2;
+  DevBuf pair_tgt_next, pair_raw_next;   // ndt_match_pairs, host clouds: the batch being uploaded while the current one is matched
+  cudaStream_t copy_stream = nullptr;    // its upload stream (created on first use)
+  cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   DevBuf stage;        // 4 KB persistent staging (single pose / single result)
   DevBuf io;           // host<->device staging of batched poses / results
   bool ms_pending = false;  // last_ms not yet resolved (async device-space call)

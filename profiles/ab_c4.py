@@ -54,6 +54,23 @@ def child(args):
         a.record(stream); g.eval_batch(d_h.data_ptr(), n=n, want_hessian=False, space=capi.MEM_DEVICE, out=d_o.data_ptr()); b.record(stream)
         torch.cuda.synchronize(); sw.append(a.elapsed_time(b))
     out["sweep_ms"] = float(min(sw))
+    if "--team" in args:
+        # warps per match (ndt_params.align_team) x hypotheses per call: ms per call, median of 5 after 2 warm-ups, L2 flushed
+        table = {}
+        for nh in (65536, 32768, 16384, 8192, 4096, 2048, 512):
+            for team in (1, 2, 4, 8):
+                gt = capi.Ndt(capi.default_params(resolution=0.5, stream=stream.cuda_stream, align_team=team))
+                gt.set_target(wl["tgt"]); gt.set_source(wl["src"])
+                tt = []
+                for it in range(7):
+                    flush.zero_()
+                    a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+                    a.record(stream); gt.align_batch(d_h.data_ptr(), n=nh, space=capi.MEM_DEVICE, out=d_r.data_ptr(), want_fitness=False); b.record(stream)
+                    torch.cuda.synchronize()
+                    if it >= 2:
+                        tt.append(a.elapsed_time(b))
+                table[f"{nh}x{team}"] = round(float(np.median(tt)), 4)
+        out["team_ms"] = table
     if "--pairs" in args:
         for npairs, sched in ((8192, capi.PAIRS_WARP), (8192, capi.PAIRS_CTA), (2048, capi.PAIRS_CTA), (1024, capi.PAIRS_CTA)):
             c5 = bench.build_c5(0, npairs)

@@ -67,7 +67,7 @@ def test_default_params_are_the_reference_defaults():
     assert (p.resolution, p.step_size, p.trans_eps, p.max_iter) == (1.0, 0.1, 0.01, 35)
     assert (p.outlier_ratio, p.min_points, p.eig_mult) == (0.55, 6, 0.01)
     assert p.quirks == capi.QUIRKS_PCL_1_10
-    assert (p.align_skip_fitness, p.pairs_schedule, p.pairs_batch_points) == (0, capi.PAIRS_AUTO, 0)
+    assert (p.align_skip_fitness, p.pairs_schedule, p.pairs_batch_points, p.align_team) == (0, capi.PAIRS_AUTO, 0, 0)
 
 
 def test_sass_is_sm100a_only():

@@ -101,6 +101,33 @@ def test_c4_align_batch_matches_oracle_on_2048_hypotheses(c4):
     assert few[3]["fitness"] == pytest.approx(o1.fitness(list(few[3]["pose"])), rel=1e-9)
 
 
+@pytest.mark.parametrize("team", [1, 2, 4, 8])
+def test_c4_align_batch_teams_of_warps_match_oracle(c4, team):
+    """ndt_params.align_team: 1, 2, 4 or 8 warps share one match (`k_align_warp` / `k_align_team<WPM>`). Every team size ends
+    where the oracle ends, by the same path, and gives the same bytes when the call is repeated."""
+    d, prm, g, tgt, src = c4
+    guesses, _ = c4_hypothesis_sample(d)
+    pick = np.r_[0:192, 1984:2048]                   # lattice sample + off-map + border + near-truth poses
+    gs = np.ascontiguousarray(guesses[pick])
+    gt = capi.Ndt(common.params(resolution=0.5, align_team=team))
+    gt.set_target(tgt); gt.set_source(src)
+    res = gt.align_batch(gs, want_fitness=True)
+    ref = common.oracle_align_many(prm, tgt, src, gs)
+    o1 = oa.Oracle(prm); o1.set_target(tgt); o1.set_source(src)
+    for k, b in enumerate(ref):
+        r = res[k]
+        assert r["converged"] == b.converged and r["iters"] == b.iters and r["evals"] == b.evals, (team, k)
+        assert np.hypot(r["pose"][0] - b.pose[0], r["pose"][1] - b.pose[1]) < POSE_M and abs(r["pose"][2] - b.pose[2]) < POSE_RAD
+        if b.score != 0.0:
+            assert abs(r["score"] - b.score) / abs(b.score) < REL_EVAL
+        if np.max(np.abs(np.array(b.hess))) > 0:
+            assert common.rel_err(r["hess"], np.array(b.hess)) < REL_EVAL
+    for k in (3, 200, 250):
+        assert res[k]["fitness"] == pytest.approx(o1.fitness(list(res[k]["pose"])), rel=1e-9)
+    again = gt.align_batch(gs, want_fitness=True)
+    assert again.tobytes() == res.tobytes()          # fixed-order team reduction: run-to-run deterministic
+
+
 def test_c4_passes_run_are_the_oracle_passes_minus_exact_repeats(c4):
     """ndt_result.passes_run: the device skips exactly (a) line-search trials whose step equals the step of the trial before
     (same pose: the oracle's trace shows the same score again) and (b) the Hessian-only pass after a search (its trial passes

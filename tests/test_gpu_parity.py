@@ -499,6 +499,23 @@ def test_match_pairs_parity_with_oracle_per_pair():
     g.synchronize()
     res2 = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype=capi.RESULT_DTYPE)
     assert np.array_equal(res2["pose"], res["pose"]) and np.array_equal(res2["score"], res["score"])
+    # compact (x, y) clouds, 8 bytes per point (ndt_match_pairs_xy): the same bytes, from host and from device buffers
+    src0 = src.copy(); src0[:, 2:] = 0.0             # pair 21 above carries z != 0 (it takes part in the voxel hash): planar copy
+    assert not tgt[:, 2:].any()
+    res = g.match_pairs(src0, so, tgt, to, guesses, n, source_leaf=common.LAUNCH["leaf"])
+    src_xy, tgt_xy = np.ascontiguousarray(src0[:, :2]), np.ascontiguousarray(tgt[:, :2])
+    res_xy = g.match_pairs(src_xy, so, tgt_xy, to, guesses, n, source_leaf=common.LAUNCH["leaf"], xy=True)
+    for f in ("pose", "score", "fitness", "iters", "evals", "hess"):
+        assert np.array_equal(res_xy[f], res[f], equal_nan=(f == "fitness")), f
+    d_sxy, d_txy = torch.from_numpy(src_xy).cuda(), torch.from_numpy(tgt_xy).cuda()
+    d_res.zero_()
+    g.match_pairs(d_sxy.data_ptr(), so, d_txy.data_ptr(), to, d_g.data_ptr(), n, source_leaf=common.LAUNCH["leaf"],
+                  space=capi.MEM_DEVICE, out=d_res.data_ptr(), xy=True)
+    g.synchronize()
+    res3 = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype=capi.RESULT_DTYPE)
+    assert np.array_equal(res3["pose"], res["pose"]) and np.array_equal(res3["fitness"], res["fitness"], equal_nan=True)
+    res_bxy = g_b.match_pairs(src_xy, so, tgt_xy, to, guesses, n, source_leaf=common.LAUNCH["leaf"], xy=True)   # several batches
+    assert np.array_equal(res_bxy["pose"], res["pose"])
     # recovery of the true offset for ordinary pairs
     ok = 0
     for k in range(20, 70):
