@@ -413,17 +413,16 @@ __global__ void __launch_bounds__(256, 2) k_align_grid(GridView G, MatchParams m
 #ifndef NDT_WARP_KERNEL_MIN_CTAS
 #define NDT_WARP_KERNEL_MIN_CTAS 2
 #endif
-// ndt_align_batch picks the warps per match from the matches per resident warp (2,368 warps on a B200)
-// (measured on C4, ms per call for 1 / 2 / 4 / 8 warps per match: 65,536 matches 7.85 / 9.74 / 14.3 / 25.3; 8,192: 1.60 / 1.56 /
-// 1.99 / 3.34; 4,096: 1.28 / 1.04 / 1.16 / 1.82; 2,048: 0.82 / 0.64 / 0.61 / 0.90; 512: 0.62 / 0.44 / 0.36 / 0.46)
-#ifndef NDT_TEAM1_FROM
-#define NDT_TEAM1_FROM 4
+// ndt_align_batch picks the warps per match from the batch size relative to the resident warps R (2,368 on a B200).
+// Measured on C4 (ms per call for 1 / 2 / 4 / 8 warps per match, profiles/ab_c4.py --team):
+//   65,536 matches 7.84 / 9.61 / 12.6 / 18.2     8,192: 1.54 / 1.53 / 1.75 / 2.41     4,096: 1.26 / 1.05 / 1.03 / 1.30
+//    2,048: 0.80 / 0.64 / 0.57 / 0.65              512: 0.65 / 0.44 / 0.34 / 0.34
+// A team trades throughput (helpers idle while their leader runs the optimiser) for the length of the longest match.
+#ifndef NDT_TEAM1_FROM_X
+#define NDT_TEAM1_FROM_X 3        // n >= 3 R: one warp per match
 #endif
-#ifndef NDT_TEAM2_FROM
-#define NDT_TEAM2_FROM 1
-#endif
-#ifndef NDT_TEAM4_FROM
-#define NDT_TEAM4_FROM 0
+#ifndef NDT_TEAM2_FROM_X
+#define NDT_TEAM2_FROM_X 2        // n >= 2 R: two; below: four, and eight when not even every CTA gets a match
 #endif
 #ifndef NDT_WARP_OCC_SMEM_MAX
 #define NDT_WARP_OCC_SMEM_MAX (64 * 1024)
@@ -510,35 +509,98 @@ __global__ void __launch_bounds__(WK_THREADS, NDT_WARP_KERNEL_MIN_CTAS) k_align_
 // ---------------------------------------------------------------------------------------------
 // The same persistent schedule with a TEAM of WPM warps per match (WPM = 2, 4, 8). A match is a serial chain of passes:
 // when a call brings only a few matches per resident warp (a shard of a relocalisation on 8 GPUs, a small multi-start),
-// the call lasts as long as its longest match, however many warps sit idle. A team splits every pass of a match over its
-// warps (points rank, rank + 32 WPM, ...), each warp with its own rings, and adds the WPM warp totals in warp order after
-// one named barrier -- a fixed order, so every thread of the team holds bit-identical totals and runs the optimiser in
-// lock step, and results are run-to-run deterministic (they differ from the one-warp kernel's in the last bits: another
-// summation tree). Throughput per SM is a little lower than with one warp per match (barrier + redundant optimiser).
+// the call lasts as long as its longest match, however many warps sit idle. In a team the first warp (the leader) runs
+// the match -- optimiser, line search, job queue -- and posts the pose of every objective pass in a shared-memory mailbox;
+// all WPM warps then take their slice of the points (rank, rank + 32 WPM, ...) through the three stages with their own
+// rings, leave their warp totals in the mailbox, and the leader adds them in warp order. Two named barriers per pass
+// (pose posted / totals written); between them the helpers are parked on the barrier and cost no issue slots -- the
+// optimiser runs once per match, not once per warp. Fixed summation order: results are run-to-run deterministic (they
+// differ from the one-warp kernel's in the last bits: another summation tree).
 // ---------------------------------------------------------------------------------------------
+enum { TEAM_CMD_PASS = 1, TEAM_CMD_FITNESS = 2, TEAM_CMD_EXIT = 3 };
 template <int WPM>
-struct TeamCoop {
-  double *rows;          // [2][WPM][NACC] doubles of this team in shared memory (double-buffered by pass parity)
-  int *epoch;            // per-thread pass counter (kernel local)
-  int warp_in_team, lane, bar_id;
-  __device__ __forceinline__ int rank() const { return warp_in_team * 32 + lane; }
-  __device__ __forceinline__ int size() const { return 32 * WPM; }
-  __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(32 * WPM) : "memory"); }
-  template <int N> __device__ __forceinline__ void allreduce(double *v) const {
-    warp_allreduce<N>(v);
-    double *buf = rows + ((*epoch) & 1) * (WPM * NACC);
-    ++(*epoch);
+struct __align__(16) TeamBox {
+  PoseF pf;
+  double cs, sn;
+  int cmd, pad;
+  double rows[WPM][NACC];
+};
+
+template <int WPM, class OccL, class NbrL, class CenL, class SlotL, class RecL, class SrcL>
+struct TeamObjective {
+  ProbeGeom geom;
+  OccL occ; NbrL nbr; CenL cen; SlotL slot; RecL rec; SrcL src;
+  int ns;
+  double d1, d2;
+  int sse;
+  TeamBox<WPM> *box;
+  int wit, lane, bar_id;
+  HitQueue Q;
+  __device__ __forceinline__ void barrier() const { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(32 * WPM) : "memory"); }
+  // what every warp of the team runs for a posted pass: its slice of the points, its warp total into its mailbox row
+  __device__ __noinline__ void slice(const PoseF pf, const double cs, const double sn) {
+    double acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+    int pairs = 0;
+    accumulate_points(0, geom, occ, nbr, cen, slot, rec, src, wit * 32 + lane, 32 * WPM, ns, pf, sse != 0, cs, sn, d1, d2, Q, acc, pairs);
+    warp_allreduce<NACC>(acc);
     if (lane == 0) {
 #pragma unroll
-      for (int k = 0; k < N; ++k) buf[warp_in_team * NACC + k] = v[k];
+      for (int k = 0; k < NACC; ++k) box->rows[wit][k] = acc[k];
     }
-    sync();                 // one barrier per reduction: the other buffer is rewritten only after everyone passed this one again
+    barrier();
+  }
+  __device__ __noinline__ void fitness_slice(const GridView &G, const PoseF pf) {
+    double sum[1] = {0.0};
+    for (int i0 = wit * 32; i0 < ns; i0 += 32 * WPM) {         // warp-uniform trip count: the 1-NN is warp-collective
+      const int i = i0 + lane;
+      const bool valid = i < ns;
+      const float2 xy = src(valid ? i : ns - 1);
+      float xt, yt;
+      xform(pf, sse != 0, xy.x, xy.y, xt, yt);
+      const float d = nn_dist2_warp(G, xt, yt, valid);
+      if (valid) sum[0] += (double)d;
+    }
+    warp_allreduce<1>(sum);
+    if (lane == 0) box->rows[wit][0] = sum[0];
+    barrier();
+  }
+  __device__ __forceinline__ void post(const PoseF pf, double cs, double sn, int cmd) const {
+    if (lane == 0) { box->pf = pf; box->cs = cs; box->sn = sn; box->cmd = cmd; }
+    barrier();
+  }
+  // leader only: the objective pass match_device asks for (always the full mode: score, gradient, Hessian)
+  __device__ __forceinline__ void pass(const int, const double *p, const AngleCache &ac, double *out) {
+    const PoseF pf = pose_to_float(p);
+    post(pf, ac.cs, ac.sn, TEAM_CMD_PASS);
+    slice(pf, ac.cs, ac.sn);
 #pragma unroll
-    for (int k = 0; k < N; ++k) {
-      double t = buf[k];
+    for (int k = 0; k < NACC; ++k) {
+      double t = box->rows[0][k];
 #pragma unroll
-      for (int i = 1; i < WPM; ++i) t += buf[i * NACC + k];
-      v[k] = t;
+      for (int i = 1; i < WPM; ++i) t += box->rows[i][k];
+      out[k] = t;
+    }
+  }
+  __device__ __forceinline__ double fitness(const GridView &G, const double *p) {
+    const PoseF pf = pose_to_float(p);
+    post(pf, 0.0, 0.0, TEAM_CMD_FITNESS);
+    fitness_slice(G, pf);
+    double t = box->rows[0][0];
+#pragma unroll
+    for (int i = 1; i < WPM; ++i) t += box->rows[i][0];
+    return t;
+  }
+  // helpers: serve posted passes until the leader says the queue is empty
+  __device__ __forceinline__ void serve(const GridView &G) {
+    for (;;) {
+      barrier();
+      const int cmd = box->cmd;
+      if (cmd == TEAM_CMD_EXIT) break;
+      const PoseF pf = box->pf;
+      if (cmd == TEAM_CMD_PASS) slice(pf, box->cs, box->sn);
+      else fitness_slice(G, pf);
     }
   }
 };
@@ -563,32 +625,27 @@ __global__ void __launch_bounds__(WK_THREADS, NDT_WARP_KERNEL_MIN_CTAS) k_align_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, team = warp / WPM, wit = warp % WPM;
   WarpState *ws = reinterpret_cast<WarpState *>(smem_raw + WK_QUEUE_BYTES + occ_bytes + ((ns * 8 + 15) & ~15)) + team * WPM;
   __shared__ unsigned long long s_state;
-  __shared__ double s_rows[TEAMS][2][WPM][NACC];
-  __shared__ int s_job[TEAMS];
-  if (threadIdx.x == 0) s_state = TEAMS;                       // "chunk exhausted": the first team fetches one (a chunk = one job per team)
+  __shared__ TeamBox<WPM> s_box[TEAMS];
+  if (threadIdx.x == 0) s_state = TEAMS;                       // "chunk exhausted": the first leader fetches one (a chunk = one job per team)
   __syncthreads();
-  int epoch = 0;
-  TeamCoop<WPM> coop{&s_rows[team][0][0][0], &epoch, wit, lane, 1 + team};
-  const SmemOcc occ_acc{smem_addr(s_occ)};
-  const SmemSrc src_acc{smem_addr(s_src)};
+  TeamObjective<WPM, SmemOcc, GlobalNbr, GlobalCen, GlobalSlot, GlobalRec, SmemSrc> obj{
+      probe_geom(G), SmemOcc{smem_addr(s_occ)}, GlobalNbr{G.nbr}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs},
+      SmemSrc{smem_addr(s_src)}, ns, mp.d1, mp.d2, (mp.quirks & NDT_QUIRK_TRANSFORM_SSE_ORDER) ? 1 : 0,
+      &s_box[team], wit, lane, 1 + team, my_queue(smem_raw)};
+  if (wit != 0) { obj.serve(G); return; }
   for (;;) {
-    if (wit == 0) {
-      const int j = next_job<TEAMS>(&s_state, job_counter, lane);
-      if (lane == 0) s_job[team] = j;
-    }
-    coop.sync();            // the next write of s_job lies behind at least one reduction barrier of the match below
-    const int job = s_job[team];
+    const int job = next_job<TEAMS>(&s_state, job_counter, lane);
     if (job >= n_jobs) break;
     const double guess[3] = {guesses[3 * (size_t)job], guesses[3 * (size_t)job + 1], guesses[3 * (size_t)job + 2]};
-    MatchOut &mo = ws->mo;  // every warp of the team writes the same bits
+    MatchOut &mo = ws->mo;
     OptState opt;
-    auto obj = make_objective(G, mp, coop, occ_acc, GlobalNbr{G.nbr}, GlobalCen{G.cen}, GlobalSlot{G.slot}, GlobalRec{G.recs}, src_acc, ns, my_queue(smem_raw));
     match_device(obj, mp, guess, mo, opt);
     double fsum = 0.0;
-    if (mp.want_fitness) fsum = fitness_pass_cold(G, src_acc, ns, mp, mo.p, coop);
-    if (wit == 0 && lane == 0) write_result(out + job, mo, ns, fsum, mp.want_fitness != 0, G.n_tgt);
+    if (mp.want_fitness) fsum = obj.fitness(G, mo.p);
+    if (lane == 0) write_result(out + job, mo, ns, fsum, mp.want_fitness != 0, G.n_tgt);
     __syncwarp();
   }
+  obj.post(PoseF{0.f, 0.f, 0.f, 0.f}, 0.0, 0.0, TEAM_CMD_EXIT);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1028,8 +1085,8 @@ int launch_align(Handle *h, const double *d_guesses, int64_t n, ndt_result *d_re
     // (measured on C4, profiles/ab_c4.py --team: see DESIGN.md 4.3). Teams need the staged source + bitmap.
     int wpm = h->prm.align_team;
     if (wpm != 1 && wpm != 2 && wpm != 4 && wpm != 8) {
-      const int64_t per_warp = n / std::max<int64_t>(1, (int64_t)h->sm_count * ctas_per_sm * WK_WARPS);   // matches per resident warp
-      wpm = per_warp >= NDT_TEAM1_FROM ? 1 : per_warp >= NDT_TEAM2_FROM ? 2 : per_warp >= NDT_TEAM4_FROM ? 4 : 8;
+      const int64_t R = (int64_t)h->sm_count * ctas_per_sm * WK_WARPS;     // resident warps
+      wpm = n >= NDT_TEAM1_FROM_X * R ? 1 : n >= NDT_TEAM2_FROM_X * R ? 2 : n >= R / 8 ? 4 : 8;
     }
     if (!occ_smem) wpm = 1;
     if (wpm > 1) {
