@@ -98,10 +98,9 @@ def build_c4(n_total: int):
 
 
 def shard(n_total: int, rank: int, world: int):
-    """This rank's hypotheses: blocks of 16 (the headings of one lattice position) dealt round-robin over the ranks, so
-    every rank sees every region of the map (a contiguous split gives the ranks regions of different cost)."""
-    from ndt_slam_b200.sharding import shard_indices
-    return shard_indices(n_total, rank, world, block=16)
+    """Block partition [r*H/G, (r+1)*H/G)."""
+    from ndt_slam_b200.sharding import shard_range
+    return shard_range(n_total, rank, world)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -309,7 +308,7 @@ def main():
 
     wl = build_c4(args.hyp_total)
     n_total = wl["hyp"].shape[0]
-    mine = shard(n_total, rank, world)
+    lo, hi = shard(n_total, rank, world)
     ns = wl["src"].shape[0]
 
     # a dedicated (non-default) stream: the library launches on it and torch records the timing events on it
@@ -429,7 +428,7 @@ def main():
                     value=float(c[0].item()) / (ms_per_step * 1e-3), matches_per_s=float(c[1].item()) / (ms_per_step * 1e-3),
                     e2e_value=float(c[0].item()) * K / float(t[1].item()), e2e_matches_per_s=float(c[1].item()) * K / float(t[1].item()))
 
-    hyp = np.ascontiguousarray(wl["hyp"][mine])
+    hyp = np.ascontiguousarray(wl["hyp"][lo:hi])
     m = measure(hyp)
     res, n_h = m["res"], m["n_h"]
     evals_mean = float(res["evals"].mean())
@@ -438,13 +437,14 @@ def main():
     from ndt_slam_b200.sharding import best_over_ranks
     bi_local, best_local = g.best_of(m["d_res"].data_ptr(), n=n_h, space=capi.MEM_DEVICE)
     b_score = best_local.score if bi_local >= 0 else -np.inf
-    g_score, g_index, g_pose, g_owner = best_over_ranks(b_score, int(mine[max(bi_local, 0)]), list(best_local.pose), device="cuda")
+    g_score, g_index, g_pose, g_owner = best_over_ranks(b_score, lo + max(bi_local, 0), list(best_local.pose), device="cuda")
 
     # ---- secondary: weak scaling (65,536 hypotheses per GPU) when there is more than one rank ----------------
     weak = None
     if world > 1 and not args.no_weak:
         wl_w = build_c4(HYP_TOTAL * world)
-        mw = measure(np.ascontiguousarray(wl_w["hyp"][shard(wl_w["hyp"].shape[0], rank, world)]))
+        lo_w, hi_w = shard(wl_w["hyp"].shape[0], rank, world)
+        mw = measure(np.ascontiguousarray(wl_w["hyp"][lo_w:hi_w]))
         weak = {"scaling": "weak", "hypotheses_per_gpu": HYP_TOTAL, "hypotheses_total": int(mw["nh_all"]), "value": mw["value"], "unit": UNIT,
                 "ms_per_step": mw["ms_per_step"], "matches_per_sec": mw["matches_per_s"], "e2e_value": mw["e2e_value"]}
         del mw
@@ -545,7 +545,7 @@ def main():
                                "vs 200 m x 200 m map, 0.5 m cells" % (n_total, ns),
                    "hypotheses_total": int(m["nh_all"]), "hypotheses_per_gpu": int(n_h), "target_points": int(wl["tgt"].shape[0]),
                    "grid_cells": [int(gi.div_b[0]), int(gi.div_b[1])], "occupied_cells": int(gi.n_slots),
-                   "resolution_m": RESOLUTION, "parallelism": f"hypothesis-shard x{n_gpus} (blocks of 16 dealt round-robin), grid replicated once",
+                   "resolution_m": RESOLUTION, "parallelism": f"hypothesis-shard x{n_gpus}, grid replicated once",
                    "l2": "flushed between timed iterations (256 MiB write), device-timed and end-to-end loops alike"},
         "matches_per_sec": m["matches_per_s"], "evals_per_match": evals_mean, "point_evals_per_step": m["pe_all"],
         "executed": {"point_evals_per_step": m["pe_run_all"], "value": m["value_run"], "unit": UNIT,

@@ -58,45 +58,32 @@ void Relocalizer::reserve(size_t k, int64_t n) {
 
 int64_t Relocalizer::relocalize(const double *hyp, int64_t n, ndt_result *best, ndt_result *results) {
   const int64_t G = (int64_t)handles.size();
-  // Blocks of 16 hypotheses (the headings of one lattice position) are dealt to the GPUs round-robin: a match costs more
-  // or less depending on where it lies on the map, a lattice enumerates hypotheses region by region, and the call ends
-  // with the slowest GPU -- every GPU should see every region.
-  const int64_t block = 16;
-  std::vector<std::vector<int64_t>> mine((size_t)G);
-  for (int64_t i = 0; i < n; ++i) mine[(size_t)((i / block) % G)].push_back(i);
-  std::vector<double> packed;
+  std::vector<int64_t> lo(G + 1);
+  for (int64_t k = 0; k <= G; ++k) lo[k] = k * n / G;                     // block partition [k n / G, (k + 1) n / G)
   // launch every shard (device-space calls return without waiting), then wait for all of them
   for (int64_t k = 0; k < G; ++k) {
-    const int64_t m = (int64_t)mine[(size_t)k].size();
+    const int64_t m = lo[k + 1] - lo[k];
     if (m == 0) continue;
     reserve((size_t)k, m);
-    packed.resize((size_t)m * 3);
-    for (int64_t j = 0; j < m; ++j)
-      for (int c = 0; c < 3; ++c) packed[(size_t)j * 3 + c] = hyp[3 * mine[(size_t)k][(size_t)j] + c];
-    ck(ndt_upload(handles[k], d_guess[k], packed.data(), m * 3 * (int64_t)sizeof(double)), handles[k], "ndt_upload");   // synchronous copy
+    ck(ndt_upload(handles[k], d_guess[k], hyp + 3 * lo[k], m * 3 * (int64_t)sizeof(double)), handles[k], "ndt_upload");
     ck(ndt_align_batch(handles[k], static_cast<const double *>(d_guess[k]), m, NDT_MEM_DEVICE, /*want_fitness=*/0,
                        static_cast<ndt_result *>(d_res[k])), handles[k], "ndt_align_batch");
   }
   lastDeviceMs = 0.0;
   std::vector<const ndt_result *> ptrs(G);
   std::vector<int64_t> counts(G);
-  std::vector<ndt_result> shard;
   for (int64_t k = 0; k < G; ++k) {
     ptrs[k] = static_cast<const ndt_result *>(d_res[k]);
-    counts[k] = (int64_t)mine[(size_t)k].size();
+    counts[k] = lo[k + 1] - lo[k];
     if (counts[k] == 0) continue;
     ck(ndt_synchronize(handles[k]), handles[k], "ndt_synchronize");
     float ms = 0.f;
     ndt_last_kernel_ms(handles[k], &ms);
     lastDeviceMs = std::max(lastDeviceMs, (double)ms);
-    if (results) {
-      shard.resize((size_t)counts[k]);
-      ck(ndt_download(handles[k], shard.data(), d_res[k], counts[k] * (int64_t)sizeof(ndt_result)), handles[k], "ndt_download");
-      for (int64_t j = 0; j < counts[k]; ++j) results[mine[(size_t)k][(size_t)j]] = shard[(size_t)j];
-    }
+    if (results) ck(ndt_download(handles[k], results + lo[k], d_res[k], counts[k] * (int64_t)sizeof(ndt_result)), handles[k], "ndt_download");
   }
   int bh = -1;
   int64_t bi = -1;
   ck(ndt_best_of_multi(handles.data(), ptrs.data(), counts.data(), (int)G, &bh, &bi, best), handles[0], "ndt_best_of_multi");
-  return bh < 0 ? -1 : mine[(size_t)bh][(size_t)bi];
+  return bh < 0 ? -1 : lo[bh] + bi;
 }

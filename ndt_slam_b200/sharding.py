@@ -15,16 +15,6 @@ def shard_range(n_total: int, rank: int, world: int) -> tuple[int, int]:
     return (n_total * rank) // world, (n_total * (rank + 1)) // world
 
 
-def shard_indices(n_total: int, rank: int, world: int, block: int = 16) -> np.ndarray:
-    """Dealt partition: blocks of `block` consecutive units go to the ranks round-robin (unit i belongs to rank
-    (i // block) % world). Disjoint, covers everything, sizes differ by at most one block. Used for the relocalisation
-    hypotheses: their cost depends on where they lie on the map, and a lattice enumerates them region by region, so a
-    contiguous split gives the ranks regions of different cost (the job ends with the slowest rank); dealing 16 headings
-    of one lattice position at a time keeps a block's shared neighbourhood together and evens the regions out."""
-    i = np.arange(n_total, dtype=np.int64)
-    return i[(i // block) % world == rank]
-
-
 def replicate_blob(blob: torch.Tensor | None, nbytes_hint: int, src: int = 0, device="cuda") -> torch.Tensor:
     """Broadcast a flat uint8 grid blob (ndt_grid_export) from `src` to every rank. Returns the local copy."""
     world = dist.get_world_size() if dist.is_initialized() else 1

@@ -24,20 +24,6 @@ def test_shard_range_properties():
             assert max(sizes) - min(sizes) <= 1
 
 
-def test_shard_indices_deal_blocks_round_robin():
-    for n in (0, 1, 15, 16, 17, 1000, 65_536):
-        for world in (1, 2, 3, 4, 8):
-            parts = [sharding.shard_indices(n, k, world, block=16) for k in range(world)]
-            allidx = np.concatenate(parts) if parts else np.zeros(0, np.int64)
-            assert np.array_equal(np.sort(allidx), np.arange(n))            # disjoint, covers everything
-            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 16
-            for k, p in enumerate(parts):
-                assert np.all((p // 16) % world == k) and np.all(np.diff(p) > 0)
-    # 65,536 lattice hypotheses on 8 ranks: every rank gets 8,192, 16 headings of a position stay together
-    p3 = sharding.shard_indices(65_536, 3, 8)
-    assert len(p3) == 8192 and list(p3[:17]) == list(range(48, 64)) + [176]
-
-
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
@@ -59,14 +45,14 @@ def _worker(rank, world, port, ret):
     blob = sharding.replicate_blob(blob, 0, src=0, device="cpu")
     tgt = blob.numpy().view(np.float32).reshape(-1, 4)
     o = oa.Oracle(cm.params(resolution=0.5)); o.set_target(tgt); o.set_source(pb["src"]); o.want_fitness(False)
-    mine = sharding.shard_indices(hyp.shape[0], rank, world, block=4)      # like bench.py's C4 shards (there: blocks of 16)
+    lo, hi = sharding.shard_range(hyp.shape[0], rank, world)
     best = (-np.inf, -1, np.zeros(3))
-    for i in mine:
+    for i in range(lo, hi):
         r = o.align(hyp[i])
         if r.converged and (r.score > best[0]):
-            best = (r.score, int(i), np.array(r.pose))
+            best = (r.score, i, np.array(r.pose))
     score, gi, pose, owner = sharding.best_over_ranks(best[0], best[1], best[2], device="cpu")
-    ret[rank] = (score, gi, list(pose), owner, int(mine[0]), len(mine))
+    ret[rank] = (score, gi, list(pose), owner, lo, hi)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -77,7 +63,7 @@ def test_two_rank_shard_and_best_matches_single_process():
     mgr = mp.Manager(); ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert ret[0][:4] == ret[1][:4]                        # every rank ends with the same answer
-    assert (ret[0][4], ret[0][5], ret[1][4], ret[1][5]) == (0, 24, 4, 24)
+    assert (ret[0][4], ret[0][5], ret[1][4], ret[1][5]) == (0, 24, 24, 48)
     pb = common.c1_problem()
     rng = np.random.Generator(np.random.PCG64(5))
     hyp = pb["guess"] + rng.normal(0, [0.3, 0.3, 0.05], size=(48, 3))
@@ -86,7 +72,7 @@ def test_two_rank_shard_and_best_matches_single_process():
     scores = np.array([r.score if r.converged else -np.inf for r in res])
     bi = int(np.argmax(scores))
     assert ret[0][1] == bi and ret[0][0] == pytest.approx(scores[bi], rel=1e-15)
-    assert ret[0][3] == (bi // 4) % 2
+    assert ret[0][3] == (0 if bi < 24 else 1)
 
 
 def _pairs_worker(rank, world, port, ret):
