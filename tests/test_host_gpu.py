@@ -219,7 +219,10 @@ def test_relocalizer_cpp_host_shards_hypotheses_over_replicated_grids():
     g = capi.Ndt(common.params(resolution=0.5))
     g.set_target(tgt); g.set_source(src)
     ref = g.align_batch(hyp, want_fitness=False)
-    assert np.array_equal(res["pose"], ref["pose"]) and np.array_equal(res["score"], ref["score"]) and np.array_equal(res["evals"], ref["evals"])
+    # a shard may run with another number of warps per match than the whole batch (ndt_params.align_team = auto): same
+    # path, another summation tree
+    assert np.allclose(res["pose"], ref["pose"], rtol=0, atol=1e-9) and np.allclose(res["score"], ref["score"], rtol=1e-10, atol=0)
+    assert np.array_equal(res["evals"], ref["evals"]) and np.array_equal(res["iters"], ref["iters"])
     bi_ref, best_ref = g.best_of(ref)
-    assert bi == bi_ref == 1023 and best.score == best_ref.score
+    assert bi == bi_ref == 1023 and best.score == pytest.approx(best_ref.score, rel=1e-10)
     assert np.hypot(best.pose[0] - d["true_pose"][0], best.pose[1] - d["true_pose"][1]) < 0.05 and ms > 0
