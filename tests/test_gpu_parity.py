@@ -523,3 +523,33 @@ def test_match_pairs_parity_with_oracle_per_pair():
         if res[k]["converged"] and np.hypot(res[k]["pose"][0] - off[0], res[k]["pose"][1] - off[1]) < 0.05:
             ok += 1
     assert ok >= 35
+
+
+def test_batched_entry_points_reject_bad_arguments_and_odd_knobs():
+    """Error behaviour of the batched calls (no exception crosses the ABI: a negative status + ndt_last_error), and knobs
+    outside their range fall back to the library's choice."""
+    prm = common.params(resolution=0.5)
+    g = capi.Ndt(prm)
+    srcs, tgts = _c5_batch(range(3))
+    src, so = _pack(srcs); tgt, to = _pack(tgts)
+    guesses = np.zeros((3, 3))
+    for xy in (False, True):
+        s_in = np.ascontiguousarray(src[:, :2]) if xy else src
+        t_in = np.ascontiguousarray(tgt[:, :2]) if xy else tgt
+        bad = so.copy(); bad[0] = 1
+        with pytest.raises(capi.NdtError, match="start at 0"):
+            g.match_pairs(s_in, bad, t_in, to, guesses, 3, source_leaf=0.05, xy=xy)
+        bad = to.copy(); bad[2] = bad[1] - 1
+        with pytest.raises(capi.NdtError, match="non-decreasing"):
+            g.match_pairs(s_in, so, t_in, bad, guesses, 3, source_leaf=0.05, xy=xy)
+        ok = g.match_pairs(s_in, so, t_in, to, guesses, 3, source_leaf=0.05, xy=xy)      # the handle is still usable
+        assert ok["converged"].all()
+    assert g.match_pairs(src, so, tgt, to, guesses, 0).shape[0] == 0                       # nothing to do
+    # align_team outside {0, 1, 2, 4, 8}: the library picks (same answers as the default)
+    pb = common.c1_problem()
+    rng = np.random.Generator(np.random.PCG64(3))
+    hyp = pb["guess"] + rng.normal(0, [0.2, 0.2, 0.03], size=(80, 3))
+    ga, gb = capi.Ndt(common.params(resolution=0.5)), capi.Ndt(common.params(resolution=0.5, align_team=3))
+    for gg in (ga, gb):
+        gg.set_target(pb["tgt"]); gg.set_source(pb["src"])
+    assert ga.align_batch(hyp).tobytes() == gb.align_batch(hyp).tobytes()
