@@ -553,3 +553,60 @@ def test_batched_entry_points_reject_bad_arguments_and_odd_knobs():
     for gg in (ga, gb):
         gg.set_target(pb["tgt"]); gg.set_source(pb["src"])
     assert ga.align_batch(hyp).tobytes() == gb.align_batch(hyp).tobytes()
+
+
+def test_hit_rejected_by_the_guard_on_e_contributes_nothing(c1):
+    """PCL's updateDerivatives returns 0 for a hit whose e = d2 * exp(-d2 q / 2) is NaN, negative or > 1: no score term, no
+    gradient, no Hessian (the hit still counts as a neighbour). Unreachable with the inverse covariances the grid build
+    produces, so the records are crafted: a replica is imported from a blob in which one tree cell's inverse covariance is
+    (a) NaN, (b) strongly negative definite (q < 0, e > 1). Both must give exactly what a grid without that cell gives."""
+    import torch
+    pb, g, o = c1
+    guess = np.array(pb["guess"])
+    e0 = g.eval(guess)
+    nbytes = g.grid_blob_size(flags=0)
+    blob = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    g.grid_export(blob.data_ptr(), nbytes, flags=0)
+    b = blob.cpu().numpy()
+    gi = g.grid_info()
+    npad = (gi.div_b[0] + 4) * (gi.div_b[1] + 4)
+    hdr = b[:512].view(np.int64)
+    at = [w for w in range(hdr.shape[0] - 1, 0, -1) if hdr[w] == nbytes][0]
+    off = hdr[at - 10: at]                         # slot, cen, occ, recs, ...
+    slot = b[off[0]: off[0] + 4 * npad].view(np.int32)
+    cen = b[off[1]: off[1] + 8 * npad].view(np.float32).reshape(npad, 2)
+    tree = np.flatnonzero(~np.isnan(cen[:, 0]))
+    # the tree cell closest to the transformed scan: it certainly has hits at this pose
+    c, s = np.cos(guess[2]), np.sin(guess[2])
+    pts = pb["src"][:, :2].astype(np.float64) @ np.array([[c, s], [-s, c]]) + guess[:2]
+    d = ((cen[tree][:, None, :].astype(np.float64) - pts[None, :, :]) ** 2).sum(axis=2)
+    victim = int(tree[np.argmin(d.min(axis=1))])
+    hits_on_victim = int((d[np.flatnonzero(tree == victim)[0]] < 0.25 - 1e-6).sum())
+    assert hits_on_victim > 0
+
+    def replica(edit):
+        bb = b.copy()
+        edit(bb)
+        gg = capi.Ndt(common.params(resolution=0.5))
+        t = torch.from_numpy(bb).cuda()
+        gg.grid_import(t.data_ptr(), nbytes)
+        gg.set_source(pb["src"])
+        return gg.eval(guess)
+
+    def icov_of(bb):
+        r0 = off[3] + 64 * int(slot[victim]) + 32
+        return bb[r0: r0 + 32].view(np.float64)
+
+    def set_nan(bb): icov_of(bb)[:] = np.nan
+    def set_negative(bb): icov_of(bb)[:] = [-1e3, 0.0, 0.0, -1e3]
+    def remove_cell(bb): bb[off[1] + 8 * victim: off[1] + 8 * victim + 8].view(np.uint32)[:] = 0xFFFFFFFF
+
+    without = replica(remove_cell)
+    removed = e0.n_pairs - without.n_pairs                 # (the float64 count above may differ by a point on the radius)
+    assert removed >= 1 and abs(removed - hits_on_victim) <= 1 and without.score != e0.score
+    for edit in (set_nan, set_negative):
+        e = replica(edit)
+        assert e.n_pairs == e0.n_pairs                       # still a neighbour
+        assert np.isfinite(e.score) and e.score == pytest.approx(without.score, rel=1e-12)
+        assert np.allclose(np.array(e.grad), np.array(without.grad), rtol=1e-10, atol=1e-12)
+        assert np.allclose(np.array(e.hess), np.array(without.hess), rtol=1e-10, atol=1e-10)
