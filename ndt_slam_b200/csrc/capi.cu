@@ -471,6 +471,19 @@ int ndt_best_of(ndt_handle hh, const ndt_result *results, int64_t n, int memspac
   return NDT_OK;
 }
 
+// ndt_grid_import: the matcher's arithmetic assumes finite records (a rejected hit is turned into exact zeros by selects on
+// its inputs, and 0 * NaN is not 0). The grid build only ever writes finite records; a blob is checked.
+__global__ void k_check_records(const CellRec *__restrict__ recs, int n, int32_t *__restrict__ bad) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double *d = reinterpret_cast<const double *>(recs + i);        // 64 B: {float cx, cy; int nr, cell; double mx, my, c00, c01, c10, c11}
+    const float *f = reinterpret_cast<const float *>(recs + i);
+    bool ok = isfinite(f[0]) && isfinite(f[1]);
+#pragma unroll
+    for (int k = 2; k < 8; ++k) ok = ok && isfinite(d[k]);
+    if (!ok) atomicExch(bad, 1);
+  }
+}
+
 // z = 0 planes of 2-D SLAM carry 8 useful bytes per point: the compact entry uploads (x, y) pairs and widens them on the device
 __global__ void k_expand_xy(const float2 *__restrict__ in, float4 *__restrict__ out, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -764,7 +777,16 @@ int ndt_grid_import(ndt_handle hh, const void *device_blob, int64_t bytes) {
     h->have_nbr = false; h->nbr_grids = 1;
     h->nbr_cells = z.slot > 0 ? (int64_t)pd.W * pd.H : 0;
   }
+  const int n_recs = (int)(z.recs / (int64_t)sizeof(CellRec));
+  int32_t *bad = h->gb.counters.as<int32_t>() + CTR_BIG;
+  NDT_CUDA(h, cudaMemsetAsync(bad, 0, sizeof(int32_t), st));
+  if (n_recs > 0) {
+    k_check_records<<<std::min(std::max(1, (n_recs + 255) / 256), h->sm_count * 8), 256, 0, st>>>(h->gb.recs.as<CellRec>(), n_recs, bad);
+    ++h->launches;
+  }
+  NDT_CUDA(h, cudaMemcpyAsync(h->pinned_ctr, bad, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   NDT_CUDA(h, cudaStreamSynchronize(st));
+  if (h->pinned_ctr[0] != 0) return set_err(h, NDT_ERR_ARG, "ndt_grid_import: non-finite cell record");
   h->have_grid = true;
   h->grid_has_points = (b.flags & NDT_BLOB_POINTS) != 0;
   return NDT_OK;
