@@ -17,3 +17,6 @@ python profiles/prof_c2c3.py > $OUT/r2_c2c3_plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $OUT/r2_launches_c2c3.csv python profiles/prof_c2c3.py > /dev/null 2>&1
 ncu --set full --clock-control none -k regex:"k_count|k_alloc|k_fill|k_rank|k_finalize|k_bounds" -s 14 -c 6 -f -o $OUT/r2_full_grid_c3 python profiles/prof_c2c3.py > $OUT/r2_full_grid.log 2>&1
 ls -la $OUT | grep r2_
+# 5. small batch: team of warps per match (k_align_team)
+python profiles/prof_team.py 4096 > $OUT/r2_team_plain.log 2>&1 && \
+ncu --set full --clock-control none -k regex:k_align_team -s 3 -c 1 -f -o $OUT/r2_full_k_align_team python profiles/prof_team.py 4096 > $OUT/r2_full_team.log 2>&1

@@ -118,6 +118,11 @@ if fp.exists():
     out.write("## `k_align_pairs` (C5: 8,192 scan pairs, one warp per pair), `ncu --set full`\n\n")
     metrics_table(fp, out)
     shutil.copy(fp, P / fp.name)
+ft = G / f"{rnd}_full_k_align_team.raw.csv"
+if ft.exists():
+    out.write("## `k_align_team<4>` (4,096 hypotheses of C4 in one call: a team of four warps per match), `ncu --set full`\n\n")
+    metrics_table(ft, out)
+    shutil.copy(ft, P / ft.name)
 fg = G / f"{rnd}_full_grid_c3.raw.csv"
 if fg.exists():
     out.write("## Grid-build kernels at C3 size (4.0 M target points, 0.1 m cells, 3930 x 3952 cells), `ncu --set full`\n\n")
