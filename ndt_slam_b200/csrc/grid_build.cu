@@ -1412,19 +1412,18 @@ int grid_build_incremental(Handle *h, const float *xyzw, int64_t n, int64_t n_sa
   NDT_CUDA(h, cudaMemcpyAsync(cnt + INC_P, cnt + INC_B, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));   // this call's tail cells are the next call's "previous tail"
   h->inc_list_prev = buf[0];
   NDT_CUDA(h, cudaGetLastError());
+  gd.n_tgt = n;
+  // the 1-NN lattice is sized from the leaf count of the previous call (h_counters: a handful of leaves off at most, and only
+  // the lattice pitch depends on it), so the whole update needs one stream synchronisation, at its end
+  if (int rc = build_nn_lattice(h, n, mn, mx, nfin, /*force=*/true)) return rc;
+  if (h->timing) cudaEventRecord(h->ev1, st);
   // counters -> host (also the stream fence that lets the pinned stage be reused)
   NDT_CUDA(h, cudaMemcpyAsync(h->pinned_ctr, ctr, sizeof(h->h_counters), cudaMemcpyDeviceToHost, st));
   NDT_CUDA(h, cudaStreamSynchronize(st));
   std::memcpy(h->h_counters, h->pinned_ctr, sizeof(h->h_counters));
   h->h_counters[CTR_NFIN] = (int32_t)nfin;
   h->h_counters[CTR_PTS] = (int32_t)nfin;
-  gd.n_tgt = n;
-  if (int rc = build_nn_lattice(h, n, mn, mx, nfin, /*force=*/true)) return rc;
-  if (h->timing) {
-    cudaEventRecord(h->ev1, st);
-    NDT_CUDA(h, cudaEventSynchronize(h->ev1));
-    cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
-  }
+  if (h->timing) cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
   h->inc_mn[0] = mnA[0]; h->inc_mn[1] = mnA[1]; h->inc_mx[0] = mxA[0]; h->inc_mx[1] = mxA[1];
   h->inc_nfin = nfinA;
   h->inc_m = n_stable;
