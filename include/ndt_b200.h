@@ -141,6 +141,12 @@ int ndt_set_target_prefix(ndt_handle h, const float *xyzw, int64_t n, int64_t n_
  * settled prefix shrank, device input. After an incremental update ndt_grid_readback returns NDT_ERR_STATE (the per-leaf
  * read-back tables are not maintained); the matcher, the fitness score and ndt_get_grid_info see the same grid. */
 int ndt_set_target_incremental(ndt_handle h, const float *xyzw, int64_t n, int64_t n_same, int64_t n_stable, int memspace);
+/* The same update, queued: returns once the new points are copied to a staging buffer and the kernels are launched, so the
+ * host can prepare the next scan (resampling, source filter) while the device brings the grid up to date. xyzw may be
+ * reused at once; the next call on the handle, whatever it is, waits for the update first. What cannot be continued
+ * incrementally is rebuilt in full before the call returns, as above. (ScanMatcher::growMap calls this right after
+ * makeLocalMap, src/ScanMatcher.cpp:93-117, instead of leaving the whole cost to the next estimatePose.) */
+int ndt_set_target_incremental_async(ndt_handle h, const float *xyzw, int64_t n, int64_t n_same, int64_t n_stable, int memspace);
 int ndt_get_grid_info(ndt_handle h, ndt_grid_info *info);
 /* Leaves in ascending cell-index order (the std::map order of PCL's leaves_), for parity
  * checks: cell index, nr_points (-1 = failed eigen check), mean[2], icov[4] (xx,xy,yx,yy),

@@ -58,7 +58,7 @@ RESULT_DTYPE = np.dtype([("pose", "<f8", 3), ("T", "<f4", 16), ("score", "<f8"),
 
 EXPORTS = [
     "ndt_params_default", "ndt_create", "ndt_destroy", "ndt_last_error", "ndt_version",
-    "ndt_set_target", "ndt_set_target_prefix", "ndt_set_target_incremental", "ndt_get_grid_info", "ndt_grid_readback", "ndt_cell_index",
+    "ndt_set_target", "ndt_set_target_prefix", "ndt_set_target_incremental", "ndt_set_target_incremental_async", "ndt_get_grid_info", "ndt_grid_readback", "ndt_cell_index",
     "ndt_set_source", "ndt_approx_voxel_filter", "ndt_eval", "ndt_eval_batch",
     "ndt_align", "ndt_align_batch", "ndt_best_of", "ndt_match_pairs", "ndt_match_pairs_xy",
     "ndt_grid_blob_size", "ndt_grid_export", "ndt_grid_import", "ndt_replicate_grid", "ndt_best_of_multi", "ndt_trim",
@@ -94,6 +94,7 @@ def load() -> C.CDLL:
     L.ndt_set_target.argtypes = [vp, vp, i64, i32]
     L.ndt_set_target_prefix.argtypes = [vp, vp, i64, i64, i32]
     L.ndt_set_target_incremental.argtypes = [vp, vp, i64, i64, i64, i32]
+    L.ndt_set_target_incremental_async.argtypes = [vp, vp, i64, i64, i64, i32]
     L.ndt_get_grid_info.argtypes = [vp, C.POINTER(NdtGridInfo)]
     L.ndt_grid_readback.argtypes = [vp, i64, vp, vp, vp, vp, vp, C.POINTER(i64)]
     L.ndt_cell_index.argtypes = [vp, vp, i64, i32, vp]
@@ -177,13 +178,15 @@ class Ndt:
             raise NdtError(f"ndt call failed ({rc}): {msg.decode() if msg else ''}")
 
     # -- grid --
-    def set_target(self, xyzw, n=None, space=MEM_HOST, n_same=0, n_stable=None):
+    def set_target(self, xyzw, n=None, space=MEM_HOST, n_same=0, n_stable=None, queued=False):
         """n_same > 0: the first n_same points equal the previous target's (only the rest is uploaded).
-        n_stable: the first n_stable points will stay a prefix of later targets (incremental grid update on the device)."""
+        n_stable: the first n_stable points will stay a prefix of later targets (incremental grid update on the device);
+        queued=True: return once the update is launched (ndt_set_target_incremental_async), the next call waits for it."""
         if n is None:
             n = xyzw.shape[0]
         if n_stable is not None:
-            self._ck(self.L.ndt_set_target_incremental(self.h, _ptr(xyzw), n, n_same, n_stable, space))
+            fn = self.L.ndt_set_target_incremental_async if queued else self.L.ndt_set_target_incremental
+            self._ck(fn(self.h, _ptr(xyzw), n, n_same, n_stable, space))
         elif n_same:
             self._ck(self.L.ndt_set_target_prefix(self.h, _ptr(xyzw), n, n_same, space))
         else:

@@ -94,7 +94,8 @@ using namespace ndt;
 #define H_OR_FAIL(hh)                                     \
   Handle *h = reinterpret_cast<Handle *>(hh);             \
   if (!h) return NDT_ERR_ARG;                             \
-  if (cudaSetDevice(h->device) != cudaSuccess) return set_err(h, NDT_ERR_CUDA, "cudaSetDevice")
+  if (cudaSetDevice(h->device) != cudaSuccess) return set_err(h, NDT_ERR_CUDA, "cudaSetDevice"); \
+  if (h->pending) { if (int rc_pending = finish_pending(h)) return rc_pending; }
 
 extern "C" {
 
@@ -225,6 +226,11 @@ int ndt_set_target_prefix(ndt_handle hh, const float *xyzw, int64_t n, int64_t n
 int ndt_set_target_incremental(ndt_handle hh, const float *xyzw, int64_t n, int64_t n_same, int64_t n_stable, int memspace) {
   H_OR_FAIL(hh);
   return grid_build_incremental(h, xyzw, n, n_same, n_stable, memspace);
+}
+
+int ndt_set_target_incremental_async(ndt_handle hh, const float *xyzw, int64_t n, int64_t n_same, int64_t n_stable, int memspace) {
+  H_OR_FAIL(hh);
+  return grid_build_incremental(h, xyzw, n, n_same, n_stable, memspace, /*defer=*/true);
 }
 
 int ndt_get_grid_info(ndt_handle hh, ndt_grid_info *info) {

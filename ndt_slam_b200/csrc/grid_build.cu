@@ -1335,7 +1335,20 @@ int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace, int64_t n_
 }
 
 
-int grid_build_incremental(Handle *h, const float *xyzw, int64_t n, int64_t n_same, int64_t n_stable, int memspace) {
+// End of an incremental update whose caller did not wait (ndt_set_target_incremental_async): wait for the stream, take the
+// counters the kernels left in pinned memory. Every entry point of the ABI comes through here first.
+int finish_pending(Handle *h) {
+  if (!h->pending) return NDT_OK;
+  h->pending = false;
+  NDT_CUDA(h, cudaStreamSynchronize(h->stream));
+  std::memcpy(h->h_counters, h->pinned_ctr, sizeof(h->h_counters));
+  h->h_counters[CTR_NFIN] = (int32_t)h->pending_nfin;
+  h->h_counters[CTR_PTS] = (int32_t)h->pending_nfin;
+  if (h->timing) cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
+  return NDT_OK;
+}
+
+int grid_build_incremental(Handle *h, const float *xyzw, int64_t n, int64_t n_same, int64_t n_stable, int memspace, bool defer) {
   if (n < 0 || (n > 0 && !xyzw)) return set_err(h, NDT_ERR_ARG, "ndt_set_target_incremental: bad points");
   if (n_stable < 0) n_stable = 0;
   if (n_stable > n) n_stable = n;
@@ -1419,11 +1432,9 @@ int grid_build_incremental(Handle *h, const float *xyzw, int64_t n, int64_t n_sa
   if (h->timing) cudaEventRecord(h->ev1, st);
   // counters -> host (also the stream fence that lets the pinned stage be reused)
   NDT_CUDA(h, cudaMemcpyAsync(h->pinned_ctr, ctr, sizeof(h->h_counters), cudaMemcpyDeviceToHost, st));
-  NDT_CUDA(h, cudaStreamSynchronize(st));
-  std::memcpy(h->h_counters, h->pinned_ctr, sizeof(h->h_counters));
-  h->h_counters[CTR_NFIN] = (int32_t)nfin;
-  h->h_counters[CTR_PTS] = (int32_t)nfin;
-  if (h->timing) cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
+  h->pending_nfin = nfin;
+  h->pending = true;                                 // the host copy of the counters is taken by finish_pending()
+  if (!defer) { if (int rc = finish_pending(h)) return rc; }
   h->inc_mn[0] = mnA[0]; h->inc_mn[1] = mnA[1]; h->inc_mx[0] = mxA[0]; h->inc_mx[1] = mxA[1];
   h->inc_nfin = nfinA;
   h->inc_m = n_stable;

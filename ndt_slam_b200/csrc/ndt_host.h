@@ -146,13 +146,16 @@ struct Handle {
   void *pinned = nullptr;       // pinned host staging
   size_t pinned_cap = 0;
   bool timing = true;           // record ev0/ev1 around kernels
+  bool pending = false;         // an incremental target update was queued without waiting (finish_pending)
+  int64_t pending_nfin = 0;
 };
 
 // grid_build.cu
 // n_stable >= 0: the caller promises that the first n_stable points stay a prefix of future targets; the build then also
 // prepares the state ndt_set_target_incremental continues from
 int grid_build(Handle *h, const float *xyzw, int64_t n, int memspace, int64_t n_same = 0, int64_t n_stable = -1);
-int grid_build_incremental(Handle *h, const float *xyzw, int64_t n, int64_t n_same, int64_t n_stable, int memspace);
+int grid_build_incremental(Handle *h, const float *xyzw, int64_t n, int64_t n_same, int64_t n_stable, int memspace, bool defer = false);
+int finish_pending(Handle *h);
 // shared by ndt_set_target (one grid) and ndt_match_pairs (one grid per pair): target points are in gb.tgt,
 // geometry in gb.dims (device), point ranges in gb.pair_off (device, n_grids + 1 entries; unused for one grid)
 int grid_build_tables(Handle *h, int64_t n, int n_grids, int64_t total_pad, int max_h);

@@ -39,6 +39,9 @@ class PoseEstimator {
   uint64_t hintEpoch = 0, uploadedEpoch = 0;     // see hintTargetPrefix
   size_t hintPrefix = 0, hintSettled = 0;
   const void *uploadedCloud = nullptr;
+  uint64_t prefetchedEpoch = 0;                  // see prefetchTarget
+  size_t prefetchedPoints = 0;
+  bool prefetchTargetEnabled = true;             // parameter prefetch_target (default true)
 
   bool incrementalTarget;   // parameter incremental_target (default true): use ndt_set_target_incremental when the map hints a settled prefix
   ndt_handle ndt;       // stands where the reference has  pcl::NDT<pcl::PointXYZ, pcl::PointXYZ> ndt;
@@ -70,6 +73,11 @@ class PoseEstimator {
   void hintTargetPrefix(uint64_t epoch, size_t stablePoints, size_t settledPoints = 0) {
     hintEpoch = epoch; hintPrefix = stablePoints; hintSettled = settledPoints;
   }
+
+  // Optional, right after the map has produced the cloud the NEXT estimatePose will match against (ScanMatcher::growMap ->
+  // makeLocalMap): queue the device grid update now (ndt_set_target_incremental_async) so that it runs while the host
+  // resamples and filters the next scan; estimatePose then finds its target in place. Same arguments as hintTargetPrefix.
+  void prefetchTarget(pcl::PointCloud<pcl::PointXYZ>::Ptr refScan, uint64_t epoch, size_t stablePoints, size_t settledPoints);
 
   void setScanPair(const Scan2D *curScan, pcl::PointCloud<pcl::PointXYZ>::Ptr refScan);
   void setScanPair(const Scan2D *curScan, const Scan2D *refScan);

@@ -32,6 +32,7 @@ PoseEstimator::PoseEstimator()
   ros::param::get("MaximumIterations", MaximumIterations);
   ros::param::get("LeafSize", LeafSize);
   ros::param::get("incremental_target", incrementalTarget);
+  ros::param::get("prefetch_target", prefetchTargetEnabled);
   source_cloud = std::make_shared<pcl::PointCloud<pcl::PointXYZ>>();
   target_cloud = std::make_shared<pcl::PointCloud<pcl::PointXYZ>>();
   std::memset(&lastResult, 0, sizeof(lastResult));
@@ -86,6 +87,19 @@ void PoseEstimator::setScanPair(const Scan2D *cur, const Scan2D *ref) {
   fillFromScan(ref, *target_cloud);
 }
 
+void PoseEstimator::prefetchTarget(pcl::PointCloud<pcl::PointXYZ>::Ptr ref, uint64_t epoch, size_t stablePoints, size_t settledPoints) {
+  if (!prefetchTargetEnabled || !incrementalTarget || epoch == 0 || !ref) return;
+  ensureHandle();
+  int64_t n_same = 0;
+  if (uploadedEpoch != 0 && epoch == uploadedEpoch + 1 && uploadedCloud == ref.get()) n_same = (int64_t)std::min(stablePoints, ref->points.size());
+  const int64_t n_target = (int64_t)ref->points.size();
+  if (ndt_set_target_incremental_async(ndt, reinterpret_cast<const float *>(ref->points.data()), n_target, n_same,
+                                       (int64_t)std::min(settledPoints, ref->points.size()), NDT_MEM_HOST) != NDT_OK)
+    fail(ndt, "ndt_set_target_incremental_async");
+  uploadedEpoch = epoch; uploadedCloud = ref.get();
+  prefetchedEpoch = epoch; prefetchedPoints = ref->points.size();
+}
+
 double PoseEstimator::estimatePose(Pose2D &initPose, Pose2D &estPose, Eigen::Matrix3d &cov) {
   ensureHandle();
 
@@ -110,14 +124,18 @@ double PoseEstimator::estimatePose(Pose2D &initPose, Pose2D &estPose, Eigen::Mat
     n_same = (int64_t)std::min(hintPrefix, target_cloud->points.size());
   const int64_t n_target = (int64_t)target_cloud->points.size();
   const float *target_pts = reinterpret_cast<const float *>(target_cloud->points.data());
-  int rc;
-  if (hintEpoch != 0 && incrementalTarget)
+  int rc = NDT_OK;
+  if (hintEpoch != 0 && prefetchedEpoch == hintEpoch && uploadedCloud == target_cloud.get() && prefetchedPoints == target_cloud->points.size()) {
+    // the grid of exactly this cloud was queued by prefetchTarget (ndt_set_source above already waited for it)
+  } else if (hintEpoch != 0 && incrementalTarget) {
     rc = ndt_set_target_incremental(ndt, target_pts, n_target, n_same, (int64_t)std::min(hintSettled, target_cloud->points.size()), NDT_MEM_HOST);
-  else
+  } else {
     rc = ndt_set_target_prefix(ndt, target_pts, n_target, n_same, NDT_MEM_HOST);
+  }
   if (rc != NDT_OK) fail(ndt, "ndt_set_target");
   uploadedEpoch = hintEpoch; uploadedCloud = target_cloud.get();
   hintEpoch = 0; hintPrefix = 0; hintSettled = 0;
+  prefetchedEpoch = 0;
   lastSetTargetWallMs = now_ms() - t0;
   float ms = 0.f;
   ndt_last_kernel_ms(ndt, &ms);

@@ -118,4 +118,7 @@ void ScanMatcher::growMap(const Scan2D &scan, const Pose2D &pose) {
   pcmap->setLastPose(pose);
   pcmap->setLastScan(scan);
   pcmap->makeLocalMap();
+  // the cloud the next estimatePose matches against exists now: let the device bring its grid up to date while the host
+  // goes on (FrontEnd bookkeeping, the next scan's resampling and source filter)
+  if (estim) estim->prefetchTarget(pcmap->localMap_cloud, pcmap->localMapEpoch, pcmap->localMapStablePrefix, pcmap->localMapSettled);
 }
