@@ -422,7 +422,7 @@ struct FinalizeOut {
 };
 
 // Mean, single-pass covariance, eigenvalue clamp and inverse of one cell from its in-order sums (VoxelGridCovariance pass 2,
-// SURVEY App. A.2). Shared by the full build (finish_leaf) and the incremental update (k_inc_finalize): same IEEE operations
+// SURVEY App. A.2). Shared by the full build (finish_leaf) and the incremental update (k_inc_update): same IEEE operations
 // in the same order, so a cell comes out bit-identical whichever path touched it last.
 struct LeafStats { int nr; bool in_tree; float cx, cy; double m0, m1, ic0, ic1, ic2, ic3; };
 __device__ __forceinline__ LeafStats leaf_stats(const int n, const LeafSums sums, const FinalizeParams fp) {
@@ -756,131 +756,145 @@ enum { ST_OCC = 1, ST_TREE = 2, ST_VALID = 4, ST_SLOT = 8, ST_CHANGED = 128 };
 enum { INC_A = 0, INC_B = 1, INC_P = 2, INC_U = 3 };     // inc_cnt entries: fold cells, tail cells, previous tail cells, union
 
 // The batch of a call = the points that became settled since the last call followed by the provisional tail: cloud[lo .. hi),
-// at most INC_BATCH_CAP points. Three small kernels order it by cell (stable):
-//   k_inc_rank     cell of every batch point; its rank among the batch points of the same cell (all-pairs compare over a
-//                  shared-memory copy of the batch's cells: B^2 / threads steps, B ~ 1,000); the first point of a cell
-//                  registers the cell (list, local id, point count)
-//   k_inc_starts   exclusive scan of the per-cell counts (one CTA)
-//   k_inc_scatter  order[start(cell) + rank] = batch index
+// at most INC_BATCH_CAP points, touching a few hundred cells. The whole update is ONE kernel on ONE CTA (the phases are
+// far too small to fill a GPU, and as eight separate launches they cost the host more time to issue than the device
+// needs to run them); phases are separated by __syncthreads(), buffers written and read inside the kernel are accessed
+// through plain pointers (no read-only path):
+//   rank      cell of every batch point; its rank among the batch points of the same cell (all-pairs compare over a
+//             shared-memory copy of the batch's cells: B^2 / threads steps, B ~ 1,000); the first point of a cell
+//             registers the cell (list, local id, point count)
+//   starts    exclusive scan of the per-cell counts
+//   scatter   order[start(cell) + rank] = batch index: the batch ordered by (cell, input index)
+//   union     U = batch cells + the previous call's tail cells, without duplicates
+//   finalize  every cell of U: add its batch points in input order to the settled sums -- the settled ones (cloud index
+//             < n_stable) for good (stored back), the tail ones on top for this call only -- then statistics -> probe
+//             tables, record, counters
+//   occ       dilated occupancy around every cell whose tree status changed: each of its nine neighbours gets the OR over
+//             ITS 3x3 block
 constexpr int INC_BATCH_CAP = 4096;
+constexpr int INC_THREADS = 512;
 
-__global__ void __launch_bounds__(256) k_inc_rank(const float4 *__restrict__ pts, int64_t lo, int B, const PairDims *__restrict__ dims, float inv_leaf,
-                                                 int32_t *__restrict__ cell_of, int32_t *__restrict__ rank_of, int2 *__restrict__ lid_tab,
-                                                 int32_t epoch, int32_t *__restrict__ list, int32_t *__restrict__ list_n,
-                                                 int32_t *__restrict__ cell_cnt) {
+struct IncTables {
+  uint8_t *status; int32_t *slot; float2 *cen;
+  CellRec *recs; int32_t *ctr;
+};
+struct IncBatch {
+  const float4 *__restrict__ pts;      // the whole target cloud (device copy), read-only here
+  int64_t lo, n_stable;                // batch = pts[lo .. lo + B); indices < n_stable are settled for good
+  int B;
+  const PairDims *__restrict__ dims;
+  float inv_leaf;
+  int32_t epoch;
+  int W;                               // padded row length
+  int32_t *cell_of, *rank_of, *order, *cell_cnt, *cell_start;    // [INC_BATCH_CAP] each
+  int2 *lid_tab;                       // per padded cell: (epoch, local id) of a cell that has batch points
+  int32_t *lb, *lp, *lu;               // this call's batch cells, the previous call's, their union
+  int32_t *cnt, *mark;
+  CellAcc *acc;
+  uint32_t *occ;
+};
+
+__global__ void __launch_bounds__(INC_THREADS) k_inc_update(IncBatch b, FinalizeParams fp, IncTables T) {
   __shared__ __align__(16) int s_cell[INC_BATCH_CAP];
-  const PairDims d = dims[0];
+  __shared__ int s_warp[INC_THREADS / 32];
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, w = tid >> 5, nw = nthr >> 5;
+  const int B = b.B;
+  if (tid == 0) { b.cnt[INC_B] = 0; b.cnt[INC_U] = 0; }
+  // ---- rank ----
+  const PairDims d = b.dims[0];
   const int B4 = (B + 3) & ~3;
-  for (int k = threadIdx.x; k < B4; k += blockDim.x) {
+  for (int k = tid; k < B4; k += nthr) {
     int c = -2;                                    // padding up to a multiple of four: matches nothing
     if (k < B) {
-      const float4 p = __ldg(pts + lo + k);
+      const float4 p = __ldg(b.pts + b.lo + k);
       c = -1;
       if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z))
-        c = d.base + (cell_coord(p.y, inv_leaf, d.min_by) + 2) * d.W + cell_coord(p.x, inv_leaf, d.min_bx) + 2;
+        c = d.base + (cell_coord(p.y, b.inv_leaf, d.min_by) + 2) * d.W + cell_coord(p.x, b.inv_leaf, d.min_bx) + 2;
     }
     s_cell[k] = c;
   }
   __syncthreads();
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= B) return;
-  const int c = s_cell[k];
-  int before = 0, total = 0;
-  if (c >= 0) {
-    // four cells per 16-byte shared load; every thread of the CTA reads the same words (broadcast). Matches in the group
-    // that contains k itself are split by position, groups before k count fully towards the rank.
-    const int4 *s4 = reinterpret_cast<const int4 *>(s_cell);
-    const int kg = k >> 2;
+  for (int k = tid; k < B; k += nthr) {
+    const int c = s_cell[k];
+    int before = 0, total = 0;
+    if (c >= 0) {
+      // four cells per 16-byte shared load; the threads of a warp read the same words (broadcast). Matches in the group
+      // that contains k itself are split by position, groups before k count fully towards the rank.
+      const int4 *s4 = reinterpret_cast<const int4 *>(s_cell);
+      const int kg = k >> 2;
 #pragma unroll 4
-    for (int g = 0; g < B4 / 4; ++g) {
-      const int4 v = s4[g];
-      const int m = (v.x == c) + (v.y == c) + (v.z == c) + (v.w == c);
-      total += m;
-      before += g < kg ? m : 0;
+      for (int g = 0; g < B4 / 4; ++g) {
+        const int4 v = s4[g];
+        const int m = (v.x == c) + (v.y == c) + (v.z == c) + (v.w == c);
+        total += m;
+        before += g < kg ? m : 0;
+      }
+      const int4 v = s4[kg];
+      const int r = k & 3;
+      before += (r > 0 && v.x == c) + (r > 1 && v.y == c) + (r > 2 && v.z == c);
     }
-    const int4 v = s4[kg];
-    const int r = k & 3;
-    before += (r > 0 && v.x == c) + (r > 1 && v.y == c) + (r > 2 && v.z == c);
+    b.cell_of[k] = c;
+    b.rank_of[k] = before;
+    if (c >= 0 && before == 0) {
+      const int lid = atomicAdd(b.cnt + INC_B, 1);
+      b.lb[lid] = c;
+      b.lid_tab[c] = make_int2(b.epoch, lid);
+      b.cell_cnt[lid] = total;
+    }
   }
-  cell_of[k] = c;
-  rank_of[k] = before;
-  if (c >= 0 && before == 0) {
-    const int lid = atomicAdd(list_n, 1);
-    list[lid] = c;
-    lid_tab[c] = make_int2(epoch, lid);
-    cell_cnt[lid] = total;
-  }
-}
-
-__global__ void __launch_bounds__(1024) k_inc_starts(const int32_t *__restrict__ cell_cnt, const int32_t *__restrict__ list_n, int32_t *__restrict__ cell_start) {
-  __shared__ int s_warp[32];
-  const int n = *list_n, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  int carry = 0;
-  for (int base = 0; base < n; base += 1024) {
-    const int i = base + threadIdx.x;
-    const int v = i < n ? cell_cnt[i] : 0;
-    int incl = v;
+  __syncthreads();
+  // ---- starts: exclusive scan of cell_cnt[0 .. nb) ----
+  const int nb = b.cnt[INC_B];
+  {
+    int carry = 0;
+    for (int base = 0; base < nb; base += nthr) {
+      const int i = base + tid;
+      const int v = i < nb ? b.cell_cnt[i] : 0;
+      int incl = v;
 #pragma unroll
-    for (int dlt = 1; dlt < 32; dlt <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, dlt); if (lane >= dlt) incl += t; }
-    if (lane == 31) s_warp[w] = incl;
-    __syncthreads();
-    int before = carry;
-    for (int q = 0; q < w; ++q) before += s_warp[q];
-    if (i < n) cell_start[i] = before + incl - v;
-    int tot = 0;
-    for (int q = 0; q < 32; ++q) tot += s_warp[q];
-    carry += tot;
-    __syncthreads();
+      for (int dlt = 1; dlt < 32; dlt <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, dlt); if (lane >= dlt) incl += t; }
+      if (lane == 31) s_warp[w] = incl;
+      __syncthreads();
+      int before = carry;
+      for (int q = 0; q < w; ++q) before += s_warp[q];
+      if (i < nb) b.cell_start[i] = before + incl - v;
+      int tot = 0;
+      for (int q = 0; q < nw; ++q) tot += s_warp[q];
+      carry += tot;
+      __syncthreads();
+    }
   }
-}
-
-__global__ void __launch_bounds__(256) k_inc_scatter(int B, const int32_t *__restrict__ cell_of, const int32_t *__restrict__ rank_of,
-                                                    const int2 *__restrict__ lid_tab, const int32_t *__restrict__ cell_start, int32_t *__restrict__ order) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= B) return;
-  const int c = cell_of[k];
-  if (c < 0) return;
-  order[cell_start[lid_tab[c].y] + rank_of[k]] = k;
-}
-
-// U = batch cells + previous call's cells, without duplicates
-__global__ void __launch_bounds__(256) k_inc_union(const int32_t *__restrict__ lb, const int32_t *__restrict__ lp,
-                                                  int32_t *__restrict__ cnt, int32_t *__restrict__ mark, int32_t epoch, int32_t *__restrict__ lu) {
-  const int nb = cnt[INC_B], np = cnt[INC_P];
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nb + np; t += gridDim.x * blockDim.x) {
-    const int c = t < nb ? lb[t] : lp[t - nb];
-    if (atomicExch(mark + c, epoch) != epoch) lu[atomicAdd(cnt + INC_U, 1)] = c;
+  __syncthreads();
+  // ---- scatter ----
+  for (int k = tid; k < B; k += nthr) {
+    const int c = b.cell_of[k];
+    if (c >= 0) b.order[b.cell_start[b.lid_tab[c].y] + b.rank_of[k]] = k;
   }
-}
-
-struct IncTables {
-  uint8_t *__restrict__ status; int32_t *__restrict__ slot; float2 *__restrict__ cen;
-  CellRec *__restrict__ recs; int32_t *__restrict__ ctr;
-};
-
-// Every cell of U: add its batch points in input order to the settled sums -- the settled ones (cloud index < n_stable) for
-// good (stored back), the tail ones on top for this call only -- then statistics -> probe tables, record, counters
-__global__ void __launch_bounds__(128) k_inc_finalize(const float4 *__restrict__ pts, int64_t lo, int64_t n_stable, const int32_t *__restrict__ order,
-                                                     const int2 *__restrict__ lid_tab, int32_t epoch, const int32_t *__restrict__ cell_start,
-                                                     const int32_t *__restrict__ cell_cnt, const int32_t *__restrict__ lu, const int32_t *__restrict__ cnt,
-                                                     CellAcc *__restrict__ acc, FinalizeParams fp, IncTables T) {
-  const int m = cnt[INC_U];
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < m; t += gridDim.x * blockDim.x) {
-    const int c = lu[t];
-    CellAcc v = acc[c];
+  // ---- union (independent of the scatter) ----
+  const int np = b.cnt[INC_P];
+  for (int t = tid; t < nb + np; t += nthr) {
+    const int c = t < nb ? b.lb[t] : b.lp[t - nb];
+    if (atomicExch(b.mark + c, b.epoch) != b.epoch) b.lu[atomicAdd(b.cnt + INC_U, 1)] = c;
+  }
+  __syncthreads();
+  // ---- finalize ----
+  const int m = b.cnt[INC_U];
+  for (int t = tid; t < m; t += nthr) {
+    const int c = b.lu[t];
+    CellAcc v = b.acc[c];
     LeafSums a{v.sx, v.sy, v.sxx, v.syx, v.syy, v.cx, v.cy};
     int n = v.n;
-    const int2 e = lid_tab[c];
-    if (e.x == epoch) {                              // the cell has points in this call's batch
-      const int st = cell_start[e.y], num = cell_cnt[e.y];
+    const int2 e = b.lid_tab[c];
+    if (e.x == b.epoch) {                            // the cell has points in this call's batch
+      const int st = b.cell_start[e.y], num = b.cell_cnt[e.y];
       bool settled_part = true, grew = false;
       for (int q = 0; q < num; ++q) {
-        const int64_t i = lo + order[st + q];
-        if (settled_part && i >= n_stable) {         // everything from here on is tail: park the settled sums first
-          if (grew) { v.sx = a.sx; v.sy = a.sy; v.sxx = a.sxx; v.syx = a.syx; v.syy = a.syy; v.cx = a.cx; v.cy = a.cy; v.n = n; acc[c] = v; }
+        const int64_t i = b.lo + b.order[st + q];
+        if (settled_part && i >= b.n_stable) {       // everything from here on is tail: park the settled sums first
+          if (grew) { v.sx = a.sx; v.sy = a.sy; v.sxx = a.sxx; v.syx = a.syx; v.syy = a.syy; v.cx = a.cx; v.cy = a.cy; v.n = n; b.acc[c] = v; }
           settled_part = false;
         }
-        const float4 p = __ldg(pts + i);
+        const float4 p = __ldg(b.pts + i);
         const double xd = (double)p.x, yd = (double)p.y;
         a.sx += xd; a.sy += yd;
         a.sxx += xd * xd; a.syx += yd * xd; a.syy += yd * yd;
@@ -888,7 +902,7 @@ __global__ void __launch_bounds__(128) k_inc_finalize(const float4 *__restrict__
         ++n;
         grew = true;
       }
-      if (settled_part && grew) { v.sx = a.sx; v.sy = a.sy; v.sxx = a.sxx; v.syx = a.syx; v.syy = a.syy; v.cx = a.cx; v.cy = a.cy; v.n = n; acc[c] = v; }
+      if (settled_part && grew) { v.sx = a.sx; v.sy = a.sy; v.sxx = a.sxx; v.syx = a.syx; v.syy = a.syy; v.cx = a.cx; v.cy = a.cy; v.n = n; b.acc[c] = v; }
     }
     const int old = T.status[c];
     int now = old & ST_SLOT;
@@ -914,28 +928,23 @@ __global__ void __launch_bounds__(128) k_inc_finalize(const float4 *__restrict__
     if (d_val) atomicAdd(T.ctr + CTR_VALID, d_val);
     T.status[c] = (uint8_t)now;
   }
-}
-
-// dilated occupancy around every cell whose tree status changed: each of its nine neighbours gets the OR over ITS 3x3 block
-__global__ void __launch_bounds__(128) k_inc_occ(const int32_t *__restrict__ lu, const int32_t *__restrict__ cnt, uint8_t *__restrict__ status,
-                                                int W, uint32_t *__restrict__ occ) {
-  const int m = cnt[INC_U];
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < m; t += gridDim.x * blockDim.x) {
-    const int c = lu[t];
-    if (!(status[c] & ST_CHANGED)) continue;
+  __syncthreads();
+  // ---- occ ----
+  for (int t = tid; t < m; t += nthr) {
+    const int c = b.lu[t];
+    if (!(T.status[c] & ST_CHANGED)) continue;
     for (int dj = -1; dj <= 1; ++dj)
       for (int di = -1; di <= 1; ++di) {
-        const int q = c + dj * W + di;
+        const int q = c + dj * b.W + di;
         bool any = false;
         for (int ej = -1; ej <= 1; ++ej)
-          for (int ei = -1; ei <= 1; ++ei) any = any || (status[q + ej * W + ei] & ST_TREE);
-        if (any) atomicOr(occ + (q >> 5), 1u << (q & 31)); else atomicAnd(occ + (q >> 5), ~(1u << (q & 31)));
+          for (int ei = -1; ei <= 1; ++ei) any = any || (T.status[q + ej * b.W + ei] & ST_TREE);
+        if (any) atomicOr(b.occ + (q >> 5), 1u << (q & 31)); else atomicAnd(b.occ + (q >> 5), ~(1u << (q & 31)));
       }
   }
-}
-__global__ void __launch_bounds__(128) k_inc_clear_changed(const int32_t *__restrict__ lu, const int32_t *__restrict__ cnt, uint8_t *__restrict__ status) {
-  const int m = cnt[INC_U];
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < m; t += gridDim.x * blockDim.x) status[lu[t]] &= (uint8_t)~ST_CHANGED;
+  __syncthreads();
+  for (int t = tid; t < m; t += nthr) T.status[b.lu[t]] &= (uint8_t)~ST_CHANGED;
+  if (tid == 0) b.cnt[INC_P] = nb;                   // this call's batch cells are the next call's "previous" cells
 }
 
 // After a full build: the settled sums of every leaf (its bucket is in input order; sorted_idx carries the original indices, the
@@ -1100,7 +1109,24 @@ int pairs_prepare(Handle *h, int64_t n_pairs, int64_t *total_pad, int *max_h) {
 
 // Finer lattice for the exact 1-NN of the fitness score: built when the NDT buckets are dense (walls: hundreds of points per
 // 0.5 m cell), or always (force: factor >= 1) for incrementally maintained targets, whose ordered buckets go stale.
-static int build_nn_lattice(Handle *h, int64_t n, const float mn[2], const float mx[2], int64_t nfin, bool force) {
+// side = true: the kernels run on the handle's second stream, forked from the main stream here (everything queued on it so
+// far -- the upload of the points -- comes first); the caller joins with join_side_stream() before anything reads the lattice.
+static int side_stream(Handle *h) {
+  if (h->copy_stream) return NDT_OK;
+  NDT_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (int k = 0; k < 2; ++k) {
+    NDT_CUDA(h, cudaEventCreateWithFlags(&h->ev_up[k], cudaEventDisableTiming));
+    NDT_CUDA(h, cudaEventCreateWithFlags(&h->ev_done[k], cudaEventDisableTiming));
+  }
+  return NDT_OK;
+}
+static int join_side_stream(Handle *h) {
+  NDT_CUDA(h, cudaEventRecord(h->ev_done[0], h->copy_stream));
+  NDT_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_done[0], 0));
+  return NDT_OK;
+}
+
+static int build_nn_lattice(Handle *h, int64_t n, const float mn[2], const float mx[2], int64_t nfin, bool force, bool side = false) {
   GridBuffers &gb = h->gb;
   GridDims &gd = h->gd;
   cudaStream_t st = h->stream;
@@ -1129,6 +1155,12 @@ static int build_nn_lattice(Handle *h, int64_t n, const float mn[2], const float
     NDT_CUDA(h, gb.nn_cnt.reserve((size_t)ncf * 4));
     NDT_CUDA(h, gb.nn_range.reserve((size_t)ncf * sizeof(int2)));
     NDT_CUDA(h, gb.nn_pts.reserve(npts * sizeof(float2)));
+    if (side) {
+      if (int rc = side_stream(h)) return rc;
+      NDT_CUDA(h, cudaEventRecord(h->ev_up[0], st));
+      st = h->copy_stream;
+      NDT_CUDA(h, cudaStreamWaitEvent(st, h->ev_up[0], 0));
+    }
     NDT_CUDA(h, cudaMemsetAsync(gb.nn_cnt.p, 0, (size_t)ncf * 4, st));
     NDT_CUDA(h, cudaMemsetAsync(ctr + CTR_JOB, 0, 4, st));
     Dims df{gd.nn_min_bx, gd.nn_min_by, gd.nn_div_x, gd.nn_div_y, gd.nn_inv_leaf};
@@ -1399,36 +1431,25 @@ int grid_build_incremental(Handle *h, const float *xyzw, int64_t n, int64_t n_sa
   int buf[3], k = 0;
   for (int b = 0; b < 4; ++b) if (b != h->inc_list_prev) buf[k++] = b;
   int32_t *LB = lists + (size_t)buf[0] * npad, *LU = lists + (size_t)buf[1] * npad, *LP = lists + (size_t)h->inc_list_prev * npad;
-  NDT_CUDA(h, cudaMemsetAsync(cnt + INC_B, 0, sizeof(int32_t), st));
-  NDT_CUDA(h, cudaMemsetAsync(cnt + INC_U, 0, sizeof(int32_t), st));
   const PairDims *dims = gb.dims.as<PairDims>();
   const float4 *pts = gb.tgt.as<float4>();
   int32_t *cell_of = gb.inc_cellof.as<int32_t>(), *rank_of = cell_of + INC_BATCH_CAP, *order = rank_of + INC_BATCH_CAP,
           *cell_cnt = order + INC_BATCH_CAP, *cell_start = cell_cnt + INC_BATCH_CAP;
-  int2 *lid_tab = gb.inc_lid.as<int2>();
-  if (B > 0) {
-    const int blocks = (B + 255) / 256;
-    k_inc_rank<<<blocks, 256, 0, st>>>(pts, m, B, dims, gd.inv_leaf, cell_of, rank_of, lid_tab, epoch, LB, cnt + INC_B, cell_cnt);
-    k_inc_starts<<<1, 1024, 0, st>>>(cell_cnt, cnt + INC_B, cell_start);
-    k_inc_scatter<<<blocks, 256, 0, st>>>(B, cell_of, rank_of, lid_tab, cell_start, order);
-    h->launches += 3;
-  }
-  const int64_t work = B + npad / 16 + 1024;          // the previous call's list length lives on the device: enough threads either way
-  k_inc_union<<<grid_for(work, 256, h->sm_count), 256, 0, st>>>(LB, LP, cnt, mark, epoch, LU);
   FinalizeParams fp{h->prm.min_points, h->prm.eig_mult, h->prm.quirks};
   IncTables T{gb.inc_status.as<uint8_t>(), gb.slot.as<int32_t>(), gb.cen.as<float2>(), gb.recs.as<CellRec>(), ctr};
-  k_inc_finalize<<<grid_for(work, 128, h->sm_count), 128, 0, st>>>(pts, m, n_stable, order, lid_tab, epoch, cell_start, cell_cnt, LU, cnt,
-                                                                  gb.inc_acc.as<CellAcc>(), fp, T);
-  k_inc_occ<<<grid_for(work, 128, h->sm_count), 128, 0, st>>>(LU, cnt, gb.inc_status.as<uint8_t>(), gd.div_x + 4, gb.occ.as<uint32_t>());
-  k_inc_clear_changed<<<grid_for(work, 128, h->sm_count), 128, 0, st>>>(LU, cnt, gb.inc_status.as<uint8_t>());
-  h->launches += 4;
-  NDT_CUDA(h, cudaMemcpyAsync(cnt + INC_P, cnt + INC_B, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));   // this call's tail cells are the next call's "previous tail"
+  IncBatch ib{pts, m, n_stable, B, dims, gd.inv_leaf, epoch, gd.div_x + 4, cell_of, rank_of, order, cell_cnt, cell_start,
+              gb.inc_lid.as<int2>(), LB, LP, LU, cnt, mark, gb.inc_acc.as<CellAcc>(), gb.occ.as<uint32_t>()};
+  gd.n_tgt = n;
+  // The exact 1-NN lattice only depends on the points: it is rebuilt on the second stream while k_inc_update runs. It is
+  // sized from the leaf count of the previous call (h_counters: a handful of leaves off at most, and only the lattice pitch
+  // depends on it), so the whole update needs one stream synchronisation, at its end.
+  if (int rc = build_nn_lattice(h, n, mn, mx, nfin, /*force=*/true, /*side=*/true)) return rc;
+  const bool forked = gd.nn_f > 0;
+  k_inc_update<<<1, INC_THREADS, 0, st>>>(ib, fp, T);
+  ++h->launches;
+  if (forked) { if (int rc = join_side_stream(h)) return rc; }
   h->inc_list_prev = buf[0];
   NDT_CUDA(h, cudaGetLastError());
-  gd.n_tgt = n;
-  // the 1-NN lattice is sized from the leaf count of the previous call (h_counters: a handful of leaves off at most, and only
-  // the lattice pitch depends on it), so the whole update needs one stream synchronisation, at its end
-  if (int rc = build_nn_lattice(h, n, mn, mx, nfin, /*force=*/true)) return rc;
   if (h->timing) cudaEventRecord(h->ev1, st);
   // counters -> host (also the stream fence that lets the pinned stage be reused)
   NDT_CUDA(h, cudaMemcpyAsync(h->pinned_ctr, ctr, sizeof(h->h_counters), cudaMemcpyDeviceToHost, st));
