@@ -260,6 +260,7 @@ def main():
     ap.add_argument("--c2-scans", type=int, default=2000)
     ap.add_argument("--no-cpu-baseline", action="store_true", help="profiling runs only")
     ap.add_argument("--c5-pairs", type=int, default=C5_PAIRS, help="scan pairs of the C5 figure in total (0 = skip)")
+    ap.add_argument("--align-team", type=int, default=0, help="ndt_params.align_team: warps per match in ndt_align_batch (0 = the library's choice)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -314,7 +315,7 @@ def main():
     # a dedicated (non-default) stream: the library launches on it and torch records the timing events on it
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    prm = capi.default_params(resolution=RESOLUTION, device=local_rank, stream=stream.cuda_stream)
+    prm = capi.default_params(resolution=RESOLUTION, device=local_rank, stream=stream.cuda_stream, align_team=args.align_team)
     g = capi.Ndt(prm)
 
     # ---- grid: built once on rank 0, replicated once, no collective afterwards -------------------
