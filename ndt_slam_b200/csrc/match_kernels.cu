@@ -418,8 +418,10 @@ __global__ void __launch_bounds__(256, 2) k_align_grid(GridView G, MatchParams m
 //   65,536 matches 7.84 / 9.61 / 12.6 / 18.2     8,192: 1.54 / 1.53 / 1.75 / 2.41     4,096: 1.26 / 1.05 / 1.03 / 1.30
 //    2,048: 0.80 / 0.64 / 0.57 / 0.65              512: 0.65 / 0.44 / 0.34 / 0.34
 // A team trades throughput (helpers idle while their leader runs the optimiser) for the length of the longest match.
+// The eight 8,192-hypothesis shards of the 65,536-hypothesis job (profiles/shard_sweep.py): 1.55 - 1.79 ms with one warp per
+// match, 1.40 - 1.59 ms with two; the four 16,384-hypothesis shards: 2.42 - 2.66 against 2.61 - 2.79.
 #ifndef NDT_TEAM1_FROM_X
-#define NDT_TEAM1_FROM_X 3        // n >= 3 R: one warp per match
+#define NDT_TEAM1_FROM_X 4        // n >= 4 R: one warp per match
 #endif
 #ifndef NDT_TEAM2_FROM_X
 #define NDT_TEAM2_FROM_X 2        // n >= 2 R: two; below: four, and eight when not even every CTA gets a match
