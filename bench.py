@@ -247,7 +247,29 @@ def peaks_extra():
 
 
 # ---------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries the one JSON line and nothing else: libraries that print to file descriptor 1 (NCCL's version banner,
+    device-side printf of diagnostic builds) are sent to stderr, the line itself is written to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(text: str):
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        print(text, flush=True)
+    else:
+        os.write(_REAL_STDOUT, (text + "\n").encode())
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -278,7 +300,7 @@ def main():
     if args.extras_only:
         import torch
         from ndt_slam_b200 import capi
-        print(json.dumps(run_extras(None, capi.default_params(resolution=RESOLUTION), capi, torch, c2_scans=args.c2_scans)), flush=True)
+        emit(json.dumps(run_extras(None, capi.default_params(resolution=RESOLUTION), capi, torch, c2_scans=args.c2_scans)))
         return
 
     # Secondary single-GPU figures (C1 / C2 / C3) run first, in a fresh process, before this one creates its CUDA context:
@@ -305,7 +327,6 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries the one JSON line and nothing else
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     wl = build_c4(args.hyp_total)
@@ -577,7 +598,7 @@ def main():
         "c5": c5_line,
         "extras": extras,
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -956,7 +977,7 @@ def reference_arm(args, rank, n_gpus, K, W):
                                       "matches_per_sec": port["matches"] / port["seconds"],
                                       "note": "the 3-DoF oracle restatement on the same threads (faster than the 6-DoF reference build)"}},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 if __name__ == "__main__":
